@@ -1,0 +1,55 @@
+// Shared helpers for libgphm (sm_100a).  Internal header - the public C-ABI is include/gphm.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include "../../include/gphm.h"   // status codes GPHM_OK / GPHM_EINVAL / ...
+
+namespace gphm {
+
+void set_last_error(const char* fmt, ...);
+
+#define GPHM_CUDA_OK(expr)                                                                   \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ::gphm::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,             \
+                                   cudaGetErrorString(_e));                                  \
+            return GPHM_ECUDA;                                                       \
+        }                                                                                    \
+    } while (0)
+
+#define GPHM_LAUNCH_OK()  GPHM_CUDA_OK(cudaGetLastError())
+
+#define GPHM_TRY(expr)                                                                       \
+    do {                                                                                     \
+        int _s = (expr);                                                                     \
+        if (_s != 0) return _s;                                                              \
+    } while (0)
+
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block sum (fixed tree): every thread gets the result.  `red` holds >= 33 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();                 // protect `red` from a previous call
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        double t = (lane < nw) ? red[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+}  // namespace gphm

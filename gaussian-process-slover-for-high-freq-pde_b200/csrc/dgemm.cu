@@ -1,0 +1,249 @@
+// FP64 GEMM engine for the Kronecker contractions, triangular applications of L^-1 and the
+// blocked factorisations:  C = alpha * op(A) * op(B) + beta * C, row-major, batched.
+//
+// These are the dense contractions of the reference's jitted step - jnp.linalg.solve and
+// jnp.matmul at model_GP_solver_2d.py:104-105,112,119 and their reverse-mode counterparts
+// (:179) - and carry ~99.9% of the 28 N^3 FLOPs per iteration at N=4096.
+//
+// Design (sm_100a): tcgen05 has no f64 kind, so native FP64 runs on the DMMA pipe
+// (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4).  One CTA computes a BM x BN tile with a
+// 3-stage cp.async (LDGSTS, zero-fill predicated) shared-memory pipeline over BK=16 slices;
+// 8 warps each own a 64x32 sub-tile (64 FP64 accumulators per thread).  Shared-memory rows are
+// padded by 4 doubles so every fragment LDS.64 is bank-conflict free.  Roofline: FP64 compute
+// (DMMA issue rate); operand traffic per tile is 32 KB per 0.5 MFLOP, far below L2 bandwidth.
+// Triangular operands (L^-1 applications, LAUUM-style products) restrict the k-range per tile
+// (kmode flags) so the zero halves are never loaded or multiplied.
+#include <algorithm>
+#include <cstdint>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gphm {
+
+constexpr int BK = 16;
+constexpr int STAGES = 3;
+constexpr int PAD = 4;
+
+template <int VEC>
+__device__ __forceinline__ void cp_async(double* smem, const double* gmem, int src_bytes) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    if (VEC == 2)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// Copy one operand tile (MN rows/cols of the m- or n-index by BK of k) into shared memory.
+// KCONTIG: global element (mn, k) at G[mn*ld + k]  -> S[mn][k], row pitch BK+PAD
+// else   : global element (k, mn) at G[k*ld + mn]  -> S[k][mn],  row pitch MN+PAD
+// Everything outside [0,mn_max) x [k0,kend) is zero-filled by cp.async's src-size operand.
+template <int MN, bool KCONTIG, int VEC, int NT>
+__device__ __forceinline__ void load_tile(double* S, const double* __restrict__ G, int ld, int mn0, int mn_max,
+                                          int k0, int kend) {
+    if (KCONTIG) {
+        constexpr int CPR = BK / VEC;
+        for (int c = threadIdx.x; c < MN * CPR; c += NT) {
+            const int r = c / CPR, kc = (c % CPR) * VEC;
+            const int gr = mn0 + r, gk = k0 + kc;
+            int nv = (gr < mn_max) ? min(max(kend - gk, 0), VEC) : 0;
+            const double* src = nv > 0 ? G + (size_t)gr * ld + gk : G;
+            cp_async<VEC>(S + r * (BK + PAD) + kc, src, nv * 8);
+        }
+    } else {
+        constexpr int CPR = MN / VEC;
+        for (int c = threadIdx.x; c < BK * CPR; c += NT) {
+            const int r = c / CPR, cc = (c % CPR) * VEC;
+            const int gk = k0 + r, gc = mn0 + cc;
+            int nv = (gk < kend) ? min(max(mn_max - gc, 0), VEC) : 0;
+            const double* src = nv > 0 ? G + (size_t)gk * ld + gc : G;
+            cp_async<VEC>(S + r * (MN + PAD) + cc, src, nv * 8);
+        }
+    }
+}
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool TA, bool TB, int VEC, int MINB>
+__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MINB)
+dgemm_kernel(const GemmArgs p) {
+    constexpr int NT = WARPS_M * WARPS_N * 32;
+    constexpr int WTM = BM / WARPS_M, WTN = BN / WARPS_N;
+    constexpr int MI = WTM / 8, NI = WTN / 8;
+    constexpr int A_TILE = TA ? BK * (BM + PAD) : BM * (BK + PAD);
+    constexpr int B_TILE = TB ? BN * (BK + PAD) : BK * (BN + PAD);
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;
+    double* Bs = smem + STAGES * A_TILE;
+
+    // ---- tile coordinates: groups of 8 tile-rows share B columns in L2; heavy tiles first ----
+    const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+    int pid = blockIdx.x;
+    if (p.kmode & (KM_A_LOWER | KM_B_UPPER)) pid = tiles_m * tiles_n - 1 - pid;
+    constexpr int GROUP = 8;
+    const int per_group = GROUP * tiles_n;
+    const int group_id = pid / per_group;
+    const int first_m = group_id * GROUP;
+    const int gsz = min(tiles_m - first_m, GROUP);
+    const int tm = first_m + (pid % per_group) % gsz;
+    const int tn = (pid % per_group) / gsz;
+    const int m0 = tm * BM, n0 = tn * BN;
+    if ((p.kmode & KM_C_LOWER) && n0 >= m0 + BM) return;
+
+    const double* __restrict__ A = p.A + (size_t)blockIdx.y * p.sA;
+    const double* __restrict__ B = p.B + (size_t)blockIdx.y * p.sB;
+    double* __restrict__ C = p.C + (size_t)blockIdx.y * p.sC;
+
+    int kbegin = 0, kend = p.K;
+    if (p.kmode & KM_A_LOWER) kend = min(kend, m0 + BM);
+    if (p.kmode & KM_A_UPPER) kbegin = max(kbegin, m0);
+    if (p.kmode & KM_B_LOWER) kbegin = max(kbegin, n0);
+    if (p.kmode & KM_B_UPPER) kend = min(kend, n0 + BN);
+    const int KT = kend > kbegin ? (kend - kbegin + BK - 1) / BK : 0;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+    const int g = lane >> 2, t = lane & 3;
+
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    auto issue = [&](int kt) {
+        const int slot = kt % STAGES;
+        const int k0 = kbegin + kt * BK;
+        load_tile<BM, !TA, VEC, NT>(As + slot * A_TILE, A, p.lda, m0, p.M, k0, kend);
+        load_tile<BN, TB, VEC, NT>(Bs + slot * B_TILE, B, p.ldb, n0, p.N, k0, kend);
+    };
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT) issue(s);
+        cp_async_commit();
+    }
+
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (kt + STAGES - 1 < KT) issue(kt + STAGES - 1);
+        cp_async_commit();
+
+        const double* as = As + (kt % STAGES) * A_TILE;
+        const double* bs = Bs + (kt % STAGES) * B_TILE;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double af[MI], bf[NI];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) {
+                const int r = wm * WTM + i * 8 + g;
+                af[i] = TA ? as[(kk * 4 + t) * (BM + PAD) + r] : as[r * (BK + PAD) + kk * 4 + t];
+            }
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                const int c = wn * WTN + j * 8 + g;
+                bf[j] = TB ? bs[c * (BK + PAD) + kk * 4 + t] : bs[(kk * 4 + t) * (BN + PAD) + c];
+            }
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- epilogue: each thread owns 2 adjacent columns per 8x8 fragment -> 16 B stores ----
+    const bool cvec = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int row = m0 + wm * WTM + i * 8 + g;
+        if (row >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            const int col = n0 + wn * WTN + j * 8 + 2 * t;
+            if (col >= p.N) continue;
+            double* ptr = C + (size_t)row * p.ldc + col;
+            double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
+            const bool two = (col + 1 < p.N);
+            if (two && cvec) {
+                if (p.beta != 0.0) {
+                    const double2 o = *reinterpret_cast<const double2*>(ptr);
+                    v0 += p.beta * o.x; v1 += p.beta * o.y;
+                }
+                *reinterpret_cast<double2*>(ptr) = make_double2(v0, v1);
+            } else {
+                if (p.beta != 0.0) { v0 += p.beta * ptr[0]; if (two) v1 += p.beta * ptr[1]; }
+                ptr[0] = v0;
+                if (two) ptr[1] = v1;
+            }
+        }
+    }
+}
+
+template <int BM, int BN, bool TA, bool TB>
+constexpr size_t gemm_smem_bytes() {
+    return (size_t)STAGES * ((TA ? BK * (BM + PAD) : BM * (BK + PAD)) + (TB ? BN * (BK + PAD) : BK * (BN + PAD))) *
+           sizeof(double);
+}
+
+template <int BM, int BN, int WM, int WN, bool TA, bool TB, int VEC, int MINB>
+static int launch_cfg(const GemmArgs& g, cudaStream_t st) {
+    const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+    dim3 grid(tiles, g.batch), block(WM * WN * 32);
+    dgemm_kernel<BM, BN, WM, WN, TA, TB, VEC, MINB><<<grid, block, gemm_smem_bytes<BM, BN, TA, TB>(), st>>>(g);
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+template <int BM, int BN, int WM, int WN, bool TA, bool TB, int VEC, int MINB>
+static int set_attr() {
+    GPHM_CUDA_OK(cudaFuncSetAttribute(dgemm_kernel<BM, BN, WM, WN, TA, TB, VEC, MINB>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)gemm_smem_bytes<BM, BN, TA, TB>()));
+    return GPHM_OK;
+}
+
+#define GPHM_FOR_ALL_GEMM(F)                                                                   \
+    F(false, false, 2) F(false, true, 2) F(true, false, 2) F(true, true, 2)                    \
+    F(false, false, 1) F(false, true, 1) F(true, false, 1) F(true, true, 1)
+
+int dgemm_init() {
+    static int done = -1;
+    if (done >= 0) return done;
+#define GPHM_SET(TA, TB, VEC)                                         \
+    GPHM_TRY((set_attr<128, 128, 2, 4, TA, TB, VEC, 1>()));           \
+    GPHM_TRY((set_attr<64, 64, 2, 2, TA, TB, VEC, 3>()));
+    GPHM_FOR_ALL_GEMM(GPHM_SET)
+#undef GPHM_SET
+    done = GPHM_OK;
+    return done;
+}
+
+int launch_dgemm(const GemmArgs& g, cudaStream_t st) {
+    if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return GPHM_OK;
+    if (g.K < 0 || g.lda < 1 || g.ldb < 1 || g.ldc < 1) { set_last_error("dgemm: bad shape"); return GPHM_EINVAL; }
+    GPHM_TRY(dgemm_init());
+    auto aligned = [](const double* p, int ld, long long s) {
+        return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld & 1) == 0 && (s & 1) == 0;
+    };
+    const int vec = (aligned(g.A, g.lda, g.sA) && aligned(g.B, g.ldb, g.sB)) ? 2 : 1;
+    const long long big_tiles = (long long)((g.M + 127) / 128) * ((g.N + 127) / 128) * g.batch;
+    const bool big = big_tiles >= 96;   // otherwise 64x64 tiles to fill the 148 SMs
+#define GPHM_GO(TA, TB, VEC)                                                                       \
+    if ((g.transA != 0) == TA && (g.transB != 0) == TB && vec == VEC)                              \
+        return big ? launch_cfg<128, 128, 2, 4, TA, TB, VEC, 1>(g, st)                             \
+                   : launch_cfg<64, 64, 2, 2, TA, TB, VEC, 3>(g, st);
+    GPHM_FOR_ALL_GEMM(GPHM_GO)
+#undef GPHM_GO
+    set_last_error("dgemm: no kernel variant");
+    return GPHM_EINVAL;
+}
+
+}  // namespace gphm

@@ -1,0 +1,80 @@
+// Internal launcher declarations shared by the translation units of libgphm.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+
+namespace gphm {
+
+// ---- gram.cu -------------------------------------------------------------------------------
+int launch_gram_general(int kid, int order, const double* x1, int n1, const double* x2, int n2,
+                        const double* theta, int Q, double jitter, double* Kout, double* Dout, int ld,
+                        cudaStream_t st);
+int launch_gram_toeplitz(int kid, int order, const double* x, int n, const double* theta, int Q, double jitter,
+                         double dirsign, double* tabK, double* tabD, double* Kout, double* Dout, int ld,
+                         cudaStream_t st);
+
+int launch_kappa_pairs(int kid, int order, const double* x1, const double* x2, size_t np, const double* theta, int Q,
+                       double* out, cudaStream_t st);
+
+// ---- dgemm.cu ------------------------------------------------------------------------------
+// k-range / output structure flags.  "op(A) lower" means op(A)[m][k] == 0 for k > m, etc.
+enum : int { KM_A_LOWER = 1, KM_A_UPPER = 2, KM_B_LOWER = 4, KM_B_UPPER = 8, KM_C_LOWER = 16 };
+
+struct GemmArgs {
+    const double* A; const double* B; double* C;   // row-major, leading dimensions lda/ldb/ldc
+    int M, N, K;                                   // C[M,N] = alpha*op(A)[M,K]*op(B)[K,N] + beta*C
+    int lda, ldb, ldc;
+    double alpha, beta;
+    int transA, transB;                            // op(X) = X^T when set (X stored K x M / N x K)
+    int kmode;
+    long long sA, sB, sC;                          // batch strides (elements)
+    int batch;
+};
+inline GemmArgs gemm_args(const double* A, int lda, bool tA, const double* B, int ldb, bool tB, double* C, int ldc,
+                          int M, int N, int K, double alpha = 1.0, double beta = 0.0, int kmode = 0) {
+    GemmArgs g{A, B, C, M, N, K, lda, ldb, ldc, alpha, beta, tA ? 1 : 0, tB ? 1 : 0, kmode, 0, 0, 0, 1};
+    return g;
+}
+int launch_dgemm(const GemmArgs& g, cudaStream_t st);
+int dgemm_init();   // opt in to large dynamic shared memory once per process
+
+// ---- factor.cu -----------------------------------------------------------------------------
+constexpr int kNB = 128;   // diagonal block size of the blocked Cholesky / triangular inverse
+inline int num_blocks_nb(int n) { return (n + kNB - 1) / kNB; }
+// K (n x n, ld, lower triangle read, destroyed) -> L (lower, separate buffer), inverse diagonal
+// blocks invdiag[nblk][kNB][kNB], logdet_part[nblk] = sum log diag(L_bb); status[0] = 1 + index
+// of the first non-positive pivot (0 if SPD).
+int chol_factor(double* K, double* L, int n, int ld, double* invdiag, double* logdet_part, int* status,
+                cudaStream_t st);
+// Linv (n x n, ld; strictly-upper triangle must already be zero) = L^-1, T = n x n scratch.
+int trtri_lower(const double* L, double* Linv, int n, int ld, const double* invdiag, double* T, cudaStream_t st);
+int factor_init();
+
+// ---- elemwise.cu ---------------------------------------------------------------------------
+struct LossConsts { int dim, eq_type, n1, n2, nb, Q; double llk_weight, logdet, c1; };
+constexpr int kRedBlocks = 592;         // 148 SMs x 4
+int launch_residual(double* R, const double* U, const double* F, const double* A, const double* Bt, size_t n,
+                    int eq_type, const double* small, int Q, double* part, cudaStream_t st);
+int launch_finalize(const LossConsts& c, const double* U, const double* bvals, const int* xind,
+                    const double* part, const double* ldp1, int nblk1, const double* ldp2, int nblk2,
+                    const double* small, double* eb, double* terms, double* gsmall, int* status, cudaStream_t st);
+int launch_grad_u(const LossConsts& c, const double* U, const double* G, const double* W, const double* S1,
+                  const double* S2, const double* eb, const int* xind, const double* small, double* gU,
+                  double* V1, double* V2, cudaStream_t st);
+int launch_diag_sums(const double* Kbar, const double* Dbar, int n, int ld, bool antisym, double dirsign,
+                     double* part, double* sK, double* sD, cudaStream_t st);
+size_t diag_sums_part_doubles(int n);
+int launch_theta_grad_toeplitz(int kid, int order, const double* x, int n, const double* theta, int Q,
+                               const double* sK, const double* sD, double* gtheta, cudaStream_t st);
+int launch_theta_grad_general(int kid, int order, const double* x, int n, const double* theta, int Q,
+                              const double* Kbar, const double* Dbar, int ld, double* part, double* gtheta,
+                              cudaStream_t st);
+size_t theta_general_part_doubles(int n, int Q);
+int launch_adam(double* p, const double* g, double* m, double* v, size_t n, const long long* count, double lr,
+                cudaStream_t st);
+int launch_count_inc(long long* count, cudaStream_t st);
+int launch_rel_l2(const double* pred, const double* truth, size_t n, double* part, double* out, cudaStream_t st);
+int launch_copy(double* dst, const double* src, size_t n, cudaStream_t st);
+int launch_sum_scaled(const double* v, int n, double scale, double* out, cudaStream_t st);
+
+}  // namespace gphm

@@ -1,0 +1,546 @@
+// Plan object, per-iteration orchestration and the extern "C" boundary of libgphm.
+//
+// One gphm_plan = one reference solver instance (GP_solver_1d_single, GP_solver_2d_single,
+// GP_solver_2d_single_advection): the constants the reference captures through the static
+// `self` of its jitted methods plus every device buffer the step needs, so that nothing is
+// allocated and nothing touches the host while iterating (CUDA-graph capturable).
+//
+// Per-iteration dataflow (reference lines in include/gphm.h):
+//   per axis a:  K_a, D_a  <- Gram builders        L_a <- chol(K_a)      Linv_a <- L_a^-1
+//   A  = K1^-1 U  = Linv1^T (Linv1 U)              Bt = U K2^-1 = (U Linv2^T) Linv2
+//   R  = c1 * D1 A + Bt D2^T      G = e^v (R + nl(U) - F)       eqgap, quad, bgap, logdets
+//   W  = K1^-1 Bt     S1 = K1^-1 (c1 D1^T G)     S2 = (G D2) K2^-1
+//   dU = W + S1 + S2 [+ G (3U^2-1)] + lambda e^tau E_b
+//   Kbar1 = ld/2 N2 K1^-1 - (S1 + W/2) A^T        Dbar1 = c1 G A^T
+//   Kbar2 = ld/2 N1 K2^-1 - (S2 + W/2)^T Bt       Dbar2 = G^T Bt
+//   dtheta_a = sum_ij Kbar_a * dK/dtheta + Dbar_a * dD/dtheta   (diagonal sums on uniform grids)
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <vector>
+#include "../../include/gphm.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gphm {
+
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct Axis {
+    int n = 0, nblk = 0;
+    bool toeplitz = false;
+    double dirsign = 1.0;
+    double *x = nullptr, *K = nullptr, *D = nullptr, *L = nullptr, *Linv = nullptr, *Kinv = nullptr, *Dbar = nullptr,
+           *T = nullptr, *invdiag = nullptr, *ldpart = nullptr, *tabK = nullptr, *tabD = nullptr, *dspart = nullptr,
+           *sK = nullptr, *sD = nullptr, *tgpart = nullptr;
+};
+
+}  // namespace gphm
+
+using namespace gphm;
+
+struct gphm_plan {
+    gphm_problem_desc d;
+    Axis ax[2];
+    double *src = nullptr, *bvals = nullptr;
+    int* xind = nullptr;
+    double *A = nullptr, *Bt = nullptr, *Tf = nullptr, *R = nullptr, *W = nullptr, *P = nullptr, *S1 = nullptr,
+           *S2 = nullptr, *V1 = nullptr, *V2 = nullptr, *gU = nullptr;
+    double *part = nullptr, *eb = nullptr, *gsmall = nullptr, *terms = nullptr;
+    int* status = nullptr;
+    void* ws = nullptr;
+    bool owns_ws = false;
+    bool size_query = false;   // carve(): reserve the larger theta-gradient scratch per axis
+    // device staging for gphm_step_host (allocated on first use)
+    double* hs = nullptr;
+    long long* hs_count = nullptr;
+};
+
+namespace {
+
+constexpr size_t kAlign = 256;
+
+// Walks the workspace: with base == nullptr only sizes are accumulated.
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+    template <typename T>
+    void take(T*& p, size_t count) {
+        const size_t bytes = (count * sizeof(T) + kAlign - 1) / kAlign * kAlign;
+        p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += bytes;
+    }
+};
+
+bool uniform_grid(const double* x, int n) {
+    if (n < 3) return true;
+    const double h0 = x[1] - x[0];
+    double hmax = 0.0, dev = 0.0;
+    for (int i = 1; i < n; ++i) {
+        const double h = x[i] - x[i - 1];
+        hmax = std::max(hmax, std::fabs(h));
+        dev = std::max(dev, std::fabs(h - h0));
+    }
+    return h0 != 0.0 && dev <= 1e-9 * hmax;
+}
+
+size_t carve(gphm_plan& p, void* base) {
+    Carver c(base);
+    const gphm_problem_desc& d = p.d;
+    const size_t nf = (size_t)d.n1 * d.n2;
+    const int naxes = d.dim == 2 ? 2 : 1;
+    for (int a = 0; a < naxes; ++a) {
+        Axis& X = p.ax[a];
+        const size_t n = X.n, nn = n * n;
+        c.take(X.x, n);
+        c.take(X.K, nn); c.take(X.D, nn); c.take(X.L, nn); c.take(X.Linv, nn); c.take(X.Kinv, nn);
+        c.take(X.Dbar, nn); c.take(X.T, nn);
+        c.take(X.invdiag, (size_t)X.nblk * kNB * kNB);
+        c.take(X.ldpart, X.nblk);
+        c.take(X.tabK, n); c.take(X.tabD, n);
+        c.take(X.sK, n); c.take(X.sD, n);
+        const size_t ds = diag_sums_part_doubles((int)n), tg = theta_general_part_doubles((int)n, d.Q);
+        if (p.size_query) { double* dummy; c.take(dummy, std::max(ds, tg)); }
+        else if (X.toeplitz) c.take(X.dspart, ds);
+        else c.take(X.tgpart, tg);
+    }
+    c.take(p.src, nf); c.take(p.bvals, d.nb); c.take(p.xind, std::max(d.nb, 1));
+    c.take(p.A, nf); c.take(p.Tf, nf); c.take(p.R, nf); c.take(p.P, nf); c.take(p.S1, nf); c.take(p.V1, nf);
+    c.take(p.gU, nf);
+    if (d.dim == 2) { c.take(p.Bt, nf); c.take(p.W, nf); c.take(p.S2, nf); c.take(p.V2, nf); }
+    c.take(p.part, 2 * (size_t)kRedBlocks);
+    c.take(p.eb, std::max(d.nb, 1));
+    c.take(p.gsmall, 6 * (size_t)d.Q + 2);
+    c.take(p.terms, 8);
+    c.take(p.status, 4);
+    return c.off;
+}
+
+int check_desc(const gphm_problem_desc* d) {
+    if (!d) { set_last_error("null problem descriptor"); return GPHM_EINVAL; }
+    if (d->dim != 1 && d->dim != 2) { set_last_error("dim must be 1 or 2 (got %d)", d->dim); return GPHM_EINVAL; }
+    if (d->kernel_id < 0 || d->kernel_id > 3) { set_last_error("Invalid Kernel id %d", d->kernel_id); return GPHM_EINVAL; }
+    if (d->eq_type < 0 || d->eq_type > 2) { set_last_error("unknown equation type %d", d->eq_type); return GPHM_EINVAL; }
+    if (d->eq_type == GPHM_EQ_ADVECTION && d->dim != 2) { set_last_error("advection needs dim == 2"); return GPHM_EINVAL; }
+    if (d->n1 < 1 || d->n2 < 1 || (d->dim == 1 && d->n2 != 1)) { set_last_error("bad grid %d x %d", d->n1, d->n2); return GPHM_EINVAL; }
+    if (d->Q < 1 || d->Q > 256) { set_last_error("Q=%d outside [1,256]", d->Q); return GPHM_EINVAL; }
+    if (d->dim == 2 && d->nb != 2 * d->n1 + 2 * d->n2) { set_last_error("2-D nb must be 2*n1+2*n2"); return GPHM_EINVAL; }
+    if (d->nb < 0) { set_last_error("nb < 0"); return GPHM_EINVAL; }
+    return GPHM_OK;
+}
+
+void init_axes(gphm_plan& p, const double* hx, const double* hy) {
+    p.ax[0].n = p.d.n1; p.ax[1].n = p.d.dim == 2 ? p.d.n2 : 0;
+    const double* h[2] = {hx, hy};
+    for (int a = 0; a < 2; ++a) {
+        Axis& X = p.ax[a];
+        X.nblk = X.n > 0 ? num_blocks_nb(X.n) : 0;
+        if (X.n > 0 && h[a]) {
+            X.toeplitz = !p.d.force_general && uniform_grid(h[a], X.n);
+            X.dirsign = (h[a][X.n - 1] >= h[a][0]) ? 1.0 : -1.0;
+        } else {
+            X.toeplitz = !p.d.force_general;   // size query: assume the (larger) general layout below
+        }
+    }
+}
+
+inline int deriv_order(const gphm_plan& p) { return p.d.eq_type == GPHM_EQ_ADVECTION ? 1 : 2; }
+inline double coef_c1(const gphm_plan& p) { return p.d.eq_type == GPHM_EQ_ADVECTION ? p.d.beta : 1.0; }
+inline const double* theta_of(const gphm_plan& p, const double* small, int a) { return small + (size_t)a * 3 * p.d.Q; }
+
+LossConsts loss_consts(const gphm_plan& p) {
+    LossConsts c;
+    c.dim = p.d.dim; c.eq_type = p.d.eq_type; c.n1 = p.d.n1; c.n2 = p.d.n2; c.nb = p.d.nb; c.Q = p.d.Q;
+    c.llk_weight = p.d.llk_weight; c.logdet = p.d.logdet; c.c1 = coef_c1(p);
+    return c;
+}
+
+// Gram + Cholesky + L^-1 (+ K^-1) for one axis.
+int factor_axis(gphm_plan& p, int a, const double* small, bool with_kinv, cudaStream_t st) {
+    Axis& X = p.ax[a];
+    const double* th = theta_of(p, small, a);
+    const int n = X.n, order = deriv_order(p);
+    if (X.toeplitz)
+        GPHM_TRY(launch_gram_toeplitz(p.d.kernel_id, order, X.x, n, th, p.d.Q, p.d.jitter, X.dirsign, X.tabK, X.tabD,
+                                      X.K, X.D, n, st));
+    else
+        GPHM_TRY(launch_gram_general(p.d.kernel_id, order, X.x, n, X.x, n, th, p.d.Q, p.d.jitter, X.K, X.D, n, st));
+    GPHM_TRY(chol_factor(X.K, X.L, n, n, X.invdiag, X.ldpart, p.status + a, st));
+    GPHM_TRY(trtri_lower(X.L, X.Linv, n, n, X.invdiag, X.T, st));
+    if (with_kinv)
+        GPHM_TRY(launch_dgemm(gemm_args(X.Linv, n, true, X.Linv, n, false, X.Kinv, n, n, n, n, 1.0, 0.0,
+                                        KM_A_UPPER | KM_B_LOWER), st));
+    return GPHM_OK;
+}
+
+// out = K_a^-1 X (side 0, X is n x cols) or X K_a^-1 (side 1, X is rows x n); tmp has X's shape.
+int apply_kinv(gphm_plan& p, int a, int side, const double* Xm, int rows, int cols, double* out, double* tmp,
+               cudaStream_t st) {
+    const Axis& X = p.ax[a];
+    const int n = X.n;
+    if (side == 0) {
+        if (rows != n) { set_last_error("apply_kinv: rows %d != n %d", rows, n); return GPHM_EINVAL; }
+        GPHM_TRY(launch_dgemm(gemm_args(X.Linv, n, false, Xm, cols, false, tmp, cols, n, cols, n, 1.0, 0.0, KM_A_LOWER), st));
+        GPHM_TRY(launch_dgemm(gemm_args(X.Linv, n, true, tmp, cols, false, out, cols, n, cols, n, 1.0, 0.0, KM_A_UPPER), st));
+    } else {
+        if (cols != n) { set_last_error("apply_kinv: cols %d != n %d", cols, n); return GPHM_EINVAL; }
+        GPHM_TRY(launch_dgemm(gemm_args(Xm, n, false, X.Linv, n, true, tmp, n, rows, n, n, 1.0, 0.0, KM_B_UPPER), st));
+        GPHM_TRY(launch_dgemm(gemm_args(tmp, n, false, X.Linv, n, false, out, n, rows, n, n, 1.0, 0.0, KM_B_LOWER), st));
+    }
+    return GPHM_OK;
+}
+
+int logjoint_grad(gphm_plan& p, const double* U, const double* small, double* gU, double* gsmall, double* terms,
+                  int flags, cudaStream_t st) {
+    const gphm_problem_desc& d = p.d;
+    const bool two = d.dim == 2, fwd_only = (flags & GPHM_FORWARD_ONLY) != 0;
+    const int n1 = d.n1, n2 = d.n2, Q = d.Q;
+    const size_t nf = (size_t)n1 * n2;
+    const double c1 = coef_c1(p);
+    Axis& X1 = p.ax[0];
+    Axis& X2 = p.ax[1];
+
+    GPHM_TRY(factor_axis(p, 0, small, !fwd_only, st));
+    if (two) GPHM_TRY(factor_axis(p, 1, small, !fwd_only, st));
+
+    // ---- forward ----
+    GPHM_TRY(apply_kinv(p, 0, 0, U, n1, n2, p.A, p.Tf, st));                                   // A = K1^-1 U
+    const double* Bt = U;
+    if (two) { GPHM_TRY(apply_kinv(p, 1, 1, U, n1, n2, p.Bt, p.Tf, st)); Bt = p.Bt; }           // Bt = U K2^-1
+    GPHM_TRY(launch_dgemm(gemm_args(X1.D, n1, false, p.A, n2, false, p.R, n2, n1, n2, n1, c1, 0.0), st));   // c1 D1 A
+    if (two)
+        GPHM_TRY(launch_dgemm(gemm_args(Bt, n2, false, X2.D, n2, true, p.R, n2, n1, n2, n2, 1.0, 1.0), st)); // + Bt D2^T
+    GPHM_TRY(launch_residual(p.R, U, p.src, p.A, Bt, nf, d.eq_type, small, Q, p.part, st));    // R <- G
+    const LossConsts lc = loss_consts(p);
+    GPHM_TRY(launch_finalize(lc, U, p.bvals, p.xind, p.part, X1.ldpart, X1.nblk, two ? X2.ldpart : nullptr,
+                             two ? X2.nblk : 0, small, p.eb, terms, fwd_only ? nullptr : gsmall, p.status, st));
+    if (fwd_only) return GPHM_OK;
+
+    // ---- backward ----
+    const double* G = p.R;
+    const double* W = p.A;
+    if (two) { GPHM_TRY(apply_kinv(p, 0, 0, Bt, n1, n2, p.W, p.Tf, st)); W = p.W; }             // W = K1^-1 Bt
+    GPHM_TRY(launch_dgemm(gemm_args(X1.D, n1, true, G, n2, false, p.P, n2, n1, n2, n1, c1, 0.0), st));      // c1 D1^T G
+    GPHM_TRY(apply_kinv(p, 0, 0, p.P, n1, n2, p.S1, p.Tf, st));                                 // S1
+    if (two) {
+        GPHM_TRY(launch_dgemm(gemm_args(G, n2, false, X2.D, n2, false, p.P, n2, n1, n2, n2, 1.0, 0.0), st)); // G D2
+        GPHM_TRY(apply_kinv(p, 1, 1, p.P, n1, n2, p.S2, p.Tf, st));                             // S2
+    }
+    GPHM_TRY(launch_grad_u(lc, U, G, W, p.S1, two ? p.S2 : nullptr, p.eb, p.xind, small, gU, p.V1,
+                           two ? p.V2 : nullptr, st));
+    // Kbar1 = ld/2*N2*K1^-1 - V1 A^T  (in place in Kinv);  Dbar1 = c1 G A^T
+    GPHM_TRY(launch_dgemm(gemm_args(p.V1, n2, false, p.A, n2, true, X1.Kinv, n1, n1, n1, n2, -1.0,
+                                    0.5 * d.logdet * n2), st));
+    GPHM_TRY(launch_dgemm(gemm_args(G, n2, false, p.A, n2, true, X1.Dbar, n1, n1, n1, n2, c1, 0.0), st));
+    if (two) {
+        // Kbar2 = ld/2*N1*K2^-1 - V2^T Bt ;  Dbar2 = G^T Bt
+        GPHM_TRY(launch_dgemm(gemm_args(p.V2, n2, true, Bt, n2, false, X2.Kinv, n2, n2, n2, n1, -1.0,
+                                        0.5 * d.logdet * n1), st));
+        GPHM_TRY(launch_dgemm(gemm_args(G, n2, true, Bt, n2, false, X2.Dbar, n2, n2, n2, n1, 1.0, 0.0), st));
+    }
+    const int order = deriv_order(p);
+    for (int a = 0; a < (two ? 2 : 1); ++a) {
+        Axis& X = p.ax[a];
+        const double* th = theta_of(p, small, a);
+        double* gth = gsmall + (size_t)a * 3 * Q;
+        if (X.toeplitz) {
+            GPHM_TRY(launch_diag_sums(X.Kinv, X.Dbar, X.n, X.n, order == 1, X.dirsign, X.dspart, X.sK, X.sD, st));
+            GPHM_TRY(launch_theta_grad_toeplitz(d.kernel_id, order, X.x, X.n, th, Q, X.sK, X.sD, gth, st));
+        } else {
+            GPHM_TRY(launch_theta_grad_general(d.kernel_id, order, X.x, X.n, th, Q, X.Kinv, X.Dbar, X.n, X.tgpart,
+                                               gth, st));
+        }
+    }
+    if (!two) GPHM_CUDA_OK(cudaMemsetAsync(gsmall + 3 * Q, 0, sizeof(double) * 3 * Q, st));
+    return GPHM_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int gphm_version(void) { return GPHM_VERSION; }
+const char* gphm_last_error(void) { return g_err; }
+
+int gphm_gram(int kernel_id, int deriv_order, const double* d_x1, int n1, const double* d_x2, int n2,
+              const double* d_theta, int Q, double jitter, double* d_out, void* stream) {
+    if (!d_x1 || !d_x2 || !d_theta || !d_out) { set_last_error("gphm_gram: null pointer"); return GPHM_EINVAL; }
+    if (n1 < 0 || n2 < 0) { set_last_error("gphm_gram: negative size"); return GPHM_EINVAL; }
+    if (kernel_id < 0 || kernel_id > 3) { set_last_error("Invalid Kernel id %d", kernel_id); return GPHM_EINVAL; }
+    if (deriv_order < 0 || deriv_order > 2) { set_last_error("gphm_gram: deriv_order %d", deriv_order); return GPHM_EINVAL; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const double jit = (n1 == n2) ? jitter : 0.0;
+    if (deriv_order == 0)
+        return launch_gram_general(kernel_id, 0, d_x1, n1, d_x2, n2, d_theta, Q, jit, d_out, nullptr, n2, st);
+    return launch_gram_general(kernel_id, deriv_order, d_x1, n1, d_x2, n2, d_theta, Q, 0.0, nullptr, d_out, n2, st);
+}
+
+int gphm_kappa_pairs(int kernel_id, int deriv_order, const double* d_x1, const double* d_x2, size_t npairs,
+                     const double* d_theta, int Q, double* d_out, void* stream) {
+    if (npairs == 0) return GPHM_OK;
+    if (!d_x1 || !d_x2 || !d_theta || !d_out) { set_last_error("gphm_kappa_pairs: null pointer"); return GPHM_EINVAL; }
+    if (kernel_id < 0 || kernel_id > 3) { set_last_error("Invalid Kernel id %d", kernel_id); return GPHM_EINVAL; }
+    if (deriv_order < 0 || deriv_order > 2) { set_last_error("gphm_kappa_pairs: deriv_order %d", deriv_order); return GPHM_EINVAL; }
+    return launch_kappa_pairs(kernel_id, deriv_order, d_x1, d_x2, npairs, d_theta, Q, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int gphm_dgemm(int transA, int transB, int M, int N, int K, double alpha, const double* d_A, int lda,
+               const double* d_B, int ldb, double beta, double* d_C, int ldc, void* stream) {
+    if (M < 0 || N < 0 || K < 0) { set_last_error("gphm_dgemm: negative size"); return GPHM_EINVAL; }
+    if (M == 0 || N == 0) return GPHM_OK;
+    if (!d_A || !d_B || !d_C) { set_last_error("gphm_dgemm: null pointer"); return GPHM_EINVAL; }
+    return launch_dgemm(gemm_args(d_A, lda, transA != 0, d_B, ldb, transB != 0, d_C, ldc, M, N, K, alpha, beta, 0),
+                        static_cast<cudaStream_t>(stream));
+}
+
+size_t gphm_potrf_work_bytes(int n) {
+    if (n <= 0) return 0;
+    Carver c(nullptr);
+    double* p;
+    c.take(p, (size_t)num_blocks_nb(n) * kNB * kNB); c.take(p, num_blocks_nb(n)); c.take(p, (size_t)n * n);
+    return c.off;
+}
+
+int gphm_potrf_inv(double* d_K, int n, double* d_L, double* d_Linv, double* d_logdet, int* d_status, void* d_work,
+                   void* stream) {
+    if (n <= 0) { set_last_error("gphm_potrf_inv: n <= 0"); return GPHM_EINVAL; }
+    if (!d_K || !d_L || !d_Linv || !d_logdet || !d_status || !d_work) { set_last_error("gphm_potrf_inv: null pointer"); return GPHM_EINVAL; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Carver c(d_work);
+    double *invdiag, *ldpart, *T;
+    const int nblk = num_blocks_nb(n);
+    c.take(invdiag, (size_t)nblk * kNB * kNB); c.take(ldpart, nblk); c.take(T, (size_t)n * n);
+    GPHM_CUDA_OK(cudaMemsetAsync(d_L, 0, sizeof(double) * (size_t)n * n, st));
+    GPHM_CUDA_OK(cudaMemsetAsync(d_Linv, 0, sizeof(double) * (size_t)n * n, st));
+    GPHM_CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+    GPHM_TRY(chol_factor(d_K, d_L, n, n, invdiag, ldpart, d_status, st));
+    GPHM_TRY(trtri_lower(d_L, d_Linv, n, n, invdiag, T, st));
+    GPHM_TRY(launch_sum_scaled(ldpart, nblk, 2.0, d_logdet, st));
+    return GPHM_OK;
+}
+
+size_t gphm_workspace_bytes(const gphm_problem_desc* desc) {
+    if (check_desc(desc) != GPHM_OK) return 0;
+    gphm_plan tmp;
+    tmp.d = *desc;
+    tmp.size_query = true;     // uniform or not is only known at create time: size for either
+    init_axes(tmp, nullptr, nullptr);
+    return carve(tmp, nullptr);
+}
+
+int gphm_plan_create(const gphm_problem_desc* desc, const double* h_x, const double* h_y, const double* h_src,
+                     const double* h_bvals, const int* h_xind, void* d_workspace, size_t workspace_bytes,
+                     gphm_plan** out) {
+    GPHM_TRY(check_desc(desc));
+    if (!out || !h_x || !h_src || (desc->nb > 0 && !h_bvals)) { set_last_error("gphm_plan_create: null pointer"); return GPHM_EINVAL; }
+    if (desc->dim == 2 && !h_y) { set_last_error("gphm_plan_create: h_y required for dim == 2"); return GPHM_EINVAL; }
+    if (desc->dim == 1 && desc->nb > 0 && !h_xind) { set_last_error("gphm_plan_create: h_xind required for dim == 1"); return GPHM_EINVAL; }
+    if (desc->dim == 1)
+        for (int e = 0; e < desc->nb; ++e)
+            if (h_xind[e] < 0 || h_xind[e] >= desc->n1) { set_last_error("Xind[%d]=%d out of range", e, h_xind[e]); return GPHM_EINVAL; }
+    GPHM_TRY(dgemm_init());
+    GPHM_TRY(factor_init());
+    gphm_plan* p = new gphm_plan();
+    p->d = *desc;
+    init_axes(*p, h_x, h_y);
+    const size_t need = carve(*p, nullptr);
+    if (d_workspace) {
+        if (workspace_bytes < need) {
+            set_last_error("workspace too small: %zu < %zu", workspace_bytes, need);
+            delete p;
+            return GPHM_ENOMEM;
+        }
+        p->ws = d_workspace;
+    } else {
+        if (cudaMalloc(&p->ws, need) != cudaSuccess) {
+            set_last_error("cudaMalloc(%zu) failed", need);
+            delete p;
+            return GPHM_ENOMEM;
+        }
+        p->owns_ws = true;
+    }
+    carve(*p, p->ws);
+    auto fail = [&](const char* what) { set_last_error("gphm_plan_create: %s failed", what); gphm_plan_destroy(p); return GPHM_ECUDA; };
+    const size_t nf = (size_t)desc->n1 * desc->n2;
+    if (cudaMemset(p->ws, 0, need) != cudaSuccess) return fail("memset");
+    if (cudaMemcpy(p->ax[0].x, h_x, sizeof(double) * desc->n1, cudaMemcpyHostToDevice) != cudaSuccess) return fail("copy x");
+    if (desc->dim == 2 && cudaMemcpy(p->ax[1].x, h_y, sizeof(double) * desc->n2, cudaMemcpyHostToDevice) != cudaSuccess) return fail("copy y");
+    if (cudaMemcpy(p->src, h_src, sizeof(double) * nf, cudaMemcpyHostToDevice) != cudaSuccess) return fail("copy src");
+    if (desc->nb > 0 && cudaMemcpy(p->bvals, h_bvals, sizeof(double) * desc->nb, cudaMemcpyHostToDevice) != cudaSuccess) return fail("copy bvals");
+    if (desc->dim == 1 && desc->nb > 0 && cudaMemcpy(p->xind, h_xind, sizeof(int) * desc->nb, cudaMemcpyHostToDevice) != cudaSuccess) return fail("copy xind");
+    *out = p;
+    return GPHM_OK;
+}
+
+void gphm_plan_destroy(gphm_plan* plan) {
+    if (!plan) return;
+    if (plan->owns_ws && plan->ws) cudaFree(plan->ws);
+    if (plan->hs) cudaFree(plan->hs);
+    if (plan->hs_count) cudaFree(plan->hs_count);
+    delete plan;
+}
+
+int gphm_plan_status(gphm_plan* plan, int* pivot, void* stream) {
+    if (!plan) { set_last_error("null plan"); return GPHM_EINVAL; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int h[4] = {0, 0, 0, 0};
+    GPHM_CUDA_OK(cudaMemcpyAsync(h, plan->status, sizeof(h), cudaMemcpyDeviceToHost, st));
+    GPHM_CUDA_OK(cudaStreamSynchronize(st));
+    GPHM_CUDA_OK(cudaMemsetAsync(plan->status, 0, sizeof(h), st));
+    if (pivot) *pivot = h[0] ? h[0] : (h[1] ? plan->d.n1 + h[1] : 0);
+    if (h[0] || h[1]) return GPHM_NOT_SPD;
+    if (h[2]) return GPHM_NONFINITE;
+    return GPHM_OK;
+}
+
+int gphm_plan_uses_toeplitz(const gphm_plan* plan, int axis) {
+    if (!plan || axis < 0 || axis > 1) return 0;
+    return plan->ax[axis].n > 0 && plan->ax[axis].toeplitz ? 1 : 0;
+}
+
+int gphm_logjoint_grad(gphm_plan* plan, const double* d_U, const double* d_small, double* d_gU, double* d_gsmall,
+                       double* d_terms, int flags, void* stream) {
+    if (!plan || !d_U || !d_small || !d_terms) { set_last_error("gphm_logjoint_grad: null pointer"); return GPHM_EINVAL; }
+    if (!(flags & GPHM_FORWARD_ONLY) && (!d_gU || !d_gsmall)) { set_last_error("gphm_logjoint_grad: null gradient buffer"); return GPHM_EINVAL; }
+    return logjoint_grad(*plan, d_U, d_small, d_gU, d_gsmall, d_terms, flags, static_cast<cudaStream_t>(stream));
+}
+
+int gphm_adam_update(double* d_p, const double* d_g, double* d_m, double* d_v, size_t n, const long long* d_count,
+                     double lr, void* stream) {
+    if (n == 0) return GPHM_OK;
+    if (!d_p || !d_g || !d_m || !d_v || !d_count) { set_last_error("gphm_adam_update: null pointer"); return GPHM_EINVAL; }
+    return launch_adam(d_p, d_g, d_m, d_v, n, d_count, lr, static_cast<cudaStream_t>(stream));
+}
+
+int gphm_step(gphm_plan* plan, double* d_U, double* d_small, double* d_mU, double* d_vU, double* d_msmall,
+              double* d_vsmall, long long* d_count, double lr, double* d_terms, void* stream) {
+    if (!plan || !d_U || !d_small || !d_mU || !d_vU || !d_msmall || !d_vsmall || !d_count || !d_terms) {
+        set_last_error("gphm_step: null pointer");
+        return GPHM_EINVAL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GPHM_TRY(logjoint_grad(*plan, d_U, d_small, plan->gU, plan->gsmall, d_terms, 0, st));
+    const size_t nf = (size_t)plan->d.n1 * plan->d.n2, ns = 6 * (size_t)plan->d.Q + 2;
+    GPHM_TRY(launch_adam(d_U, plan->gU, d_mU, d_vU, nf, d_count, lr, st));
+    GPHM_TRY(launch_adam(d_small, plan->gsmall, d_msmall, d_vsmall, ns, d_count, lr, st));
+    GPHM_TRY(launch_count_inc(d_count, st));
+    return GPHM_OK;
+}
+
+int gphm_step_host(gphm_plan* plan, double* h_U, double* h_small, double* h_mU, double* h_vU, double* h_msmall,
+                   double* h_vsmall, long long* h_count, double lr, double* h_terms, void* stream) {
+    if (!plan || !h_U || !h_small || !h_mU || !h_vU || !h_msmall || !h_vsmall || !h_count || !h_terms) {
+        set_last_error("gphm_step_host: null pointer");
+        return GPHM_EINVAL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t nf = (size_t)plan->d.n1 * plan->d.n2, ns = 6 * (size_t)plan->d.Q + 2;
+    const size_t nfp = (nf + 31) / 32 * 32, nsp = (ns + 31) / 32 * 32;
+    if (!plan->hs) {
+        GPHM_CUDA_OK(cudaMalloc(&plan->hs, sizeof(double) * (3 * nfp + 3 * nsp + 32)));
+        GPHM_CUDA_OK(cudaMalloc(&plan->hs_count, sizeof(long long)));
+    }
+    double *U = plan->hs, *mU = U + nfp, *vU = mU + nfp, *sm = vU + nfp, *msm = sm + nsp, *vsm = msm + nsp,
+           *terms = vsm + nsp;
+    GPHM_CUDA_OK(cudaMemcpyAsync(U, h_U, sizeof(double) * nf, cudaMemcpyHostToDevice, st));
+    GPHM_CUDA_OK(cudaMemcpyAsync(mU, h_mU, sizeof(double) * nf, cudaMemcpyHostToDevice, st));
+    GPHM_CUDA_OK(cudaMemcpyAsync(vU, h_vU, sizeof(double) * nf, cudaMemcpyHostToDevice, st));
+    GPHM_CUDA_OK(cudaMemcpyAsync(sm, h_small, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
+    GPHM_CUDA_OK(cudaMemcpyAsync(msm, h_msmall, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
+    GPHM_CUDA_OK(cudaMemcpyAsync(vsm, h_vsmall, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
+    GPHM_CUDA_OK(cudaMemcpyAsync(plan->hs_count, h_count, sizeof(long long), cudaMemcpyHostToDevice, st));
+    GPHM_TRY(gphm_step(plan, U, sm, mU, vU, msm, vsm, plan->hs_count, lr, terms, stream));
+    GPHM_CUDA_OK(cudaMemcpyAsync(h_U, U, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+    GPHM_CUDA_OK(cudaMemcpyAsync(h_mU, mU, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+    GPHM_CUDA_OK(cudaMemcpyAsync(h_vU, vU, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+    GPHM_CUDA_OK(cudaMemcpyAsync(h_small, sm, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
+    GPHM_CUDA_OK(cudaMemcpyAsync(h_msmall, msm, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
+    GPHM_CUDA_OK(cudaMemcpyAsync(h_vsmall, vsm, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
+    GPHM_CUDA_OK(cudaMemcpyAsync(h_count, plan->hs_count, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    GPHM_CUDA_OK(cudaMemcpyAsync(h_terms, terms, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
+    GPHM_CUDA_OK(cudaStreamSynchronize(st));
+    return GPHM_OK;
+}
+
+size_t gphm_predict_work_bytes(const gphm_plan* plan, int m1, int m2) {
+    if (!plan || m1 <= 0) return 0;
+    Carver c(nullptr);
+    double* p;
+    const size_t n1 = plan->d.n1, n2 = plan->d.n2;
+    c.take(p, (size_t)m1 * n1); c.take(p, (size_t)m1 * n2); c.take(p, (size_t)m1 * n2); c.take(p, (size_t)m1 * n2);
+    if (plan->d.dim == 2) c.take(p, (size_t)std::max(m2, 1) * n2);
+    return c.off;
+}
+
+int gphm_predict(gphm_plan* plan, const double* d_U, const double* d_small, const double* d_xt, int m1,
+                 const double* d_yt, int m2, double* d_out, void* d_work, void* stream) {
+    if (!plan || !d_U || !d_small || !d_xt || !d_out || !d_work) { set_last_error("gphm_predict: null pointer"); return GPHM_EINVAL; }
+    gphm_plan& p = *plan;
+    const bool two = p.d.dim == 2;
+    if (m1 <= 0 || (two && (m2 <= 0 || !d_yt))) { set_last_error("gphm_predict: bad test grid"); return GPHM_EINVAL; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int n1 = p.d.n1, n2 = p.d.n2, Q = p.d.Q;
+    Carver c(d_work);
+    double *Kmn1, *M1, *M1t, *M1K, *Kmn2 = nullptr;
+    c.take(Kmn1, (size_t)m1 * n1); c.take(M1, (size_t)m1 * n2); c.take(M1t, (size_t)m1 * n2); c.take(M1K, (size_t)m1 * n2);
+    if (two) c.take(Kmn2, (size_t)m2 * n2);
+    GPHM_TRY(factor_axis(p, 0, d_small, false, st));
+    if (two) GPHM_TRY(factor_axis(p, 1, d_small, false, st));
+    GPHM_TRY(apply_kinv(p, 0, 0, d_U, n1, n2, p.A, p.Tf, st));
+    GPHM_TRY(launch_gram_general(p.d.kernel_id, 0, d_xt, m1, p.ax[0].x, n1, theta_of(p, d_small, 0), Q, 0.0, Kmn1,
+                                 nullptr, n1, st));
+    double* dst1 = two ? M1 : d_out;
+    GPHM_TRY(launch_dgemm(gemm_args(Kmn1, n1, false, p.A, n2, false, dst1, n2, m1, n2, n1), st));
+    if (two) {
+        GPHM_TRY(apply_kinv(p, 1, 1, M1, m1, n2, M1K, M1t, st));
+        GPHM_TRY(launch_gram_general(p.d.kernel_id, 0, d_yt, m2, p.ax[1].x, n2, theta_of(p, d_small, 1), Q, 0.0, Kmn2,
+                                     nullptr, n2, st));
+        GPHM_TRY(launch_dgemm(gemm_args(M1K, n2, false, Kmn2, n2, true, d_out, m2, m1, m2, n2), st));
+    }
+    return GPHM_OK;
+}
+
+size_t gphm_rel_l2_work_bytes(void) { return sizeof(double) * 2 * kRedBlocks; }
+
+int gphm_rel_l2(const double* d_pred, const double* d_truth, size_t n, double* d_out, void* d_work, void* stream) {
+    if (!d_pred || !d_truth || !d_out || !d_work) { set_last_error("gphm_rel_l2: null pointer"); return GPHM_EINVAL; }
+    return launch_rel_l2(d_pred, d_truth, n, static_cast<double*>(d_work), d_out, static_cast<cudaStream_t>(stream));
+}
+
+int gphm_plan_factor(gphm_plan* plan, const double* d_small, int axis_mask, void* stream) {
+    if (!plan || !d_small) { set_last_error("gphm_plan_factor: null pointer"); return GPHM_EINVAL; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (axis_mask & 1) GPHM_TRY(factor_axis(*plan, 0, d_small, true, st));
+    if ((axis_mask & 2) && plan->d.dim == 2) GPHM_TRY(factor_axis(*plan, 1, d_small, true, st));
+    return GPHM_OK;
+}
+
+int gphm_apply_kinv(gphm_plan* plan, int axis, int side, const double* d_X, int rows, int cols, double* d_out,
+                    double* d_tmp, void* stream) {
+    if (!plan || !d_X || !d_out || !d_tmp) { set_last_error("gphm_apply_kinv: null pointer"); return GPHM_EINVAL; }
+    if (axis < 0 || axis > 1 || plan->ax[axis].n == 0 || (side != 0 && side != 1)) { set_last_error("gphm_apply_kinv: bad axis/side"); return GPHM_EINVAL; }
+    if (rows <= 0 || cols <= 0) return GPHM_OK;
+    return apply_kinv(*plan, axis, side, d_X, rows, cols, d_out, d_tmp, static_cast<cudaStream_t>(stream));
+}
+
+const double* gphm_plan_matrix(const gphm_plan* plan, int axis, int which) {
+    if (!plan || axis < 0 || axis > 1 || plan->ax[axis].n == 0) return nullptr;
+    const Axis& X = plan->ax[axis];
+    switch (which) {
+        case 0: return X.Kinv;
+        case 1: return X.D;
+        case 2: return X.Linv;
+        case 3: return X.L;
+        default: return nullptr;
+    }
+}
+
+}  // extern "C"

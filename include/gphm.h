@@ -1,0 +1,166 @@
+/* libgphm - B200 (sm_100a) implementation of the GP-HM solver's inner loop.
+ *
+ * Plain C ABI: no torch / jax types in any signature.  Every pointer named `d_*` is a DEVICE
+ * pointer owned by the caller (torch CUDA tensors in the Python host layer); `h_*` is a HOST
+ * pointer.  All matrices are row-major FP64.  Kernels launch on the caller's `stream`
+ * (a cudaStream_t passed as void*; NULL = legacy default stream); nothing synchronises the host
+ * except gphm_plan_create, gphm_plan_status and the *_host entry points.
+ *
+ * The reference (xuangu-fang/Gaussian-Process-Slover-for-High-Freq-PDE) has no FFI: its seam is
+ * Python methods.  Each entry point below names the reference method it replaces (paths are
+ * relative to the reference's code/ directory).
+ *
+ * Return value: 0 ok; <0 usage/runtime error (gphm_last_error() has the text);
+ * numerical conditions (non-SPD Gram) are reported asynchronously through gphm_plan_status.
+ */
+#ifndef GPHM_H_
+#define GPHM_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPHM_VERSION 100
+
+#if defined(__GNUC__)
+#define GPHM_API __attribute__((visibility("default")))
+#else
+#define GPHM_API
+#endif
+
+/* kernel ids = the four kernel classes of kernel_matrix.py */
+#define GPHM_KERNEL_SE_COS        0   /* SE_Cos_1d        kernel_matrix.py:107-128 */
+#define GPHM_KERNEL_MATERN52_COS  1   /* Matern52_Cos_1d  kernel_matrix.py:131-155 */
+#define GPHM_KERNEL_MATERN52      2   /* Matern52_1d      kernel_matrix.py:158-176 */
+#define GPHM_KERNEL_SE            3   /* SE_1d            kernel_matrix.py:179-193 */
+
+/* equation types = eq_type branches of boundary_and_eq_gap */
+#define GPHM_EQ_POISSON    0   /* model_GP_solver_2d.py:131-133, model_GP_solver_1d.py:107-110 */
+#define GPHM_EQ_ALLENCAHN  1   /* model_GP_solver_2d.py:135-138, model_GP_solver_1d.py:112-115 */
+#define GPHM_EQ_ADVECTION  2   /* model_GP_solver_advection.py:132-134 (first-derivative Grams) */
+
+/* status codes */
+#define GPHM_OK          0
+#define GPHM_EINVAL     -1
+#define GPHM_ECUDA      -2
+#define GPHM_ENOMEM     -3
+#define GPHM_NOT_SPD     1   /* gphm_plan_status: a Gram matrix had a non-positive pivot */
+#define GPHM_NONFINITE   2   /* gphm_plan_status: the loss is not finite */
+
+/* flags for gphm_logjoint_grad */
+#define GPHM_FORWARD_ONLY  1   /* loss terms only (compute_early_stopping, loss) */
+
+/* Problem constants the reference bakes into its jitted executable through the static `self`
+ * (model_GP_solver_2d.py:40-85, model_GP_solver_1d.py:38-78, model_GP_solver_advection.py:40-85). */
+typedef struct gphm_problem_desc {
+    int dim;             /* 1: GP_solver_1d_single; 2: GP_solver_2d_single[_advection] */
+    int kernel_id;       /* GPHM_KERNEL_* (trick_paras['kernel']) */
+    int eq_type;         /* GPHM_EQ_* */
+    int n1, n2;          /* collocation points per axis (n2 = 1 when dim == 1) */
+    int Q;               /* mixture components (trick_paras['Q']) */
+    int nb;              /* boundary points: 2*n1+2*n2 (2-D) or len(Xind) (1-D) */
+    int force_general;   /* 1: never use the Toeplitz fast path even on uniform grids */
+    double llk_weight;   /* trick_paras['llk_weight'] */
+    double logdet;       /* trick_paras['logdet'] (True -> 1.0) */
+    double beta;         /* advection speed, trick_paras['beta'] (ignored otherwise) */
+    double jitter;       /* 1e-6 at every reference call site */
+} gphm_problem_desc;
+
+typedef struct gphm_plan gphm_plan;   /* opaque */
+
+GPHM_API int gphm_version(void);
+GPHM_API const char* gphm_last_error(void);
+
+/* ---- Gram builders -------------------------------------------------------------------------
+ * gphm_gram replaces Kernel_matrix.get_kernel_matrix (kernel_matrix.py:21-30; deriv_order 0,
+ * jitter added on the diagonal when n1 == n2 and jitter != 0), vmap(D_x1_kappa)
+ * (kernel_matrix.py:49-52; deriv_order 1), vmap(DD_x1_kappa) (:54-57; deriv_order 2) and the
+ * rectangular cross-Grams of preds (model_GP_solver_2d.py:198-202; deriv_order 0, jitter 0).
+ * d_theta = [log-w (Q) | log-ls (Q) | freq (Q)].  d_out is n1 x n2.                           */
+GPHM_API int gphm_gram(int kernel_id, int deriv_order, const double* d_x1, int n1, const double* d_x2, int n2,
+              const double* d_theta, int Q, double jitter, double* d_out, void* stream);
+
+/* Element-wise ("vmapped") kappa / D_x1_kappa / DD_x1_kappa over explicit pair lists, exactly the
+ * call shape of vmap(self.K_u.kappa, (0, 0, None))(X1.flatten(), X2.flatten(), paras)
+ * (kernel_matrix.py:26-27): d_out[p] = d^order/dx1^order kappa(d_x1[p], d_x2[p]).              */
+GPHM_API int gphm_kappa_pairs(int kernel_id, int deriv_order, const double* d_x1, const double* d_x2, size_t npairs,
+                     const double* d_theta, int Q, double* d_out, void* stream);
+
+/* ---- dense FP64 primitives (exported for parity tests and the prediction path) --------------
+ * C[M,N] = alpha*op(A)*op(B) + beta*C, row-major (jnp.matmul, model_GP_solver_2d.py:112,119).  */
+GPHM_API int gphm_dgemm(int transA, int transB, int M, int N, int K, double alpha, const double* d_A, int lda,
+               const double* d_B, int ldb, double beta, double* d_C, int ldc, void* stream);
+/* Cholesky K = L L^T plus explicit L^-1 and log|K| (replaces the LU inside jnp.linalg.solve /
+ * slogdet, model_GP_solver_2d.py:104-105,158-161).  d_K (n x n) is destroyed; d_L, d_Linv are
+ * n x n lower-triangular outputs; d_logdet gets one double; d_status one int (0 = SPD).
+ * d_work must hold gphm_potrf_work_bytes(n) bytes.                                            */
+GPHM_API size_t gphm_potrf_work_bytes(int n);
+GPHM_API int gphm_potrf_inv(double* d_K, int n, double* d_L, double* d_Linv, double* d_logdet, int* d_status,
+                   void* d_work, void* stream);
+
+/* ---- plan: one solver instance ---------------------------------------------------------------
+ * Host inputs are copied to the device once.  h_x (n1), h_y (n2; NULL when dim == 1),
+ * h_src (n1*n2, row-major), h_bvals (nb; 2-D edge order U[0,:],U[-1,:],U[:,0],U[:,-1] as in
+ * model_GP_solver_2d.py:127,377-379; 1-D: the values y), h_xind (nb ints, 1-D only: Xind).
+ * d_workspace may be NULL (the library cudaMallocs gphm_workspace_bytes(desc) itself).        */
+GPHM_API size_t gphm_workspace_bytes(const gphm_problem_desc* desc);
+GPHM_API int gphm_plan_create(const gphm_problem_desc* desc, const double* h_x, const double* h_y, const double* h_src,
+                     const double* h_bvals, const int* h_xind, void* d_workspace, size_t workspace_bytes,
+                     gphm_plan** out);
+GPHM_API void gphm_plan_destroy(gphm_plan* plan);
+/* Synchronises `stream`, returns GPHM_OK / GPHM_NOT_SPD / GPHM_NONFINITE; *pivot = 1 + index of
+ * the first bad pivot (axis 1: 1..n1, axis 2: n1+1..) or 0. Clears the flag.                  */
+GPHM_API int gphm_plan_status(gphm_plan* plan, int* pivot, void* stream);
+GPHM_API int gphm_plan_uses_toeplitz(const gphm_plan* plan, int axis);
+
+/* Parameter layout (the reference params pytree, model_GP_solver_2d.py:245-261, _1d.py:203-213):
+ *   d_U     : n1*n2 doubles (params['U'], or params['u'] (N,1) in 1-D)
+ *   d_small : 6Q+2 doubles = [log-w1|log-ls1|freq1|log-w2|log-ls2|freq2|log_tau|log_v]
+ *             (kernel_paras_1 / kernel_paras_2; in 1-D the second triple is ignored, grads 0)
+ * Gradients use the same layout.  d_terms receives 8 doubles:
+ *   [loss, log|K1|, log|K2|, quad=<K1^-1 U, U K2^-1>, boundary_gap, eq_gap, dL/dlog_tau, dL/dlog_v] */
+
+/* value_and_grad(loss): model_GP_solver_2d.py:145-174,179 (1-D: _1d.py:123-149,154;
+ * advection: _advection.py:141-170,175).                                                       */
+GPHM_API int gphm_logjoint_grad(gphm_plan* plan, const double* d_U, const double* d_small, double* d_gU,
+                       double* d_gsmall, double* d_terms, int flags, void* stream);
+
+/* optax.adam update of one leaf, in place (model_GP_solver_2d.py:180-182); d_count is a device
+ * int64 holding the number of completed steps (read, not modified).                           */
+GPHM_API int gphm_adam_update(double* d_p, const double* d_g, double* d_m, double* d_v, size_t n, const long long* d_count,
+                     double lr, void* stream);
+
+/* step(): value_and_grad + Adam on every leaf, in place, then ++count
+ * (model_GP_solver_2d.py:176-183).  d_terms holds the PRE-update loss terms.                   */
+GPHM_API int gphm_step(gphm_plan* plan, double* d_U, double* d_small, double* d_mU, double* d_vU, double* d_msmall,
+              double* d_vsmall, long long* d_count, double lr, double* d_terms, void* stream);
+
+/* The same step with HOST buffers (functional JAX calling convention: params and opt_state come
+ * from and return to host memory).  Copies in, steps, copies out, synchronises.               */
+GPHM_API int gphm_step_host(gphm_plan* plan, double* h_U, double* h_small, double* h_mU, double* h_vU, double* h_msmall,
+                   double* h_vsmall, long long* h_count, double lr, double* h_terms, void* stream);
+
+/* preds(): posterior mean on a test grid (model_GP_solver_2d.py:185-220, _1d.py:160-180).
+ * d_xt (m1), d_yt (m2; ignored in 1-D) are device test coordinates; d_out is m1 x m2 (m1 x 1).
+ * d_work must hold gphm_predict_work_bytes(plan, m1, m2) bytes.                                */
+GPHM_API size_t gphm_predict_work_bytes(const gphm_plan* plan, int m1, int m2);
+GPHM_API int gphm_predict(gphm_plan* plan, const double* d_U, const double* d_small, const double* d_xt, int m1,
+                 const double* d_yt, int m2, double* d_out, void* d_work, void* stream);
+/* ||pred - truth|| / ||truth|| into one device double (model_GP_solver_2d.py:297-300).
+ * d_work: gphm_rel_l2_work_bytes() bytes.                                                      */
+GPHM_API size_t gphm_rel_l2_work_bytes(void);
+GPHM_API int gphm_rel_l2(const double* d_pred, const double* d_truth, size_t n, double* d_out, void* d_work, void* stream);
+
+/* Multi-GPU building blocks (row/column block layouts; the exchange itself is done by the host
+ * layer with NCCL between these calls).  See DESIGN.md "multi-GPU".                            */
+GPHM_API int gphm_plan_factor(gphm_plan* plan, const double* d_small, int axis_mask, void* stream);
+GPHM_API int gphm_apply_kinv(gphm_plan* plan, int axis, int side, const double* d_X, int rows, int cols, double* d_out,
+                    double* d_tmp, void* stream);
+GPHM_API const double* gphm_plan_matrix(const gphm_plan* plan, int axis, int which);   /* 0 K^-1, 1 D, 2 Linv, 3 L */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPHM_H_ */

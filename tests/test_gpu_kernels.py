@@ -1,0 +1,116 @@
+"""GPU: every CUDA kernel family against the CPU oracle / torch FP64 at identical inputs.
+Tolerances are stated per test; FP64 throughout."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import DT, nonuniform_grid, rel, theta_state
+
+pytestmark = pytest.mark.gpu
+KERNELS = ["SE_Cos_1d", "Matern52_Cos_1d", "Matern52_1d", "SE_1d"]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("order", [0, 1, 2])
+def test_gram_matches_oracle(gphm, oracle, kernel, order):
+    """gphm_gram vs oracle.gram: <= 1e-12 relative to the matrix norm (pure elementwise FP64)."""
+    th = theta_state(30, 20.0)
+    for n1, n2, grid in [(257, 257, "uniform"), (130, 301, "uniform"), (63, 64, "random"), (1, 5, "uniform")]:
+        x1 = torch.linspace(0, 1, n1, dtype=DT) * 2 * math.pi if grid == "uniform" else nonuniform_grid(max(n1, 3), 6.0, 1)[:n1]
+        x2 = torch.linspace(0, 1, n2, dtype=DT) * 2 * math.pi if grid == "uniform" else nonuniform_grid(max(n2, 3), 6.0, 2)[:n2]
+        jit = 1e-6 if (n1 == n2 and order == 0) else 0.0
+        want = oracle.gram(kernel, x1, x2, th, order, jit)
+        got = getattr(gphm, kernel)().gram(x1, x2, th, order, jit)
+        assert got.shape == (n1, n2)
+        assert rel(got, want) <= 1e-12, (n1, n2, grid)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_kernel_class_api(gphm, oracle, kernel):
+    """kappa / D_x1_kappa / DD_x1_kappa over pair lists and Kernel_matrix.get_kernel_matrix on the
+    reference's flattened meshgrid inputs (kernel_matrix.py:21-30, model_GP_solver_2d.py:74-79)."""
+    th = theta_state(7, 5.0)
+    x = np.linspace(0, 1, 41) * 3.0
+    X1, X2 = np.meshgrid(x, x, indexing="ij")
+    cov = getattr(gphm, kernel)()
+    K = gphm.Kernel_matrix(1e-6, cov).get_kernel_matrix(X1, X2, th)
+    xt = torch.as_tensor(x)
+    assert rel(K, oracle.gram(kernel, xt, xt, th, 0, 1e-6)) <= 1e-12
+    assert rel(cov.D_x1_kappa(X1.reshape(-1), X2.reshape(-1), th).reshape(41, 41), oracle.gram(kernel, xt, xt, th, 1)) <= 1e-12
+    DD = cov.DD_x1_kappa(X1.reshape(-1), X2.reshape(-1), th).reshape(41, 41)
+    assert rel(DD, oracle.gram(kernel, xt, xt, th, 2)) <= 1e-12
+    assert float(DD.diagonal().abs().min()) > 0          # analytic k''(0) on the diagonal, not 0
+    s = cov.kappa(0.3, 1.1, th)
+    assert abs(float(s) - float(oracle.gram(kernel, torch.tensor([0.3], dtype=DT), torch.tensor([1.1], dtype=DT), th, 0))) < 1e-13
+    with pytest.raises(NotImplementedError):
+        gphm.Kernel_1d().kappa(0.0, 1.0, th)
+
+
+SHAPES = [(128, 128, 128), (256, 384, 512), (300, 257, 129), (1, 1, 1), (5, 1, 400), (400, 1, 400), (129, 130, 1),
+          (640, 1280, 96), (1000, 1000, 1000), (64, 64, 0)]
+
+
+@pytest.mark.parametrize("tA", [False, True])
+@pytest.mark.parametrize("tB", [False, True])
+def test_dgemm_matches_torch(gphm, tA, tB):
+    """gphm_dgemm (DMMA) vs torch.matmul in FP64: <= 1e-13 relative (same arithmetic, other order)."""
+    g = torch.Generator().manual_seed(3)
+    for (M, N, K) in SHAPES:
+        A = torch.randn((K, M) if tA else (M, K), generator=g, dtype=DT).cuda()
+        B = torch.randn((N, K) if tB else (K, N), generator=g, dtype=DT).cuda()
+        C0 = torch.randn(M, N, generator=g, dtype=DT).cuda()
+        want = 0.7 * ((A.T if tA else A) @ (B.T if tB else B)) - 1.3 * C0
+        got = gphm.solver_core.dgemm(A, B, tA, tB, alpha=0.7, beta=-1.3, C=C0.clone())
+        assert rel(got, want) <= 1e-13, (M, N, K)
+        got0 = gphm.solver_core.dgemm(A, B, tA, tB)
+        assert rel(got0, (A.T if tA else A) @ (B.T if tB else B)) <= 1e-13, (M, N, K)
+
+
+@pytest.mark.parametrize("n", [1, 7, 128, 129, 200, 400, 517, 1024])
+def test_cholesky_and_inverse(gphm, oracle, n):
+    """gphm_potrf_inv on a real Gram matrix (cond ~ 1e6): L vs torch.linalg.cholesky, Linv @ L = I,
+    logdet.  Bounds reflect cond(L) ~ 2e3: <= 1e-10."""
+    x = torch.linspace(0, 1, n, dtype=DT) * 2 * math.pi
+    K = oracle.gram("Matern52_Cos_1d", x, x, theta_state(30, 20.0), 0, 1e-6)
+    L, Linv, logdet, status = gphm.solver_core.potrf_inv(K)
+    assert int(status) == 0
+    Lref = torch.linalg.cholesky(K)
+    assert rel(L, Lref) <= 1e-10
+    assert float(torch.triu(L.cpu(), 1).abs().max()) == 0.0 and float(torch.triu(Linv.cpu(), 1).abs().max()) == 0.0
+    eye = torch.eye(n, dtype=DT)
+    assert rel(Linv.cpu() @ Lref, eye) <= 1e-9
+    assert abs(float(logdet) - float(torch.linalg.slogdet(K)[1])) <= 1e-9 * max(1.0, abs(float(logdet)))
+    B = torch.sin(torch.arange(n * 3, dtype=DT)).reshape(n, 3)
+    assert rel(gphm.solver_core.solve_spd(K, B), torch.linalg.solve(K, B)) <= 1e-7
+
+
+def test_cholesky_flags_non_spd(gphm):
+    K = torch.eye(200, dtype=DT)
+    K[150, 150] = -1.0
+    _, _, _, status = gphm.solver_core.potrf_inv(K)
+    assert int(status) == 151                       # 1 + index of the first bad pivot
+
+
+def test_adam_matches_oracle(gphm, oracle):
+    lib = gphm._lib.load()
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(1000, generator=g, dtype=DT)
+    params, st = {"p": p0.clone()}, oracle.adam_init({"p": p0})
+    p, m, v = p0.clone().cuda(), torch.zeros(1000, dtype=DT).cuda(), torch.zeros(1000, dtype=DT).cuda()
+    count = torch.zeros(1, dtype=torch.int64).cuda()
+    for t in range(5):
+        grad = torch.randn(1000, generator=g, dtype=DT) * 10 ** (t - 2)
+        params, st = oracle.adam_update(params, {"p": grad}, st, 0.01)
+        gd = grad.cuda()
+        gphm._lib.check(lib.gphm_adam_update(gphm._lib.ptr(p), gphm._lib.ptr(gd), gphm._lib.ptr(m), gphm._lib.ptr(v),
+                                             1000, gphm._lib.ptr(count), 0.01, gphm._lib.stream_ptr()), "adam")
+        count += 1
+        assert rel(p, params["p"]) <= 1e-14
+    zero = torch.zeros(4, dtype=DT).cuda()      # zero gradient leaves the parameter exactly unchanged (freq of plain kernels)
+    pz = torch.ones(4, dtype=DT).cuda()
+    gphm._lib.check(lib.gphm_adam_update(gphm._lib.ptr(pz), gphm._lib.ptr(zero), gphm._lib.ptr(zero.clone()),
+                                         gphm._lib.ptr(zero.clone()), 4, gphm._lib.ptr(count), 0.01,
+                                         gphm._lib.stream_ptr()), "adam")
+    assert bool((pz == 1.0).all())

@@ -1,0 +1,239 @@
+"""GPU: the solver classes (the reference-facing API) against the oracle - per-term and per-leaf
+single-step parity at identical inputs (bound 1e-6 relative, north_star), golden trajectories, and
+size-independent properties at larger N."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import DT, nonuniform_grid, rel, tree_flatten
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-6            # north_star: loss and gradients within 1e-6 relative in FP64
+
+
+def trick(equation, kernel, Q, freq_scale, N, llk=200.0, lr=0.01, **kw):
+    d = {"equation": equation, "kernel": kernel, "Q": Q, "freq_scale": freq_scale, "N_col": N, "llk_weight": llk,
+         "lr": lr, "logdet": True, "nepoch": 100, "tol": -1, "num_fold": 1, "num_u_trick": 1, "other_paras": ""}
+    d.update(kw)
+    return d
+
+
+def make_2d(gphm, oracle, equation, kernel, N1, N2, Q, fs, scale, beta=1.0, uniform=True, llk=200.0, M=40):
+    O = oracle
+    p, (xt, yt), ut = O.make_problem_2d(equation, kernel, N1, scale, llk_weight=llk, beta=beta, M=M, N2=N2)
+    if not uniform:
+        p.x, p.y = nonuniform_grid(N1, scale, 1), nonuniform_grid(N2, scale, 2)
+    cls = gphm.GP_solver_2d_single_advection if equation.startswith("advection") else gphm.GP_solver_2d_single
+    tp = trick(equation, kernel, Q, fs, N1, llk=llk, beta=beta)
+    model = cls(p.bvals.numpy(), (p.x.numpy(), p.y.numpy()), p.src.numpy(), 1e-6, (xt.numpy(), yt.numpy()), ut.numpy(), tp)
+    return p, model, (xt, yt), ut
+
+
+def check_terms_and_grads(oracle, p, model, params, tol=TOL):
+    tl, gl = oracle.loss_and_grad_literal(p, params)
+    terms = model.loss_terms(params)
+    loss, grads = model.value_and_grad(params)
+    names = {"loss": "loss", "logdet1": "logdet1", "logdet2": "logdet2", "quad": "quad", "bgap": "boundary_gap", "eqgap": "eq_gap"}
+    for k, v in tl.items():
+        got = float(terms[names[k]])
+        assert abs(got - v) <= tol * max(abs(v), 1e-12) + 1e-18, (k, got, v)
+    assert abs(float(loss) - tl["loss"]) <= tol * abs(tl["loss"])
+    want = dict(tree_flatten(gl))
+    for path, g in tree_flatten(grads):
+        w = want[path]
+        scale = float(w.norm())
+        assert float((g.reshape(-1) - w.reshape(-1)).norm()) <= tol * scale + 1e-300, (path, float(g.norm()), scale)
+    return tl
+
+
+CASES_2D = [
+    ("poisson_2d-sin_add_cos", "Matern52_Cos_1d", 150, 131, 30, 20.0, 2 * math.pi, 1.0, True),
+    ("poisson_2d-sin_add_cos", "SE_Cos_1d", 96, 140, 12, 8.0, 2 * math.pi, 1.0, True),
+    ("poisson_2d-sin_sin", "Matern52_1d", 129, 128, 5, 1.0, 2 * math.pi, 1.0, True),
+    ("allencahn_2d-mix-sincos", "SE_Cos_1d", 130, 130, 9, 10.0, 1.0, 1.0, True),
+    ("allencahn_2d-mix-sincos", "Matern52_Cos_1d", 64, 257, 9, 10.0, 1.0, 1.0, True),
+    ("advection-sin", "SE_Cos_1d", 100, 120, 8, 4.0, 1.0, 20.0, True),
+    ("advection-sin", "Matern52_Cos_1d", 131, 90, 8, 4.0, 1.0, 200.0, True),
+    ("poisson_2d-sin_add_cos", "Matern52_Cos_1d", 90, 70, 6, 5.0, 2 * math.pi, 1.0, False),
+    ("advection-sin", "SE_Cos_1d", 60, 75, 5, 3.0, 1.0, 20.0, False),
+    ("poisson_2d-sin_add_cos", "SE_1d", 70, 66, 4, 1.0, 1.0, 1.0, True),
+]
+
+
+@pytest.mark.parametrize("equation,kernel,N1,N2,Q,fs,scale,beta,uniform", CASES_2D)
+def test_logjoint_grad_2d_parity(gphm, oracle, equation, kernel, N1, N2, Q, fs, scale, beta, uniform):
+    p, model, _, _ = make_2d(gphm, oracle, equation, kernel, N1, N2, Q, fs, scale, beta, uniform)
+    assert bool(model.core.lib.gphm_plan_uses_toeplitz(model.core.plan, 0)) == uniform
+    check_terms_and_grads(oracle, p, model, oracle.state_S1(p, Q=Q, freq_scale=fs))
+    check_terms_and_grads(oracle, p, model, oracle.init_params_2d(N1, N2, Q, fs))
+
+
+def test_logjoint_grad_2d_golden_final_state(gphm, oracle):
+    """State S2: the final params of the reference's shipped 2-D run (N=400, Q=30)."""
+    g = np.load(os.path.join(GOLD, "poisson_2d_sin_sin_matern52cos_e100.npz"))
+    p, model, _, _ = make_2d(gphm, oracle, "poisson_2d-sin_sin", "Matern52_Cos_1d", 400, 400, 30, 20.0, 2 * math.pi, M=300)
+    params = {"U": torch.tensor(g["U"]), "log_tau": torch.tensor(float(g["log_tau"]), dtype=DT),
+              "log_v": torch.tensor(float(g["log_v"]), dtype=DT)}
+    for a in ("1", "2"):
+        params["kernel_paras_" + a] = {k: torch.tensor(g["kp%s_%s" % (a, k)]) for k in ("log-w", "log-ls", "freq")}
+    check_terms_and_grads(oracle, p, model, params)
+    err = float(model.core.rel_l2(model.preds(params)[0], model.ute))
+    assert abs(err - 0.46758844) <= 1e-6              # log.txt: err_list [0.46758844]
+
+
+CASES_1D = [("poisson_1d-single_sin", "Matern52_Cos_1d", 400, 30, 20.0, 2 * math.pi),
+            ("poisson_1d-mix_sin", "SE_Cos_1d", 300, 10, 30.0, 1.0),
+            ("allencahn_1d-sin_cos", "SE_Cos_1d", 257, 12, 20.0, 2 * math.pi),
+            ("allencahn_1d-single_sin", "Matern52_1d", 128, 4, 1.0, 2 * math.pi),
+            ("poisson_1d-x2_add_sinx", "SE_1d", 77, 3, 1.0, 1.0)]
+
+
+def make_1d(gphm, oracle, equation, kernel, N, Q, fs, scale):
+    p, xte, yte = oracle.make_problem_1d(equation, kernel, N, scale)
+    tp = trick(equation, kernel, Q, fs, N)
+    model = gphm.GP_solver_1d_single(p.xind.numpy(), p.yb.numpy(), p.x.numpy().reshape(-1, 1), p.src.numpy(), 1e-6,
+                                     xte.numpy().reshape(-1, 1), yte.numpy().reshape(-1, 1), tp)
+    return p, model, xte, yte
+
+
+@pytest.mark.parametrize("equation,kernel,N,Q,fs,scale", CASES_1D)
+def test_logjoint_grad_1d_parity(gphm, oracle, equation, kernel, N, Q, fs, scale):
+    p, model, _, _ = make_1d(gphm, oracle, equation, kernel, N, Q, fs, scale)
+    params = oracle.init_params_1d(N, Q, fs)
+    check_terms_and_grads(oracle, p, model, params)
+    q = torch.arange(Q, dtype=DT)
+    params["u"] = (0.6 * torch.sin(7 * p.x) + 0.2 * torch.cos(3 * p.x)).reshape(-1, 1)
+    params["kernel_paras"]["log-ls"] = 0.1 * torch.sin(q)
+    params["kernel_paras"]["freq"] = params["kernel_paras"]["freq"] + 0.05 * torch.sin(2 * q)
+    params["log_tau"], params["log_v"] = torch.tensor(0.3, dtype=DT), torch.tensor(-0.2, dtype=DT)
+    check_terms_and_grads(oracle, p, model, params)
+
+
+def test_step_matches_oracle_and_is_functional(gphm, oracle):
+    p, model, _, _ = make_2d(gphm, oracle, "poisson_2d-sin_add_cos", "Matern52_Cos_1d", 100, 90, 10, 10.0, 2 * math.pi)
+    params = oracle.state_S1(p, Q=10, freq_scale=10.0)
+    ost = oracle.adam_init(params)
+    gparams, gst = params, model.core.init_opt_state(params)
+    for it in range(3):
+        before = gparams["U"].clone() if isinstance(gparams["U"], torch.Tensor) else None
+        params, ost, terms = oracle.step(p, params, ost, 0.01, "literal")
+        new_params, gst, loss = model.step(gparams, gst)
+        if before is not None:
+            assert torch.equal(torch.as_tensor(gparams["U"]), before)          # inputs are not modified
+        gparams = new_params
+        assert abs(float(loss) - terms["loss"]) <= TOL * abs(terms["loss"])
+        assert int(gst["count"]) == it + 1
+        for (path, a), (_, b) in zip(tree_flatten(gparams), tree_flatten(params)):
+            # Adam's first updates are +-lr*sign(g): parameters agree to ~1e-9 absolute
+            assert float((a.reshape(-1) - b.reshape(-1)).abs().max()) <= 1e-7 * max(1.0, float(b.abs().max())), (it, path)
+
+
+def test_golden_1d_training_run(gphm, oracle):
+    """train() replays the reference's shipped 1-D run: 20 checkpoints of log-loss / rel-L2 error /
+    kernel parameters, 100 epochs (code/result_log/poisson_1d-single_sin/...)."""
+    g = np.load(os.path.join(GOLD, "poisson_1d_single_sin_matern52cos_e100.npz"))
+    cfg = gphm.model_GP_solver_2d.make_config("poisson_1d-single_sin", "Matern52_Cos_1d", 100,
+                                              allowed=gphm.model_GP_solver_1d.EQUATIONS, config_dir="/nonexistent")
+    Xind, y, X_col, src, X_test, Y_test = gphm.model_GP_solver_1d.build_problem(cfg)
+    model = gphm.GP_solver_1d_single(Xind, y, X_col, src, 1e-6, X_test, Y_test, cfg)
+    log, early, min_err = model.train(100)
+    assert log["epoch_list"] == list(range(0, 100, 5))
+    assert np.allclose(log["loss_list"], g["log_loss_list"], rtol=1e-6, atol=0)
+    assert np.allclose(log["err_list"], g["log_err_list"], rtol=1e-5, atol=0)
+    assert np.allclose(np.stack(log["w_list"]), g["log_w_list"], rtol=1e-5)
+    assert np.allclose(np.stack(log["freq_list"]), g["log_freq_list"], rtol=1e-5, atol=1e-8)
+    assert np.allclose(np.stack(log["ls_list"]), g["log_ls_list"], rtol=1e-5)
+    assert abs(min_err - 0.27562065) <= 1e-5 and early["flag"] is False
+    assert rel(model.params["u"], g["u"]) <= 1e-5
+
+
+def test_golden_2d_training_run(gphm, oracle):
+    """2-D shipped run.  Trajectories are chaotic (cond(K) ~ 4e6): exact at step 0,
+    1e-7 through step 5, 1e-4 / 1e-3 through step 95, final rel-L2 error within 5 %."""
+    g = np.load(os.path.join(GOLD, "poisson_2d_sin_sin_matern52cos_e100.npz"))
+    cfg = gphm.model_GP_solver_2d.make_config("poisson_2d-sin_sin", "Matern52_Cos_1d", 100, config_dir="/nonexistent")
+    model = gphm.GP_solver_2d_single(*_args2d(gphm, cfg), cfg)
+    log, _, min_err = model.train(100)
+    ll, ee = np.array(log["loss_list"]), np.array(log["err_list"])
+    assert abs(ll[0] - g["log_loss_list"][0]) <= 1e-12 * abs(ll[0])
+    assert abs(ll[1] - g["log_loss_list"][1]) <= 1e-7 * abs(ll[1]) and abs(ee[1] - g["log_err_list"][1]) <= 1e-7
+    assert np.allclose(ll, g["log_loss_list"], rtol=1e-4) and np.allclose(ee, g["log_err_list"], rtol=1e-3)
+    assert abs(ee[-1] - 0.46758844) <= 0.05 * 0.46758844
+
+
+def _args2d(gphm, cfg):
+    bvals, X_col, src, X_test, u_test = gphm.model_GP_solver_2d.build_problem(cfg)
+    return bvals, X_col, src, 1e-6, X_test, u_test
+
+
+def test_preds_and_early_stopping(gphm, oracle):
+    p, model, (xt, yt), ut = make_2d(gphm, oracle, "poisson_2d-sin_add_cos", "SE_Cos_1d", 120, 100, 8, 6.0, 2 * math.pi, M=37)
+    params = oracle.state_S1(p, Q=8, freq_scale=6.0)
+    pred, _ = model.preds(params)
+    want = oracle.preds_2d(p, params, xt, yt)
+    assert pred.shape == (37, 37) and rel(pred, want) <= TOL
+    assert abs(float(model.core.rel_l2(pred, model.ute)) - oracle.rel_l2(want, ut)) <= 1e-8
+    fw = oracle.forward_terms_2d(p, params)
+    crit = float(fw["bgap"]) / p.bvals.numel() + float(fw["eqgap"]) / (120 * 100)
+    assert abs(float(model.compute_early_stopping(params)) - crit) <= TOL * crit
+    K1, K2, A, B, Uxx, Uyy = model.value_and_grad_kernel(params)
+    assert rel(Uxx, fw["Ux"]) <= TOL and rel(Uyy, fw["Uy"]) <= TOL and rel(K1, fw["K1"]) <= 1e-12
+    bg, eg = model.boundary_and_eq_gap(params["U"], Uxx, Uyy)
+    assert abs(float(bg) - float(fw["bgap"])) <= TOL * float(fw["bgap"]) and abs(float(eg) - float(fw["eqgap"])) <= TOL * float(fw["eqgap"])
+    p1, m1, xte, yte = make_1d(gphm, oracle, "poisson_1d-sin_cos", "Matern52_Cos_1d", 200, 9, 20.0, 2 * math.pi)
+    par1 = oracle.init_params_1d(200, 9, 20.0)
+    par1["u"] = torch.sin(5 * p1.x).reshape(-1, 1)
+    pr1, K = m1.preds(par1)
+    assert pr1.shape == (300, 1) and rel(pr1, oracle.preds_1d(p1, par1, xte)) <= TOL and K.shape == (200, 200)
+
+
+def test_errors_and_status(gphm, oracle):
+    p, model, _, _ = make_2d(gphm, oracle, "poisson_2d-sin_sin", "SE_1d", 40, 40, 3, 1.0, 1.0)
+    params = oracle.init_params_2d(40, 40, 3, 1.0)
+    params["kernel_paras_1"]["log-w"] = torch.full((3,), float("nan"), dtype=DT)   # NaN Gram -> not SPD
+    model.loss(params)
+    with pytest.raises(FloatingPointError):
+        model.core.raise_on_bad_status()
+    with pytest.raises(AssertionError):
+        gphm.GP_solver_2d_single(p.bvals.numpy(), (p.x.numpy(), p.y.numpy()), p.src.numpy(), 1e-6,
+                                 (p.x.numpy(), p.y.numpy()), p.src.numpy(), trick("advection-sin", "SE_1d", 3, 1.0, 40))
+    with pytest.raises(ValueError):
+        model.step({**params, "kernel_paras_1": {k: v[:2] for k, v in params["kernel_paras_1"].items()}},
+                   model.core.init_opt_state(params))
+
+
+@pytest.mark.parametrize("N", [1024])
+def test_properties_at_scale(gphm, oracle, N):
+    """Size-independent checks where the literal oracle is too slow: efficient-oracle parity,
+    Toeplitz path == general path, run-to-run bitwise determinism, descent along -grad."""
+    O = oracle
+    p, model, _, _ = make_2d(gphm, oracle, "poisson_2d-sin_add_cos", "Matern52_Cos_1d", N, N, 30, 20.0, 2 * math.pi)
+    s1 = O.state_S1(p)
+    te, ge = O.loss_and_grad_efficient(p, s1)
+    loss, grads = model.value_and_grad(s1)
+    assert abs(float(loss) - te["loss"]) <= TOL * abs(te["loss"])
+    want = dict(tree_flatten(ge))
+    for path, gch in tree_flatten(grads):
+        assert float((gch.reshape(-1) - want[path].reshape(-1)).norm()) <= TOL * float(want[path].norm()), path
+    loss2, grads2 = model.value_and_grad(s1)
+    assert float(loss2) == float(loss) and all(torch.equal(a, b) for (_, a), (_, b) in zip(tree_flatten(grads), tree_flatten(grads2)))
+    tp = trick("poisson_2d-sin_add_cos", "Matern52_Cos_1d", 30, 20.0, N, force_general=True)
+    gen = gphm.GP_solver_2d_single(p.bvals.numpy(), (p.x.numpy(), p.y.numpy()), p.src.numpy(), 1e-6,
+                                   (p.x.numpy()[:5], p.y.numpy()[:5]), np.zeros((5, 5)), tp)
+    assert not gen.core.lib.gphm_plan_uses_toeplitz(gen.core.plan, 0)
+    lg, gg = gen.value_and_grad(s1)
+    assert abs(float(lg) - float(loss)) <= 1e-9 * abs(float(loss))
+    for (path, a), (_, b) in zip(tree_flatten(gg), tree_flatten(grads)):
+        assert float((a - b).norm()) <= 1e-7 * float(b.norm()), path
+    # a small step along -dL/dU decreases the loss by ~ eps * |g|^2 (first-order check of the gradient)
+    gU = grads["U"]
+    eps = 1e-3 / float(gU.abs().max())
+    moved = dict(s1)
+    moved["U"] = torch.as_tensor(s1["U"]).cuda() - eps * gU
+    dl = float(model.loss(moved)) - float(loss)
+    pred = -eps * float((gU * gU).sum())
+    assert dl < 0 and abs(dl - pred) <= 0.05 * abs(pred)
