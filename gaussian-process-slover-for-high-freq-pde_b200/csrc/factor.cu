@@ -79,6 +79,7 @@ chol_diag_kernel(const double* __restrict__ Kbb, double* __restrict__ Lbb, int l
     //      X[j][j] = 1/L[j][j];  X[i][j] = -(sum_{k=j+1..i} X[i][k] L[k][j]) * X[j][j]
     //      8 lanes cooperate on one row. ----
     const int sub = tid & 7, rgrp = tid >> 3;           // 128 row groups
+    const unsigned gmask = 0xffu << (tid & 24);         // the 8 lanes of this row group (same trip count)
     for (int j = nb - 1; j >= 0; --j) {
         for (int i = j + 1 + tid; i < nb; i += DIAG_THREADS) col[i] = S[i * SLD + j];
         __syncthreads();
@@ -89,9 +90,9 @@ chol_diag_kernel(const double* __restrict__ Kbb, double* __restrict__ Lbb, int l
                 const double xik = (k == i) ? 1.0 / dg[i] : S[i * SLD + k];
                 s += xik * col[k];
             }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            s += __shfl_xor_sync(gmask, s, 1);
+            s += __shfl_xor_sync(gmask, s, 2);
+            s += __shfl_xor_sync(gmask, s, 4);
             if (sub == 0) S[i * SLD + j] = -s * xjj;
         }
         __syncthreads();
