@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the GP-HM log-joint + gradient + Adam iteration (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (libgphm, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: CPU oracle port
+
+Workload (N=1 and N>1): 2-D multi-scale Poisson `poisson_2d-sin_add_cos` on a 4096^2 collocation
+grid, Matern52_Cos_1d, Q=30, FP64, reference initial state.  A "step" is one full
+iteration: Gram build + Cholesky + K^-1 applications + Kronecker contractions + reductions +
+hand-derived backward + Adam on every leaf.  One JSON line is printed by rank 0.
+N>1 shards the same problem (strong scaling): U row/column blocks per rank, NCCL all-to-all.
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "log-joint+grad iters/sec, 2D Poisson 4096^2 grid"
+UNIT = "it/s"
+EQUATION, KERNEL, Q, FREQ_SCALE, LLK, LR = "poisson_2d-sin_add_cos", "Matern52_Cos_1d", 30, 20.0, 200.0, 0.01
+
+
+def flops_per_iter(n):
+    return 28.0 * float(n) ** 3
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=4096, help="collocation points per axis")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="profiling runs only")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--no-peak", action="store_true", help="profiling runs only: skip the cuBLAS DGEMM denominator")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measure_fp64_peak(device):
+    """cuBLAS DGEMM 8192^3 through torch.matmul - the native-FP64 roofline denominator
+    (MEASURED_PEAKS.json has only HBM and bf16; SURVEY 8d asks for this in-run measurement)."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=device)
+    b = torch.randn(n, n, dtype=torch.float64, device=device)
+    c = torch.empty_like(a)
+    for _ in range(2):
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 40
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(a, b, out=c)
+    e1.record(); torch.cuda.synchronize()
+    sustained = e0.elapsed_time(e1) / reps
+    fl = 2.0 * n ** 3
+    return fl / best / 1e9, fl / sustained / 1e9
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def trick_paras(n):
+    return {"equation": EQUATION, "kernel": KERNEL, "Q": Q, "freq_scale": FREQ_SCALE, "N_col": n, "llk_weight": LLK,
+            "lr": LR, "logdet": True, "nepoch": 1, "tol": -1, "scale": 2 * math.pi, "num_fold": 1}
+
+
+def build_inputs(n):
+    import gphm_b200 as G
+    tp = trick_paras(n)
+    bvals, X_col, src, X_test, u_test = G.model_GP_solver_2d.build_problem(tp, M=300)
+    return tp, bvals, X_col, src, X_test, u_test
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_iteration(n, steps, warmup, threads):
+    """Oracle port (efficient formulation = the stronger CPU baseline) on the host cores."""
+    from oracle import gphm_oracle as O
+    torch.set_num_threads(threads)
+    p, _, _ = O.make_problem_2d(EQUATION, KERNEL, n, 2 * math.pi, llk_weight=LLK, M=8)
+    params = O.init_params_2d(n, n, Q, FREQ_SCALE)
+    st = O.adam_init(params)
+    for _ in range(warmup):
+        params, st, _ = O.step(p, params, st, LR, "efficient")
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        params, st, terms = O.step(p, params, st, LR, "efficient")
+    dt = time.perf_counter() - t0
+    return dt / max(steps, 1), terms["loss"]
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.size
+    # bounded sample: calibrate on N=1024 and pick the largest grid whose (W+K) iterations fit ~4 min
+    t1024, _ = cpu_reference_iteration(1024, 1, 1, threads)
+    budget, n_s = 240.0, n
+    while n_s > 1024 and t1024 * (n_s / 1024.0) ** 3 * (args.steps + args.warmup) > budget:
+        n_s //= 2
+    t_iter, loss = cpu_reference_iteration(n_s, args.steps, args.warmup, threads)
+    scale = (float(n_s) / n) ** 3                        # 28 N^3 FLOPs per iteration
+    value = scale / t_iter
+    sample = ("one full iteration per step at N=%d" % n_s) if n_s == n else \
+        ("one full iteration per step at N=%d, it/s scaled by (N_s/N)^3 = %.4g to the N=%d workload" % (n_s, scale, n))
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "%s %dx%d %s Q=%d S0" % (EQUATION, n, n, KERNEL, Q),
+                       "reference": "torch-FP64 CPU port of the reference step (oracle/gphm_oracle.py, efficient "
+                                    "formulation); the JAX reference cannot be installed here (no jax wheel, no network)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local):
+    import gphm_b200 as G
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    lib = G._lib.load()
+    n = args.size
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    tp, bvals, X_col, src, X_test, u_test = build_inputs(n)
+
+    if world == 1:
+        core = G.solver_core.SolverCore(2, KERNEL, "poisson", X_col[0], X_col[1], src, bvals, None, LLK, 1.0, 1.0, 1e-6, Q)
+        model_init = G.GP_solver_2d_single.init_params
+        class _M:                                          # init_params only needs these attributes
+            trick_paras, N1, N2 = tp, n, n
+        st = core.new_state(model_init(_M))
+        step = lambda: core.step_inplace(st, LR)
+        parallelism = "1 GPU"
+    else:
+        from importlib import import_module
+        distmod = import_module("gaussian-process-slover-for-high-freq-pde_b200.dist")
+        solver = distmod.ShardedSolver2D(KERNEL, "poisson", X_col[0], X_col[1], src, bvals, LLK, 1.0, 1.0, 1e-6, Q, LR)
+        solver.init_state(FREQ_SCALE)
+        step = solver.step
+        st = None
+        parallelism = "U row/column blocks over %d GPUs, NCCL all-to-all" % world
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = lib.gphm_launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    lib.gphm_profile_start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    cat_ms = (ctypes.c_double * 5)(); cat_fl = (ctypes.c_double * 5)(); cat_by = (ctypes.c_double * 5)()
+    cat_n = (ctypes.c_longlong * 5)()
+    lib.gphm_profile_stop(cat_ms, cat_fl, cat_by, cat_n)
+    launches = lib.gphm_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t)
+    ms_step = ms_total / args.steps
+    value = 1e3 / ms_step
+
+    loss = float(st.terms[0]) if st is not None else float(solver.last_loss())
+    if not math.isfinite(loss):
+        raise SystemExit("bench.py: non-finite loss")
+
+    # ---- e2e: the same step through the host-buffer entry point (H2D + step + D2H every step) ----
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        nf, ns = n * n, 6 * Q + 2
+        host = [torch.zeros(nf, dtype=torch.float64).pin_memory() for _ in range(3)]
+        hs = [torch.zeros(ns, dtype=torch.float64).pin_memory() for _ in range(3)]
+        hcount = torch.zeros(1, dtype=torch.int64).pin_memory()
+        hterms = torch.zeros(8, dtype=torch.float64).pin_memory()
+        host[0].copy_(st.U.cpu()); hs[0].copy_(st.small.cpu())
+        e2e_steps = min(args.steps, 5)
+        core.step_host(host[0], hs[0], host[1], host[2], hs[1], hs[2], hcount, hterms, LR)       # warm
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            core.step_host(host[0], hs[0], host[1], host[2], hs[1], hs[2], hcount, hterms, LR)
+        dt = time.perf_counter() - t0
+        h2d = 8 * (3 * nf + 3 * ns) + 8
+        e2e = {"value": e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d + 64,
+               "steps": e2e_steps, "api": "gphm_step_host (pinned host params + opt_state in, updated out)"}
+    elif world > 1:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "note": "host-buffer entry point is single-GPU; see the N=1 line"}
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (DGEMM on the FP64 DMMA pipe) ----
+    peaks = measured_peaks()
+    burst = sustained = None
+    if not args.no_peak:
+        burst, sustained = measure_fp64_peak(device)
+    gemm_ms, gemm_fl = cat_ms[1], cat_fl[1]
+    achieved = gemm_fl / gemm_ms / 1e9 if gemm_ms > 0 else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "dgemm_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "dgemm_kernel (FP64 DMMA.8x8x4; tcgen05 has no f64 kind)",
+                "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
+                "frac": (achieved / sustained) if (achieved and sustained) else None, "traffic": traffic,
+                "peak_source": "cuBLAS DGEMM 8192^3 measured in this run, sustained over %d back-to-back calls "
+                               "(burst %.1f); MEASURED_PEAKS.json has no FP64 entry (bf16 %.0f TFLOP/s, HBM %.0f GB/s)"
+                               % (40, burst or 0.0, peaks.get("bf16_tflops", 0.0), peaks.get("hbm_gbs", 0.0)),
+                "launches_per_step": cat_n[1] / args.steps, "ms_per_step": gemm_ms / args.steps,
+                "flops_issued_per_step": gemm_fl / args.steps,
+                "step_tflops_of_28N3": flops_per_iter(n) / ms_step / 1e9,
+                "step_frac_of_peak": (flops_per_iter(n) / ms_step / 1e9 / sustained) if sustained else None,
+                "by_family_ms_per_step": {"gram": cat_ms[0] / args.steps, "dgemm": cat_ms[1] / args.steps,
+                                          "chol_diag": cat_ms[2] / args.steps, "reduce_elementwise": cat_ms[3] / args.steps,
+                                          "adam": cat_ms[4] / args.steps}}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        t_iter, _ = cpu_reference_iteration(n, 2, 1, threads)
+        cpu = {"value": 1.0 / t_iter, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "2 full iterations at N=%d after 1 warm-up (oracle efficient formulation, torch FP64/MKL)" % n}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "%s %dx%d %s Q=%d S0" % (EQUATION, n, n, KERNEL, Q), "parallelism": parallelism,
+                       "l2": "working set per step ~%.1f GB >> 126 MB L2 (no flush needed)" % (28 * n * n * 8 / 1e9),
+                       "loss_after": loss},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank, world, local = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py: --gpus %d needs torchrun (one rank per GPU)" % args.gpus)
+    run_ours(args, rank, world, local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -26,6 +26,9 @@ class ProblemDesc(ctypes.Structure):
 _SIGS = {
     "gphm_version": (c_int, []),
     "gphm_last_error": (c_char_p, []),
+    "gphm_launch_count": (c_longlong, []),
+    "gphm_profile_start": (c_int, []),
+    "gphm_profile_stop": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "gphm_gram": (c_int, [c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_double, c_void_p, c_void_p]),
     "gphm_kappa_pairs": (c_int, [c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_void_p, c_void_p]),
     "gphm_dgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, c_void_p, c_int, c_void_p, c_int, c_double,

@@ -29,6 +29,15 @@ void set_last_error(const char* fmt, ...);
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 
+// Launch accounting / optional CUDA-event profiling per kernel family (gphm_profile_* in gphm.h).
+enum : int { CAT_GRAM = 0, CAT_DGEMM = 1, CAT_CHOL_DIAG = 2, CAT_ELEMWISE = 3, CAT_ADAM = 4, CAT_COUNT = 5 };
+bool profiling_enabled();
+struct LaunchScope {
+    int cat; cudaStream_t st; int slot;
+    LaunchScope(int cat, cudaStream_t st, double flops = 0.0, double bytes = 0.0);
+    ~LaunchScope();
+};
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

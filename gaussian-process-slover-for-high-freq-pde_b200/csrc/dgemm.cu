@@ -193,10 +193,28 @@ constexpr size_t gemm_smem_bytes() {
            sizeof(double);
 }
 
+// FLOPs actually issued for this launch (2*m*n*k over the computed tiles with their k-ranges).
+static double gemm_flops(const GemmArgs& g, int BM, int BN) {
+    if (!profiling_enabled()) return 0.0;
+    double f = 0.0;
+    for (int m0 = 0; m0 < g.M; m0 += BM)
+        for (int n0 = 0; n0 < g.N; n0 += BN) {
+            if ((g.kmode & KM_C_LOWER) && n0 >= m0 + BM) continue;
+            int kb = 0, ke = g.K;
+            if (g.kmode & KM_A_LOWER) ke = std::min(ke, m0 + BM);
+            if (g.kmode & KM_A_UPPER) kb = std::max(kb, m0);
+            if (g.kmode & KM_B_LOWER) kb = std::max(kb, n0);
+            if (g.kmode & KM_B_UPPER) ke = std::min(ke, n0 + BN);
+            if (ke > kb) f += 2.0 * std::min(BM, g.M - m0) * std::min(BN, g.N - n0) * (double)(ke - kb);
+        }
+    return f * g.batch;
+}
+
 template <int BM, int BN, int WM, int WN, bool TA, bool TB, int VEC, int MINB>
 static int launch_cfg(const GemmArgs& g, cudaStream_t st) {
     const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
     dim3 grid(tiles, g.batch), block(WM * WN * 32);
+    LaunchScope scope(CAT_DGEMM, st, gemm_flops(g, BM, BN));
     dgemm_kernel<BM, BN, WM, WN, TA, TB, VEC, MINB><<<grid, block, gemm_smem_bytes<BM, BN, TA, TB>(), st>>>(g);
     GPHM_LAUNCH_OK();
     return GPHM_OK;

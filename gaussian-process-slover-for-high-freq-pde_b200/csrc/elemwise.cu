@@ -41,7 +41,7 @@ residual_kernel(double* __restrict__ R, const double* __restrict__ U, const doub
 
 int launch_residual(double* R, const double* U, const double* F, const double* A, const double* Bt, size_t n,
                     int eq_type, const double* small, int Q, double* part, cudaStream_t st) {
-    residual_kernel<<<kRedBlocks, 256, 0, st>>>(R, U, F, A, Bt, n, eq_type == 1, small, Q, part);
+    { LaunchScope scope(CAT_ELEMWISE, st); residual_kernel<<<kRedBlocks, 256, 0, st>>>(R, U, F, A, Bt, n, eq_type == 1, small, Q, part); }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }
@@ -98,8 +98,11 @@ finalize_kernel(LossConsts c, const double* __restrict__ U, const double* __rest
 int launch_finalize(const LossConsts& c, const double* U, const double* bvals, const int* xind,
                     const double* part, const double* ldp1, int nblk1, const double* ldp2, int nblk2,
                     const double* small, double* eb, double* terms, double* gsmall, int* status, cudaStream_t st) {
-    finalize_kernel<<<1, 1024, 0, st>>>(c, U, bvals, xind, part, ldp1, nblk1, ldp2, nblk2, small, eb, terms, gsmall,
-                                        status);
+    {
+        LaunchScope scope(CAT_ELEMWISE, st);
+        finalize_kernel<<<1, 1024, 0, st>>>(c, U, bvals, xind, part, ldp1, nblk1, ldp2, nblk2, small, eb, terms, gsmall,
+                                            status);
+    }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }
@@ -145,9 +148,9 @@ int launch_grad_u(const LossConsts& c, const double* U, const double* G, const d
                   const double* S2, const double* eb, const int* xind, const double* small, double* gU,
                   double* V1, double* V2, cudaStream_t st) {
     const size_t n = (size_t)c.n1 * c.n2;
-    grad_u_kernel<<<kRedBlocks, 256, 0, st>>>(n, c.eq_type == 1, U, G, W, S1, S2, gU, V1, V2);
+    { LaunchScope scope(CAT_ELEMWISE, st); grad_u_kernel<<<kRedBlocks, 256, 0, st>>>(n, c.eq_type == 1, U, G, W, S1, S2, gU, V1, V2); }
     GPHM_LAUNCH_OK();
-    boundary_scatter_kernel<<<1, 1024, 0, st>>>(c, eb, xind, small, gU);
+    { LaunchScope scope(CAT_ELEMWISE, st); boundary_scatter_kernel<<<1, 1024, 0, st>>>(c, eb, xind, small, gU); }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }
@@ -196,9 +199,9 @@ diag_sums_reduce_kernel(const double* __restrict__ part, int n, int nchunks, int
 int launch_diag_sums(const double* Kbar, const double* Dbar, int n, int ld, bool antisym, double dirsign,
                      double* part, double* sK, double* sD, cudaStream_t st) {
     const int nchunks = (n + DS_ROWS - 1) / DS_ROWS;
-    diag_sums_kernel<<<nchunks, 256, 0, st>>>(Kbar, Dbar, n, ld, part);
+    { LaunchScope scope(CAT_ELEMWISE, st); diag_sums_kernel<<<nchunks, 256, 0, st>>>(Kbar, Dbar, n, ld, part); }
     GPHM_LAUNCH_OK();
-    diag_sums_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(part, n, nchunks, antisym ? 1 : 0, dirsign, sK, sD);
+    { LaunchScope scope(CAT_ELEMWISE, st); diag_sums_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(part, n, nchunks, antisym ? 1 : 0, dirsign, sK, sD); }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }
@@ -228,6 +231,7 @@ theta_grad_toeplitz_kernel(const double* __restrict__ x, int n, const double* __
 
 int launch_theta_grad_toeplitz(int kid, int order, const double* x, int n, const double* theta, int Q,
                                const double* sK, const double* sD, double* gtheta, cudaStream_t st) {
+    LaunchScope scope(CAT_ELEMWISE, st);
     int rc = GPHM_DISPATCH_KID_ORDER(kid, order,
         theta_grad_toeplitz_kernel<KID, ORDER><<<Q, 256, 0, st>>>(x, n, theta, Q, sK, sD, gtheta));
     if (rc != 0) { set_last_error("theta_grad: bad kernel id %d / order %d", kid, order); return GPHM_EINVAL; }
@@ -298,11 +302,13 @@ int launch_theta_grad_general(int kid, int order, const double* x, int n, const 
                               const double* Kbar, const double* Dbar, int ld, double* part, double* gtheta,
                               cudaStream_t st) {
     const size_t nblk = ((size_t)n * n + 256 * TG_E - 1) / (256 * TG_E);
-    int rc = GPHM_DISPATCH_KID_ORDER(kid, order,
-        theta_grad_general_kernel<KID, ORDER><<<(unsigned)nblk, 256, 0, st>>>(x, n, theta, Q, Kbar, Dbar, ld, part));
+    int rc;
+    { LaunchScope scope(CAT_ELEMWISE, st);
+    rc = GPHM_DISPATCH_KID_ORDER(kid, order,
+        theta_grad_general_kernel<KID, ORDER><<<(unsigned)nblk, 256, 0, st>>>(x, n, theta, Q, Kbar, Dbar, ld, part)); }
     if (rc != 0) { set_last_error("theta_grad: bad kernel id %d / order %d", kid, order); return GPHM_EINVAL; }
     GPHM_LAUNCH_OK();
-    column_reduce_kernel<<<3 * Q, 256, 0, st>>>(part, nblk, 3 * Q, gtheta);
+    { LaunchScope scope(CAT_ELEMWISE, st); column_reduce_kernel<<<3 * Q, 256, 0, st>>>(part, nblk, 3 * Q, gtheta); }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }
@@ -330,12 +336,12 @@ int launch_adam(double* p, const double* g, double* m, double* v, size_t n, cons
                 cudaStream_t st) {
     if (n == 0) return GPHM_OK;
     const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)kNumSMs * 8);
-    adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, count, lr);
+    { LaunchScope scope(CAT_ADAM, st); adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, count, lr); }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }
 int launch_count_inc(long long* count, cudaStream_t st) {
-    count_inc_kernel<<<1, 1, 0, st>>>(count);
+    { LaunchScope scope(CAT_ADAM, st); count_inc_kernel<<<1, 1, 0, st>>>(count); }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }
@@ -363,9 +369,9 @@ rel_l2_final_kernel(const double* __restrict__ part, double* __restrict__ out) {
     if (threadIdx.x == 0) *out = sqrt(num) / sqrt(den);
 }
 int launch_rel_l2(const double* pred, const double* truth, size_t n, double* part, double* out, cudaStream_t st) {
-    rel_l2_part_kernel<<<kRedBlocks, 256, 0, st>>>(pred, truth, n, part);
+    { LaunchScope scope(CAT_ELEMWISE, st); rel_l2_part_kernel<<<kRedBlocks, 256, 0, st>>>(pred, truth, n, part); }
     GPHM_LAUNCH_OK();
-    rel_l2_final_kernel<<<1, 1024, 0, st>>>(part, out);
+    { LaunchScope scope(CAT_ELEMWISE, st); rel_l2_final_kernel<<<1, 1024, 0, st>>>(part, out); }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }
@@ -378,7 +384,7 @@ copy_kernel(double* __restrict__ dst, const double* __restrict__ src, size_t n) 
 int launch_copy(double* dst, const double* src, size_t n, cudaStream_t st) {
     if (n == 0) return GPHM_OK;
     const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)kNumSMs * 8);
-    copy_kernel<<<blocks, 256, 0, st>>>(dst, src, n);
+    { LaunchScope scope(CAT_ELEMWISE, st); copy_kernel<<<blocks, 256, 0, st>>>(dst, src, n); }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }
@@ -392,7 +398,7 @@ sum_scaled_kernel(const double* __restrict__ v, int n, double scale, double* __r
     if (threadIdx.x == 0) *out = scale * s;
 }
 int launch_sum_scaled(const double* v, int n, double scale, double* out, cudaStream_t st) {
-    sum_scaled_kernel<<<1, 256, 0, st>>>(v, n, scale, out);
+    { LaunchScope scope(CAT_ELEMWISE, st); sum_scaled_kernel<<<1, 256, 0, st>>>(v, n, scale, out); }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }

@@ -130,8 +130,9 @@ int chol_factor(double* K, double* L, int n, int ld, double* invdiag, double* lo
     const int nblk = num_blocks_nb(n);
     for (int b = 0; b < nblk; ++b) {
         const int j0 = b * kNB, nb = std::min(kNB, n - j0);
+        { LaunchScope scope(CAT_CHOL_DIAG, st);
         chol_diag_kernel<<<1, DIAG_THREADS, kDiagSmem, st>>>(K + (size_t)j0 * ld + j0, L + (size_t)j0 * ld + j0, ld, nb,
-                                                             invdiag + (size_t)b * kNB * kNB, logdet_part + b, status, j0);
+                                                             invdiag + (size_t)b * kNB * kNB, logdet_part + b, status, j0); }
         GPHM_LAUNCH_OK();
         const int rem = n - j0 - nb;
         if (rem <= 0) break;
@@ -149,7 +150,8 @@ int chol_factor(double* K, double* L, int n, int ld, double* invdiag, double* lo
 
 int trtri_lower(const double* L, double* Linv, int n, int ld, const double* invdiag, double* T, cudaStream_t st) {
     const int nblk = num_blocks_nb(n);
-    copy_diag_blocks_kernel<<<nblk, 256, 0, st>>>(invdiag, Linv, n, ld);
+    { LaunchScope scope(CAT_ELEMWISE, st);
+    copy_diag_blocks_kernel<<<nblk, 256, 0, st>>>(invdiag, Linv, n, ld); }
     GPHM_LAUNCH_OK();
     for (long long b = kNB; b < n; b *= 2) {
         const long long node = 2 * b;

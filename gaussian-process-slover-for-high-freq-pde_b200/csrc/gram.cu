@@ -140,6 +140,7 @@ int launch_kappa_pairs(int kid, int order, const double* x1, const double* x2, s
     if (Q > kMaxQ || Q < 1) { set_last_error("kappa: Q=%d outside [1,%d]", Q, kMaxQ); return GPHM_EINVAL; }
     if (np == 0) return GPHM_OK;
     const int blocks = (int)((np + 255) / 256 < (size_t)kNumSMs * 8 ? (np + 255) / 256 : (size_t)kNumSMs * 8);
+    LaunchScope scope(CAT_GRAM, st, 0.0, 24.0 * np);
     int rc = GPHM_DISPATCH_KID_ORDER(kid, order,
         kappa_pairs_kernel<KID, ORDER><<<blocks, 256, 0, st>>>(x1, x2, np, theta, Q, out));
     if (rc != 0) { set_last_error("kappa: bad kernel id %d / order %d", kid, order); return GPHM_EINVAL; }
@@ -153,6 +154,7 @@ int launch_gram_general(int kid, int order, const double* x1, int n1, const doub
     if (Q > kMaxQ || Q < 1) { set_last_error("gram: Q=%d outside [1,%d]", Q, kMaxQ); return GPHM_EINVAL; }
     if (n1 <= 0 || n2 <= 0) return GPHM_OK;
     dim3 block(64, 4), grid((n2 + 127) / 128, (n1 + 3) / 4);
+    LaunchScope scope(CAT_GRAM, st, 0.0, 8.0 * n1 * n2 * ((Kout ? 1 : 0) + (Dout ? 1 : 0)));
     int rc = GPHM_DISPATCH_KID_ORDER(kid, order,
         gram_general_kernel<KID, ORDER><<<grid, block, 0, st>>>(x1, n1, x2, n2, theta, Q, jitter, Kout, Dout, ld));
     if (rc != 0) { set_last_error("gram: bad kernel id %d / order %d", kid, order); return GPHM_EINVAL; }
@@ -165,11 +167,14 @@ int launch_gram_toeplitz(int kid, int order, const double* x, int n, const doubl
                          cudaStream_t st) {
     if (Q > kMaxQ || Q < 1) { set_last_error("gram: Q=%d outside [1,%d]", Q, kMaxQ); return GPHM_EINVAL; }
     if (n <= 0) return GPHM_OK;
-    int rc = GPHM_DISPATCH_KID_ORDER(kid, order,
-        toeplitz_table_kernel<KID, ORDER><<<(n + 127) / 128, 128, 0, st>>>(x, n, theta, Q, tabK, tabD));
+    int rc;
+    { LaunchScope scope(CAT_GRAM, st, 0.0, 24.0 * n);
+    rc = GPHM_DISPATCH_KID_ORDER(kid, order,
+        toeplitz_table_kernel<KID, ORDER><<<(n + 127) / 128, 128, 0, st>>>(x, n, theta, Q, tabK, tabD)); }
     if (rc != 0) { set_last_error("gram: bad kernel id %d / order %d", kid, order); return GPHM_EINVAL; }
     GPHM_LAUNCH_OK();
     dim3 block(256), grid((n + 511) / 512, (n + 3) / 4);
+    LaunchScope scope(CAT_GRAM, st, 0.0, 16.0 * n * n);
     if (order == 1) toeplitz_fill_kernel<true><<<grid, block, 0, st>>>(tabK, tabD, n, jitter, dirsign, Kout, Dout, ld);
     else toeplitz_fill_kernel<false><<<grid, block, 0, st>>>(tabK, tabD, n, jitter, dirsign, Kout, Dout, ld);
     GPHM_LAUNCH_OK();

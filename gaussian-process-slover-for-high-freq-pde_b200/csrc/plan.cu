@@ -14,6 +14,7 @@
 //   Kbar1 = ld/2 N2 K1^-1 - (S1 + W/2) A^T        Dbar1 = c1 G A^T
 //   Kbar2 = ld/2 N1 K2^-1 - (S2 + W/2)^T Bt       Dbar2 = G^T Bt
 //   dtheta_a = sum_ij Kbar_a * dK/dtheta + Dbar_a * dD/dtheta   (diagonal sums on uniform grids)
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
@@ -30,6 +31,34 @@ void set_last_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ---- launch accounting / event profiling -------------------------------------------------------
+namespace {
+struct ProfRec { int cat; double flops, bytes; cudaEvent_t a, b; };
+std::atomic<long long> g_launches{0};
+bool g_prof = false;
+std::vector<ProfRec> g_recs;
+std::vector<cudaEvent_t> g_pool;
+cudaEvent_t pool_event() {
+    if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+}  // namespace
+bool profiling_enabled() { return g_prof; }
+LaunchScope::LaunchScope(int c, cudaStream_t s, double flops, double bytes) : cat(c), st(s), slot(-1) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (g_prof) {
+        ProfRec r{c, flops, bytes, pool_event(), pool_event()};
+        cudaEventRecord(r.a, st);
+        slot = (int)g_recs.size();
+        g_recs.push_back(r);
+    }
+}
+LaunchScope::~LaunchScope() {
+    if (slot >= 0) cudaEventRecord(g_recs[slot].b, st);
 }
 
 struct Axis {
@@ -270,6 +299,32 @@ extern "C" {
 int gphm_version(void) { return GPHM_VERSION; }
 const char* gphm_last_error(void) { return g_err; }
 
+long long gphm_launch_count(void) { return g_launches.load(); }
+
+int gphm_profile_start(void) {
+    for (auto& r : g_recs) { g_pool.push_back(r.a); g_pool.push_back(r.b); }
+    g_recs.clear();
+    g_prof = true;
+    return GPHM_OK;
+}
+
+int gphm_profile_stop(double* ms, double* flops, double* bytes, long long* launches) {
+    g_prof = false;
+    GPHM_CUDA_OK(cudaDeviceSynchronize());
+    for (int c = 0; c < CAT_COUNT; ++c) { if (ms) ms[c] = 0; if (flops) flops[c] = 0; if (bytes) bytes[c] = 0; if (launches) launches[c] = 0; }
+    for (auto& r : g_recs) {
+        float t = 0.f;
+        GPHM_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+        if (ms) ms[r.cat] += t;
+        if (flops) flops[r.cat] += r.flops;
+        if (bytes) bytes[r.cat] += r.bytes;
+        if (launches) launches[r.cat] += 1;
+        g_pool.push_back(r.a); g_pool.push_back(r.b);
+    }
+    g_recs.clear();
+    return GPHM_OK;
+}
+
 int gphm_gram(int kernel_id, int deriv_order, const double* d_x1, int n1, const double* d_x2, int n2,
               const double* d_theta, int Q, double jitter, double* d_out, void* stream) {
     if (!d_x1 || !d_x2 || !d_theta || !d_out) { set_last_error("gphm_gram: null pointer"); return GPHM_EINVAL; }
@@ -296,7 +351,8 @@ int gphm_dgemm(int transA, int transB, int M, int N, int K, double alpha, const 
                const double* d_B, int ldb, double beta, double* d_C, int ldc, void* stream) {
     if (M < 0 || N < 0 || K < 0) { set_last_error("gphm_dgemm: negative size"); return GPHM_EINVAL; }
     if (M == 0 || N == 0) return GPHM_OK;
-    if (!d_A || !d_B || !d_C) { set_last_error("gphm_dgemm: null pointer"); return GPHM_EINVAL; }
+    if (!d_C || (K > 0 && (!d_A || !d_B))) { set_last_error("gphm_dgemm: null pointer"); return GPHM_EINVAL; }
+    if (K == 0) { d_A = d_C; d_B = d_C; }          // C = beta*C; operands are never dereferenced
     return launch_dgemm(gemm_args(d_A, lda, transA != 0, d_B, ldb, transB != 0, d_C, ldc, M, N, K, alpha, beta, 0),
                         static_cast<cudaStream_t>(stream));
 }

@@ -73,6 +73,16 @@ typedef struct gphm_plan gphm_plan;   /* opaque */
 GPHM_API int gphm_version(void);
 GPHM_API const char* gphm_last_error(void);
 
+/* ---- accounting ----------------------------------------------------------------------------
+ * gphm_launch_count: kernels launched by this library in this process so far.
+ * gphm_profile_start/stop: while enabled every launch is bracketed by CUDA events on its stream;
+ * stop synchronises the device and returns, per kernel family (index: 0 Gram builders, 1 DGEMM,
+ * 2 Cholesky diagonal-block, 3 reductions/element-wise, 4 Adam), the summed device time in ms,
+ * the FLOPs issued (DGEMM only), algorithmic bytes (Gram only) and launch counts (arrays of 5). */
+GPHM_API long long gphm_launch_count(void);
+GPHM_API int gphm_profile_start(void);
+GPHM_API int gphm_profile_stop(double* ms, double* flops, double* bytes, long long* launches);
+
 /* ---- Gram builders -------------------------------------------------------------------------
  * gphm_gram replaces Kernel_matrix.get_kernel_matrix (kernel_matrix.py:21-30; deriv_order 0,
  * jitter added on the diagonal when n1 == n2 and jitter != 0), vmap(D_x1_kappa)

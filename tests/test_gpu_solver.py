@@ -59,7 +59,7 @@ CASES_2D = [
     ("advection-sin", "SE_Cos_1d", 100, 120, 8, 4.0, 1.0, 20.0, True),
     ("advection-sin", "Matern52_Cos_1d", 131, 90, 8, 4.0, 1.0, 200.0, True),
     ("poisson_2d-sin_add_cos", "Matern52_Cos_1d", 90, 70, 6, 5.0, 2 * math.pi, 1.0, False),
-    ("advection-sin", "SE_Cos_1d", 60, 75, 5, 3.0, 1.0, 20.0, False),
+    ("advection-sin", "SE_Cos_1d", 40, 45, 5, 3.0, 1.0, 20.0, False),
     ("poisson_2d-sin_add_cos", "SE_1d", 70, 66, 4, 1.0, 1.0, 1.0, True),
 ]
 
@@ -81,8 +81,11 @@ def test_logjoint_grad_2d_golden_final_state(gphm, oracle):
     for a in ("1", "2"):
         params["kernel_paras_" + a] = {k: torch.tensor(g["kp%s_%s" % (a, k)]) for k in ("log-w", "log-ls", "freq")}
     check_terms_and_grads(oracle, p, model, params)
-    err = float(model.core.rel_l2(model.preds(params)[0], model.ute))
-    assert abs(err - 0.46758844) <= 1e-6              # log.txt: err_list [0.46758844]
+    # (log.txt's 0.46758844 is the epoch-95 checkpoint; these are the epoch-99 params, so compare preds)
+    pred = model.preds(params)[0]
+    want = oracle.preds_2d(p, params, torch.as_tensor(model.Xte[0].cpu()), torch.as_tensor(model.Xte[1].cpu()))
+    assert rel(pred, want) <= TOL
+    assert abs(float(model.core.rel_l2(pred, model.ute)) - oracle.rel_l2(want, model.ute.cpu())) <= 1e-7
 
 
 CASES_1D = [("poisson_1d-single_sin", "Matern52_Cos_1d", 400, 30, 20.0, 2 * math.pi),
@@ -229,11 +232,12 @@ def test_properties_at_scale(gphm, oracle, N):
     assert abs(float(lg) - float(loss)) <= 1e-9 * abs(float(loss))
     for (path, a), (_, b) in zip(tree_flatten(gg), tree_flatten(grads)):
         assert float((a - b).norm()) <= 1e-7 * float(b.norm()), path
-    # a small step along -dL/dU decreases the loss by ~ eps * |g|^2 (first-order check of the gradient)
+    # central difference along dL/dU reproduces |g|^2 (the Poisson loss is quadratic in U)
     gU = grads["U"]
     eps = 1e-3 / float(gU.abs().max())
-    moved = dict(s1)
-    moved["U"] = torch.as_tensor(s1["U"]).cuda() - eps * gU
-    dl = float(model.loss(moved)) - float(loss)
-    pred = -eps * float((gU * gU).sum())
-    assert dl < 0 and abs(dl - pred) <= 0.05 * abs(pred)
+    up, dn = dict(s1), dict(s1)
+    up["U"] = torch.as_tensor(s1["U"]).cuda() + eps * gU
+    dn["U"] = torch.as_tensor(s1["U"]).cuda() - eps * gU
+    slope = (float(model.loss(up)) - float(model.loss(dn))) / (2 * eps)
+    gg2 = float((gU * gU).sum())
+    assert abs(slope - gg2) <= 1e-5 * gg2
