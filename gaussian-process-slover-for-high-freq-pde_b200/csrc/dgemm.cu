@@ -8,7 +8,9 @@
 // Design (sm_100a): tcgen05 has no f64 kind, so native FP64 runs on the DMMA pipe
 // (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4).  One CTA computes a BM x BN tile with a
 // 3-stage cp.async (LDGSTS, zero-fill predicated) shared-memory pipeline over BK=16 slices;
-// 8 warps each own a 64x32 sub-tile (64 FP64 accumulators per thread).  Shared-memory rows are
+// 16 warps each own a 32x32 sub-tile (32 FP64 accumulators per thread).  ptxas spaces dependent
+// DMMAs of one warp with NOPs, so 2 warps per scheduler left the pipe 78 % busy (ncu, round 1);
+// 4 warps per scheduler at <=128 registers keep it fed.  Shared-memory rows are
 // padded by 4 doubles so every fragment LDS.64 is bank-conflict free.  Roofline: FP64 compute
 // (DMMA issue rate); operand traffic per tile is 32 KB per 0.5 MFLOP, far below L2 bandwidth.
 // Triangular operands (L^-1 applications, LAUUM-style products) restrict the k-range per tile
@@ -42,33 +44,56 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
                  : "d"(a), "d"(b));
 }
 
-// Copy one operand tile (MN rows/cols of the m- or n-index by BK of k) into shared memory.
+// Per-thread descriptors for copying one operand tile (MN of the m- or n-index by BK of k) into
+// shared memory with cp.async.  Everything that does not depend on the k-tile (row/column
+// validity, shared-memory offset, global pointer) is computed once; per k-tile a chunk costs a
+// clamp, one LDGSTS and a pointer bump, and the chunks are interleaved with the DMMAs.
 // KCONTIG: global element (mn, k) at G[mn*ld + k]  -> S[mn][k], row pitch BK+PAD
 // else   : global element (k, mn) at G[k*ld + mn]  -> S[k][mn],  row pitch MN+PAD
-// Everything outside [0,mn_max) x [k0,kend) is zero-filled by cp.async's src-size operand.
+// Everything outside [0,mn_max) x [kbegin,kend) is zero-filled by cp.async's src-size operand.
 template <int MN, bool KCONTIG, int VEC, int NT>
-__device__ __forceinline__ void load_tile(double* S, const double* __restrict__ G, int ld, int mn0, int mn_max,
-                                          int k0, int kend) {
-    if (KCONTIG) {
-        constexpr int CPR = BK / VEC;
-        for (int c = threadIdx.x; c < MN * CPR; c += NT) {
-            const int r = c / CPR, kc = (c % CPR) * VEC;
-            const int gr = mn0 + r, gk = k0 + kc;
-            int nv = (gr < mn_max) ? min(max(kend - gk, 0), VEC) : 0;
-            const double* src = nv > 0 ? G + (size_t)gr * ld + gk : G;
-            cp_async<VEC>(S + r * (BK + PAD) + kc, src, nv * 8);
-        }
-    } else {
-        constexpr int CPR = MN / VEC;
-        for (int c = threadIdx.x; c < BK * CPR; c += NT) {
+struct TileLoader {
+    static constexpr int CPR = KCONTIG ? BK / VEC : MN / VEC;        // chunks per shared-memory row
+    static constexpr int TOTAL = MN * BK / VEC;
+    static constexpr int NCH = TOTAL / NT;
+    static_assert(TOTAL % NT == 0, "tile chunks must divide evenly over the threads");
+    const double* g[NCH];     // next global address of each chunk
+    int soff[NCH];            // offset inside a stage buffer (doubles)
+    int aux[NCH];             // KCONTIG: k offset of the chunk (huge if the row is out of range)
+                              // else   : k row of the chunk | valid element count << 8
+    const double* base;
+    long long step;
+
+    __device__ __forceinline__ void init(const double* G, int ld, int mn0, int mn_max, int kbegin) {
+        base = G;
+        step = KCONTIG ? (long long)BK : (long long)BK * ld;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+            const int c = threadIdx.x + i * NT;
             const int r = c / CPR, cc = (c % CPR) * VEC;
-            const int gk = k0 + r, gc = mn0 + cc;
-            int nv = (gk < kend) ? min(max(mn_max - gc, 0), VEC) : 0;
-            const double* src = nv > 0 ? G + (size_t)gk * ld + gc : G;
-            cp_async<VEC>(S + r * (MN + PAD) + cc, src, nv * 8);
+            if (KCONTIG) {
+                const int gr = mn0 + r;
+                soff[i] = r * (BK + PAD) + cc;
+                aux[i] = gr < mn_max ? cc : (1 << 28);
+                g[i] = G + (size_t)min(gr, mn_max - 1) * ld + kbegin + cc;
+            } else {
+                const int gc = mn0 + cc;
+                const int nv = min(max(mn_max - gc, 0), VEC);
+                soff[i] = r * (MN + PAD) + cc;
+                aux[i] = r | (nv << 8);
+                g[i] = G + (size_t)(kbegin + r) * ld + min(gc, mn_max - 1);
+            }
         }
     }
-}
+    // issue chunk i of the k-tile starting at k0 into the stage buffer S, then advance
+    __device__ __forceinline__ void issue(int i, double* S, int k0, int kend) {
+        int nv;
+        if (KCONTIG) nv = min(max(kend - k0 - aux[i], 0), VEC);
+        else nv = (k0 + (aux[i] & 255) < kend) ? (aux[i] >> 8) : 0;
+        cp_async<VEC>(S + soff[i], nv > 0 ? g[i] : base, nv * 8);
+        g[i] += step;
+    }
+};
 
 template <int BM, int BN, int WARPS_M, int WARPS_N, bool TA, bool TB, int VEC, int MINB>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MINB)
@@ -117,29 +142,42 @@ dgemm_kernel(const GemmArgs p) {
 #pragma unroll
         for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    auto issue = [&](int kt) {
-        const int slot = kt % STAGES;
-        const int k0 = kbegin + kt * BK;
-        load_tile<BM, !TA, VEC, NT>(As + slot * A_TILE, A, p.lda, m0, p.M, k0, kend);
-        load_tile<BN, TB, VEC, NT>(Bs + slot * B_TILE, B, p.ldb, n0, p.N, k0, kend);
+    using LoaderA = TileLoader<BM, !TA, VEC, NT>;
+    using LoaderB = TileLoader<BN, TB, VEC, NT>;
+    constexpr int NCH = LoaderA::NCH + LoaderB::NCH;
+    constexpr int KSTEPS = BK / 4;
+    static_assert(NCH % KSTEPS == 0, "chunks are spread evenly over the k4-steps");
+    LoaderA la;
+    LoaderB lb;
+    if (KT > 0) {
+        la.init(A, p.lda, m0, p.M, kbegin);
+        lb.init(B, p.ldb, n0, p.N, kbegin);
+    }
+    auto issue_chunk = [&](int c, int slot, int k0) {      // c is a compile-time constant after unrolling
+        if (c < LoaderA::NCH) la.issue(c, As + slot * A_TILE, k0, kend);
+        else lb.issue(c - LoaderA::NCH, Bs + slot * B_TILE, k0, kend);
     };
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < KT) issue(s);
+        if (s < KT) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) issue_chunk(c, s, kbegin + s * BK);
+        }
         cp_async_commit();
     }
 
     for (int kt = 0; kt < KT; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        if (kt + STAGES - 1 < KT) issue(kt + STAGES - 1);
-        cp_async_commit();
+        const int ktn = kt + STAGES - 1;
+        const bool more = ktn < KT;
+        const int slot_n = ktn % STAGES, k0_n = kbegin + ktn * BK;
 
         const double* as = As + (kt % STAGES) * A_TILE;
         const double* bs = Bs + (kt % STAGES) * B_TILE;
 #pragma unroll
-        for (int kk = 0; kk < BK / 4; ++kk) {
+        for (int kk = 0; kk < KSTEPS; ++kk) {
             double af[MI], bf[NI];
 #pragma unroll
             for (int i = 0; i < MI; ++i) {
@@ -155,7 +193,13 @@ dgemm_kernel(const GemmArgs p) {
             for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < NI; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            // the stage being refilled was consumed in iteration kt-1 (barrier above)
+            if (more) {
+#pragma unroll
+                for (int c = kk * (NCH / KSTEPS); c < (kk + 1) * (NCH / KSTEPS); ++c) issue_chunk(c, slot_n, k0_n);
+            }
         }
+        cp_async_commit();
     }
     cp_async_wait<0>();
 
@@ -236,7 +280,7 @@ int dgemm_init() {
     static int done = -1;
     if (done >= 0) return done;
 #define GPHM_SET(TA, TB, VEC)                                         \
-    GPHM_TRY((set_attr<128, 128, 2, 4, TA, TB, VEC, 1>()));           \
+    GPHM_TRY((set_attr<128, 128, 4, 4, TA, TB, VEC, 1>()));           \
     GPHM_TRY((set_attr<64, 64, 2, 2, TA, TB, VEC, 3>()));
     GPHM_FOR_ALL_GEMM(GPHM_SET)
 #undef GPHM_SET
@@ -256,7 +300,7 @@ int launch_dgemm(const GemmArgs& g, cudaStream_t st) {
     const bool big = big_tiles >= 96;   // otherwise 64x64 tiles to fill the 148 SMs
 #define GPHM_GO(TA, TB, VEC)                                                                       \
     if ((g.transA != 0) == TA && (g.transB != 0) == TB && vec == VEC)                              \
-        return big ? launch_cfg<128, 128, 2, 4, TA, TB, VEC, 1>(g, st)                             \
+        return big ? launch_cfg<128, 128, 4, 4, TA, TB, VEC, 1>(g, st)                             \
                    : launch_cfg<64, 64, 2, 2, TA, TB, VEC, 3>(g, st);
     GPHM_FOR_ALL_GEMM(GPHM_GO)
 #undef GPHM_GO

@@ -204,8 +204,8 @@ def dgemm(A, B, transA=False, transB=False, alpha=1.0, beta=0.0, C=None):
         raise ValueError("dgemm: inner dimensions differ")
     if C is None:
         C = torch.zeros((M, N), dtype=DT, device=A.device)
-    _lib.check(lib.gphm_dgemm(int(transA), int(transB), M, N, K, float(alpha), _lib.ptr(A), A.shape[1], _lib.ptr(B),
-                              B.shape[1], float(beta), _lib.ptr(C), C.shape[1], _lib.stream_ptr()), "gphm_dgemm")
+    _lib.check(lib.gphm_dgemm(int(transA), int(transB), M, N, K, float(alpha), _lib.ptr(A), max(A.shape[1], 1), _lib.ptr(B),
+                              max(B.shape[1], 1), float(beta), _lib.ptr(C), max(C.shape[1], 1), _lib.stream_ptr()), "gphm_dgemm")
     return C
 
 
