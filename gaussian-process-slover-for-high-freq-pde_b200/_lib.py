@@ -52,6 +52,14 @@ _SIGS = {
     "gphm_plan_factor": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "gphm_apply_kinv": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "gphm_plan_matrix": (c_void_p, [c_void_p, c_int, c_int]),
+    "gphm_plan_logdet": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "gphm_mg_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
+                                 c_void_p]),
+    "gphm_mg_boundary": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "gphm_mg_grad_u": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
+                               c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gphm_mg_theta_grad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gphm_lincomb": (c_int, [c_void_p, c_double, c_void_p, c_double, c_void_p, c_size_t, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGS))

@@ -120,7 +120,7 @@ grad_u_kernel(size_t n, int allencahn, const double* __restrict__ U, const doubl
         double g = w + s1 + s2;
         if (allencahn) { const double u = U[i]; g += G[i] * (3.0 * u * u - 1.0); }
         gU[i] = g;
-        V1[i] = s1 + 0.5 * w;
+        if (V1) V1[i] = s1 + 0.5 * w;
         if (V2) V2[i] = s2 + 0.5 * w;
     }
 }
@@ -385,6 +385,82 @@ int launch_copy(double* dst, const double* src, size_t n, cudaStream_t st) {
     if (n == 0) return GPHM_OK;
     const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)kNumSMs * 8);
     { LaunchScope scope(CAT_ELEMWISE, st); copy_kernel<<<blocks, 256, 0, st>>>(dst, src, n); }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+// ---- building blocks of the sharded (multi-GPU) step: the same math on a rank-local block ----
+__global__ void __launch_bounds__(1024)
+pair_reduce_kernel(const double* __restrict__ part, int nblocks, double* __restrict__ out2) {
+    __shared__ double red[33];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) { a += part[2 * i]; b += part[2 * i + 1]; }
+    a = block_sum(a, red); b = block_sum(b, red);
+    if (threadIdx.x == 0) { out2[0] = a; out2[1] = b; }
+}
+int launch_pair_reduce(const double* part, double* out2, cudaStream_t st) {
+    { LaunchScope scope(CAT_ELEMWISE, st); pair_reduce_kernel<<<1, 1024, 0, st>>>(part, kRedBlocks, out2); }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+// eb[e] = U[bidx[e]] - bvals[e];  out[0] = sum eb^2      (rank-local boundary points)
+__global__ void __launch_bounds__(1024)
+boundary_indexed_kernel(const double* __restrict__ U, const int* __restrict__ bidx, const double* __restrict__ bvals,
+                        int nb, double* __restrict__ eb, double* __restrict__ out) {
+    __shared__ double red[33];
+    double b = 0.0;
+    for (int e = threadIdx.x; e < nb; e += blockDim.x) {
+        const double d = U[bidx[e]] - bvals[e];
+        eb[e] = d;
+        b += d * d;
+    }
+    b = block_sum(b, red);
+    if (threadIdx.x == 0) out[0] = b;
+}
+int launch_boundary_indexed(const double* U, const int* bidx, const double* bvals, int nb, double* eb, double* out,
+                            cudaStream_t st) {
+    { LaunchScope scope(CAT_ELEMWISE, st); boundary_indexed_kernel<<<1, 1024, 0, st>>>(U, bidx, bvals, nb, eb, out); }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+// gU[bidx[e]] += llk_weight * exp(log_tau) * eb[e]; indices are unique inside each of the two
+// segments [0,nseg0) and [nseg0,nb) (row edges, column edges), which run one after the other.
+__global__ void __launch_bounds__(1024)
+boundary_scatter_indexed_kernel(double* __restrict__ gU, const int* __restrict__ bidx, const double* __restrict__ eb,
+                                int nseg0, int nb, double llk_weight, const double* __restrict__ log_tau) {
+    const double s = llk_weight * exp(*log_tau);
+    for (int e = threadIdx.x; e < nseg0; e += blockDim.x) gU[bidx[e]] += s * eb[e];
+    __syncthreads();
+    __threadfence_block();
+    for (int e = nseg0 + threadIdx.x; e < nb; e += blockDim.x) gU[bidx[e]] += s * eb[e];
+}
+int launch_boundary_scatter_indexed(double* gU, const int* bidx, const double* eb, int nseg0, int nb, double llk_weight,
+                                    const double* log_tau, cudaStream_t st) {
+    { LaunchScope scope(CAT_ELEMWISE, st);
+      boundary_scatter_indexed_kernel<<<1, 1024, 0, st>>>(gU, bidx, eb, nseg0, nb, llk_weight, log_tau); }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+__global__ void __launch_bounds__(256)
+lincomb_kernel(double* __restrict__ out, double a, const double* __restrict__ x, double b, const double* __restrict__ y,
+               size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = a * x[i] + (y ? b * y[i] : 0.0);
+}
+int launch_lincomb(double* out, double a, const double* x, double b, const double* y, size_t n, cudaStream_t st) {
+    if (n == 0) return GPHM_OK;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)kNumSMs * 8);
+    { LaunchScope scope(CAT_ELEMWISE, st); lincomb_kernel<<<blocks, 256, 0, st>>>(out, a, x, b, y, n); }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+int launch_grad_u_local(size_t n, int allencahn, const double* U, const double* G, const double* W, const double* S1,
+                        const double* S2, double* gU, double* V1, double* V2, cudaStream_t st) {
+    { LaunchScope scope(CAT_ELEMWISE, st); grad_u_kernel<<<kRedBlocks, 256, 0, st>>>(n, allencahn, U, G, W, S1, S2, gU, V1, V2); }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }

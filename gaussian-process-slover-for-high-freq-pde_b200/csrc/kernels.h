@@ -75,6 +75,14 @@ int launch_adam(double* p, const double* g, double* m, double* v, size_t n, cons
 int launch_count_inc(long long* count, cudaStream_t st);
 int launch_rel_l2(const double* pred, const double* truth, size_t n, double* part, double* out, cudaStream_t st);
 int launch_copy(double* dst, const double* src, size_t n, cudaStream_t st);
+int launch_pair_reduce(const double* part, double* out2, cudaStream_t st);
+int launch_boundary_indexed(const double* U, const int* bidx, const double* bvals, int nb, double* eb, double* out,
+                            cudaStream_t st);
+int launch_boundary_scatter_indexed(double* gU, const int* bidx, const double* eb, int nseg0, int nb, double llk_weight,
+                                    const double* log_tau, cudaStream_t st);
+int launch_lincomb(double* out, double a, const double* x, double b, const double* y, size_t n, cudaStream_t st);
+int launch_grad_u_local(size_t n, int allencahn, const double* U, const double* G, const double* W, const double* S1,
+                        const double* S2, double* gU, double* V1, double* V2, cudaStream_t st);
 int launch_sum_scaled(const double* v, int n, double scale, double* out, cudaStream_t st);
 
 }  // namespace gphm

@@ -587,6 +587,63 @@ int gphm_apply_kinv(gphm_plan* plan, int axis, int side, const double* d_X, int 
     return apply_kinv(*plan, axis, side, d_X, rows, cols, d_out, d_tmp, static_cast<cudaStream_t>(stream));
 }
 
+int gphm_plan_logdet(gphm_plan* plan, double* d_out2, void* stream) {
+    if (!plan || !d_out2) { set_last_error("gphm_plan_logdet: null pointer"); return GPHM_EINVAL; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GPHM_TRY(launch_sum_scaled(plan->ax[0].ldpart, plan->ax[0].nblk, 2.0, d_out2, st));
+    if (plan->d.dim == 2) GPHM_TRY(launch_sum_scaled(plan->ax[1].ldpart, plan->ax[1].nblk, 2.0, d_out2 + 1, st));
+    else GPHM_CUDA_OK(cudaMemsetAsync(d_out2 + 1, 0, sizeof(double), st));
+    return GPHM_OK;
+}
+
+int gphm_mg_residual(gphm_plan* plan, double* d_R, const double* d_U, const double* d_F, const double* d_A,
+                     const double* d_Bt, size_t n_local, const double* d_small, double* d_out2, void* stream) {
+    if (!plan || !d_R || !d_U || !d_F || !d_A || !d_Bt || !d_small || !d_out2) { set_last_error("gphm_mg_residual: null pointer"); return GPHM_EINVAL; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GPHM_TRY(launch_residual(d_R, d_U, d_F, d_A, d_Bt, n_local, plan->d.eq_type, d_small, plan->d.Q, plan->part, st));
+    return launch_pair_reduce(plan->part, d_out2, st);
+}
+
+int gphm_mg_boundary(const double* d_U, const int* d_bidx, const double* d_bvals, int nb_local, double* d_eb,
+                     double* d_out1, void* stream) {
+    if (!d_U || !d_out1 || (nb_local > 0 && (!d_bidx || !d_bvals || !d_eb))) { set_last_error("gphm_mg_boundary: null pointer"); return GPHM_EINVAL; }
+    return launch_boundary_indexed(d_U, d_bidx, d_bvals, nb_local, d_eb, d_out1, static_cast<cudaStream_t>(stream));
+}
+
+int gphm_mg_grad_u(gphm_plan* plan, const double* d_U, const double* d_G, const double* d_W, const double* d_S1,
+                   const double* d_S2, size_t n_local, const int* d_bidx, const double* d_eb, int nseg0, int nb_local,
+                   const double* d_small, double* d_gU, double* d_V2, void* stream) {
+    if (!plan || !d_U || !d_G || !d_W || !d_S1 || !d_S2 || !d_small || !d_gU || !d_V2) { set_last_error("gphm_mg_grad_u: null pointer"); return GPHM_EINVAL; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GPHM_TRY(launch_grad_u_local(n_local, plan->d.eq_type == GPHM_EQ_ALLENCAHN, d_U, d_G, d_W, d_S1, d_S2, d_gU, nullptr, d_V2, st));
+    if (nb_local > 0)
+        GPHM_TRY(launch_boundary_scatter_indexed(d_gU, d_bidx, d_eb, nseg0, nb_local, plan->d.llk_weight,
+                                                 d_small + 6 * plan->d.Q, st));
+    return GPHM_OK;
+}
+
+int gphm_lincomb(double* d_out, double a, const double* d_x, double b, const double* d_y, size_t n, void* stream) {
+    if (n == 0) return GPHM_OK;
+    if (!d_out || !d_x) { set_last_error("gphm_lincomb: null pointer"); return GPHM_EINVAL; }
+    return launch_lincomb(d_out, a, d_x, b, d_y, n, static_cast<cudaStream_t>(stream));
+}
+
+int gphm_mg_theta_grad(gphm_plan* plan, int axis, const double* d_Kbar, const double* d_Dbar, const double* d_small,
+                       double* d_gtheta, void* stream) {
+    if (!plan || !d_Kbar || !d_Dbar || !d_small || !d_gtheta) { set_last_error("gphm_mg_theta_grad: null pointer"); return GPHM_EINVAL; }
+    if (axis < 0 || axis > 1 || plan->ax[axis].n == 0) { set_last_error("gphm_mg_theta_grad: bad axis"); return GPHM_EINVAL; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Axis& X = plan->ax[axis];
+    const int order = deriv_order(*plan);
+    const double* th = theta_of(*plan, d_small, axis);
+    if (X.toeplitz) {
+        GPHM_TRY(launch_diag_sums(d_Kbar, d_Dbar, X.n, X.n, order == 1, X.dirsign, X.dspart, X.sK, X.sD, st));
+        return launch_theta_grad_toeplitz(plan->d.kernel_id, order, X.x, X.n, th, plan->d.Q, X.sK, X.sD, d_gtheta, st);
+    }
+    return launch_theta_grad_general(plan->d.kernel_id, order, X.x, X.n, th, plan->d.Q, d_Kbar, d_Dbar, X.n, X.tgpart,
+                                     d_gtheta, st);
+}
+
 const double* gphm_plan_matrix(const gphm_plan* plan, int axis, int which) {
     if (!plan || axis < 0 || axis > 1 || plan->ax[axis].n == 0) return nullptr;
     const Axis& X = plan->ax[axis];

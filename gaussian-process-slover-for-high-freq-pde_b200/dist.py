@@ -1,0 +1,303 @@
+"""Multi-GPU (one process per GPU) version of the 2-D step: U, the source term and the Adam state
+are sharded by row blocks; per-axis operators (Gram factors, derivative Grams) are replicated.
+
+Why it shards: left-multiplications by axis-1 operators (K1^-1, D1) act on every
+column of the N1 x N2 field independently, right-multiplications by axis-2 operators (K2^-1, D2)
+on every row.  So axis-2 work runs on the resident row blocks ("R" layout, h x N2, h = N1/P),
+axis-1 work on column blocks ("C" layout, N1 x w, w = N2/P), and the only data-path collective is
+the block transpose between the two layouts (NCCL all-to-all, N1*N2*8/P bytes per rank), seven
+times per step.  Scalars (loss terms, 6Q theta-gradients) use one small all-reduce each.
+
+    R->C : U, G, Bt            C->R : c1*D1*A, A, W, S1
+
+The numerical pieces are calls into libgphm through the `ops` object (CudaOps below).  The step
+logic itself is backend-agnostic so that tests can drive it with a CPU stand-in over gloo.
+"""
+import ctypes
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+DT = torch.float64
+
+
+# ------------------------------------------------------------------------------------------------
+class CudaOps(object):
+    """libgphm-backed primitives on the current CUDA device (the production backend)."""
+
+    def __init__(self, core):
+        self.core = core
+        self.lib = core.lib
+        self.plan = core.plan
+        self.device = core.device
+        self.Q = core.Q
+        self._cache = {}
+
+    def _buf(self, tag, shape):
+        key = (tag,) + tuple(shape)
+        if key not in self._cache:
+            self._cache[key] = torch.empty(shape, dtype=DT, device=self.device)
+        return self._cache[key]
+
+    def zeros(self, shape, dtype=DT):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def tensor(self, data, dtype=DT):
+        return torch.as_tensor(data, dtype=dtype).to(self.device).contiguous()
+
+    def _s(self):
+        return _lib.stream_ptr()
+
+    def factor(self, small, axis_mask=3):
+        _lib.check(self.lib.gphm_plan_factor(self.plan, _lib.ptr(small), axis_mask, self._s()), "gphm_plan_factor")
+
+    def mat(self, axis, which):
+        """(n, n) view of a plan-owned matrix: which = 0 K^-1, 1 D, 2 Linv, 3 L."""
+        p = self.lib.gphm_plan_matrix(self.plan, axis, which)
+        if not p:
+            raise _lib.GphmError("gphm_plan_matrix returned NULL")
+        n = self.core.n1 if axis == 0 else self.core.n2
+        off = p - self.core.workspace.data_ptr()
+        return self.core.workspace[off:off + n * n * 8].view(DT).view(n, n)
+
+    def logdet_parts(self, axis):
+        raise NotImplementedError
+
+    def logdets(self):
+        out = self._buf("logdets", (2,))
+        _lib.check(self.lib.gphm_plan_logdet(self.plan, _lib.ptr(out), self._s()), "gphm_plan_logdet")
+        return out
+
+    def apply_kinv(self, axis, side, X, tag):
+        out, tmp = self._buf(tag, X.shape), self._buf("kinv_tmp", X.shape)
+        _lib.check(self.lib.gphm_apply_kinv(self.plan, axis, side, _lib.ptr(X), X.shape[0], X.shape[1], _lib.ptr(out),
+                                            _lib.ptr(tmp), self._s()), "gphm_apply_kinv")
+        return out
+
+    def gemm(self, A, B, tA, tB, alpha, beta, C):
+        M, K = (A.shape[1], A.shape[0]) if tA else A.shape
+        N = B.shape[0] if tB else B.shape[1]
+        _lib.check(self.lib.gphm_dgemm(int(tA), int(tB), M, N, K, float(alpha), _lib.ptr(A), A.stride(0), _lib.ptr(B),
+                                       B.stride(0), float(beta), _lib.ptr(C), C.stride(0), self._s()), "gphm_dgemm")
+        return C
+
+    def new(self, tag, shape):
+        return self._buf(tag, shape)
+
+    def residual(self, R, U, F, A, Bt, small):
+        out = self._buf("res2", (2,))
+        _lib.check(self.lib.gphm_mg_residual(self.plan, _lib.ptr(R), _lib.ptr(U), _lib.ptr(F), _lib.ptr(A), _lib.ptr(Bt),
+                                             R.numel(), _lib.ptr(small), _lib.ptr(out), self._s()), "gphm_mg_residual")
+        return out
+
+    def boundary(self, U, bidx, bvals):
+        eb, out = self._buf("eb", (max(bidx.numel(), 1),)), self._buf("bg1", (1,))
+        _lib.check(self.lib.gphm_mg_boundary(_lib.ptr(U), _lib.ptr(bidx), _lib.ptr(bvals), bidx.numel(), _lib.ptr(eb),
+                                             _lib.ptr(out), self._s()), "gphm_mg_boundary")
+        return eb, out
+
+    def grad_u(self, U, G, W, S1, S2, bidx, eb, nseg0, small):
+        gU, V2 = self._buf("gU", U.shape), self._buf("V2", U.shape)
+        _lib.check(self.lib.gphm_mg_grad_u(self.plan, _lib.ptr(U), _lib.ptr(G), _lib.ptr(W), _lib.ptr(S1), _lib.ptr(S2),
+                                           U.numel(), _lib.ptr(bidx), _lib.ptr(eb), nseg0, bidx.numel(), _lib.ptr(small),
+                                           _lib.ptr(gU), _lib.ptr(V2), self._s()), "gphm_mg_grad_u")
+        return gU, V2
+
+    def lincomb(self, a, x, b, y, tag):
+        out = self._buf(tag, x.shape)
+        _lib.check(self.lib.gphm_lincomb(_lib.ptr(out), float(a), _lib.ptr(x), float(b), _lib.ptr(y), x.numel(), self._s()),
+                   "gphm_lincomb")
+        return out
+
+    def theta_grad(self, axis, Kbar, Dbar, small, out):
+        _lib.check(self.lib.gphm_mg_theta_grad(self.plan, axis, _lib.ptr(Kbar), _lib.ptr(Dbar), _lib.ptr(small),
+                                               _lib.ptr(out), self._s()), "gphm_mg_theta_grad")
+
+    def adam(self, p, g, m, v, count, lr):
+        _lib.check(self.lib.gphm_adam_update(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), p.numel(), _lib.ptr(count),
+                                             float(lr), self._s()), "gphm_adam_update")
+
+
+# ------------------------------------------------------------------------------------------------
+def local_boundary(rank, P, N1, N2, bvals):
+    """Rank-local boundary points of the row block [rank*h, (rank+1)*h): flat indices into the
+    (h, N2) block and target values, in two segments with unique indices each (row edges first,
+    then column edges) so that corner contributions are added in a fixed order.
+    bvals order: U[0,:], U[-1,:], U[:,0], U[:,-1] (model_GP_solver_2d.py:127)."""
+    h = N1 // P
+    idx, val = [], []
+    if rank == 0:
+        idx += list(range(N2)); val += list(bvals[0:N2])
+    if rank == P - 1:
+        idx += [(h - 1) * N2 + j for j in range(N2)]; val += list(bvals[N2:2 * N2])
+    nseg0 = len(idx)
+    r0 = rank * h
+    idx += [i * N2 for i in range(h)]; val += list(bvals[2 * N2 + r0:2 * N2 + r0 + h])
+    idx += [i * N2 + N2 - 1 for i in range(h)]; val += list(bvals[2 * N2 + N1 + r0:2 * N2 + N1 + r0 + h])
+    return idx, val, nseg0
+
+
+class ShardedSolver2D(object):
+    """Row-sharded GP_solver_2d_single step (Poisson / Allen-Cahn / advection).  All ranks must
+    construct it with identical arguments; `step()` is collective."""
+
+    def __init__(self, kernel_name, eq_name, x, y, src, bvals, llk_weight, logdet, beta, jitter, Q, lr, ops=None,
+                 group=None):
+        import numpy as np
+        self.group = group
+        self.P = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        x, y = np.asarray(x, dtype=np.float64).reshape(-1), np.asarray(y, dtype=np.float64).reshape(-1)
+        self.N1, self.N2, self.Q = x.size, y.size, int(Q)
+        if self.N1 % self.P or self.N2 % self.P:
+            raise ValueError("sharded step needs N1 and N2 divisible by the number of ranks (%d x %d, P=%d)"
+                             % (self.N1, self.N2, self.P))
+        self.h, self.w = self.N1 // self.P, self.N2 // self.P
+        src = np.asarray(src, dtype=np.float64).reshape(self.N1, self.N2)
+        bvals = np.asarray(bvals, dtype=np.float64).reshape(-1)
+        self.eq_name, self.llk_weight, self.logdet, self.lr = eq_name, float(llk_weight), float(logdet), float(lr)
+        self.c1 = float(beta) if eq_name == "advection" else 1.0
+        if ops is None:
+            from .solver_core import SolverCore
+            core = SolverCore(2, kernel_name, eq_name, x, y, src, bvals, None, llk_weight, logdet, beta, jitter, Q)
+            ops = CudaOps(core)
+        self.ops = ops
+        r0 = self.rank * self.h
+        self.F = ops.tensor(src[r0:r0 + self.h, :])
+        idx, val, self.nseg0 = local_boundary(self.rank, self.P, self.N1, self.N2, bvals)
+        self.bidx = ops.tensor(idx, dtype=torch.int32)
+        self.bvals = ops.tensor(val)
+        self.Nb, self.Nc = 2 * self.N1 + 2 * self.N2, self.N1 * self.N2
+        ns = 6 * self.Q + 2
+        self.U = ops.zeros((self.h, self.N2))
+        self.mU, self.vU = ops.zeros((self.h, self.N2)), ops.zeros((self.h, self.N2))
+        self.small, self.msmall, self.vsmall = ops.zeros((ns,)), ops.zeros((ns,)), ops.zeros((ns,))
+        self.gsmall = ops.zeros((ns,))
+        self.count = ops.zeros((1,), dtype=torch.int64)
+        self.terms = ops.zeros((8,))
+        self.bytes_exchanged = 0
+
+    # ---- state ---------------------------------------------------------------------------------
+    def init_state(self, freq_scale):
+        """Reference initial state (model_GP_solver_2d.py:245-261), identical on every rank."""
+        Q = self.Q
+        s = torch.zeros(6 * Q + 2, dtype=DT)
+        for a in range(2):
+            s[(3 * a) * Q:(3 * a + 1) * Q] = math.log(1.0 / Q)
+            s[(3 * a + 2) * Q:(3 * a + 3) * Q] = torch.linspace(0, 1, Q, dtype=DT) * freq_scale
+        self.set_state(torch.zeros(self.N1, self.N2, dtype=DT), s)
+
+    def set_state(self, U_full, small):
+        r0 = self.rank * self.h
+        self.U.copy_(torch.as_tensor(U_full, dtype=DT)[r0:r0 + self.h, :])
+        self.small.copy_(torch.as_tensor(small, dtype=DT))
+        for t in (self.mU, self.vU, self.msmall, self.vsmall):
+            t.zero_()
+        self.count.zero_()
+
+    def gather_U(self):
+        """Full (N1, N2) U on every rank (for checks / prediction)."""
+        if self.P == 1:
+            return self.U.clone()
+        parts = [torch.empty_like(self.U) for _ in range(self.P)]
+        dist.all_gather(parts, self.U.contiguous(), group=self.group)
+        return torch.cat(parts, 0)
+
+    def last_loss(self):
+        return self.terms[0]
+
+    # ---- layout exchanges ------------------------------------------------------------------------
+    def _a2a(self, send):
+        recv = torch.empty_like(send)
+        if self.P == 1:
+            recv.copy_(send)
+        else:
+            dist.all_to_all_single(recv, send, group=self.group)
+            self.bytes_exchanged += send.numel() * 8 * (self.P - 1) // self.P
+        return recv
+
+    def r2c(self, X):
+        """(h, N2) row block -> (N1, w) column block."""
+        P, h, w = self.P, self.h, self.w
+        send = X.reshape(h, P, w).transpose(0, 1).contiguous()          # chunk s = my rows, columns of rank s
+        return self._a2a(send).reshape(self.N1, w)                      # chunk s = rows of rank s, my columns
+
+    def c2r(self, X):
+        """(N1, w) column block -> (h, N2) row block."""
+        P, h, w = self.P, self.h, self.w
+        recv = self._a2a(X.contiguous().reshape(P, h, w))               # chunk s = my rows, columns of rank s
+        return recv.transpose(0, 1).reshape(h, self.N2).contiguous()
+
+    def _allreduce(self, t):
+        if self.P > 1:
+            dist.all_reduce(t, group=self.group)
+        return t
+
+    # ---- one iteration ---------------------------------------------------------------------------
+    def value_and_grad(self):
+        """Collective.  Returns (terms[8], gU_r (h,N2), gsmall (6Q+2)) - same layout as gphm_logjoint_grad."""
+        o, Q, c1 = self.ops, self.Q, self.c1
+        N1, N2, h, w = self.N1, self.N2, self.h, self.w
+        small, U_r = self.small, self.U
+        o.factor(small, 3)
+        D1, D2, Kinv1, Kinv2 = o.mat(0, 1), o.mat(1, 1), o.mat(0, 0), o.mat(1, 0)
+        # forward
+        Bt_r = o.apply_kinv(1, 1, U_r, "Bt_r")                           # U K2^-1            (R)
+        U_c = self.r2c(U_r)
+        A_c = o.apply_kinv(0, 0, U_c, "A_c")                             # K1^-1 U            (C)
+        Uxx_c = o.gemm(D1, A_c, False, False, c1, 0.0, o.new("Uxx_c", (N1, w)))
+        R_r = self.c2r(Uxx_c)
+        A_r = self.c2r(A_c)
+        o.gemm(Bt_r, D2, False, True, 1.0, 1.0, R_r)                     # + Bt D2^T          (R)
+        red = torch.empty(3, dtype=DT, device=R_r.device)
+        red[0:2] = o.residual(R_r, U_r, self.F, A_r, Bt_r, small)        # R_r <- G_r ; [eqgap, quad]
+        G_r = R_r
+        eb, bg = o.boundary(U_r, self.bidx, self.bvals)
+        red[2:3] = bg
+        self._allreduce(red)
+        eq, quad, bgap = red[0], red[1], red[2]
+        ld = o.logdets()
+        tau, v = small[6 * Q], small[6 * Q + 1]
+        loss = (0.5 * self.logdet * (N2 * ld[0] + N1 * ld[1]) + 0.5 * quad
+                - self.llk_weight * (0.5 * self.Nb * tau - 0.5 * torch.exp(tau) * bgap)
+                - (0.5 * self.Nc * v - 0.5 * torch.exp(v) * eq))
+        gtau = -self.llk_weight * (0.5 * self.Nb - 0.5 * torch.exp(tau) * bgap)
+        gv = -(0.5 * self.Nc - 0.5 * torch.exp(v) * eq)
+        self.terms.copy_(torch.stack((loss, ld[0], ld[1], quad, bgap, eq, gtau, gv)))
+        # backward, axis-1 work in C layout
+        G_c = self.r2c(G_r)
+        Bt_c = self.r2c(Bt_r)
+        W_c = o.apply_kinv(0, 0, Bt_c, "W_c")
+        P_c = o.gemm(D1, G_c, True, False, c1, 0.0, o.new("P_c", (N1, w)))
+        S1_c = o.apply_kinv(0, 0, P_c, "S1_c")
+        V1_c = o.lincomb(1.0, S1_c, 0.5, W_c, "V1_c")
+        lead = 1.0 if self.rank == 0 else 0.0                            # the K^-1 (log-det) term is added once
+        o.gemm(V1_c, A_c, False, True, -1.0, lead * 0.5 * self.logdet * N2, Kinv1)          # Kbar1 partial
+        Dbar1 = o.gemm(G_c, A_c, False, True, c1, 0.0, o.new("Dbar1", (N1, N1)))
+        gs = self.gsmall
+        gs.zero_()
+        o.theta_grad(0, Kinv1, Dbar1, small, gs[0:3 * Q])
+        # axis-2 work in R layout
+        P_r = o.gemm(G_r, D2, False, False, 1.0, 0.0, o.new("P_r", (h, N2)))
+        S2_r = o.apply_kinv(1, 1, P_r, "S2_r")
+        W_r = self.c2r(W_c)
+        S1_r = self.c2r(S1_c)
+        gU_r, V2_r = o.grad_u(U_r, G_r, W_r, S1_r, S2_r, self.bidx, eb, self.nseg0, small)
+        o.gemm(V2_r, Bt_r, True, False, -1.0, lead * 0.5 * self.logdet * N1, Kinv2)         # Kbar2 partial
+        Dbar2 = o.gemm(G_r, Bt_r, True, False, 1.0, 0.0, o.new("Dbar2", (N2, N2)))
+        o.theta_grad(1, Kinv2, Dbar2, small, gs[3 * Q:6 * Q])
+        self._allreduce(gs)
+        gs[6 * Q] = gtau
+        gs[6 * Q + 1] = gv
+        return self.terms, gU_r, gs
+
+    def step(self):
+        """Collective: value_and_grad + Adam on the local U rows and on the (replicated) small params."""
+        _, gU_r, gs = self.value_and_grad()
+        o = self.ops
+        o.adam(self.U, gU_r, self.mU, self.vU, self.count, self.lr)
+        o.adam(self.small, gs, self.msmall, self.vsmall, self.count, self.lr)
+        self.count += 1

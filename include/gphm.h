@@ -169,6 +169,26 @@ GPHM_API int gphm_plan_factor(gphm_plan* plan, const double* d_small, int axis_m
 GPHM_API int gphm_apply_kinv(gphm_plan* plan, int axis, int side, const double* d_X, int rows, int cols, double* d_out,
                     double* d_tmp, void* stream);
 GPHM_API const double* gphm_plan_matrix(const gphm_plan* plan, int axis, int which);   /* 0 K^-1, 1 D, 2 Linv, 3 L */
+/* [log|K1|, log|K2|] of the last factorisation into two device doubles.                        */
+GPHM_API int gphm_plan_logdet(gphm_plan* plan, double* d_out2, void* stream);
+/* Rank-local pieces of boundary_and_eq_gap / loss / their reverse pass on a block of the grid
+ * (model_GP_solver_2d.py:123-174,179), used by the sharded step:
+ *  residual : d_R <- e^{log_v} (d_R + nl(U) - F) in place; d_out2 = [sum r^2, sum A*Bt] of the block
+ *  boundary : d_eb[e] = U[bidx[e]] - bvals[e]; d_out1 = sum eb^2 (bidx: flat local indices)
+ *  grad_u   : d_gU = W + S1 + S2 [+ G(3U^2-1)] + llk_weight e^{log_tau} E_b; d_V2 = S2 + W/2.
+ *             bidx/eb as above; indices unique inside [0,nseg0) and [nseg0,nb_local)
+ *  theta_grad: sum_ij Kbar dK/dtheta + Dbar dD/dtheta for `axis` (3Q doubles) from caller matrices. */
+GPHM_API int gphm_mg_residual(gphm_plan* plan, double* d_R, const double* d_U, const double* d_F, const double* d_A,
+                     const double* d_Bt, size_t n_local, const double* d_small, double* d_out2, void* stream);
+GPHM_API int gphm_mg_boundary(const double* d_U, const int* d_bidx, const double* d_bvals, int nb_local, double* d_eb,
+                     double* d_out1, void* stream);
+GPHM_API int gphm_mg_grad_u(gphm_plan* plan, const double* d_U, const double* d_G, const double* d_W, const double* d_S1,
+                   const double* d_S2, size_t n_local, const int* d_bidx, const double* d_eb, int nseg0, int nb_local,
+                   const double* d_small, double* d_gU, double* d_V2, void* stream);
+GPHM_API int gphm_mg_theta_grad(gphm_plan* plan, int axis, const double* d_Kbar, const double* d_Dbar, const double* d_small,
+                       double* d_gtheta, void* stream);
+/* d_out = a*d_x + b*d_y (d_y may be NULL).                                                      */
+GPHM_API int gphm_lincomb(double* d_out, double a, const double* d_x, double b, const double* d_y, size_t n, void* stream);
 
 #ifdef __cplusplus
 }

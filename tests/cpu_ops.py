@@ -1,0 +1,95 @@
+"""torch-CPU stand-in for dist.CudaOps (TEST INFRASTRUCTURE): lets the sharded step's host logic
+(layouts, exchanges, partial reductions) run over gloo on a CPU-only box.  Numerics come from the
+oracle's formulas; nothing here is shipped."""
+import math
+
+import torch
+
+from oracle import gphm_oracle as O
+
+DT = torch.float64
+
+
+class CpuOps(object):
+    def __init__(self, kernel, eq_name, x, y, llk_weight, Q, beta=1.0, jitter=1e-6):
+        self.kernel, self.eq_name, self.Q, self.jitter = kernel, eq_name, Q, jitter
+        self.x, self.y = torch.as_tensor(x, dtype=DT), torch.as_tensor(y, dtype=DT)
+        self.order = 1 if eq_name == "advection" else 2
+        self.llk_weight = llk_weight
+        self.m = {}
+        self.ld = torch.zeros(2, dtype=DT)
+
+    def zeros(self, shape, dtype=DT):
+        return torch.zeros(shape, dtype=dtype)
+
+    def tensor(self, data, dtype=DT):
+        return torch.as_tensor(data, dtype=dtype).contiguous()
+
+    def new(self, tag, shape):
+        return torch.empty(shape, dtype=DT)
+
+    def _theta(self, small, a):
+        Q = self.Q
+        return {"log-w": small[(3 * a) * Q:(3 * a + 1) * Q], "log-ls": small[(3 * a + 1) * Q:(3 * a + 2) * Q],
+                "freq": small[(3 * a + 2) * Q:(3 * a + 3) * Q]}
+
+    def factor(self, small, axis_mask=3):
+        for a, xs in enumerate((self.x, self.y)):
+            if not (axis_mask >> a) & 1:
+                continue
+            K, D = O._gram_pair(self.kernel, xs, self._theta(small, a), self.order, self.jitter)
+            L = torch.linalg.cholesky(K)
+            self.m[(a, 3)], self.m[(a, 1)] = L, D
+            self.m[(a, 0)] = torch.cholesky_inverse(L)
+            self.ld[a] = 2.0 * torch.log(torch.diagonal(L)).sum()
+
+    def mat(self, axis, which):
+        return self.m[(axis, which)]
+
+    def logdets(self):
+        return self.ld.clone()
+
+    def apply_kinv(self, axis, side, X, tag):
+        L = self.m[(axis, 3)]
+        if side == 0:
+            return torch.cholesky_solve(X, L)
+        return torch.cholesky_solve(X.T.contiguous(), L).T.contiguous()
+
+    def gemm(self, A, B, tA, tB, alpha, beta, C):
+        prod = (A.T if tA else A) @ (B.T if tB else B)
+        C.copy_(alpha * prod + (beta * C if beta != 0.0 else 0.0))
+        return C
+
+    def residual(self, R, U, F, A, Bt, small):
+        r = R - F
+        if self.eq_name == "allencahn":
+            r = r + U * (U * U - 1.0)
+        out = torch.stack(((r * r).sum(), (A * Bt).sum()))
+        R.copy_(torch.exp(small[6 * self.Q + 1]) * r)
+        return out
+
+    def boundary(self, U, bidx, bvals):
+        eb = U.reshape(-1)[bidx.long()] - bvals
+        return eb, (eb * eb).sum().reshape(1)
+
+    def grad_u(self, U, G, W, S1, S2, bidx, eb, nseg0, small):
+        g = W + S1 + S2
+        if self.eq_name == "allencahn":
+            g = g + G * (3.0 * U * U - 1.0)
+        s = self.llk_weight * torch.exp(small[6 * self.Q])
+        g.reshape(-1).index_add_(0, bidx.long(), s * eb)
+        return g, S2 + 0.5 * W
+
+    def lincomb(self, a, x, b, y, tag):
+        return a * x + b * y
+
+    def theta_grad(self, axis, Kbar, Dbar, small, out):
+        xs = self.x if axis == 0 else self.y
+        g = O._theta_grad_axis(self.kernel, xs, self._theta(small, axis), self.order, Kbar, Dbar)
+        out.copy_(torch.cat((g["log-w"], g["log-ls"], g["freq"])))
+
+    def adam(self, p, g, m, v, count, lr):
+        t = int(count) + 1
+        m.mul_(0.9).add_(0.1 * g)
+        v.mul_(0.999).add_(0.001 * g * g)
+        p.sub_(lr * (m / (1 - 0.9 ** t)) / (torch.sqrt(v / (1 - 0.999 ** t)) + 1e-8))

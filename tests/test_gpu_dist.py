@@ -1,0 +1,79 @@
+"""GPU: the sharded step on real devices.  World size 1 runs on any box (CudaOps primitives vs the
+fused single-GPU path); world size 2 over NCCL runs when the box has >= 2 GPUs."""
+import importlib
+import math
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from helpers import DT
+
+pytestmark = pytest.mark.gpu
+
+
+def _small_from(params, Q):
+    s = torch.zeros(6 * Q + 2, dtype=DT)
+    for a, key in enumerate(("kernel_paras_1", "kernel_paras_2")):
+        for j, leaf in enumerate(("log-w", "log-ls", "freq")):
+            s[(3 * a + j) * Q:(3 * a + j + 1) * Q] = params[key][leaf]
+    s[6 * Q], s[6 * Q + 1] = params["log_tau"], params["log_v"]
+    return s
+
+
+def _compare(equation, eq_name, kernel, beta, N, Q, steps=2):
+    import gphm_b200 as G
+    from oracle import gphm_oracle as O
+    D = importlib.import_module("gaussian-process-slover-for-high-freq-pde_b200.dist")
+    p, _, _ = O.make_problem_2d(equation, kernel, N, 2 * math.pi, beta=beta, M=8)
+    params = O.state_S1(p, Q=Q, freq_scale=6.0)
+    small = _small_from(params, Q)
+    solver = D.ShardedSolver2D(kernel, eq_name, p.x.numpy(), p.y.numpy(), p.src.numpy(), p.bvals.numpy(), p.llk_weight,
+                               1.0, beta, 1e-6, Q, 0.01)
+    solver.set_state(params["U"], small)
+    core = G.solver_core.SolverCore(2, kernel, eq_name, p.x.numpy(), p.y.numpy(), p.src.numpy(), p.bvals.numpy(), None,
+                                    p.llk_weight, 1.0, beta, 1e-6, Q)
+    st = core.new_state()
+    st.U.copy_(params["U"].reshape(-1).cuda()); st.small.copy_(small.cuda())
+    terms, gU, gs = core.value_and_grad(st)
+    t2, gU_r, gs2 = solver.value_and_grad()
+    r0, h = solver.rank * solver.h, solver.h
+    ref_rows = gU.reshape(N, N)[r0:r0 + h]
+    assert float((t2 - terms).abs().max() / terms.abs().max()) <= 1e-9
+    assert float((gU_r - ref_rows).norm() / ref_rows.norm()) <= 1e-9
+    assert float((gs2 - gs).norm() / gs.norm()) <= 1e-9
+    for _ in range(steps):
+        core.step_inplace(st, 0.01)
+        solver.step()
+    assert float((solver.gather_U() - st.U.reshape(N, N)).abs().max()) <= 1e-9
+    assert float((solver.small - st.small).abs().max()) <= 1e-9
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("equation,eq_name,kernel,beta", [("poisson_2d-sin_add_cos", "poisson", "Matern52_Cos_1d", 1.0),
+                                                          ("allencahn_2d-mix-sincos", "allencahn", "SE_Cos_1d", 1.0),
+                                                          ("advection-sin", "advection", "Matern52_Cos_1d", 5.0)])
+def test_sharded_world1_matches_fused_path(equation, eq_name, kernel, beta):
+    _compare(equation, eq_name, kernel, beta, 256, 8)
+
+
+def _worker(rank, world, port):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        _compare("poisson_2d-sin_add_cos", "poisson", "Matern52_Cos_1d", 1.0, 512, 8)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_world2_nccl():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(2, port), nprocs=2, join=True)
