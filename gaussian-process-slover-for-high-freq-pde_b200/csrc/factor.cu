@@ -8,8 +8,8 @@
 // with full tile parallelism); forward error is cond(L)*u per factor, like substitution.
 //
 //   chol_factor : right-looking, NB=128.  Per block column: (1) one-CTA factorisation of the
-//                 diagonal block in shared memory, which also inverts it and accumulates
-//                 log-det; (2) panel L[i,b] = K[i,b] * inv(L_bb)^T (GEMM); (3) trailing update
+//                 diagonal block in shared memory (4x4 sub-blocks of 32x32, warp-level register
+//                 Cholesky), which also inverts it and accumulates log-det; (2) panel L[i,b] = K[i,b] * inv(L_bb)^T (GEMM); (3) trailing update
 //                 K[i,k] -= L[i,b] L[k,b]^T on lower tiles only (GEMM, KM_C_LOWER).
 //   trtri_lower : level-by-level merge  inv([[L11,0],[L21,L22]]) = [[X11,0],[-X22 L21 X11, X22]]
 //                 with all nodes of a level batched into two GEMM launches.
@@ -18,47 +18,106 @@
 
 namespace gphm {
 
-constexpr int DIAG_THREADS = 1024;
+constexpr int DIAG_THREADS = 512;
+constexpr int DIAG_WARPS = DIAG_THREADS / 32;
 constexpr int SLD = kNB + 1;   // odd pitch: column walks hit distinct banks
+constexpr int SB = 32;         // sub-block edge: one warp factors a 32x32 sub-block in registers
+constexpr int XLD = SB + 1;
+constexpr int TLD = 2 * SB + 1;
+static_assert(kNB == 4 * SB, "the diagonal-block kernel is written for 4x4 sub-blocks");
 
 // One CTA: factor the nb x nb block at Kbb (lower triangle read), write L_bb (upper zeroed) and
 // inv(L_bb) (kNB x kNB, zero padded), and the block's log-det contribution.
+//
+// The block is padded to 128x128 with an identity and processed as 4x4 sub-blocks of 32x32:
+//   for J = 0..3:  warp 0 factors sub-block (J,J) in registers (lane = row; one shared-memory
+//                  broadcast of the pivot column per step) and inverts it (lane = column);
+//                  all warps: panel  S[r][J] <- S[r][J] * inv(L_JJ)^T, then the rank-32 update of
+//                  the trailing sub-blocks.                      -> 12 block barriers, not 256.
+//   inverse: inv([[A,0],[B,C]]) = [[A^-1,0],[-C^-1 B A^-1, C^-1]] applied at 64 and 128, in place.
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 chol_diag_kernel(const double* __restrict__ Kbb, double* __restrict__ Lbb, int ld, int nb,
                  double* __restrict__ invd, double* __restrict__ logdet_part, int* __restrict__ status,
                  int pivot_base) {
     extern __shared__ double sm[];
-    double* S = sm;                       // nb x nb block, pitch SLD
-    double* col = sm + kNB * SLD;         // scaled pivot column
-    double* dg = col + kNB;               // diagonal of L
-    const int tid = threadIdx.x;
-    const int tx = tid & 31, ty = tid >> 5;
+    double* S = sm;                          // kNB x SLD
+    double* Xd = S + kNB * SLD;              // 4 diagonal inverse sub-blocks, SB x XLD each
+    double* T = Xd + 4 * SB * XLD;           // 64 x TLD scratch
+    double* rdiag = T + 2 * SB * TLD;        // 1 / L[i][i]
+    double* ddiag = rdiag + kNB;             // L[i][i]
+    double* colbuf = ddiag + kNB;            // pivot column exchange inside warp 0
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int idx = tid; idx < nb * nb; idx += DIAG_THREADS) {
-        const int i = idx / nb, j = idx - i * nb;
-        S[i * SLD + j] = Kbb[(size_t)i * ld + j];
+    for (int idx = tid; idx < kNB * kNB; idx += DIAG_THREADS) {
+        const int i = idx >> 7, j = idx & (kNB - 1);
+        double v = (i == j) ? 1.0 : 0.0;
+        if (i < nb && j < nb) v = (j <= i) ? Kbb[(size_t)i * ld + j] : 0.0;
+        S[i * SLD + j] = v;
     }
     __syncthreads();
 
-    // ---- Cholesky, right-looking rank-1 updates (2 barriers per column) ----
-    for (int j = 0; j < nb; ++j) {
-        double ajj = S[j * SLD + j];
-        if (!(ajj > 0.0)) {               // also catches NaN
-            if (tid == 0) atomicCAS(status, 0, pivot_base + j + 1);
-            ajj = 1.0;
+    for (int J = 0; J < 4; ++J) {
+        const int o = J * SB;
+        double* X = Xd + J * SB * XLD;
+        if (warp == 0) {
+            // ---- Cholesky of the 32x32 sub-block, lane = row ----
+            double a[SB];
+#pragma unroll
+            for (int k = 0; k < SB; ++k) a[k] = S[(o + lane) * SLD + o + k];
+#pragma unroll
+            for (int j = 0; j < SB; ++j) {
+                double ajj = __shfl_sync(0xffffffffu, a[j], j);
+                if (!(ajj > 0.0)) {                       // also catches NaN; uniform across the warp
+                    if (lane == 0) atomicCAS(status, 0, pivot_base + o + j + 1);
+                    ajj = 1.0;
+                }
+                const double d = sqrt(ajj);
+                const double r = 1.0 / d;
+                double l = a[j] * r;                      // meaningful for lane > j
+                if (lane == j) { l = d; ddiag[o + j] = d; rdiag[o + j] = r; }
+                a[j] = l;
+                colbuf[lane] = l;
+                __syncwarp();
+#pragma unroll
+                for (int k = j + 1; k < SB; ++k) a[k] = fma(-l, colbuf[k], a[k]);   // rows < k carry unused values
+                __syncwarp();
+            }
+#pragma unroll
+            for (int k = 0; k < SB; ++k) S[(o + lane) * SLD + o + k] = (k <= lane) ? a[k] : 0.0;
+            __syncwarp();
+            // ---- inverse of the lower-triangular sub-block, lane = column c:
+            //      x_c = 1/l_cc;  x_i = -(sum_{k<i} l_ik x_k) / l_ii  (x_k = 0 for k < c) ----
+            double acc[SB];
+#pragma unroll
+            for (int k = 0; k < SB; ++k) acc[k] = 0.0;
+#pragma unroll
+            for (int k = 0; k < SB; ++k) {
+                const double rk = rdiag[o + k];
+                const double xk = (k == lane) ? rk : ((k > lane) ? -acc[k] * rk : 0.0);
+                X[k * XLD + lane] = xk;                   // X[k][c]
+#pragma unroll
+                for (int i = k + 1; i < SB; ++i) acc[i] = fma(S[(o + i) * SLD + o + k], xk, acc[i]);
+            }
         }
-        const double d = sqrt(ajj);
-        const double r = 1.0 / d;
-        for (int i = j + 1 + tid; i < nb; i += DIAG_THREADS) {
-            const double v = S[i * SLD + j] * r;
-            col[i] = v;
-            S[i * SLD + j] = v;
-        }
-        if (tid == 0) dg[j] = d;
         __syncthreads();
-        for (int i = j + 1 + ty; i < nb; i += 32) {
-            const double ci = col[i];
-            for (int k = j + 1 + tx; k <= i; k += 32) S[i * SLD + k] -= ci * col[k];
+        // ---- panel: rows below the sub-block, P[r][c] = sum_k S[r][o+k] * X[c][k] ----
+        for (int r = o + SB + warp; r < kNB; r += DIAG_WARPS) {
+            double s = 0.0;
+#pragma unroll 8
+            for (int k = 0; k < SB; ++k) s = fma(S[r * SLD + o + k], X[lane * XLD + k], s);
+            __syncwarp();
+            S[r * SLD + o + lane] = s;
+        }
+        __syncthreads();
+        // ---- trailing update: S[i][k] -= sum_c P[i][c] P[k][c] for o+32 <= k <= i ----
+        for (int i = o + SB + warp; i < kNB; i += DIAG_WARPS) {
+            for (int kb = o + SB; kb <= i; kb += SB) {
+                const int k = kb + lane;
+                double s = 0.0;
+#pragma unroll 8
+                for (int c = 0; c < SB; ++c) s = fma(S[i * SLD + o + c], S[k * SLD + o + c], s);
+                if (k <= i) S[i * SLD + k] -= s;
+            }
         }
         __syncthreads();
     }
@@ -66,42 +125,60 @@ chol_diag_kernel(const double* __restrict__ Kbb, double* __restrict__ Lbb, int l
     // ---- write L_bb; log-det partial (fixed order) ----
     for (int idx = tid; idx < nb * nb; idx += DIAG_THREADS) {
         const int i = idx / nb, j = idx - i * nb;
-        Lbb[(size_t)i * ld + j] = (j < i) ? S[i * SLD + j] : (j == i ? dg[i] : 0.0);
+        Lbb[(size_t)i * ld + j] = (j <= i) ? S[i * SLD + j] : 0.0;
     }
-    if (tid < 32) {
+    if (warp == 0) {
         double s = 0.0;
-        for (int i = tid; i < nb; i += 32) s += log(dg[i]);
+        for (int i = lane; i < nb; i += 32) s += log(ddiag[i]);
         s = warp_sum(s);
-        if (tid == 0) *logdet_part = s;
+        if (lane == 0) *logdet_part = s;
     }
+    __syncthreads();
 
-    // ---- in-place inverse of the lower-triangular block (columns from last to first):
-    //      X[j][j] = 1/L[j][j];  X[i][j] = -(sum_{k=j+1..i} X[i][k] L[k][j]) * X[j][j]
-    //      8 lanes cooperate on one row. ----
-    const int sub = tid & 7, rgrp = tid >> 3;           // 128 row groups
-    const unsigned gmask = 0xffu << (tid & 24);         // the 8 lanes of this row group (same trip count)
-    for (int j = nb - 1; j >= 0; --j) {
-        for (int i = j + 1 + tid; i < nb; i += DIAG_THREADS) col[i] = S[i * SLD + j];
-        __syncthreads();
-        const double xjj = 1.0 / dg[j];
-        for (int i = j + 1 + rgrp; i < nb; i += DIAG_THREADS / 8) {
+    // ---- inverse, in place in S ----
+    for (int idx = tid; idx < 4 * SB * SB; idx += DIAG_THREADS) {
+        const int J = idx >> 10, i = (idx >> 5) & 31, c = idx & 31;
+        S[(J * SB + i) * SLD + J * SB + c] = Xd[J * SB * XLD + i * XLD + c];
+    }
+    __syncthreads();
+    // level 1: two 64-blocks.  T = L10 * X00 ; X10 = -X11 * T
+    {
+        const int pr = warp / (DIAG_WARPS / 2), o = pr * 2 * SB;
+        const int i0 = (warp % (DIAG_WARPS / 2)) * (SB / (DIAG_WARPS / 2));
+        for (int i = i0; i < i0 + SB / (DIAG_WARPS / 2); ++i) {
             double s = 0.0;
-            for (int k = j + 1 + sub; k <= i; k += 8) {
-                const double xik = (k == i) ? 1.0 / dg[i] : S[i * SLD + k];
-                s += xik * col[k];
-            }
-            s += __shfl_xor_sync(gmask, s, 1);
-            s += __shfl_xor_sync(gmask, s, 2);
-            s += __shfl_xor_sync(gmask, s, 4);
-            if (sub == 0) S[i * SLD + j] = -s * xjj;
+            for (int k = lane; k < SB; ++k) s = fma(S[(o + SB + i) * SLD + o + k], S[(o + k) * SLD + o + lane], s);
+            T[(pr * SB + i) * TLD + lane] = s;
+        }
+        __syncthreads();
+        for (int i = i0; i < i0 + SB / (DIAG_WARPS / 2); ++i) {
+            double s = 0.0;
+            for (int k = 0; k <= i; ++k) s = fma(S[(o + SB + i) * SLD + o + SB + k], T[(pr * SB + k) * TLD + lane], s);
+            S[(o + SB + i) * SLD + o + lane] = -s;
         }
         __syncthreads();
     }
+    // level 2: T = L21 * X11 (64x64) ; X21 = -X22 * T
+    {
+        constexpr int H = 2 * SB, RPW = H / DIAG_WARPS;
+        for (int i = warp * RPW; i < (warp + 1) * RPW; ++i)
+            for (int c = lane; c < H; c += 32) {
+                double s = 0.0;
+                for (int k = c; k < H; ++k) s = fma(S[(H + i) * SLD + k], S[k * SLD + c], s);
+                T[i * TLD + c] = s;
+            }
+        __syncthreads();
+        for (int i = warp * RPW; i < (warp + 1) * RPW; ++i)
+            for (int c = lane; c < H; c += 32) {
+                double s = 0.0;
+                for (int k = 0; k <= i; ++k) s = fma(S[(H + i) * SLD + H + k], T[k * TLD + c], s);
+                S[(H + i) * SLD + c] = -s;
+            }
+        __syncthreads();
+    }
     for (int idx = tid; idx < kNB * kNB; idx += DIAG_THREADS) {
-        const int i = idx / kNB, j = idx - i * kNB;
-        double v = 0.0;
-        if (i < nb && j < nb) v = (j < i) ? S[i * SLD + j] : (j == i ? 1.0 / dg[i] : 0.0);
-        invd[idx] = v;
+        const int i = idx >> 7, j = idx & (kNB - 1);
+        invd[idx] = (i < nb && j < nb && j <= i) ? S[i * SLD + j] : 0.0;
     }
 }
 
@@ -114,7 +191,7 @@ __global__ void copy_diag_blocks_kernel(const double* __restrict__ invd, double*
     }
 }
 
-constexpr size_t kDiagSmem = (size_t)(kNB * SLD + 2 * kNB) * sizeof(double);
+constexpr size_t kDiagSmem = (size_t)(kNB * SLD + 4 * SB * XLD + 2 * SB * TLD + 2 * kNB + SB) * sizeof(double);
 
 int factor_init() {
     static int done = -1;

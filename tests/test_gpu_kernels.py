@@ -71,13 +71,14 @@ def test_dgemm_matches_torch(gphm, tA, tB):
 @pytest.mark.parametrize("n", [1, 7, 128, 129, 200, 400, 517, 1024])
 def test_cholesky_and_inverse(gphm, oracle, n):
     """gphm_potrf_inv on a real Gram matrix (cond ~ 1e6): L vs torch.linalg.cholesky, Linv @ L = I,
-    logdet.  Bounds reflect cond(L) ~ 2e3 (x n rounding): <= 1e-9."""
+    logdet.  Two backward-stable factorisations of a matrix with cond(K) ~ 4e6 agree to
+    ~cond(K) * eps * growth: bound 1e-8."""
     x = torch.linspace(0, 1, n, dtype=DT) * 2 * math.pi
     K = oracle.gram("Matern52_Cos_1d", x, x, theta_state(30, 20.0), 0, 1e-6)
     L, Linv, logdet, status = gphm.solver_core.potrf_inv(K)
     assert int(status) == 0
     Lref = torch.linalg.cholesky(K)
-    assert rel(L, Lref) <= 1e-9
+    assert rel(L, Lref) <= 1e-8
     assert float(torch.triu(L.cpu(), 1).abs().max()) == 0.0 and float(torch.triu(Linv.cpu(), 1).abs().max()) == 0.0
     eye = torch.eye(n, dtype=DT)
     assert rel(Linv.cpu() @ Lref, eye) <= 1e-9
