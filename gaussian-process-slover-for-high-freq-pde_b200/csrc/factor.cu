@@ -18,32 +18,32 @@
 
 namespace gphm {
 
-constexpr int DIAG_THREADS = 512;
+constexpr int DIAG_THREADS = 256;
 constexpr int DIAG_WARPS = DIAG_THREADS / 32;
 constexpr int SLD = kNB + 1;   // odd pitch: column walks hit distinct banks
 constexpr int SB = 32;         // sub-block edge: one warp factors a 32x32 sub-block in registers
-constexpr int XLD = SB + 1;
-constexpr int TLD = 2 * SB + 1;
 static_assert(kNB == 4 * SB, "the diagonal-block kernel is written for 4x4 sub-blocks");
 
 // One CTA: factor the nb x nb block at Kbb (lower triangle read), write L_bb (upper zeroed) and
 // inv(L_bb) (kNB x kNB, zero padded), and the block's log-det contribution.
 //
 // The block is padded to 128x128 with an identity and processed as 4x4 sub-blocks of 32x32:
-//   for J = 0..3:  warp 0 factors sub-block (J,J) in registers (lane = row; one shared-memory
-//                  broadcast of the pivot column per step) and inverts it (lane = column);
-//                  all warps: panel  S[r][J] <- S[r][J] * inv(L_JJ)^T, then the rank-32 update of
-//                  the trailing sub-blocks.                      -> 12 block barriers, not 256.
-//   inverse: inv([[A,0],[B,C]]) = [[A^-1,0],[-C^-1 B A^-1, C^-1]] applied at 64 and 128, in place.
+//   for J = 0..3:  warp 0 factors sub-block (J,J) in registers (lane = row; the pivot column is
+//                  exchanged through shared memory once per step);
+//                  panel: every row below solves  p L_JJ^T = s  by substitution (thread = row);
+//                  all warps: rank-32 update of the trailing sub-blocks.   -> 12 block barriers.
+//   inverse: block forward substitution, block row I:  X[I][:] = L_II^-1 (E_I - L[I][<I] X[<I][:]),
+//            the product by all warps, the triangular solve by substitution (thread = column).
+// Only substitutions and products are used (no multiplication by inner inverses), so the result
+// is as accurate as an unblocked factorisation - the parity tests are sensitive to this.
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 chol_diag_kernel(const double* __restrict__ Kbb, double* __restrict__ Lbb, int ld, int nb,
                  double* __restrict__ invd, double* __restrict__ logdet_part, int* __restrict__ status,
                  int pivot_base) {
     extern __shared__ double sm[];
     double* S = sm;                          // kNB x SLD
-    double* Xd = S + kNB * SLD;              // 4 diagonal inverse sub-blocks, SB x XLD each
-    double* T = Xd + 4 * SB * XLD;           // 64 x TLD scratch
-    double* rdiag = T + 2 * SB * TLD;        // 1 / L[i][i]
+    double* T = S + kNB * SLD;               // SB x SLD scratch (one block row of the inverse)
+    double* rdiag = T + SB * SLD;            // 1 / L[i][i]
     double* ddiag = rdiag + kNB;             // L[i][i]
     double* colbuf = ddiag + kNB;            // pivot column exchange inside warp 0
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -58,7 +58,6 @@ chol_diag_kernel(const double* __restrict__ Kbb, double* __restrict__ Lbb, int l
 
     for (int J = 0; J < 4; ++J) {
         const int o = J * SB;
-        double* X = Xd + J * SB * XLD;
         if (warp == 0) {
             // ---- Cholesky of the 32x32 sub-block, lane = row ----
             double a[SB];
@@ -72,9 +71,9 @@ chol_diag_kernel(const double* __restrict__ Kbb, double* __restrict__ Lbb, int l
                     ajj = 1.0;
                 }
                 const double d = sqrt(ajj);
-                const double r = 1.0 / d;
-                double l = a[j] * r;                      // meaningful for lane > j
-                if (lane == j) { l = d; ddiag[o + j] = d; rdiag[o + j] = r; }
+                const double rd = 1.0 / d;
+                double l = a[j] * rd;                     // meaningful for lane > j
+                if (lane == j) { l = d; ddiag[o + j] = d; rdiag[o + j] = rd; }
                 a[j] = l;
                 colbuf[lane] = l;
                 __syncwarp();
@@ -84,29 +83,25 @@ chol_diag_kernel(const double* __restrict__ Kbb, double* __restrict__ Lbb, int l
             }
 #pragma unroll
             for (int k = 0; k < SB; ++k) S[(o + lane) * SLD + o + k] = (k <= lane) ? a[k] : 0.0;
-            __syncwarp();
-            // ---- inverse of the lower-triangular sub-block, lane = column c:
-            //      x_c = 1/l_cc;  x_i = -(sum_{k<i} l_ik x_k) / l_ii  (x_k = 0 for k < c) ----
-            double acc[SB];
-#pragma unroll
-            for (int k = 0; k < SB; ++k) acc[k] = 0.0;
-#pragma unroll
-            for (int k = 0; k < SB; ++k) {
-                const double rk = rdiag[o + k];
-                const double xk = (k == lane) ? rk : ((k > lane) ? -acc[k] * rk : 0.0);
-                X[k * XLD + lane] = xk;                   // X[k][c]
-#pragma unroll
-                for (int i = k + 1; i < SB; ++i) acc[i] = fma(S[(o + i) * SLD + o + k], xk, acc[i]);
-            }
         }
         __syncthreads();
-        // ---- panel: rows below the sub-block, P[r][c] = sum_k S[r][o+k] * X[c][k] ----
-        for (int r = o + SB + warp; r < kNB; r += DIAG_WARPS) {
-            double s = 0.0;
-#pragma unroll 8
-            for (int k = 0; k < SB; ++k) s = fma(S[r * SLD + o + k], X[lane * XLD + k], s);
-            __syncwarp();
-            S[r * SLD + o + lane] = s;
+        // ---- panel: row r below the sub-block solves p L_JJ^T = s by substitution (thread = row) ----
+        {
+            const int r = o + SB + tid;
+            if (r < kNB) {
+                double v[SB];
+#pragma unroll
+                for (int c = 0; c < SB; ++c) v[c] = S[r * SLD + o + c];
+#pragma unroll
+                for (int k = 0; k < SB; ++k) {
+                    const double pk = v[k] * rdiag[o + k];
+                    v[k] = pk;
+#pragma unroll
+                    for (int c = k + 1; c < SB; ++c) v[c] = fma(-pk, S[(o + c) * SLD + o + k], v[c]);
+                }
+#pragma unroll
+                for (int c = 0; c < SB; ++c) S[r * SLD + o + c] = v[c];
+            }
         }
         __syncthreads();
         // ---- trailing update: S[i][k] -= sum_c P[i][c] P[k][c] for o+32 <= k <= i ----
@@ -135,45 +130,38 @@ chol_diag_kernel(const double* __restrict__ Kbb, double* __restrict__ Lbb, int l
     }
     __syncthreads();
 
-    // ---- inverse, in place in S ----
-    for (int idx = tid; idx < 4 * SB * SB; idx += DIAG_THREADS) {
-        const int J = idx >> 10, i = (idx >> 5) & 31, c = idx & 31;
-        S[(J * SB + i) * SLD + J * SB + c] = Xd[J * SB * XLD + i * XLD + c];
-    }
-    __syncthreads();
-    // level 1: two 64-blocks.  T = L10 * X00 ; X10 = -X11 * T
-    {
-        const int pr = warp / (DIAG_WARPS / 2), o = pr * 2 * SB;
-        const int i0 = (warp % (DIAG_WARPS / 2)) * (SB / (DIAG_WARPS / 2));
-        for (int i = i0; i < i0 + SB / (DIAG_WARPS / 2); ++i) {
-            double s = 0.0;
-            for (int k = lane; k < SB; ++k) s = fma(S[(o + SB + i) * SLD + o + k], S[(o + k) * SLD + o + lane], s);
-            T[(pr * SB + i) * TLD + lane] = s;
-        }
-        __syncthreads();
-        for (int i = i0; i < i0 + SB / (DIAG_WARPS / 2); ++i) {
-            double s = 0.0;
-            for (int k = 0; k <= i; ++k) s = fma(S[(o + SB + i) * SLD + o + SB + k], T[(pr * SB + k) * TLD + lane], s);
-            S[(o + SB + i) * SLD + o + lane] = -s;
-        }
-        __syncthreads();
-    }
-    // level 2: T = L21 * X11 (64x64) ; X21 = -X22 * T
-    {
-        constexpr int H = 2 * SB, RPW = H / DIAG_WARPS;
-        for (int i = warp * RPW; i < (warp + 1) * RPW; ++i)
-            for (int c = lane; c < H; c += 32) {
-                double s = 0.0;
-                for (int k = c; k < H; ++k) s = fma(S[(H + i) * SLD + k], S[k * SLD + c], s);
-                T[i * TLD + c] = s;
+    // ---- inverse by block forward substitution, in place in S (row I of X overwrites row I of L) ----
+    for (int I = 0; I < 4; ++I) {
+        const int o = I * SB, ncol = o + SB;
+        // T[i][c] = delta(o+i, c) - sum_{k=c}^{o-1} L[o+i][k] X[k][c]      (X[k][c] = 0 for k < c)
+        for (int i = warp; i < SB; i += DIAG_WARPS)
+            for (int c = lane; c < ncol; c += 32) {
+                double s = (c == o + i) ? 1.0 : 0.0;
+                for (int k = c; k < o; ++k) s = fma(-S[(o + i) * SLD + k], S[k * SLD + c], s);
+                T[i * SLD + c] = s;
             }
         __syncthreads();
-        for (int i = warp * RPW; i < (warp + 1) * RPW; ++i)
-            for (int c = lane; c < H; c += 32) {
-                double s = 0.0;
-                for (int k = 0; k <= i; ++k) s = fma(S[(H + i) * SLD + H + k], T[k * TLD + c], s);
-                S[(H + i) * SLD + c] = -s;
+        // column c solves L_II x = T[:, c] by substitution (thread = column)
+        if (tid < ncol) {
+            const int c = tid;
+            double v[SB];
+#pragma unroll
+            for (int i = 0; i < SB; ++i) v[i] = T[i * SLD + c];
+#pragma unroll
+            for (int k = 0; k < SB; ++k) {
+                const double xk = v[k] * rdiag[o + k];
+                v[k] = xk;
+#pragma unroll
+                for (int i = k + 1; i < SB; ++i) v[i] = fma(-xk, S[(o + i) * SLD + o + k], v[i]);
             }
+#pragma unroll
+            for (int i = 0; i < SB; ++i) T[i * SLD + c] = v[i];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < SB * ncol; idx += DIAG_THREADS) {
+            const int i = idx / ncol, c = idx - i * ncol;
+            S[(o + i) * SLD + c] = T[i * SLD + c];
+        }
         __syncthreads();
     }
     for (int idx = tid; idx < kNB * kNB; idx += DIAG_THREADS) {
@@ -191,7 +179,7 @@ __global__ void copy_diag_blocks_kernel(const double* __restrict__ invd, double*
     }
 }
 
-constexpr size_t kDiagSmem = (size_t)(kNB * SLD + 4 * SB * XLD + 2 * SB * TLD + 2 * kNB + SB) * sizeof(double);
+constexpr size_t kDiagSmem = (size_t)(kNB * SLD + SB * SLD + 2 * kNB + SB) * sizeof(double);
 
 int factor_init() {
     static int done = -1;

@@ -81,7 +81,7 @@ def test_cholesky_and_inverse(gphm, oracle, n):
     assert rel(L, Lref) <= 1e-8
     assert float(torch.triu(L.cpu(), 1).abs().max()) == 0.0 and float(torch.triu(Linv.cpu(), 1).abs().max()) == 0.0
     eye = torch.eye(n, dtype=DT)
-    assert rel(Linv.cpu() @ Lref, eye) <= 1e-9
+    assert rel(Linv.cpu() @ Lref, eye) <= 5e-9
     assert abs(float(logdet) - float(torch.linalg.slogdet(K)[1])) <= 1e-9 * max(1.0, abs(float(logdet)))
     B = torch.sin(torch.arange(n * 3, dtype=DT)).reshape(n, 3)
     assert rel(gphm.solver_core.solve_spd(K, B), torch.linalg.solve(K, B)) <= 1e-7
