@@ -239,8 +239,8 @@ def run_ours(args, rank, world, local):
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    cat_ms = (ctypes.c_double * 5)(); cat_fl = (ctypes.c_double * 5)(); cat_by = (ctypes.c_double * 5)()
-    cat_n = (ctypes.c_longlong * 5)()
+    cat_ms = (ctypes.c_double * 6)(); cat_fl = (ctypes.c_double * 6)(); cat_by = (ctypes.c_double * 6)()
+    cat_n = (ctypes.c_longlong * 6)()
     lib.gphm_profile_stop(cat_ms, cat_fl, cat_by, cat_n)
     launches = lib.gphm_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
@@ -306,7 +306,7 @@ def run_ours(args, rank, world, local):
                 "step_frac_of_peak": (flops_per_iter(n) / ms_step / 1e9 / sustained) if sustained else None,
                 "by_family_ms_per_step": {"gram": cat_ms[0] / args.steps, "dgemm": cat_ms[1] / args.steps,
                                           "chol_diag": cat_ms[2] / args.steps, "reduce_elementwise": cat_ms[3] / args.steps,
-                                          "adam": cat_ms[4] / args.steps}}
+                                          "adam": cat_ms[4] / args.steps, "fft_diag_sums": cat_ms[5] / args.steps}}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

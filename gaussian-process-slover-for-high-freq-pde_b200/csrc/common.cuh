@@ -30,7 +30,7 @@ void set_last_error(const char* fmt, ...);
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 
 // Launch accounting / optional CUDA-event profiling per kernel family (gphm_profile_* in gphm.h).
-enum : int { CAT_GRAM = 0, CAT_DGEMM = 1, CAT_CHOL_DIAG = 2, CAT_ELEMWISE = 3, CAT_ADAM = 4, CAT_COUNT = 5 };
+enum : int { CAT_GRAM = 0, CAT_DGEMM = 1, CAT_CHOL_DIAG = 2, CAT_ELEMWISE = 3, CAT_ADAM = 4, CAT_FFT = 5, CAT_COUNT = 6 };
 bool profiling_enabled();
 struct LaunchScope {
     int cat; cudaStream_t st; int slot;

@@ -173,7 +173,7 @@ diag_sums_kernel(const double* __restrict__ Kbar, const double* __restrict__ Dba
         double sk = 0.0, sd = 0.0;
         for (int i = r0; i < r1; ++i) {
             const int j = i + lag;
-            if (j >= 0 && j < n) { sk += Kbar[(size_t)i * ld + j]; sd += Dbar[(size_t)i * ld + j]; }
+            if (j >= 0 && j < n) { sk += Kbar[(size_t)i * ld + j]; if (Dbar) sd += Dbar[(size_t)i * ld + j]; }
         }
         pk[l] = sk; pd[l] = sd;
     }
@@ -192,8 +192,8 @@ diag_sums_reduce_kernel(const double* __restrict__ part, int n, int nchunks, int
         ku += pk[n - 1 + m]; du += pd[n - 1 + m];          // j - i = m  (upper)
         kl += pk[n - 1 - m]; dl += pd[n - 1 - m];          // i - j = m  (lower)
     }
-    if (m == 0) { sK[0] = ku; sD[0] = antisym ? 0.0 : du; }
-    else { sK[m] = ku + kl; sD[m] = antisym ? dirsign * (dl - du) : (du + dl); }
+    if (m == 0) { sK[0] = ku; if (sD) sD[0] = antisym ? 0.0 : du; }
+    else { sK[m] = ku + kl; if (sD) sD[m] = antisym ? dirsign * (dl - du) : (du + dl); }
 }
 
 int launch_diag_sums(const double* Kbar, const double* Dbar, int n, int ld, bool antisym, double dirsign,

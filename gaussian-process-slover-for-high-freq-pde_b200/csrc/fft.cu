@@ -1,0 +1,242 @@
+// Diagonal sums of X^T Y by batched FFT cross-correlation (uniform-grid theta-gradient path).
+//
+// On a uniform grid the Gram matrices are Toeplitz, so the reverse pass only needs
+//     s[m] = sum_{col-row = m} (X^T Y)[row][col] = sum_r sum_j X[r][j] Y[r][j+m]      (m = -(C-1)..C-1)
+// of  Kbar = beta K^-1 - V^T Y  and  Dbar = c G^T Y  (and K^-1 = Linv^T Linv), never the matrices
+// themselves.  s is the sum over rows r of the cross-correlation of row r of X with row r of Y.
+// This replaces the 4 full Kbar/Dbar GEMMs and the Linv^T Linv product per step (9.3 N^3 of the
+// 28 N^3 FLOPs; the reverse pass of jnp.linalg.solve / slogdet / matmul,
+// model_GP_solver_2d.py:104-119,158-162,179) by O(N^2 log N) work that is bound by shared-memory/FP64-ALU throughput and reads each operand
+// once from HBM.
+//
+// Per row: z = x + i y zero-padded to L >= 2C, one in-place radix-2 DIF FFT in shared memory
+// (natural in, bit-reversed out); the two real spectra are separated with Z(f), conj Z(L-f);
+// conj(X^)(f) Y^(f) is accumulated in registers over all rows a CTA owns (bit-reversed order).
+// A second kernel sums the per-CTA partial spectra in a fixed order (deterministic), runs one
+// inverse DIT FFT (bit-reversed in, natural out) and emits the symmetric / antisymmetric
+// diagonal sums that theta_grad_toeplitz_kernel consumes.
+#include <algorithm>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gphm {
+
+constexpr int FFT_THREADS = 512;
+constexpr int FFT_MAX_L = 8192;                       // 128 KB of complex doubles in shared memory
+constexpr int FFT_ACC = FFT_MAX_L / FFT_THREADS;      // spectrum bins per thread
+
+int fft_length_for(int n) {                            // smallest power of two >= 2n (0 if unsupported)
+    int L = 2;
+    while (L < 2 * n) L <<= 1;
+    return L <= FFT_MAX_L ? L : 0;
+}
+int fft_grid() { return kNumSMs; }
+
+__global__ void twiddle_init_kernel(double2* __restrict__ W, int L) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= L / 2) return;
+    double s, c;
+    sincospi(2.0 * (double)t / (double)L, &s, &c);
+    W[t] = make_double2(c, -s);                        // exp(-2 pi i t / L)
+}
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// partial[blockIdx.x][p] (+)= weight * sum over the CTA's rows of conj(X^)(f_p) Y^(f_p)
+__global__ void __launch_bounds__(FFT_THREADS, 1)
+xcorr_spectrum_kernel(const double* __restrict__ X, const double* __restrict__ Y, int rows, int cols, int ldx,
+                      int ldy, int L, int logL, const double2* __restrict__ W, double weight, int accumulate,
+                      double2* __restrict__ partial) {
+    extern __shared__ double2 xs[];
+    const int tid = threadIdx.x;
+    double2 acc[FFT_ACC];
+#pragma unroll
+    for (int k = 0; k < FFT_ACC; ++k) acc[k] = make_double2(0.0, 0.0);
+
+    __shared__ double redmax[2][FFT_THREADS / 32];
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const double* xr = X + (size_t)r * ldx;
+        const double* yr = Y + (size_t)r * ldy;
+        double mx = 0.0, my = 0.0;
+        for (int j = tid; j < L; j += FFT_THREADS) {
+            double2 v = make_double2(0.0, 0.0);
+            if (j < cols) { v = make_double2(xr[j], yr[j]); mx = fmax(mx, fabs(v.x)); my = fmax(my, fabs(v.y)); }
+            xs[j] = v;
+        }
+        // z = x + i*y shares one FFT: the two spectra are separated by a difference, so y is first
+        // rescaled (exactly, by a power of two) to x's magnitude - otherwise the smaller sequence
+        // loses log10(max|x|/max|y|) digits (|V| ~ 1e8 against |A| ~ 1e2 in this problem).
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            my = fmax(my, __shfl_xor_sync(0xffffffffu, my, o));
+        }
+        if ((tid & 31) == 0) { redmax[0][tid >> 5] = mx; redmax[1][tid >> 5] = my; }
+        __syncthreads();
+        mx = 0.0; my = 0.0;
+#pragma unroll
+        for (int w = 0; w < FFT_THREADS / 32; ++w) { mx = fmax(mx, redmax[0][w]); my = fmax(my, redmax[1][w]); }
+        if (!(mx > 0.0) || !(my > 0.0) || !isfinite(mx) || !isfinite(my)) {
+            if (!isfinite(mx) || !isfinite(my)) acc[0].x += mx + my;      // propagate NaN/Inf
+            __syncthreads();
+            continue;                                                     // a zero row contributes nothing
+        }
+        const double sc = exp2(rint(log2(mx / my)));
+        const double isc = 1.0 / sc;
+        for (int j = tid; j < cols; j += FFT_THREADS) xs[j].y *= sc;
+        __syncthreads();
+        for (int s = 0; s < logL; ++s) {               // radix-2 DIF, natural in -> bit-reversed out
+            const int sh = logL - 1 - s, half = 1 << sh;
+            for (int b = tid; b < L / 2; b += FFT_THREADS) {
+                const int j = b & (half - 1);
+                const int i0 = ((b >> sh) << (sh + 1)) + j, i1 = i0 + half;
+                const double2 a = xs[i0], c = xs[i1];
+                xs[i0] = make_double2(a.x + c.x, a.y + c.y);
+                xs[i1] = cmul(make_double2(a.x - c.x, a.y - c.y), W[(size_t)j << s]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int k = 0; k < FFT_ACC; ++k) {
+            const int p = tid + k * FFT_THREADS;
+            if (p < L) {
+                const unsigned f = __brev((unsigned)p) >> (32 - logL);
+                const unsigned fm = (unsigned)(L - (int)f) & (unsigned)(L - 1);
+                const unsigned pm = __brev(fm) >> (32 - logL);
+                const double2 zf = xs[p], zm = xs[pm];
+                const double2 xh = make_double2(0.5 * (zf.x + zm.x), 0.5 * (zf.y - zm.y));       // X^(f)
+                const double2 yh = make_double2(0.5 * (zf.y + zm.y), -0.5 * (zf.x - zm.x));      // Y^(f)
+                acc[k].x += isc * (xh.x * yh.x + xh.y * yh.y);                                    // conj(X^) Y^
+                acc[k].y += isc * (xh.x * yh.y - xh.y * yh.x);
+            }
+        }
+        __syncthreads();
+    }
+    double2* out = partial + (size_t)blockIdx.x * L;
+#pragma unroll
+    for (int k = 0; k < FFT_ACC; ++k) {
+        const int p = tid + k * FFT_THREADS;
+        if (p < L) {
+            double2 v = make_double2(weight * acc[k].x, weight * acc[k].y);
+            if (accumulate) { const double2 o = out[p]; v.x += o.x; v.y += o.y; }
+            out[p] = v;
+        }
+    }
+}
+
+// blockIdx.x = 0: K spectrum -> sK (symmetric sums); 1: D spectrum -> sD (symmetric or antisymmetric)
+__global__ void __launch_bounds__(FFT_THREADS, 1)
+spectrum_to_diag_sums_kernel(const double2* __restrict__ partK, const double2* __restrict__ partD, int nparts, int L,
+                             int logL, const double2* __restrict__ W, int n, int antisym, double dirsign,
+                             const double* __restrict__ addK, double addK_scale,
+                             double* __restrict__ sK, double* __restrict__ sD) {
+    extern __shared__ double2 xs[];
+    const int tid = threadIdx.x;
+    const double2* part = blockIdx.x == 0 ? partK : partD;
+    for (int p = tid; p < L; p += FFT_THREADS) {
+        double2 s = make_double2(0.0, 0.0);
+        for (int c = 0; c < nparts; ++c) { const double2 v = part[(size_t)c * L + p]; s.x += v.x; s.y += v.y; }
+        xs[p] = s;
+    }
+    __syncthreads();
+    for (int s = 0; s < logL; ++s) {                   // radix-2 DIT inverse, bit-reversed in -> natural out
+        const int half = 1 << s;
+        for (int b = tid; b < L / 2; b += FFT_THREADS) {
+            const int j = b & (half - 1);
+            const int i0 = ((b >> s) << (s + 1)) + j, i1 = i0 + half;
+            const double2 w = W[(size_t)j << (logL - 1 - s)];
+            const double2 t = cmul(xs[i1], make_double2(w.x, -w.y));
+            const double2 a = xs[i0];
+            xs[i0] = make_double2(a.x + t.x, a.y + t.y);
+            xs[i1] = make_double2(a.x - t.x, a.y - t.y);
+        }
+        __syncthreads();
+    }
+    const double inv = 1.0 / (double)L;
+    double* out = blockIdx.x == 0 ? sK : sD;
+    const bool anti = (blockIdx.x == 1) && antisym;
+    for (int m = tid; m < n; m += FFT_THREADS) {
+        const double up = xs[m].x * inv;                           // col - row = m
+        const double lo = xs[(L - m) & (L - 1)].x * inv;           // row - col = m
+        double v;
+        if (m == 0) v = anti ? 0.0 : up;
+        else v = anti ? dirsign * (lo - up) : (up + lo);
+        if (blockIdx.x == 0 && addK) v += addK_scale * addK[m];      // directly summed K^-1 diagonals
+        out[m] = v;
+    }
+}
+
+// out[c][r] = in[r][c]
+__global__ void __launch_bounds__(256)
+transpose_kernel(const double* __restrict__ in, int R, int C, double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        if (r < R && c < C) tile[i][tx] = in[(size_t)r * C + c];
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;
+        if (r < R && c < C) out[(size_t)c * R + r] = tile[tx][i];
+    }
+}
+
+int fft_init() {
+    static int done = -1;
+    if (done >= 0) return done;
+    const int bytes = FFT_MAX_L * (int)sizeof(double2);
+    GPHM_CUDA_OK(cudaFuncSetAttribute(xcorr_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    GPHM_CUDA_OK(cudaFuncSetAttribute(spectrum_to_diag_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done = GPHM_OK;
+    return done;
+}
+
+static int ilog2(int L) { int l = 0; while ((1 << l) < L) ++l; return l; }
+
+int launch_twiddle_init(double* W, int L, cudaStream_t st) {
+    { LaunchScope scope(CAT_FFT, st); twiddle_init_kernel<<<(L / 2 + 255) / 256, 256, 0, st>>>(reinterpret_cast<double2*>(W), L); }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+int launch_xcorr_spectrum(const double* X, const double* Y, int rows, int cols, int ldx, int ldy, int L, const double* W,
+                          double weight, bool accumulate, double* partial, cudaStream_t st) {
+    GPHM_TRY(fft_init());
+    if (L > FFT_MAX_L || L < 2 * cols) { set_last_error("xcorr: L=%d does not fit cols=%d", L, cols); return GPHM_EINVAL; }
+    {
+        LaunchScope scope(CAT_FFT, st, 0.0, 16.0 * rows * (double)cols);
+        xcorr_spectrum_kernel<<<fft_grid(), FFT_THREADS, (size_t)L * sizeof(double2), st>>>(
+            X, Y, rows, cols, ldx, ldy, L, ilog2(L), reinterpret_cast<const double2*>(W), weight, accumulate ? 1 : 0,
+            reinterpret_cast<double2*>(partial));
+    }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+int launch_spectrum_to_diag_sums(const double* partK, const double* partD, int L, const double* W, int n, bool antisym,
+                                 double dirsign, const double* addK, double addK_scale, double* sK, double* sD,
+                                 cudaStream_t st) {
+    GPHM_TRY(fft_init());
+    {
+        LaunchScope scope(CAT_FFT, st);
+        spectrum_to_diag_sums_kernel<<<2, FFT_THREADS, (size_t)L * sizeof(double2), st>>>(
+            reinterpret_cast<const double2*>(partK), reinterpret_cast<const double2*>(partD), fft_grid(), L, ilog2(L),
+            reinterpret_cast<const double2*>(W), n, antisym ? 1 : 0, dirsign, addK, addK_scale, sK, sD);
+    }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+int launch_transpose(const double* in, int R, int C, double* out, cudaStream_t st) {
+    if (R <= 0 || C <= 0) return GPHM_OK;
+    dim3 grid((C + 31) / 32, (R + 31) / 32);
+    { LaunchScope scope(CAT_ELEMWISE, st); transpose_kernel<<<grid, 256, 0, st>>>(in, R, C, out); }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+}  // namespace gphm

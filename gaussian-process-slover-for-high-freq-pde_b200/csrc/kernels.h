@@ -50,6 +50,18 @@ int chol_factor(double* K, double* L, int n, int ld, double* invdiag, double* lo
 int trtri_lower(const double* L, double* Linv, int n, int ld, const double* invdiag, double* T, cudaStream_t st);
 int factor_init();
 
+// ---- fft.cu --------------------------------------------------------------------------------
+int fft_length_for(int n);          // power of two >= 2n, or 0 when it does not fit shared memory
+int fft_grid();                     // CTAs (= partial spectra) used by launch_xcorr_spectrum
+int launch_twiddle_init(double* W, int L, cudaStream_t st);
+// partial[cta][L] (complex) (+)= weight * sum_rows conj(FFT(X row)) * FFT(Y row)
+int launch_xcorr_spectrum(const double* X, const double* Y, int rows, int cols, int ldx, int ldy, int L, const double* W,
+                          double weight, bool accumulate, double* partial, cudaStream_t st);
+int launch_spectrum_to_diag_sums(const double* partK, const double* partD, int L, const double* W, int n, bool antisym,
+                                 double dirsign, const double* addK, double addK_scale, double* sK, double* sD,
+                                 cudaStream_t st);
+int launch_transpose(const double* in, int R, int C, double* out, cudaStream_t st);
+
 // ---- elemwise.cu ---------------------------------------------------------------------------
 struct LossConsts { int dim, eq_type, n1, n2, nb, Q; double llk_weight, logdet, c1; };
 constexpr int kRedBlocks = 592;         // 148 SMs x 4
@@ -61,6 +73,7 @@ int launch_finalize(const LossConsts& c, const double* U, const double* bvals, c
 int launch_grad_u(const LossConsts& c, const double* U, const double* G, const double* W, const double* S1,
                   const double* S2, const double* eb, const int* xind, const double* small, double* gU,
                   double* V1, double* V2, cudaStream_t st);
+// Dbar may be NULL (then only sK is produced)
 int launch_diag_sums(const double* Kbar, const double* Dbar, int n, int ld, bool antisym, double dirsign,
                      double* part, double* sK, double* sD, cudaStream_t st);
 size_t diag_sums_part_doubles(int n);

@@ -62,12 +62,12 @@ LaunchScope::~LaunchScope() {
 }
 
 struct Axis {
-    int n = 0, nblk = 0;
+    int n = 0, nblk = 0, fftL = 0;   // fftL: FFT length of the diagonal-sum path (0 = GEMM path)
     bool toeplitz = false;
     double dirsign = 1.0;
     double *x = nullptr, *K = nullptr, *D = nullptr, *L = nullptr, *Linv = nullptr, *Kinv = nullptr, *Dbar = nullptr,
            *T = nullptr, *invdiag = nullptr, *ldpart = nullptr, *tabK = nullptr, *tabD = nullptr, *dspart = nullptr,
-           *sK = nullptr, *sD = nullptr, *tgpart = nullptr;
+           *sK = nullptr, *sD = nullptr, *sKinv = nullptr, *tgpart = nullptr, *twid = nullptr, *specK = nullptr, *specD = nullptr;
 };
 
 }  // namespace gphm
@@ -134,11 +134,15 @@ size_t carve(gphm_plan& p, void* base) {
         c.take(X.invdiag, (size_t)X.nblk * kNB * kNB);
         c.take(X.ldpart, X.nblk);
         c.take(X.tabK, n); c.take(X.tabD, n);
-        c.take(X.sK, n); c.take(X.sD, n);
+        c.take(X.sK, n); c.take(X.sD, n); c.take(X.sKinv, n);
         const size_t ds = diag_sums_part_doubles((int)n), tg = theta_general_part_doubles((int)n, d.Q);
-        if (p.size_query) { double* dummy; c.take(dummy, std::max(ds, tg)); }
-        else if (X.toeplitz) c.take(X.dspart, ds);
-        else c.take(X.tgpart, tg);
+        const size_t Lq = (size_t)fft_length_for((int)n);
+        const size_t spec = 2 * Lq * fft_grid();              // complex partial spectra, one per CTA
+        if (p.size_query) { double* dummy; c.take(dummy, std::max(ds, tg)); c.take(dummy, Lq); c.take(dummy, spec); c.take(dummy, spec); }
+        else if (X.toeplitz) {
+            c.take(X.dspart, ds);
+            if (X.fftL > 0) { c.take(X.twid, (size_t)X.fftL); c.take(X.specK, 2 * (size_t)X.fftL * fft_grid()); c.take(X.specD, 2 * (size_t)X.fftL * fft_grid()); }
+        } else c.take(X.tgpart, tg);
     }
     c.take(p.src, nf); c.take(p.bvals, d.nb); c.take(p.xind, std::max(d.nb, 1));
     c.take(p.A, nf); c.take(p.Tf, nf); c.take(p.R, nf); c.take(p.P, nf); c.take(p.S1, nf); c.take(p.V1, nf);
@@ -172,10 +176,11 @@ void init_axes(gphm_plan& p, const double* hx, const double* hy) {
         Axis& X = p.ax[a];
         X.nblk = X.n > 0 ? num_blocks_nb(X.n) : 0;
         if (X.n > 0 && h[a]) {
-            X.toeplitz = !p.d.force_general && uniform_grid(h[a], X.n);
+            X.toeplitz = !(p.d.force_general & 1) && uniform_grid(h[a], X.n);
             X.dirsign = (h[a][X.n - 1] >= h[a][0]) ? 1.0 : -1.0;
+            X.fftL = (X.toeplitz && !(p.d.force_general & 2)) ? fft_length_for(X.n) : 0;
         } else {
-            X.toeplitz = !p.d.force_general;   // size query: assume the (larger) general layout below
+            X.toeplitz = !(p.d.force_general & 1);   // size query: assume the (larger) general layout below
         }
     }
 }
@@ -203,7 +208,7 @@ int factor_axis(gphm_plan& p, int a, const double* small, bool with_kinv, cudaSt
         GPHM_TRY(launch_gram_general(p.d.kernel_id, order, X.x, n, X.x, n, th, p.d.Q, p.d.jitter, X.K, X.D, n, st));
     GPHM_TRY(chol_factor(X.K, X.L, n, n, X.invdiag, X.ldpart, p.status + a, st));
     GPHM_TRY(trtri_lower(X.L, X.Linv, n, n, X.invdiag, X.T, st));
-    if (with_kinv)
+    if (with_kinv)     // K^-1 = Linv^T Linv (the FFT diagonal-sum path works on Linv directly and skips this)
         GPHM_TRY(launch_dgemm(gemm_args(X.Linv, n, true, X.Linv, n, false, X.Kinv, n, n, n, n, 1.0, 0.0,
                                         KM_A_UPPER | KM_B_LOWER), st));
     return GPHM_OK;
@@ -236,8 +241,9 @@ int logjoint_grad(gphm_plan& p, const double* U, const double* small, double* gU
     Axis& X1 = p.ax[0];
     Axis& X2 = p.ax[1];
 
-    GPHM_TRY(factor_axis(p, 0, small, !fwd_only, st));
-    if (two) GPHM_TRY(factor_axis(p, 1, small, !fwd_only, st));
+    const bool fft_kinv = (d.force_general & 4) == 0;   // then K^-1 itself is never formed on FFT axes
+    GPHM_TRY(factor_axis(p, 0, small, !fwd_only && !(fft_kinv && X1.fftL > 0), st));
+    if (two) GPHM_TRY(factor_axis(p, 1, small, !fwd_only && !(fft_kinv && X2.fftL > 0), st));
 
     // ---- forward ----
     GPHM_TRY(apply_kinv(p, 0, 0, U, n1, n2, p.A, p.Tf, st));                                   // A = K1^-1 U
@@ -264,28 +270,53 @@ int logjoint_grad(gphm_plan& p, const double* U, const double* small, double* gU
     }
     GPHM_TRY(launch_grad_u(lc, U, G, W, p.S1, two ? p.S2 : nullptr, p.eb, p.xind, small, gU, p.V1,
                            two ? p.V2 : nullptr, st));
-    // Kbar1 = ld/2*N2*K1^-1 - V1 A^T  (in place in Kinv);  Dbar1 = c1 G A^T
-    GPHM_TRY(launch_dgemm(gemm_args(p.V1, n2, false, p.A, n2, true, X1.Kinv, n1, n1, n1, n2, -1.0,
-                                    0.5 * d.logdet * n2), st));
-    GPHM_TRY(launch_dgemm(gemm_args(G, n2, false, p.A, n2, true, X1.Dbar, n1, n1, n1, n2, c1, 0.0), st));
-    if (two) {
-        // Kbar2 = ld/2*N1*K2^-1 - V2^T Bt ;  Dbar2 = G^T Bt
-        GPHM_TRY(launch_dgemm(gemm_args(p.V2, n2, true, Bt, n2, false, X2.Kinv, n2, n2, n2, n1, -1.0,
-                                        0.5 * d.logdet * n1), st));
-        GPHM_TRY(launch_dgemm(gemm_args(G, n2, true, Bt, n2, false, X2.Dbar, n2, n2, n2, n1, 1.0, 0.0), st));
-    }
     const int order = deriv_order(p);
+    // ---- axis 1: Kbar1 = ld/2*N2*K1^-1 - V1 A^T,  Dbar1 = c1 G A^T ----
+    if (X1.fftL > 0) {
+        // uniform grid: only the diagonal sums are needed -> FFT cross-correlations of the columns
+        // (rows after a transpose) instead of the two GEMMs and K1^-1
+        double *V1t = p.P, *At = p.Tf, *Gt = p.S1;            // free scratch at this point
+        GPHM_TRY(launch_transpose(p.V1, n1, n2, V1t, st));
+        GPHM_TRY(launch_transpose(p.A, n1, n2, At, st));
+        GPHM_TRY(launch_transpose(G, n1, n2, Gt, st));
+        const bool fk = (d.force_general & 4) == 0;       // K^-1 sums as FFT autocorrelation of the rows of Linv
+        if (fk) GPHM_TRY(launch_xcorr_spectrum(X1.Linv, X1.Linv, n1, n1, n1, n1, X1.fftL, X1.twid, 0.5 * d.logdet * n2, false, X1.specK, st));
+        else GPHM_TRY(launch_diag_sums(X1.Kinv, nullptr, n1, n1, false, 1.0, X1.dspart, X1.sKinv, nullptr, st));
+        GPHM_TRY(launch_xcorr_spectrum(V1t, At, n2, n1, n1, n1, X1.fftL, X1.twid, -1.0, fk, X1.specK, st));
+        GPHM_TRY(launch_xcorr_spectrum(Gt, At, n2, n1, n1, n1, X1.fftL, X1.twid, c1, false, X1.specD, st));
+        GPHM_TRY(launch_spectrum_to_diag_sums(X1.specK, X1.specD, X1.fftL, X1.twid, n1, order == 1, X1.dirsign,
+                                              fk ? nullptr : X1.sKinv, 0.5 * d.logdet * n2, X1.sK, X1.sD, st));
+    } else {
+        GPHM_TRY(launch_dgemm(gemm_args(p.V1, n2, false, p.A, n2, true, X1.Kinv, n1, n1, n1, n2, -1.0,
+                                        0.5 * d.logdet * n2), st));
+        GPHM_TRY(launch_dgemm(gemm_args(G, n2, false, p.A, n2, true, X1.Dbar, n1, n1, n1, n2, c1, 0.0), st));
+        if (X1.toeplitz) GPHM_TRY(launch_diag_sums(X1.Kinv, X1.Dbar, n1, n1, order == 1, X1.dirsign, X1.dspart, X1.sK, X1.sD, st));
+    }
+    // ---- axis 2: Kbar2 = ld/2*N1*K2^-1 - V2^T Bt,  Dbar2 = G^T Bt ----
+    if (two) {
+        if (X2.fftL > 0) {
+            const bool fk = (d.force_general & 4) == 0;
+            if (fk) GPHM_TRY(launch_xcorr_spectrum(X2.Linv, X2.Linv, n2, n2, n2, n2, X2.fftL, X2.twid, 0.5 * d.logdet * n1, false, X2.specK, st));
+            else GPHM_TRY(launch_diag_sums(X2.Kinv, nullptr, n2, n2, false, 1.0, X2.dspart, X2.sKinv, nullptr, st));
+            GPHM_TRY(launch_xcorr_spectrum(p.V2, Bt, n1, n2, n2, n2, X2.fftL, X2.twid, -1.0, fk, X2.specK, st));
+            GPHM_TRY(launch_xcorr_spectrum(G, Bt, n1, n2, n2, n2, X2.fftL, X2.twid, 1.0, false, X2.specD, st));
+            GPHM_TRY(launch_spectrum_to_diag_sums(X2.specK, X2.specD, X2.fftL, X2.twid, n2, order == 1, X2.dirsign,
+                                                  fk ? nullptr : X2.sKinv, 0.5 * d.logdet * n1, X2.sK, X2.sD, st));
+        } else {
+            GPHM_TRY(launch_dgemm(gemm_args(p.V2, n2, true, Bt, n2, false, X2.Kinv, n2, n2, n2, n1, -1.0,
+                                            0.5 * d.logdet * n1), st));
+            GPHM_TRY(launch_dgemm(gemm_args(G, n2, true, Bt, n2, false, X2.Dbar, n2, n2, n2, n1, 1.0, 0.0), st));
+            if (X2.toeplitz) GPHM_TRY(launch_diag_sums(X2.Kinv, X2.Dbar, n2, n2, order == 1, X2.dirsign, X2.dspart, X2.sK, X2.sD, st));
+        }
+    }
     for (int a = 0; a < (two ? 2 : 1); ++a) {
         Axis& X = p.ax[a];
         const double* th = theta_of(p, small, a);
         double* gth = gsmall + (size_t)a * 3 * Q;
-        if (X.toeplitz) {
-            GPHM_TRY(launch_diag_sums(X.Kinv, X.Dbar, X.n, X.n, order == 1, X.dirsign, X.dspart, X.sK, X.sD, st));
+        if (X.toeplitz)
             GPHM_TRY(launch_theta_grad_toeplitz(d.kernel_id, order, X.x, X.n, th, Q, X.sK, X.sD, gth, st));
-        } else {
-            GPHM_TRY(launch_theta_grad_general(d.kernel_id, order, X.x, X.n, th, Q, X.Kinv, X.Dbar, X.n, X.tgpart,
-                                               gth, st));
-        }
+        else
+            GPHM_TRY(launch_theta_grad_general(d.kernel_id, order, X.x, X.n, th, Q, X.Kinv, X.Dbar, X.n, X.tgpart, gth, st));
     }
     if (!two) GPHM_CUDA_OK(cudaMemsetAsync(gsmall + 3 * Q, 0, sizeof(double) * 3 * Q, st));
     return GPHM_OK;
@@ -432,6 +463,11 @@ int gphm_plan_create(const gphm_problem_desc* desc, const double* h_x, const dou
     if (cudaMemcpy(p->src, h_src, sizeof(double) * nf, cudaMemcpyHostToDevice) != cudaSuccess) return fail("copy src");
     if (desc->nb > 0 && cudaMemcpy(p->bvals, h_bvals, sizeof(double) * desc->nb, cudaMemcpyHostToDevice) != cudaSuccess) return fail("copy bvals");
     if (desc->dim == 1 && desc->nb > 0 && cudaMemcpy(p->xind, h_xind, sizeof(int) * desc->nb, cudaMemcpyHostToDevice) != cudaSuccess) return fail("copy xind");
+    for (int a = 0; a < 2; ++a)
+        if (p->ax[a].fftL > 0) {
+            if (launch_twiddle_init(p->ax[a].twid, p->ax[a].fftL, nullptr) != GPHM_OK) return fail("twiddle init");
+        }
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail("synchronize");
     *out = p;
     return GPHM_OK;
 }

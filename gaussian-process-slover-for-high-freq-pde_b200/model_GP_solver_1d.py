@@ -48,7 +48,7 @@ class GP_solver_1d_single(object):
                                {"poisson_1d": "poisson", "allencahn_1d": "allencahn"}[self.eq_type],
                                self.X_col.reshape(-1), None, self.src_col, self.y, self.Xind, self.llk_weight,
                                float(trick_paras["logdet"]), 1.0, self.jitter, trick_paras["Q"],
-                               force_general=bool(trick_paras.get("force_general", False)))
+                               force_general=int(trick_paras.get("force_general", 0)))
         print("equation is: ", self.trick_paras["equation"])
         print("kernel is:", self.cov_func.__class__.__name__)
 

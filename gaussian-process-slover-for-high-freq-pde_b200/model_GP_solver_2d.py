@@ -58,7 +58,7 @@ class GP_solver_2d_single(object):
         self.core = SolverCore(2, type(self.cov_func).__name__, self._eq_name(), self.X_col[0], self.X_col[1],
                                self.src_vals, self.bvals, None, self.llk_weight, float(trick_paras["logdet"]),
                                self.beta, self.jitter, trick_paras["Q"],
-                               force_general=bool(trick_paras.get("force_general", False)))
+                               force_general=int(trick_paras.get("force_general", 0)))
         print("equation is: ", self.trick_paras["equation"])
         print("kernel is:", self.cov_func.__class__.__name__)
 

@@ -52,7 +52,7 @@ class SolverCore(object):
         d = _lib.ProblemDesc()
         d.dim, d.kernel_id, d.eq_type = dim, _lib.KERNEL_IDS[kernel_name], _lib.EQ_IDS[eq_name]
         d.n1, d.n2, d.Q, d.nb = self.n1, self.n2, self.Q, bvals.size
-        d.force_general = 1 if force_general else 0
+        d.force_general = int(force_general)       # bit 0: general Gram path, bit 1: no FFT diagonal sums
         d.llk_weight, d.logdet, d.beta, d.jitter = float(llk_weight), float(logdet), float(beta), float(jitter)
         self.desc = d
         if dim == 2 and bvals.size != 2 * self.n1 + 2 * self.n2:

@@ -61,7 +61,9 @@ typedef struct gphm_problem_desc {
     int n1, n2;          /* collocation points per axis (n2 = 1 when dim == 1) */
     int Q;               /* mixture components (trick_paras['Q']) */
     int nb;              /* boundary points: 2*n1+2*n2 (2-D) or len(Xind) (1-D) */
-    int force_general;   /* 1: never use the Toeplitz fast path even on uniform grids */
+    int force_general;   /* bit 0: never use the Toeplitz fast path even on uniform grids;
+                            bit 1: Toeplitz Grams, but Kbar/Dbar by GEMM + direct diagonal sums (no FFT);
+                            bit 2: FFT diagonal sums, but K^-1 by GEMM + direct sums              */
     double llk_weight;   /* trick_paras['llk_weight'] */
     double logdet;       /* trick_paras['logdet'] (True -> 1.0) */
     double beta;         /* advection speed, trick_paras['beta'] (ignored otherwise) */
@@ -77,8 +79,9 @@ GPHM_API const char* gphm_last_error(void);
  * gphm_launch_count: kernels launched by this library in this process so far.
  * gphm_profile_start/stop: while enabled every launch is bracketed by CUDA events on its stream;
  * stop synchronises the device and returns, per kernel family (index: 0 Gram builders, 1 DGEMM,
- * 2 Cholesky diagonal-block, 3 reductions/element-wise, 4 Adam), the summed device time in ms,
- * the FLOPs issued (DGEMM only), algorithmic bytes (Gram only) and launch counts (arrays of 5). */
+ * 2 Cholesky diagonal-block, 3 reductions/element-wise, 4 Adam, 5 FFT diagonal sums), the summed
+ * device time in ms, the FLOPs issued (DGEMM only), algorithmic bytes (Gram, FFT) and launch
+ * counts (arrays of 6).                                                                        */
 GPHM_API long long gphm_launch_count(void);
 GPHM_API int gphm_profile_start(void);
 GPHM_API int gphm_profile_stop(double* ms, double* flops, double* bytes, long long* launches);

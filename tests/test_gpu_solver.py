@@ -224,14 +224,16 @@ def test_properties_at_scale(gphm, oracle, N):
         assert float((gch.reshape(-1) - want[path].reshape(-1)).norm()) <= TOL * float(want[path].norm()), path
     loss2, grads2 = model.value_and_grad(s1)
     assert float(loss2) == float(loss) and all(torch.equal(a, b) for (_, a), (_, b) in zip(tree_flatten(grads), tree_flatten(grads2)))
-    tp = trick("poisson_2d-sin_add_cos", "Matern52_Cos_1d", 30, 20.0, N, force_general=True)
-    gen = gphm.GP_solver_2d_single(p.bvals.numpy(), (p.x.numpy(), p.y.numpy()), p.src.numpy(), 1e-6,
-                                   (p.x.numpy()[:5], p.y.numpy()[:5]), np.zeros((5, 5)), tp)
-    assert not gen.core.lib.gphm_plan_uses_toeplitz(gen.core.plan, 0)
-    lg, gg = gen.value_and_grad(s1)
-    assert abs(float(lg) - float(loss)) <= 1e-9 * abs(float(loss))
-    for (path, a), (_, b) in zip(tree_flatten(gg), tree_flatten(grads)):
-        assert float((a - b).norm()) <= 1e-7 * float(b.norm()), path
+    # the theta-gradient paths agree: FFT diagonal sums (default), K^-1 by GEMM (4), GEMM + direct sums (2), general (1)
+    for mode in (4, 2, 1):
+        tp = trick("poisson_2d-sin_add_cos", "Matern52_Cos_1d", 30, 20.0, N, force_general=mode)
+        gen = gphm.GP_solver_2d_single(p.bvals.numpy(), (p.x.numpy(), p.y.numpy()), p.src.numpy(), 1e-6,
+                                       (p.x.numpy()[:5], p.y.numpy()[:5]), np.zeros((5, 5)), tp)
+        assert bool(gen.core.lib.gphm_plan_uses_toeplitz(gen.core.plan, 0)) == (mode != 1)
+        lg, gg = gen.value_and_grad(s1)
+        assert abs(float(lg) - float(loss)) <= 1e-9 * abs(float(loss))
+        for (path, a), (_, b) in zip(tree_flatten(gg), tree_flatten(grads)):
+            assert float((a - b).norm()) <= 1e-7 * float(b.norm()), (mode, path)
     # central difference along dL/dU reproduces |g|^2 (the Poisson loss is quadratic in U)
     gU = grads["U"]
     eps = 1e-3 / float(gU.abs().max())
