@@ -59,6 +59,10 @@ _SIGS = {
     "gphm_mg_grad_u": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
                                c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gphm_mg_theta_grad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gphm_plan_uses_fft": (c_int, [c_void_p, c_int]),
+    "gphm_transpose": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "gphm_mg_theta_grad_fft": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double,
+                                       c_void_p, c_void_p, c_void_p]),
     "gphm_lincomb": (c_int, [c_void_p, c_double, c_void_p, c_double, c_void_p, c_size_t, c_void_p]),
 }
 

@@ -610,9 +610,41 @@ int gphm_rel_l2(const double* d_pred, const double* d_truth, size_t n, double* d
 int gphm_plan_factor(gphm_plan* plan, const double* d_small, int axis_mask, void* stream) {
     if (!plan || !d_small) { set_last_error("gphm_plan_factor: null pointer"); return GPHM_EINVAL; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (axis_mask & 1) GPHM_TRY(factor_axis(*plan, 0, d_small, true, st));
-    if ((axis_mask & 2) && plan->d.dim == 2) GPHM_TRY(factor_axis(*plan, 1, d_small, true, st));
+    const bool kinv = (axis_mask & 4) == 0;
+    if (axis_mask & 1) GPHM_TRY(factor_axis(*plan, 0, d_small, kinv, st));
+    if ((axis_mask & 2) && plan->d.dim == 2) GPHM_TRY(factor_axis(*plan, 1, d_small, kinv, st));
     return GPHM_OK;
+}
+
+int gphm_plan_uses_fft(const gphm_plan* plan, int axis) {
+    if (!plan || axis < 0 || axis > 1) return 0;
+    return plan->ax[axis].n > 0 && plan->ax[axis].fftL > 0 ? 1 : 0;
+}
+
+int gphm_transpose(const double* d_in, int rows, int cols, double* d_out, void* stream) {
+    if (rows <= 0 || cols <= 0) return GPHM_OK;
+    if (!d_in || !d_out) { set_last_error("gphm_transpose: null pointer"); return GPHM_EINVAL; }
+    return launch_transpose(d_in, rows, cols, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int gphm_mg_theta_grad_fft(gphm_plan* plan, int axis, const double* d_X, const double* d_Y, const double* d_G, int rows,
+                           int linv_row0, int linv_row1, double beta, double cD, const double* d_small,
+                           double* d_gtheta, void* stream) {
+    if (!plan || !d_X || !d_Y || !d_G || !d_small || !d_gtheta) { set_last_error("gphm_mg_theta_grad_fft: null pointer"); return GPHM_EINVAL; }
+    if (axis < 0 || axis > 1 || plan->ax[axis].n == 0 || plan->ax[axis].fftL == 0) { set_last_error("gphm_mg_theta_grad_fft: axis %d has no FFT path", axis); return GPHM_EINVAL; }
+    Axis& X = plan->ax[axis];
+    const int n = X.n;
+    if (rows < 0 || linv_row0 < 0 || linv_row1 > n || linv_row0 > linv_row1) { set_last_error("gphm_mg_theta_grad_fft: bad row range"); return GPHM_EINVAL; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int order = deriv_order(*plan);
+    // rows == 0 / empty Linv range still have to define the spectra: weight 0 passes over row 0 of Linv
+    GPHM_TRY(launch_xcorr_spectrum(X.Linv + (size_t)linv_row0 * n, X.Linv + (size_t)linv_row0 * n, linv_row1 - linv_row0, n, n, n,
+                                   X.fftL, X.twid, beta, false, X.specK, st));
+    GPHM_TRY(launch_xcorr_spectrum(d_X, d_Y, rows, n, n, n, X.fftL, X.twid, -1.0, true, X.specK, st));
+    GPHM_TRY(launch_xcorr_spectrum(d_G, d_Y, rows, n, n, n, X.fftL, X.twid, cD, false, X.specD, st));
+    GPHM_TRY(launch_spectrum_to_diag_sums(X.specK, X.specD, X.fftL, X.twid, n, order == 1, X.dirsign, nullptr, 0.0, X.sK, X.sD, st));
+    return launch_theta_grad_toeplitz(plan->d.kernel_id, order, X.x, n, theta_of(*plan, d_small, axis), plan->d.Q, X.sK, X.sD,
+                                      d_gtheta, st);
 }
 
 int gphm_apply_kinv(gphm_plan* plan, int axis, int side, const double* d_X, int rows, int cols, double* d_out,

@@ -116,6 +116,20 @@ class CudaOps(object):
         _lib.check(self.lib.gphm_mg_theta_grad(self.plan, axis, _lib.ptr(Kbar), _lib.ptr(Dbar), _lib.ptr(small),
                                                _lib.ptr(out), self._s()), "gphm_mg_theta_grad")
 
+    def uses_fft(self, axis):
+        return bool(self.lib.gphm_plan_uses_fft(self.plan, axis))
+
+    def transpose(self, X, tag):
+        out = self._buf(tag, (X.shape[1], X.shape[0]))
+        _lib.check(self.lib.gphm_transpose(_lib.ptr(X), X.shape[0], X.shape[1], _lib.ptr(out), self._s()), "gphm_transpose")
+        return out
+
+    def theta_grad_rows(self, axis, X, Y, G, r0, r1, beta, cD, small, out):
+        """theta-gradient of  beta*Linv[r0:r1]^T Linv[r0:r1] - X^T Y  and  cD*G^T Y  via FFT diagonal sums."""
+        _lib.check(self.lib.gphm_mg_theta_grad_fft(self.plan, axis, _lib.ptr(X), _lib.ptr(Y), _lib.ptr(G), X.shape[0], r0, r1,
+                                                   float(beta), float(cD), _lib.ptr(small), _lib.ptr(out), self._s()),
+                   "gphm_mg_theta_grad_fft")
+
     def adam(self, p, g, m, v, count, lr):
         _lib.check(self.lib.gphm_adam_update(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), p.numel(), _lib.ptr(count),
                                              float(lr), self._s()), "gphm_adam_update")
@@ -236,14 +250,36 @@ class ShardedSolver2D(object):
             dist.all_reduce(t, group=self.group)
         return t
 
+    # ---- factorisation: the two axes are independent, so rank halves take one axis each ----------
+    def _factor(self, small, skip_kinv):
+        """Gram + Cholesky + L^-1 (+ K^-1) of both axes on every rank; returns [log|K1|, log|K2|].
+        With P >= 2 ranks [0, P/2) factor axis 1 and ranks [P/2, P) axis 2, then each axis' D, Linv
+        (and K^-1 when needed) is broadcast from the first rank of its half."""
+        o = self.ops
+        skip = 4 if skip_kinv else 0
+        if self.P == 1:
+            o.factor(small, 3 | skip)
+            return o.logdets()
+        half = self.P // 2
+        mine = 0 if self.rank < half else 1
+        o.factor(small, (1 << mine) | skip)
+        ld = o.logdets().clone()
+        for axis, root in ((0, 0), (1, half)):
+            src = dist.get_global_rank(self.group, root) if self.group is not None else root
+            for which in ((1, 2) if skip_kinv else (1, 2, 0)):
+                dist.broadcast(o.mat(axis, which), src=src, group=self.group)
+            dist.broadcast(ld[axis:axis + 1], src=src, group=self.group)
+        return ld
+
     # ---- one iteration ---------------------------------------------------------------------------
     def value_and_grad(self):
         """Collective.  Returns (terms[8], gU_r (h,N2), gsmall (6Q+2)) - same layout as gphm_logjoint_grad."""
         o, Q, c1 = self.ops, self.Q, self.c1
         N1, N2, h, w = self.N1, self.N2, self.h, self.w
         small, U_r = self.small, self.U
-        o.factor(small, 3)
-        D1, D2, Kinv1, Kinv2 = o.mat(0, 1), o.mat(1, 1), o.mat(0, 0), o.mat(1, 0)
+        fft1, fft2 = o.uses_fft(0), o.uses_fft(1)
+        ld = self._factor(small, fft1 and fft2)
+        D1, D2 = o.mat(0, 1), o.mat(1, 1)
         # forward
         Bt_r = o.apply_kinv(1, 1, U_r, "Bt_r")                           # U K2^-1            (R)
         U_c = self.r2c(U_r)
@@ -259,7 +295,6 @@ class ShardedSolver2D(object):
         red[2:3] = bg
         self._allreduce(red)
         eq, quad, bgap = red[0], red[1], red[2]
-        ld = o.logdets()
         tau, v = small[6 * Q], small[6 * Q + 1]
         loss = (0.5 * self.logdet * (N2 * ld[0] + N1 * ld[1]) + 0.5 * quad
                 - self.llk_weight * (0.5 * self.Nb * tau - 0.5 * torch.exp(tau) * bgap)
@@ -275,20 +310,31 @@ class ShardedSolver2D(object):
         S1_c = o.apply_kinv(0, 0, P_c, "S1_c")
         V1_c = o.lincomb(1.0, S1_c, 0.5, W_c, "V1_c")
         lead = 1.0 if self.rank == 0 else 0.0                            # the K^-1 (log-det) term is added once
-        o.gemm(V1_c, A_c, False, True, -1.0, lead * 0.5 * self.logdet * N2, Kinv1)          # Kbar1 partial
-        Dbar1 = o.gemm(G_c, A_c, False, True, c1, 0.0, o.new("Dbar1", (N1, N1)))
         gs = self.gsmall
         gs.zero_()
-        o.theta_grad(0, Kinv1, Dbar1, small, gs[0:3 * Q])
+        if fft1:      # uniform grid: diagonal sums by FFT over this rank's columns; Linv rows are split over ranks
+            r0, r1 = self.rank * N1 // self.P, (self.rank + 1) * N1 // self.P
+            o.theta_grad_rows(0, o.transpose(V1_c, "V1t"), o.transpose(A_c, "At"), o.transpose(G_c, "Gt"), r0, r1,
+                              0.5 * self.logdet * N2, c1, small, gs[0:3 * Q])
+        else:
+            Kinv1 = o.mat(0, 0)
+            o.gemm(V1_c, A_c, False, True, -1.0, lead * 0.5 * self.logdet * N2, Kinv1)      # Kbar1 partial
+            Dbar1 = o.gemm(G_c, A_c, False, True, c1, 0.0, o.new("Dbar1", (N1, N1)))
+            o.theta_grad(0, Kinv1, Dbar1, small, gs[0:3 * Q])
         # axis-2 work in R layout
         P_r = o.gemm(G_r, D2, False, False, 1.0, 0.0, o.new("P_r", (h, N2)))
         S2_r = o.apply_kinv(1, 1, P_r, "S2_r")
         W_r = self.c2r(W_c)
         S1_r = self.c2r(S1_c)
         gU_r, V2_r = o.grad_u(U_r, G_r, W_r, S1_r, S2_r, self.bidx, eb, self.nseg0, small)
-        o.gemm(V2_r, Bt_r, True, False, -1.0, lead * 0.5 * self.logdet * N1, Kinv2)         # Kbar2 partial
-        Dbar2 = o.gemm(G_r, Bt_r, True, False, 1.0, 0.0, o.new("Dbar2", (N2, N2)))
-        o.theta_grad(1, Kinv2, Dbar2, small, gs[3 * Q:6 * Q])
+        if fft2:
+            r0, r1 = self.rank * N2 // self.P, (self.rank + 1) * N2 // self.P
+            o.theta_grad_rows(1, V2_r, Bt_r, G_r, r0, r1, 0.5 * self.logdet * N1, 1.0, small, gs[3 * Q:6 * Q])
+        else:
+            Kinv2 = o.mat(1, 0)
+            o.gemm(V2_r, Bt_r, True, False, -1.0, lead * 0.5 * self.logdet * N1, Kinv2)     # Kbar2 partial
+            Dbar2 = o.gemm(G_r, Bt_r, True, False, 1.0, 0.0, o.new("Dbar2", (N2, N2)))
+            o.theta_grad(1, Kinv2, Dbar2, small, gs[3 * Q:6 * Q])
         self._allreduce(gs)
         gs[6 * Q] = gtau
         gs[6 * Q + 1] = gv

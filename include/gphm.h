@@ -190,6 +190,16 @@ GPHM_API int gphm_mg_grad_u(gphm_plan* plan, const double* d_U, const double* d_
                    const double* d_small, double* d_gU, double* d_V2, void* stream);
 GPHM_API int gphm_mg_theta_grad(gphm_plan* plan, int axis, const double* d_Kbar, const double* d_Dbar, const double* d_small,
                        double* d_gtheta, void* stream);
+/* Uniform-grid variant of the rank-local theta-gradient that never forms Kbar/Dbar: d_X, d_Y, d_G
+ * are `rows` x n_axis row-major blocks whose rows are the sequences to correlate (axis 2: rows of
+ * V2, Bt, G; axis 1: rows of V1^T, A^T, G^T), i.e. Kbar = beta*Linv[r0:r1]^T Linv[r0:r1] - X^T Y and
+ * Dbar = cD * G^T Y.  Needs gphm_plan_uses_fft(plan, axis).  gphm_plan_factor: axis_mask bit 2
+ * skips forming K^-1 (not needed on this path).                                                 */
+GPHM_API int gphm_plan_uses_fft(const gphm_plan* plan, int axis);
+GPHM_API int gphm_transpose(const double* d_in, int rows, int cols, double* d_out, void* stream);
+GPHM_API int gphm_mg_theta_grad_fft(gphm_plan* plan, int axis, const double* d_X, const double* d_Y, const double* d_G, int rows,
+                           int linv_row0, int linv_row1, double beta, double cD, const double* d_small,
+                           double* d_gtheta, void* stream);
 /* d_out = a*d_x + b*d_y (d_y may be NULL).                                                      */
 GPHM_API int gphm_lincomb(double* d_out, double a, const double* d_x, double b, const double* d_y, size_t n, void* stream);
 

@@ -35,12 +35,18 @@ class CpuOps(object):
 
     def factor(self, small, axis_mask=3):
         for a, xs in enumerate((self.x, self.y)):
+            n = xs.numel()
+            for which in (0, 1, 2, 3):               # persistent buffers: broadcasts write into them in place
+                self.m.setdefault((a, which), torch.zeros(n, n, dtype=DT))
             if not (axis_mask >> a) & 1:
                 continue
             K, D = O._gram_pair(self.kernel, xs, self._theta(small, a), self.order, self.jitter)
             L = torch.linalg.cholesky(K)
-            self.m[(a, 3)], self.m[(a, 1)] = L, D
-            self.m[(a, 0)] = torch.cholesky_inverse(L)
+            self.m[(a, 3)].copy_(L)
+            self.m[(a, 1)].copy_(D)
+            self.m[(a, 2)].copy_(torch.linalg.solve_triangular(L, torch.eye(n, dtype=DT), upper=False))
+            if not axis_mask & 4:
+                self.m[(a, 0)].copy_(torch.cholesky_inverse(L))
             self.ld[a] = 2.0 * torch.log(torch.diagonal(L)).sum()
 
     def mat(self, axis, which):
@@ -50,10 +56,20 @@ class CpuOps(object):
         return self.ld.clone()
 
     def apply_kinv(self, axis, side, X, tag):
-        L = self.m[(axis, 3)]
+        Li = self.m[(axis, 2)]                        # like the product: two triangular products with L^-1
         if side == 0:
-            return torch.cholesky_solve(X, L)
-        return torch.cholesky_solve(X.T.contiguous(), L).T.contiguous()
+            return Li.T @ (Li @ X)
+        return (X @ Li.T) @ Li
+
+    def uses_fft(self, axis):
+        return O.is_uniform(self.x if axis == 0 else self.y)
+
+    def transpose(self, X, tag):
+        return X.T.contiguous()
+
+    def theta_grad_rows(self, axis, X, Y, G, r0, r1, beta, cD, small, out):
+        Li = self.m[(axis, 2)][r0:r1]
+        self.theta_grad(axis, beta * (Li.T @ Li) - X.T @ Y, cD * (G.T @ Y), small, out)
 
     def gemm(self, A, B, tA, tB, alpha, beta, C):
         prod = (A.T if tA else A) @ (B.T if tB else B)
