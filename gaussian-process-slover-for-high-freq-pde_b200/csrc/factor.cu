@@ -39,7 +39,10 @@ static_assert(kNB == 4 * SB, "the diagonal-block kernel is written for 4x4 sub-b
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 chol_diag_kernel(const double* __restrict__ Kbb, double* __restrict__ Lbb, int ld, int nb,
                  double* __restrict__ invd, double* __restrict__ logdet_part, int* __restrict__ status,
-                 int pivot_base) {
+                 int pivot_base, long long sK, long long sL, long long sInv, long long sLd, long long sStatus) {
+    // blockIdx.x selects the system (the two axes are factored side by side when N1 == N2)
+    Kbb += blockIdx.x * sK; Lbb += blockIdx.x * sL; invd += blockIdx.x * sInv;
+    logdet_part += blockIdx.x * sLd; status += blockIdx.x * sStatus;
     extern __shared__ double sm[];
     double* S = sm;                          // kNB x SLD
     double* T = S + kNB * SLD;               // SB x SLD scratch (one block row of the inverse)
@@ -189,28 +192,40 @@ int factor_init() {
     return done;
 }
 
-int chol_factor(double* K, double* L, int n, int ld, double* invdiag, double* logdet_part, int* status,
-                cudaStream_t st) {
+// nsys = 1: one system.  nsys = 2: a second system of the same size at the given element offsets
+// (K2 - K, L2 - L, ...) is factored side by side: every launch carries both, which halves the
+// serial latency chain of the 2-D step when N1 == N2.
+int chol_factor_multi(double* K, double* L, int n, int ld, double* invdiag, double* logdet_part, int* status, int nsys,
+                      long long sK, long long sL, long long sInv, long long sLd, long long sStatus, cudaStream_t st) {
     GPHM_TRY(factor_init());
     const int nblk = num_blocks_nb(n);
     for (int b = 0; b < nblk; ++b) {
         const int j0 = b * kNB, nb = std::min(kNB, n - j0);
         { LaunchScope scope(CAT_CHOL_DIAG, st);
-        chol_diag_kernel<<<1, DIAG_THREADS, kDiagSmem, st>>>(K + (size_t)j0 * ld + j0, L + (size_t)j0 * ld + j0, ld, nb,
-                                                             invdiag + (size_t)b * kNB * kNB, logdet_part + b, status, j0); }
+        chol_diag_kernel<<<nsys, DIAG_THREADS, kDiagSmem, st>>>(K + (size_t)j0 * ld + j0, L + (size_t)j0 * ld + j0, ld, nb,
+                                                             invdiag + (size_t)b * kNB * kNB, logdet_part + b, status, j0,
+                                                             sK, sL, sInv, sLd, sStatus); }
         GPHM_LAUNCH_OK();
         const int rem = n - j0 - nb;
         if (rem <= 0) break;
         const double* Kpan = K + (size_t)(j0 + nb) * ld + j0;
         double* Lpan = L + (size_t)(j0 + nb) * ld + j0;
         // panel: L[i,b] = K[i,b] * inv(L_bb)^T
-        GPHM_TRY(launch_dgemm(gemm_args(Kpan, ld, false, invdiag + (size_t)b * kNB * kNB, kNB, true, Lpan, ld,
-                                        rem, nb, nb, 1.0, 0.0, 0), st));
+        GemmArgs g1 = gemm_args(Kpan, ld, false, invdiag + (size_t)b * kNB * kNB, kNB, true, Lpan, ld, rem, nb, nb, 1.0, 0.0, 0);
+        g1.batch = nsys; g1.sA = sK; g1.sB = sInv; g1.sC = sL;
+        GPHM_TRY(launch_dgemm(g1, st));
         // trailing update (lower tiles): K22 -= L[:,b] L[:,b]^T
-        GPHM_TRY(launch_dgemm(gemm_args(Lpan, ld, false, Lpan, ld, true, K + (size_t)(j0 + nb) * ld + j0 + nb, ld,
-                                        rem, rem, nb, -1.0, 1.0, KM_C_LOWER), st));
+        GemmArgs g2 = gemm_args(Lpan, ld, false, Lpan, ld, true, K + (size_t)(j0 + nb) * ld + j0 + nb, ld, rem, rem, nb, -1.0, 1.0,
+                                KM_C_LOWER);
+        g2.batch = nsys; g2.sA = sL; g2.sB = sL; g2.sC = sK;
+        GPHM_TRY(launch_dgemm(g2, st));
     }
     return GPHM_OK;
+}
+
+int chol_factor(double* K, double* L, int n, int ld, double* invdiag, double* logdet_part, int* status,
+                cudaStream_t st) {
+    return chol_factor_multi(K, L, n, ld, invdiag, logdet_part, status, 1, 0, 0, 0, 0, 0, st);
 }
 
 int trtri_lower(const double* L, double* Linv, int n, int ld, const double* invdiag, double* T, cudaStream_t st) {

@@ -32,12 +32,18 @@ int fft_length_for(int n) {                            // smallest power of two 
 }
 int fft_grid() { return kNumSMs; }
 
-__global__ void twiddle_init_kernel(double2* __restrict__ W, int L) {
+// Per-stage compact twiddle tables: stage s (butterfly span L >> (s+1)) reads
+//   W[(L - (L >> s)) + j] = exp(-2 pi i (j << s) / L),  j < L >> (s+1)
+// so a warp's loads are contiguous (a single strided table cost 4x the FFT time in L1 gathers).
+__global__ void twiddle_init_kernel(double2* __restrict__ W, int L, int logL) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= L / 2) return;
-    double s, c;
-    sincospi(2.0 * (double)t / (double)L, &s, &c);
-    W[t] = make_double2(c, -s);                        // exp(-2 pi i t / L)
+    if (t >= L - 1) return;
+    int s = 0, off = 0;
+    while (t >= off + (L >> (s + 1))) { off += L >> (s + 1); ++s; }
+    const int j = t - off;
+    double sn, cs;
+    sincospi(2.0 * (double)((long long)j << s) / (double)L, &sn, &cs);
+    W[t] = make_double2(cs, -sn);
 }
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -89,12 +95,13 @@ xcorr_spectrum_kernel(const double* __restrict__ X, const double* __restrict__ Y
         __syncthreads();
         for (int s = 0; s < logL; ++s) {               // radix-2 DIF, natural in -> bit-reversed out
             const int sh = logL - 1 - s, half = 1 << sh;
+            const double2* __restrict__ Ws = W + (L - (L >> s));
             for (int b = tid; b < L / 2; b += FFT_THREADS) {
                 const int j = b & (half - 1);
                 const int i0 = ((b >> sh) << (sh + 1)) + j, i1 = i0 + half;
                 const double2 a = xs[i0], c = xs[i1];
                 xs[i0] = make_double2(a.x + c.x, a.y + c.y);
-                xs[i1] = cmul(make_double2(a.x - c.x, a.y - c.y), W[(size_t)j << s]);
+                xs[i1] = cmul(make_double2(a.x - c.x, a.y - c.y), Ws[j]);
             }
             __syncthreads();
         }
@@ -143,10 +150,11 @@ spectrum_to_diag_sums_kernel(const double2* __restrict__ partK, const double2* _
     __syncthreads();
     for (int s = 0; s < logL; ++s) {                   // radix-2 DIT inverse, bit-reversed in -> natural out
         const int half = 1 << s;
+        const double2* __restrict__ Ws = W + (L - (2 << s));       // table of forward stage logL-1-s
         for (int b = tid; b < L / 2; b += FFT_THREADS) {
             const int j = b & (half - 1);
             const int i0 = ((b >> s) << (s + 1)) + j, i1 = i0 + half;
-            const double2 w = W[(size_t)j << (logL - 1 - s)];
+            const double2 w = Ws[j];
             const double2 t = cmul(xs[i1], make_double2(w.x, -w.y));
             const double2 a = xs[i0];
             xs[i0] = make_double2(a.x + t.x, a.y + t.y);
@@ -185,6 +193,8 @@ transpose_kernel(const double* __restrict__ in, int R, int C, double* __restrict
     }
 }
 
+static int ilog2(int L) { int l = 0; while ((1 << l) < L) ++l; return l; }
+
 int fft_init() {
     static int done = -1;
     if (done >= 0) return done;
@@ -195,10 +205,8 @@ int fft_init() {
     return done;
 }
 
-static int ilog2(int L) { int l = 0; while ((1 << l) < L) ++l; return l; }
-
 int launch_twiddle_init(double* W, int L, cudaStream_t st) {
-    { LaunchScope scope(CAT_FFT, st); twiddle_init_kernel<<<(L / 2 + 255) / 256, 256, 0, st>>>(reinterpret_cast<double2*>(W), L); }
+    { LaunchScope scope(CAT_FFT, st); twiddle_init_kernel<<<(L + 255) / 256, 256, 0, st>>>(reinterpret_cast<double2*>(W), L, ilog2(L)); }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }

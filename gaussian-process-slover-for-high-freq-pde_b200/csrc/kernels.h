@@ -46,6 +46,8 @@ inline int num_blocks_nb(int n) { return (n + kNB - 1) / kNB; }
 // of the first non-positive pivot (0 if SPD).
 int chol_factor(double* K, double* L, int n, int ld, double* invdiag, double* logdet_part, int* status,
                 cudaStream_t st);
+int chol_factor_multi(double* K, double* L, int n, int ld, double* invdiag, double* logdet_part, int* status, int nsys,
+                      long long sK, long long sL, long long sInv, long long sLd, long long sStatus, cudaStream_t st);
 // Linv (n x n, ld; strictly-upper triangle must already be zero) = L^-1, T = n x n scratch.
 int trtri_lower(const double* L, double* Linv, int n, int ld, const double* invdiag, double* T, cudaStream_t st);
 int factor_init();

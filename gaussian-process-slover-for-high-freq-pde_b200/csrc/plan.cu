@@ -138,10 +138,10 @@ size_t carve(gphm_plan& p, void* base) {
         const size_t ds = diag_sums_part_doubles((int)n), tg = theta_general_part_doubles((int)n, d.Q);
         const size_t Lq = (size_t)fft_length_for((int)n);
         const size_t spec = 2 * Lq * fft_grid();              // complex partial spectra, one per CTA
-        if (p.size_query) { double* dummy; c.take(dummy, std::max(ds, tg)); c.take(dummy, Lq); c.take(dummy, spec); c.take(dummy, spec); }
+        if (p.size_query) { double* dummy; c.take(dummy, std::max(ds, tg)); c.take(dummy, 2 * Lq); c.take(dummy, spec); c.take(dummy, spec); }
         else if (X.toeplitz) {
             c.take(X.dspart, ds);
-            if (X.fftL > 0) { c.take(X.twid, (size_t)X.fftL); c.take(X.specK, 2 * (size_t)X.fftL * fft_grid()); c.take(X.specD, 2 * (size_t)X.fftL * fft_grid()); }
+            if (X.fftL > 0) { c.take(X.twid, 2 * (size_t)X.fftL); c.take(X.specK, 2 * (size_t)X.fftL * fft_grid()); c.take(X.specD, 2 * (size_t)X.fftL * fft_grid()); }
         } else c.take(X.tgpart, tg);
     }
     c.take(p.src, nf); c.take(p.bvals, d.nb); c.take(p.xind, std::max(d.nb, 1));
@@ -196,22 +196,50 @@ LossConsts loss_consts(const gphm_plan& p) {
     return c;
 }
 
-// Gram + Cholesky + L^-1 (+ K^-1) for one axis.
-int factor_axis(gphm_plan& p, int a, const double* small, bool with_kinv, cudaStream_t st) {
+// Gram matrices of one axis.
+int gram_axis(gphm_plan& p, int a, const double* small, cudaStream_t st) {
     Axis& X = p.ax[a];
     const double* th = theta_of(p, small, a);
     const int n = X.n, order = deriv_order(p);
     if (X.toeplitz)
-        GPHM_TRY(launch_gram_toeplitz(p.d.kernel_id, order, X.x, n, th, p.d.Q, p.d.jitter, X.dirsign, X.tabK, X.tabD,
-                                      X.K, X.D, n, st));
-    else
-        GPHM_TRY(launch_gram_general(p.d.kernel_id, order, X.x, n, X.x, n, th, p.d.Q, p.d.jitter, X.K, X.D, n, st));
-    GPHM_TRY(chol_factor(X.K, X.L, n, n, X.invdiag, X.ldpart, p.status + a, st));
+        return launch_gram_toeplitz(p.d.kernel_id, order, X.x, n, th, p.d.Q, p.d.jitter, X.dirsign, X.tabK, X.tabD,
+                                    X.K, X.D, n, st);
+    return launch_gram_general(p.d.kernel_id, order, X.x, n, X.x, n, th, p.d.Q, p.d.jitter, X.K, X.D, n, st);
+}
+
+// L^-1 (+ K^-1 = Linv^T Linv; the FFT diagonal-sum path works on Linv directly and skips it)
+int invert_axis(gphm_plan& p, int a, bool with_kinv, cudaStream_t st) {
+    Axis& X = p.ax[a];
+    const int n = X.n;
     GPHM_TRY(trtri_lower(X.L, X.Linv, n, n, X.invdiag, X.T, st));
-    if (with_kinv)     // K^-1 = Linv^T Linv (the FFT diagonal-sum path works on Linv directly and skips this)
+    if (with_kinv)
         GPHM_TRY(launch_dgemm(gemm_args(X.Linv, n, true, X.Linv, n, false, X.Kinv, n, n, n, n, 1.0, 0.0,
                                         KM_A_UPPER | KM_B_LOWER), st));
     return GPHM_OK;
+}
+
+// Gram + Cholesky + L^-1 (+ K^-1) for one axis.
+int factor_axis(gphm_plan& p, int a, const double* small, bool with_kinv, cudaStream_t st) {
+    Axis& X = p.ax[a];
+    GPHM_TRY(gram_axis(p, a, small, st));
+    GPHM_TRY(chol_factor(X.K, X.L, X.n, X.n, X.invdiag, X.ldpart, p.status + a, st));
+    return invert_axis(p, a, with_kinv, st);
+}
+
+// Both axes of a 2-D problem.  Equal sizes: the two Cholesky chains share every launch.
+int factor_both(gphm_plan& p, const double* small, bool kinv0, bool kinv1, cudaStream_t st) {
+    Axis& X0 = p.ax[0];
+    Axis& X1 = p.ax[1];
+    if (X0.n != X1.n) {
+        GPHM_TRY(factor_axis(p, 0, small, kinv0, st));
+        return factor_axis(p, 1, small, kinv1, st);
+    }
+    GPHM_TRY(gram_axis(p, 0, small, st));
+    GPHM_TRY(gram_axis(p, 1, small, st));
+    GPHM_TRY(chol_factor_multi(X0.K, X0.L, X0.n, X0.n, X0.invdiag, X0.ldpart, p.status, 2, X1.K - X0.K, X1.L - X0.L,
+                               X1.invdiag - X0.invdiag, X1.ldpart - X0.ldpart, 1, st));
+    GPHM_TRY(invert_axis(p, 0, kinv0, st));
+    return invert_axis(p, 1, kinv1, st);
 }
 
 // out = K_a^-1 X (side 0, X is n x cols) or X K_a^-1 (side 1, X is rows x n); tmp has X's shape.
@@ -242,8 +270,9 @@ int logjoint_grad(gphm_plan& p, const double* U, const double* small, double* gU
     Axis& X2 = p.ax[1];
 
     const bool fft_kinv = (d.force_general & 4) == 0;   // then K^-1 itself is never formed on FFT axes
-    GPHM_TRY(factor_axis(p, 0, small, !fwd_only && !(fft_kinv && X1.fftL > 0), st));
-    if (two) GPHM_TRY(factor_axis(p, 1, small, !fwd_only && !(fft_kinv && X2.fftL > 0), st));
+    const bool kinv0 = !fwd_only && !(fft_kinv && X1.fftL > 0), kinv1 = !fwd_only && !(fft_kinv && X2.fftL > 0);
+    if (two) GPHM_TRY(factor_both(p, small, kinv0, kinv1, st));
+    else GPHM_TRY(factor_axis(p, 0, small, kinv0, st));
 
     // ---- forward ----
     GPHM_TRY(apply_kinv(p, 0, 0, U, n1, n2, p.A, p.Tf, st));                                   // A = K1^-1 U
@@ -584,8 +613,8 @@ int gphm_predict(gphm_plan* plan, const double* d_U, const double* d_small, cons
     double *Kmn1, *M1, *M1t, *M1K, *Kmn2 = nullptr;
     c.take(Kmn1, (size_t)m1 * n1); c.take(M1, (size_t)m1 * n2); c.take(M1t, (size_t)m1 * n2); c.take(M1K, (size_t)m1 * n2);
     if (two) c.take(Kmn2, (size_t)m2 * n2);
-    GPHM_TRY(factor_axis(p, 0, d_small, false, st));
-    if (two) GPHM_TRY(factor_axis(p, 1, d_small, false, st));
+    if (two) GPHM_TRY(factor_both(p, d_small, false, false, st));
+    else GPHM_TRY(factor_axis(p, 0, d_small, false, st));
     GPHM_TRY(apply_kinv(p, 0, 0, d_U, n1, n2, p.A, p.Tf, st));
     GPHM_TRY(launch_gram_general(p.d.kernel_id, 0, d_xt, m1, p.ax[0].x, n1, theta_of(p, d_small, 0), Q, 0.0, Kmn1,
                                  nullptr, n1, st));
@@ -611,6 +640,7 @@ int gphm_plan_factor(gphm_plan* plan, const double* d_small, int axis_mask, void
     if (!plan || !d_small) { set_last_error("gphm_plan_factor: null pointer"); return GPHM_EINVAL; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool kinv = (axis_mask & 4) == 0;
+    if ((axis_mask & 3) == 3 && plan->d.dim == 2) return factor_both(*plan, d_small, kinv, kinv, st);
     if (axis_mask & 1) GPHM_TRY(factor_axis(*plan, 0, d_small, kinv, st));
     if ((axis_mask & 2) && plan->d.dim == 2) GPHM_TRY(factor_axis(*plan, 1, d_small, kinv, st));
     return GPHM_OK;
