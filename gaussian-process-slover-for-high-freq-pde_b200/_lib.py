@@ -41,6 +41,7 @@ _SIGS = {
     "gphm_plan_destroy": (None, [c_void_p]),
     "gphm_plan_status": (c_int, [c_void_p, POINTER(c_int), c_void_p]),
     "gphm_plan_uses_toeplitz": (c_int, [c_void_p, c_int]),
+    "gphm_plan_set_base_field": (c_int, [c_void_p, c_void_p]),
     "gphm_logjoint_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "gphm_adam_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_double, c_void_p]),
     "gphm_step": (c_int, [c_void_p] * 8 + [c_double, c_void_p, c_void_p]),

@@ -22,14 +22,13 @@ namespace gphm {
 __global__ void __launch_bounds__(256)
 residual_kernel(double* __restrict__ R, const double* __restrict__ U, const double* __restrict__ F,
                 const double* __restrict__ A, const double* __restrict__ Bt, size_t n, int allencahn,
-                const double* __restrict__ small, int Q, double* __restrict__ part) {
+                const double* __restrict__ base, const double* __restrict__ small, int Q, double* __restrict__ part) {
     __shared__ double red[33];
     const double ev = exp(small[6 * Q + 1]);
     double e = 0.0, q = 0.0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const double u = U[i];
         double r = R[i] - F[i];
-        if (allencahn) r += u * (u * u - 1.0);
+        if (allencahn) { const double u = U[i] + (base ? base[i] : 0.0); r += u * (u * u - 1.0); }
         e += r * r;
         q += A[i] * Bt[i];
         R[i] = ev * r;
@@ -40,8 +39,8 @@ residual_kernel(double* __restrict__ R, const double* __restrict__ U, const doub
 }
 
 int launch_residual(double* R, const double* U, const double* F, const double* A, const double* Bt, size_t n,
-                    int eq_type, const double* small, int Q, double* part, cudaStream_t st) {
-    { LaunchScope scope(CAT_ELEMWISE, st); residual_kernel<<<kRedBlocks, 256, 0, st>>>(R, U, F, A, Bt, n, eq_type == 1, small, Q, part); }
+                    int eq_type, const double* base, const double* small, int Q, double* part, cudaStream_t st) {
+    { LaunchScope scope(CAT_ELEMWISE, st); residual_kernel<<<kRedBlocks, 256, 0, st>>>(R, U, F, A, Bt, n, eq_type == 1, base, small, Q, part); }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }
@@ -111,14 +110,14 @@ int launch_finalize(const LossConsts& c, const double* U, const double* bvals, c
 // dL/dU = W + S1 + S2 [+ G*(3U^2-1)] + lambda*e^{tau}*E_b ;  V1 = S1 + W/2, V2 = S2 + W/2
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-grad_u_kernel(size_t n, int allencahn, const double* __restrict__ U, const double* __restrict__ G,
+grad_u_kernel(size_t n, int allencahn, const double* __restrict__ base, const double* __restrict__ U, const double* __restrict__ G,
               const double* __restrict__ W, const double* __restrict__ S1, const double* __restrict__ S2,
               double* __restrict__ gU, double* __restrict__ V1, double* __restrict__ V2) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const double w = W[i], s1 = S1[i];
         const double s2 = S2 ? S2[i] : 0.0;
         double g = w + s1 + s2;
-        if (allencahn) { const double u = U[i]; g += G[i] * (3.0 * u * u - 1.0); }
+        if (allencahn) { const double u = U[i] + (base ? base[i] : 0.0); g += G[i] * (3.0 * u * u - 1.0); }
         gU[i] = g;
         if (V1) V1[i] = s1 + 0.5 * w;
         if (V2) V2[i] = s2 + 0.5 * w;
@@ -144,11 +143,11 @@ boundary_scatter_kernel(LossConsts c, const double* __restrict__ eb, const int* 
     }
 }
 
-int launch_grad_u(const LossConsts& c, const double* U, const double* G, const double* W, const double* S1,
+int launch_grad_u(const LossConsts& c, const double* base, const double* U, const double* G, const double* W, const double* S1,
                   const double* S2, const double* eb, const int* xind, const double* small, double* gU,
                   double* V1, double* V2, cudaStream_t st) {
     const size_t n = (size_t)c.n1 * c.n2;
-    { LaunchScope scope(CAT_ELEMWISE, st); grad_u_kernel<<<kRedBlocks, 256, 0, st>>>(n, c.eq_type == 1, U, G, W, S1, S2, gU, V1, V2); }
+    { LaunchScope scope(CAT_ELEMWISE, st); grad_u_kernel<<<kRedBlocks, 256, 0, st>>>(n, c.eq_type == 1, base, U, G, W, S1, S2, gU, V1, V2); }
     GPHM_LAUNCH_OK();
     { LaunchScope scope(CAT_ELEMWISE, st); boundary_scatter_kernel<<<1, 1024, 0, st>>>(c, eb, xind, small, gU); }
     GPHM_LAUNCH_OK();
@@ -460,7 +459,7 @@ int launch_lincomb(double* out, double a, const double* x, double b, const doubl
 
 int launch_grad_u_local(size_t n, int allencahn, const double* U, const double* G, const double* W, const double* S1,
                         const double* S2, double* gU, double* V1, double* V2, cudaStream_t st) {
-    { LaunchScope scope(CAT_ELEMWISE, st); grad_u_kernel<<<kRedBlocks, 256, 0, st>>>(n, allencahn, U, G, W, S1, S2, gU, V1, V2); }
+    { LaunchScope scope(CAT_ELEMWISE, st); grad_u_kernel<<<kRedBlocks, 256, 0, st>>>(n, allencahn, nullptr, U, G, W, S1, S2, gU, V1, V2); }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }

@@ -68,11 +68,11 @@ int launch_transpose(const double* in, int R, int C, double* out, cudaStream_t s
 struct LossConsts { int dim, eq_type, n1, n2, nb, Q; double llk_weight, logdet, c1; };
 constexpr int kRedBlocks = 592;         // 148 SMs x 4
 int launch_residual(double* R, const double* U, const double* F, const double* A, const double* Bt, size_t n,
-                    int eq_type, const double* small, int Q, double* part, cudaStream_t st);
+                    int eq_type, const double* base, const double* small, int Q, double* part, cudaStream_t st);
 int launch_finalize(const LossConsts& c, const double* U, const double* bvals, const int* xind,
                     const double* part, const double* ldp1, int nblk1, const double* ldp2, int nblk2,
                     const double* small, double* eb, double* terms, double* gsmall, int* status, cudaStream_t st);
-int launch_grad_u(const LossConsts& c, const double* U, const double* G, const double* W, const double* S1,
+int launch_grad_u(const LossConsts& c, const double* base, const double* U, const double* G, const double* W, const double* S1,
                   const double* S2, const double* eb, const int* xind, const double* small, double* gU,
                   double* V1, double* V2, cudaStream_t st);
 // Dbar may be NULL (then only sK is produced)

@@ -77,7 +77,8 @@ using namespace gphm;
 struct gphm_plan {
     gphm_problem_desc d;
     Axis ax[2];
-    double *src = nullptr, *bvals = nullptr;
+    double *src = nullptr, *bvals = nullptr, *base = nullptr;   // base: optional frozen field added inside nl(.)
+    bool has_base = false;
     int* xind = nullptr;
     double *A = nullptr, *Bt = nullptr, *Tf = nullptr, *R = nullptr, *W = nullptr, *P = nullptr, *S1 = nullptr,
            *S2 = nullptr, *V1 = nullptr, *V2 = nullptr, *gU = nullptr;
@@ -144,7 +145,7 @@ size_t carve(gphm_plan& p, void* base) {
             if (X.fftL > 0) { c.take(X.twid, 2 * (size_t)X.fftL); c.take(X.specK, 2 * (size_t)X.fftL * fft_grid()); c.take(X.specD, 2 * (size_t)X.fftL * fft_grid()); }
         } else c.take(X.tgpart, tg);
     }
-    c.take(p.src, nf); c.take(p.bvals, d.nb); c.take(p.xind, std::max(d.nb, 1));
+    c.take(p.src, nf); c.take(p.base, nf); c.take(p.bvals, d.nb); c.take(p.xind, std::max(d.nb, 1));
     c.take(p.A, nf); c.take(p.Tf, nf); c.take(p.R, nf); c.take(p.P, nf); c.take(p.S1, nf); c.take(p.V1, nf);
     c.take(p.gU, nf);
     if (d.dim == 2) { c.take(p.Bt, nf); c.take(p.W, nf); c.take(p.S2, nf); c.take(p.V2, nf); }
@@ -281,7 +282,7 @@ int logjoint_grad(gphm_plan& p, const double* U, const double* small, double* gU
     GPHM_TRY(launch_dgemm(gemm_args(X1.D, n1, false, p.A, n2, false, p.R, n2, n1, n2, n1, c1, 0.0), st));   // c1 D1 A
     if (two)
         GPHM_TRY(launch_dgemm(gemm_args(Bt, n2, false, X2.D, n2, true, p.R, n2, n1, n2, n2, 1.0, 1.0), st)); // + Bt D2^T
-    GPHM_TRY(launch_residual(p.R, U, p.src, p.A, Bt, nf, d.eq_type, small, Q, p.part, st));    // R <- G
+    GPHM_TRY(launch_residual(p.R, U, p.src, p.A, Bt, nf, d.eq_type, p.has_base ? p.base : nullptr, small, Q, p.part, st));    // R <- G
     const LossConsts lc = loss_consts(p);
     GPHM_TRY(launch_finalize(lc, U, p.bvals, p.xind, p.part, X1.ldpart, X1.nblk, two ? X2.ldpart : nullptr,
                              two ? X2.nblk : 0, small, p.eb, terms, fwd_only ? nullptr : gsmall, p.status, st));
@@ -297,7 +298,7 @@ int logjoint_grad(gphm_plan& p, const double* U, const double* small, double* gU
         GPHM_TRY(launch_dgemm(gemm_args(G, n2, false, X2.D, n2, false, p.P, n2, n1, n2, n2, 1.0, 0.0), st)); // G D2
         GPHM_TRY(apply_kinv(p, 1, 1, p.P, n1, n2, p.S2, p.Tf, st));                             // S2
     }
-    GPHM_TRY(launch_grad_u(lc, U, G, W, p.S1, two ? p.S2 : nullptr, p.eb, p.xind, small, gU, p.V1,
+    GPHM_TRY(launch_grad_u(lc, p.has_base ? p.base : nullptr, U, G, W, p.S1, two ? p.S2 : nullptr, p.eb, p.xind, small, gU, p.V1,
                            two ? p.V2 : nullptr, st));
     const int order = deriv_order(p);
     // ---- axis 1: Kbar1 = ld/2*N2*K1^-1 - V1 A^T,  Dbar1 = c1 G A^T ----
@@ -522,6 +523,14 @@ int gphm_plan_status(gphm_plan* plan, int* pivot, void* stream) {
     return GPHM_OK;
 }
 
+int gphm_plan_set_base_field(gphm_plan* plan, const double* h_base) {
+    if (!plan) { set_last_error("null plan"); return GPHM_EINVAL; }
+    plan->has_base = h_base != nullptr;
+    if (h_base)
+        GPHM_CUDA_OK(cudaMemcpy(plan->base, h_base, sizeof(double) * (size_t)plan->d.n1 * plan->d.n2, cudaMemcpyHostToDevice));
+    return GPHM_OK;
+}
+
 int gphm_plan_uses_toeplitz(const gphm_plan* plan, int axis) {
     if (!plan || axis < 0 || axis > 1) return 0;
     return plan->ax[axis].n > 0 && plan->ax[axis].toeplitz ? 1 : 0;
@@ -698,7 +707,7 @@ int gphm_mg_residual(gphm_plan* plan, double* d_R, const double* d_U, const doub
                      const double* d_Bt, size_t n_local, const double* d_small, double* d_out2, void* stream) {
     if (!plan || !d_R || !d_U || !d_F || !d_A || !d_Bt || !d_small || !d_out2) { set_last_error("gphm_mg_residual: null pointer"); return GPHM_EINVAL; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    GPHM_TRY(launch_residual(d_R, d_U, d_F, d_A, d_Bt, n_local, plan->d.eq_type, d_small, plan->d.Q, plan->part, st));
+    GPHM_TRY(launch_residual(d_R, d_U, d_F, d_A, d_Bt, n_local, plan->d.eq_type, nullptr, d_small, plan->d.Q, plan->part, st));
     return launch_pair_reduce(plan->part, d_out2, st);
 }
 

@@ -24,7 +24,10 @@ def _to_numpy(x):
 
 
 def get_prefix(model, trick_paras):
-    prefix = ("result_log/" + trick_paras["equation"] + "/kernel_" + model.cov_func.__class__.__name__ +
+    kname = model.cov_func.__class__.__name__
+    if trick_paras.get("kernel_extra") is not None:            # utils.py:550-556
+        kname += "-extra-" + model.cov_func_extra.__class__.__name__
+    prefix = ("result_log/" + trick_paras["equation"] + "/kernel_" + kname +
               "/epoch_" + str(trick_paras["nepoch"]) + "/Q" + str(trick_paras["Q"]) + "/")
     os.makedirs(prefix, exist_ok=True)
     return prefix
@@ -43,7 +46,11 @@ def get_save_name(trick_paras):
 def store_model(model, log_dict, trick_paras):
     path = get_prefix(model, trick_paras) + get_save_name(trick_paras) + ".pkl"
     with open(path, "wb") as f:
-        pickle.dump((_to_numpy(model.params), _to_numpy(log_dict), _to_numpy(trick_paras)), f)
+        if trick_paras.get("kernel_extra") is not None:        # (params, params_extra, log_dict, trick_paras), utils.py:587-589
+            data = (_to_numpy(model.params), _to_numpy(model.params_extra), _to_numpy(log_dict), _to_numpy(trick_paras))
+        else:
+            data = (_to_numpy(model.params), _to_numpy(log_dict), _to_numpy(trick_paras))
+        pickle.dump(data, f)
     print("save model, log_dict, trick_paras to ", path)
     return path
 

@@ -127,6 +127,10 @@ GPHM_API void gphm_plan_destroy(gphm_plan* plan);
  * the first bad pivot (axis 1: 1..n1, axis 2: n1+1..) or 0. Clears the flag.                  */
 GPHM_API int gphm_plan_status(gphm_plan* plan, int* pivot, void* stream);
 GPHM_API int gphm_plan_uses_toeplitz(const gphm_plan* plan, int axis);
+/* Frozen base field (n1*n2 host doubles, NULL clears it): the nonlinearity becomes nl(U + base).
+ * This is what the second stage of GP_solver_1d_extra needs - u of the frozen first GP inside
+ * (u + u_extra)((u + u_extra)^2 - 1), model_GP_solver_1d_extra.py:95-100.                     */
+GPHM_API int gphm_plan_set_base_field(gphm_plan* plan, const double* h_base);
 
 /* Parameter layout (the reference params pytree, model_GP_solver_2d.py:245-261, _1d.py:203-213):
  *   d_U     : n1*n2 doubles (params['U'], or params['u'] (N,1) in 1-D)

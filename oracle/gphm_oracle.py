@@ -289,6 +289,29 @@ def forward_terms_1d(p: Problem1D, params: Dict) -> Dict[str, torch.Tensor]:
             "Ux": uxx, "A": a, "K1": K}
 
 
+def loss_extra_literal(p: Problem1D, kernel_extra: str, params: Dict, params_extra: Dict) -> torch.Tensor:
+    """model_GP_solver_1d_extra.py:107-141: second-stage loss with the first GP (params) frozen.
+    params_extra: {'u' (N,1), 'kernel_paras': {'log-w','log-ls'}, 'log_tau', 'log_v'}."""
+    fw = forward_terms_1d(p, params)
+    u, uxx = params["u"].reshape(-1, 1), fw["Ux"]
+    ue = params_extra["u"].reshape(u.shape[0], -1).sum(1, keepdim=True)
+    kp = dict(params_extra["kernel_paras"])
+    kp.setdefault("freq", torch.zeros_like(kp["log-w"]))
+    K = gram(kernel_extra, p.x, p.x, kp, 0, p.jitter)
+    a = torch.linalg.solve(K, ue)
+    uxxe = gram(kernel_extra, p.x, p.x, kp, 2) @ a
+    bgap = ((u[p.xind].reshape(-1) + ue[p.xind].reshape(-1) - p.yb.reshape(-1)) ** 2).sum()
+    r = uxx.reshape(-1) + uxxe.reshape(-1) - p.src.reshape(-1)
+    if p.eq_type.startswith("allencahn"):
+        t = (u + ue).reshape(-1)
+        r = r + t * (t * t - 1.0)
+    eqgap = (r ** 2).sum()
+    log_prior = -0.5 * torch.linalg.slogdet(K)[1] * p.logdet - 0.5 * (ue * a).sum()
+    log_b = 0.5 * p.xind.numel() * params_extra["log_tau"] - 0.5 * torch.exp(params_extra["log_tau"]) * bgap
+    eq_ll = 0.5 * u.shape[0] * params_extra["log_v"] - 0.5 * torch.exp(params_extra["log_v"]) * eqgap
+    return -(log_prior + log_b * p.llk_weight + eq_ll)
+
+
 def _clone_leaves(params: Dict, requires_grad: bool) -> Dict:
     out = {}
     for k, v in params.items():

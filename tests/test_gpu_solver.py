@@ -243,3 +243,45 @@ def test_properties_at_scale(gphm, oracle, N):
     slope = (float(model.loss(up)) - float(model.loss(dn))) / (2 * eps)
     gg2 = float((gU * gU).sum())
     assert abs(slope - gg2) <= 1e-5 * gg2
+
+
+@pytest.mark.parametrize("equation", ["poisson_1d-x2_add_sinx", "allencahn_1d-sin_cos"])
+def test_extra_gp_second_stage_parity(gphm, oracle, equation):
+    """GP_solver_1d_extra: loss_extra and its gradient vs the oracle's literal restatement of
+    model_GP_solver_1d_extra.py:107-141, then a short two-stage train()."""
+    O = oracle
+    N, Q, fs, scale = 160, 8, 20.0, 1.0 if "x2" in equation else 2 * math.pi
+    p, xte, yte = O.make_problem_1d(equation, "SE_Cos_1d", N, scale)
+    tp = trick(equation, "SE_Cos_1d", Q, fs, N, kernel_extra="Matern52_1d", change_point=0.5)
+    model = gphm.GP_solver_1d_extra(p.xind.numpy(), p.yb.numpy(), p.x.numpy().reshape(-1, 1), p.src.numpy(), 1e-6,
+                                    xte.numpy().reshape(-1, 1), yte.numpy().reshape(-1, 1), tp)
+    params = O.init_params_1d(N, Q, fs)
+    params["u"] = (0.4 * torch.sin(5 * p.x) + 0.1 * p.x).reshape(-1, 1)
+    params["log_tau"] = torch.tensor(0.4, dtype=DT)
+    model.freeze_first_stage(params)
+    pe = {"u": (0.05 * torch.cos(3 * p.x)).reshape(-1, 1), "log_tau": torch.tensor(0.4, dtype=DT),
+          "log_v": torch.tensor(-0.1, dtype=DT),
+          "kernel_paras": {"log-w": torch.tensor([0.2], dtype=DT), "log-ls": torch.tensor([-0.3], dtype=DT)}}
+    leaves = {"u": pe["u"].clone().requires_grad_(True), "log_tau": pe["log_tau"].clone().requires_grad_(True),
+              "log_v": pe["log_v"].clone().requires_grad_(True),
+              "kernel_paras": {k: v.clone().requires_grad_(True) for k, v in pe["kernel_paras"].items()}}
+    want = O.loss_extra_literal(p, "Matern52_1d", params, leaves)
+    flat = [leaves["u"], leaves["log_tau"], leaves["log_v"], leaves["kernel_paras"]["log-w"], leaves["kernel_paras"]["log-ls"]]
+    gw = torch.autograd.grad(want, flat)
+    loss, g = model.value_and_grad_extra(pe)
+    assert abs(float(loss) - float(want)) <= TOL * abs(float(want))
+    got = [g["u"], g["log_tau"], g["log_v"], g["kernel_paras"]["log-w"], g["kernel_paras"]["log-ls"]]
+    for a, b in zip(got, gw):
+        assert float((a.cpu().reshape(-1) - b.reshape(-1)).norm()) <= TOL * float(b.norm()) + 1e-300
+    assert "freq" not in g["kernel_paras"]
+    pe2, opt2, l2 = model.step_extra(pe, model.core_extra.init_opt_state(model._with_freq(pe)))
+    assert abs(float(l2) - float(want)) <= TOL * abs(float(want)) and int(opt2["count"]) == 1
+    pr, _ = model.preds_extra(pe)
+    assert pr.shape == (300, 1)
+    log, early, min_err = gphm.GP_solver_1d_extra(p.xind.numpy(), p.yb.numpy(), p.x.numpy().reshape(-1, 1), p.src.numpy(),
+                                                  1e-6, xte.numpy().reshape(-1, 1), yte.numpy().reshape(-1, 1),
+                                                  dict(tp, nepoch=40)).train(40)
+    full = list(range(0, 40, 2))
+    assert log["epoch_list"] == full[:len(log["epoch_list"])] and np.isfinite(log["loss_list"]).all() and min_err < 2.0
+    # the reference's rule (model_GP_solver_1d_extra.py:316-321): stop once the error rose more than 7 times
+    assert early["flag"] == (len(log["epoch_list"]) < len(full))
