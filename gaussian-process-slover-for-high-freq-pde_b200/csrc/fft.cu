@@ -176,6 +176,96 @@ spectrum_to_diag_sums_kernel(const double2* __restrict__ partK, const double2* _
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Toeplitz (derivative-Gram) products on uniform grids:  Out = alpha * X T^T (+ beta * Out), i.e.
+// every row x of X is replaced by T x, where T[i][j] = t(i-j) is the n x n derivative Gram
+// (symmetric k''(|i-j|h), or antisymmetric k'(|i-j|h) sgn(i-j) for advection).  T is embedded in a
+// circulant of size L >= 2n; its spectrum (bit-reversed order, scaled by 1/L) is built once per
+// step from the n-entry Toeplitz table.  Two real rows share one complex FFT exactly
+// (c is real, so conv(c, x_r + i x_s) = conv(c, x_r) + i conv(c, x_s)): forward DIF, pointwise
+// product, inverse DIT, all in place in shared memory.  Replaces the four D-GEMMs of the step
+// (jnp.matmul at model_GP_solver_2d.py:112,119 and their transposes in the reverse pass).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fft_dif_inplace(double2* xs, int L, int logL, const double2* __restrict__ W, int tid) {
+    for (int s = 0; s < logL; ++s) {
+        const int sh = logL - 1 - s, half = 1 << sh;
+        const double2* __restrict__ Ws = W + (L - (L >> s));
+        for (int b = tid; b < L / 2; b += FFT_THREADS) {
+            const int j = b & (half - 1);
+            const int i0 = ((b >> sh) << (sh + 1)) + j, i1 = i0 + half;
+            const double2 a = xs[i0], c = xs[i1];
+            xs[i0] = make_double2(a.x + c.x, a.y + c.y);
+            xs[i1] = cmul(make_double2(a.x - c.x, a.y - c.y), Ws[j]);
+        }
+        __syncthreads();
+    }
+}
+__device__ __forceinline__ void fft_dit_inverse_inplace(double2* xs, int L, int logL, const double2* __restrict__ W, int tid) {
+    for (int s = 0; s < logL; ++s) {
+        const int half = 1 << s;
+        const double2* __restrict__ Ws = W + (L - (2 << s));
+        for (int b = tid; b < L / 2; b += FFT_THREADS) {
+            const int j = b & (half - 1);
+            const int i0 = ((b >> s) << (s + 1)) + j, i1 = i0 + half;
+            const double2 w = Ws[j];
+            const double2 t = cmul(xs[i1], make_double2(w.x, -w.y));
+            const double2 a = xs[i0];
+            xs[i0] = make_double2(a.x + t.x, a.y + t.y);
+            xs[i1] = make_double2(a.x - t.x, a.y - t.y);
+        }
+        __syncthreads();
+    }
+}
+
+// spec[p] = FFT(c)[brev(p)] / L  with  c[m] = t(m), c[L-m] = t(-m)
+__global__ void __launch_bounds__(FFT_THREADS, 1)
+toeplitz_spectrum_kernel(const double* __restrict__ tab, int n, int L, int logL, const double2* __restrict__ W,
+                         int antisym, double dirsign, double2* __restrict__ spec) {
+    extern __shared__ double2 xs[];
+    const int tid = threadIdx.x;
+    for (int j = tid; j < L; j += FFT_THREADS) {
+        double v = 0.0;
+        if (j < n) v = antisym ? dirsign * tab[j] : tab[j];                       // i - j = m >= 0
+        else if (L - j < n) v = antisym ? -dirsign * tab[L - j] : tab[L - j];     // i - j = -(L - j)
+        if (antisym && j == 0) v = 0.0;
+        xs[j] = make_double2(v, 0.0);
+    }
+    __syncthreads();
+    fft_dif_inplace(xs, L, logL, W, tid);
+    const double inv = 1.0 / (double)L;
+    for (int p = tid; p < L; p += FFT_THREADS) spec[p] = make_double2(xs[p].x * inv, xs[p].y * inv);
+}
+
+__global__ void __launch_bounds__(FFT_THREADS, 1)
+toeplitz_apply_kernel(const double* __restrict__ X, int rows, int n, int ldx, const double2* __restrict__ spec, int L,
+                      int logL, const double2* __restrict__ W, double alpha, double beta, double* __restrict__ Out,
+                      int ldo) {
+    extern __shared__ double2 xs[];
+    const int tid = threadIdx.x;
+    const int npairs = (rows + 1) / 2;
+    for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
+        const int r0 = 2 * pr, r1 = r0 + 1;
+        const bool two = r1 < rows;
+        const double* x0 = X + (size_t)r0 * ldx;
+        const double* x1 = X + (size_t)(two ? r1 : r0) * ldx;
+        for (int j = tid; j < L; j += FFT_THREADS)
+            xs[j] = (j < n) ? make_double2(x0[j], two ? x1[j] : 0.0) : make_double2(0.0, 0.0);
+        __syncthreads();
+        fft_dif_inplace(xs, L, logL, W, tid);
+        for (int p = tid; p < L; p += FFT_THREADS) xs[p] = cmul(xs[p], spec[p]);
+        __syncthreads();
+        fft_dit_inverse_inplace(xs, L, logL, W, tid);
+        double* o0 = Out + (size_t)r0 * ldo;
+        double* o1 = Out + (size_t)r1 * ldo;
+        for (int j = tid; j < n; j += FFT_THREADS) {
+            const double2 v = xs[j];
+            o0[j] = alpha * v.x + (beta != 0.0 ? beta * o0[j] : 0.0);
+            if (two) o1[j] = alpha * v.y + (beta != 0.0 ? beta * o1[j] : 0.0);
+        }
+        __syncthreads();
+    }
+}
+
 // out[c][r] = in[r][c]
 __global__ void __launch_bounds__(256)
 transpose_kernel(const double* __restrict__ in, int R, int C, double* __restrict__ out) {
@@ -201,6 +291,8 @@ int fft_init() {
     const int bytes = FFT_MAX_L * (int)sizeof(double2);
     GPHM_CUDA_OK(cudaFuncSetAttribute(xcorr_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     GPHM_CUDA_OK(cudaFuncSetAttribute(spectrum_to_diag_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    GPHM_CUDA_OK(cudaFuncSetAttribute(toeplitz_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    GPHM_CUDA_OK(cudaFuncSetAttribute(toeplitz_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     done = GPHM_OK;
     return done;
 }
@@ -234,6 +326,33 @@ int launch_spectrum_to_diag_sums(const double* partK, const double* partD, int L
         spectrum_to_diag_sums_kernel<<<2, FFT_THREADS, (size_t)L * sizeof(double2), st>>>(
             reinterpret_cast<const double2*>(partK), reinterpret_cast<const double2*>(partD), fft_grid(), L, ilog2(L),
             reinterpret_cast<const double2*>(W), n, antisym ? 1 : 0, dirsign, addK, addK_scale, sK, sD);
+    }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+int launch_toeplitz_spectrum(const double* tab, int n, int L, const double* W, bool antisym, double dirsign, double* spec,
+                             cudaStream_t st) {
+    GPHM_TRY(fft_init());
+    {
+        LaunchScope scope(CAT_FFT, st);
+        toeplitz_spectrum_kernel<<<1, FFT_THREADS, (size_t)L * sizeof(double2), st>>>(
+            tab, n, L, ilog2(L), reinterpret_cast<const double2*>(W), antisym ? 1 : 0, dirsign, reinterpret_cast<double2*>(spec));
+    }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+int launch_toeplitz_apply(const double* X, int rows, int n, int ldx, const double* spec, int L, const double* W, double alpha,
+                          double beta, double* Out, int ldo, cudaStream_t st) {
+    GPHM_TRY(fft_init());
+    if (rows <= 0) return GPHM_OK;
+    {
+        LaunchScope scope(CAT_FFT, st, 0.0, 16.0 * rows * (double)n);
+        const int grid = std::min(fft_grid() * 1, (rows + 1) / 2);
+        toeplitz_apply_kernel<<<grid, FFT_THREADS, (size_t)L * sizeof(double2), st>>>(
+            X, rows, n, ldx, reinterpret_cast<const double2*>(spec), L, ilog2(L), reinterpret_cast<const double2*>(W), alpha, beta,
+            Out, ldo);
     }
     GPHM_LAUNCH_OK();
     return GPHM_OK;

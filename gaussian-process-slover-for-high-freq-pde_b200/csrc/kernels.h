@@ -62,6 +62,12 @@ int launch_xcorr_spectrum(const double* X, const double* Y, int rows, int cols, 
 int launch_spectrum_to_diag_sums(const double* partK, const double* partD, int L, const double* W, int n, bool antisym,
                                  double dirsign, const double* addK, double addK_scale, double* sK, double* sD,
                                  cudaStream_t st);
+// spec (L complex, bit-reversed order, scaled by 1/L) of the circulant embedding of the Toeplitz matrix t(i-j) = tab[|i-j|] (* sign)
+int launch_toeplitz_spectrum(const double* tab, int n, int L, const double* W, bool antisym, double dirsign, double* spec,
+                             cudaStream_t st);
+// Out[r][:] = alpha * T X[r][:] + beta * Out[r][:]   for every row r (T n x n Toeplitz with spectrum `spec`)
+int launch_toeplitz_apply(const double* X, int rows, int n, int ldx, const double* spec, int L, const double* W, double alpha,
+                          double beta, double* Out, int ldo, cudaStream_t st);
 int launch_transpose(const double* in, int R, int C, double* out, cudaStream_t st);
 
 // ---- elemwise.cu ---------------------------------------------------------------------------

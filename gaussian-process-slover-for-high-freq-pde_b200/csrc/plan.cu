@@ -67,7 +67,7 @@ struct Axis {
     double dirsign = 1.0;
     double *x = nullptr, *K = nullptr, *D = nullptr, *L = nullptr, *Linv = nullptr, *Kinv = nullptr, *Dbar = nullptr,
            *T = nullptr, *invdiag = nullptr, *ldpart = nullptr, *tabK = nullptr, *tabD = nullptr, *dspart = nullptr,
-           *sK = nullptr, *sD = nullptr, *sKinv = nullptr, *tgpart = nullptr, *twid = nullptr, *specK = nullptr, *specD = nullptr;
+           *sK = nullptr, *sD = nullptr, *sKinv = nullptr, *tgpart = nullptr, *twid = nullptr, *specK = nullptr, *specD = nullptr, *specT = nullptr;   // specT: spectrum of the Toeplitz D
 };
 
 }  // namespace gphm
@@ -139,10 +139,10 @@ size_t carve(gphm_plan& p, void* base) {
         const size_t ds = diag_sums_part_doubles((int)n), tg = theta_general_part_doubles((int)n, d.Q);
         const size_t Lq = (size_t)fft_length_for((int)n);
         const size_t spec = 2 * Lq * fft_grid();              // complex partial spectra, one per CTA
-        if (p.size_query) { double* dummy; c.take(dummy, std::max(ds, tg)); c.take(dummy, 2 * Lq); c.take(dummy, spec); c.take(dummy, spec); }
+        if (p.size_query) { double* dummy; c.take(dummy, std::max(ds, tg)); c.take(dummy, 2 * Lq); c.take(dummy, spec); c.take(dummy, spec); c.take(dummy, 2 * Lq); }
         else if (X.toeplitz) {
             c.take(X.dspart, ds);
-            if (X.fftL > 0) { c.take(X.twid, 2 * (size_t)X.fftL); c.take(X.specK, 2 * (size_t)X.fftL * fft_grid()); c.take(X.specD, 2 * (size_t)X.fftL * fft_grid()); }
+            if (X.fftL > 0) { c.take(X.twid, 2 * (size_t)X.fftL); c.take(X.specK, 2 * (size_t)X.fftL * fft_grid()); c.take(X.specD, 2 * (size_t)X.fftL * fft_grid()); c.take(X.specT, 2 * (size_t)X.fftL); }
         } else c.take(X.tgpart, tg);
     }
     c.take(p.src, nf); c.take(p.base, nf); c.take(p.bvals, d.nb); c.take(p.xind, std::max(d.nb, 1));
@@ -279,9 +279,24 @@ int logjoint_grad(gphm_plan& p, const double* U, const double* small, double* gU
     GPHM_TRY(apply_kinv(p, 0, 0, U, n1, n2, p.A, p.Tf, st));                                   // A = K1^-1 U
     const double* Bt = U;
     if (two) { GPHM_TRY(apply_kinv(p, 1, 1, U, n1, n2, p.Bt, p.Tf, st)); Bt = p.Bt; }           // Bt = U K2^-1
-    GPHM_TRY(launch_dgemm(gemm_args(X1.D, n1, false, p.A, n2, false, p.R, n2, n1, n2, n1, c1, 0.0), st));   // c1 D1 A
-    if (two)
-        GPHM_TRY(launch_dgemm(gemm_args(Bt, n2, false, X2.D, n2, true, p.R, n2, n1, n2, n2, 1.0, 1.0), st)); // + Bt D2^T
+    const bool anti = deriv_order(p) == 1;                 // advection: D is antisymmetric, D^T = -D
+    const bool tfft1 = X1.fftL > 0 && !(d.force_general & 8), tfft2 = two && X2.fftL > 0 && !(d.force_general & 8);
+    if (tfft1) {   // uniform grid: D1 is Toeplitz -> circulant convolution of every column of A (rows of A^T)
+        GPHM_TRY(launch_toeplitz_spectrum(X1.tabD, n1, X1.fftL, X1.twid, anti, X1.dirsign, X1.specT, st));
+        GPHM_TRY(launch_transpose(p.A, n1, n2, p.Tf, st));
+        GPHM_TRY(launch_toeplitz_apply(p.Tf, n2, n1, n1, X1.specT, X1.fftL, X1.twid, c1, 0.0, p.P, n1, st));
+        GPHM_TRY(launch_transpose(p.P, n2, n1, p.R, st));
+    } else {
+        GPHM_TRY(launch_dgemm(gemm_args(X1.D, n1, false, p.A, n2, false, p.R, n2, n1, n2, n1, c1, 0.0), st));   // c1 D1 A
+    }
+    if (two) {
+        if (tfft2) {   // (Bt D2^T)[i,:] = D2 Bt[i,:]
+            GPHM_TRY(launch_toeplitz_spectrum(X2.tabD, n2, X2.fftL, X2.twid, anti, X2.dirsign, X2.specT, st));
+            GPHM_TRY(launch_toeplitz_apply(Bt, n1, n2, n2, X2.specT, X2.fftL, X2.twid, 1.0, 1.0, p.R, n2, st));
+        } else {
+            GPHM_TRY(launch_dgemm(gemm_args(Bt, n2, false, X2.D, n2, true, p.R, n2, n1, n2, n2, 1.0, 1.0), st)); // + Bt D2^T
+        }
+    }
     GPHM_TRY(launch_residual(p.R, U, p.src, p.A, Bt, nf, d.eq_type, p.has_base ? p.base : nullptr, small, Q, p.part, st));    // R <- G
     const LossConsts lc = loss_consts(p);
     GPHM_TRY(launch_finalize(lc, U, p.bvals, p.xind, p.part, X1.ldpart, X1.nblk, two ? X2.ldpart : nullptr,
@@ -292,10 +307,19 @@ int logjoint_grad(gphm_plan& p, const double* U, const double* small, double* gU
     const double* G = p.R;
     const double* W = p.A;
     if (two) { GPHM_TRY(apply_kinv(p, 0, 0, Bt, n1, n2, p.W, p.Tf, st)); W = p.W; }             // W = K1^-1 Bt
-    GPHM_TRY(launch_dgemm(gemm_args(X1.D, n1, true, G, n2, false, p.P, n2, n1, n2, n1, c1, 0.0), st));      // c1 D1^T G
+    if (tfft1) {   // c1 D1^T G: D1^T = +-D1 applied to the columns of G
+        GPHM_TRY(launch_transpose(G, n1, n2, p.Tf, st));
+        GPHM_TRY(launch_toeplitz_apply(p.Tf, n2, n1, n1, X1.specT, X1.fftL, X1.twid, anti ? -c1 : c1, 0.0, p.V1, n1, st));
+        GPHM_TRY(launch_transpose(p.V1, n2, n1, p.P, st));
+    } else {
+        GPHM_TRY(launch_dgemm(gemm_args(X1.D, n1, true, G, n2, false, p.P, n2, n1, n2, n1, c1, 0.0), st));  // c1 D1^T G
+    }
     GPHM_TRY(apply_kinv(p, 0, 0, p.P, n1, n2, p.S1, p.Tf, st));                                 // S1
     if (two) {
-        GPHM_TRY(launch_dgemm(gemm_args(G, n2, false, X2.D, n2, false, p.P, n2, n1, n2, n2, 1.0, 0.0), st)); // G D2
+        if (tfft2)     // (G D2)[i,:] = D2^T G[i,:]
+            GPHM_TRY(launch_toeplitz_apply(G, n1, n2, n2, X2.specT, X2.fftL, X2.twid, anti ? -1.0 : 1.0, 0.0, p.P, n2, st));
+        else
+            GPHM_TRY(launch_dgemm(gemm_args(G, n2, false, X2.D, n2, false, p.P, n2, n1, n2, n2, 1.0, 0.0), st)); // G D2
         GPHM_TRY(apply_kinv(p, 1, 1, p.P, n1, n2, p.S2, p.Tf, st));                             // S2
     }
     GPHM_TRY(launch_grad_u(lc, p.has_base ? p.base : nullptr, U, G, W, p.S1, two ? p.S2 : nullptr, p.eb, p.xind, small, gU, p.V1,

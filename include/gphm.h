@@ -63,7 +63,8 @@ typedef struct gphm_problem_desc {
     int nb;              /* boundary points: 2*n1+2*n2 (2-D) or len(Xind) (1-D) */
     int force_general;   /* bit 0: never use the Toeplitz fast path even on uniform grids;
                             bit 1: Toeplitz Grams, but Kbar/Dbar by GEMM + direct diagonal sums (no FFT);
-                            bit 2: FFT diagonal sums, but K^-1 by GEMM + direct sums              */
+                            bit 2: FFT diagonal sums, but K^-1 by GEMM + direct sums;
+                            bit 3: derivative-Gram products D*A, D^T*G by GEMM, not Toeplitz FFT */
     double llk_weight;   /* trick_paras['llk_weight'] */
     double logdet;       /* trick_paras['logdet'] (True -> 1.0) */
     double beta;         /* advection speed, trick_paras['beta'] (ignored otherwise) */

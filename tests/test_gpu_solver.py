@@ -225,7 +225,7 @@ def test_properties_at_scale(gphm, oracle, N):
     loss2, grads2 = model.value_and_grad(s1)
     assert float(loss2) == float(loss) and all(torch.equal(a, b) for (_, a), (_, b) in zip(tree_flatten(grads), tree_flatten(grads2)))
     # the theta-gradient paths agree: FFT diagonal sums (default), K^-1 by GEMM (4), GEMM + direct sums (2), general (1)
-    for mode in (4, 2, 1):
+    for mode in (8, 4, 2, 1):
         tp = trick("poisson_2d-sin_add_cos", "Matern52_Cos_1d", 30, 20.0, N, force_general=mode)
         gen = gphm.GP_solver_2d_single(p.bvals.numpy(), (p.x.numpy(), p.y.numpy()), p.src.numpy(), 1e-6,
                                        (p.x.numpy()[:5], p.y.numpy()[:5]), np.zeros((5, 5)), tp)

@@ -20,7 +20,7 @@ for eq, ker, N1, N2, Q, fs, scale, beta in CASES:
     for state_name, params in (("S1", O.state_S1(p, Q=Q, freq_scale=fs)), ("S0", O.init_params_2d(N1, N2, Q, fs))):
         _, want = O.loss_and_grad_efficient(p, params) if N1 > 200 else O.loss_and_grad_literal(p, params)
         want = dict(tree_flatten(want))
-        for mode in (0, 2, 4):
+        for mode in (0, 8, 2):
             tp = {"equation": eq, "kernel": ker, "Q": Q, "freq_scale": fs, "N_col": N1, "llk_weight": 200.0, "lr": 0.01,
                   "logdet": True, "nepoch": 1, "tol": -1, "beta": beta, "force_general": mode}
             cls = G.GP_solver_2d_single_advection if eq.startswith("advection") else G.GP_solver_2d_single
