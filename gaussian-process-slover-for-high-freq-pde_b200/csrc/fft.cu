@@ -9,8 +9,10 @@
 // model_GP_solver_2d.py:104-119,158-162,179) by O(N^2 log N) work that is bound by shared-memory/FP64-ALU throughput and reads each operand
 // once from HBM.
 //
-// Per row: z = x + i y zero-padded to L >= 2C, one in-place radix-2 DIF FFT in shared memory
-// (natural in, bit-reversed out); the two real spectra are separated with Z(f), conj Z(L-f);
+// Per row: z = x + i y zero-padded to L >= 2C, one in-place DIF FFT in shared memory (natural in,
+// bit-reversed out; register-blocked radix-8 passes, i.e. 5 shared-memory round trips for
+// L = 8192 instead of 13, on a padded layout that keeps every 128-bit access conflict-free);
+// the two real spectra are separated with Z(f), conj Z(L-f);
 // conj(X^)(f) Y^(f) is accumulated in registers over all rows a CTA owns (bit-reversed order).
 // A second kernel sums the per-CTA partial spectra in a fixed order (deterministic), runs one
 // inverse DIT FFT (bit-reversed in, natural out) and emits the symmetric / antisymmetric
@@ -22,7 +24,7 @@
 namespace gphm {
 
 constexpr int FFT_THREADS = 512;
-constexpr int FFT_MAX_L = 8192;                       // 128 KB of complex doubles in shared memory
+constexpr int FFT_MAX_L = 8192;                       // 144 KB of (padded) complex doubles in shared memory
 constexpr int FFT_ACC = FFT_MAX_L / FFT_THREADS;      // spectrum bins per thread
 
 int fft_length_for(int n) {                            // smallest power of two >= 2n (0 if unsupported)
@@ -31,6 +33,11 @@ int fft_length_for(int n) {                            // smallest power of two 
     return L <= FFT_MAX_L ? L : 0;
 }
 int fft_grid() { return kNumSMs; }
+
+// shared-memory layout: one pad slot per 8 complex values, so that the 8 lanes of a quarter-warp
+// always hit 8 different 16-byte bank groups for every stride the passes use
+__device__ __forceinline__ int PADI(int i) { return i + (i >> 3); }
+static size_t fft_smem_bytes(int L) { return (size_t)(L + (L >> 3) + 1) * sizeof(double2); }
 
 // Per-stage compact twiddle tables: stage s (butterfly span L >> (s+1)) reads
 //   W[(L - (L >> s)) + j] = exp(-2 pi i (j << s) / L),  j < L >> (s+1)
@@ -48,6 +55,82 @@ __global__ void twiddle_init_kernel(double2* __restrict__ W, int L, int logL) {
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// K radix-2 DIF stages s..s+K-1 fused in registers: each thread owns the 2^K points
+// base + m*q (q = L >> (s+K)) of one sub-transform.
+template <int K>
+__device__ __forceinline__ void dif_pass(double2* xs, int L, int logL, int s, const double2* __restrict__ W, int tid) {
+    constexpr int R = 1 << K;
+    const int lq = logL - s - K, q = 1 << lq;
+    for (int b = tid; b < (L >> K); b += FFT_THREADS) {
+        const int j = b & (q - 1);
+        const int base = ((b >> lq) << (lq + K)) + j;
+        double2 e[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) e[m] = xs[PADI(base + m * q)];
+#pragma unroll
+        for (int t = 0; t < K; ++t) {
+            const int span = R >> (t + 1);
+            const double2* __restrict__ Ws = W + (L - (L >> (s + t)));
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+                if (m & span) continue;
+                const double2 a = e[m], c = e[m + span];
+                e[m] = make_double2(a.x + c.x, a.y + c.y);
+                e[m + span] = cmul(make_double2(a.x - c.x, a.y - c.y), Ws[j + (m & (span - 1)) * q]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < R; ++m) xs[PADI(base + m * q)] = e[m];
+    }
+    __syncthreads();
+}
+
+// K radix-2 inverse DIT stages s..s+K-1 (half-spans 2^s .. 2^(s+K-1)) fused in registers.
+template <int K>
+__device__ __forceinline__ void dit_pass(double2* xs, int L, int logL, int s, const double2* __restrict__ W, int tid) {
+    constexpr int R = 1 << K;
+    const int q = 1 << s;
+    for (int b = tid; b < (L >> K); b += FFT_THREADS) {
+        const int j = b & (q - 1);
+        const int base = ((b >> s) << (s + K)) + j;
+        double2 e[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) e[m] = xs[PADI(base + m * q)];
+#pragma unroll
+        for (int t = 0; t < K; ++t) {
+            const int span = 1 << t;
+            const double2* __restrict__ Ws = W + (L - (2 << (s + t)));      // table of forward stage logL-1-(s+t)
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+                if (m & span) continue;
+                const double2 w = Ws[j + (m & (span - 1)) * q];
+                const double2 tt = cmul(e[m + span], make_double2(w.x, -w.y));
+                const double2 a = e[m];
+                e[m] = make_double2(a.x + tt.x, a.y + tt.y);
+                e[m + span] = make_double2(a.x - tt.x, a.y - tt.y);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < R; ++m) xs[PADI(base + m * q)] = e[m];
+    }
+    __syncthreads();
+}
+
+// natural order in -> bit-reversed order out
+__device__ __forceinline__ void fft_dif_inplace(double2* xs, int L, int logL, const double2* __restrict__ W, int tid) {
+    int s = 0;
+    for (; logL - s >= 3; s += 3) dif_pass<3>(xs, L, logL, s, W, tid);
+    if (logL - s == 2) dif_pass<2>(xs, L, logL, s, W, tid);
+    else if (logL - s == 1) dif_pass<1>(xs, L, logL, s, W, tid);
+}
+// bit-reversed order in -> natural order out (unscaled inverse)
+__device__ __forceinline__ void fft_dit_inverse_inplace(double2* xs, int L, int logL, const double2* __restrict__ W, int tid) {
+    int s = 0;
+    for (; logL - s >= 3; s += 3) dit_pass<3>(xs, L, logL, s, W, tid);
+    if (logL - s == 2) dit_pass<2>(xs, L, logL, s, W, tid);
+    else if (logL - s == 1) dit_pass<1>(xs, L, logL, s, W, tid);
 }
 
 // partial[blockIdx.x][p] (+)= weight * sum over the CTA's rows of conj(X^)(f_p) Y^(f_p)
@@ -69,7 +152,7 @@ xcorr_spectrum_kernel(const double* __restrict__ X, const double* __restrict__ Y
         for (int j = tid; j < L; j += FFT_THREADS) {
             double2 v = make_double2(0.0, 0.0);
             if (j < cols) { v = make_double2(xr[j], yr[j]); mx = fmax(mx, fabs(v.x)); my = fmax(my, fabs(v.y)); }
-            xs[j] = v;
+            xs[PADI(j)] = v;
         }
         // z = x + i*y shares one FFT: the two spectra are separated by a difference, so y is first
         // rescaled (exactly, by a power of two) to x's magnitude - otherwise the smaller sequence
@@ -91,20 +174,9 @@ xcorr_spectrum_kernel(const double* __restrict__ X, const double* __restrict__ Y
         }
         const double sc = exp2(rint(log2(mx / my)));
         const double isc = 1.0 / sc;
-        for (int j = tid; j < cols; j += FFT_THREADS) xs[j].y *= sc;
+        for (int j = tid; j < cols; j += FFT_THREADS) xs[PADI(j)].y *= sc;
         __syncthreads();
-        for (int s = 0; s < logL; ++s) {               // radix-2 DIF, natural in -> bit-reversed out
-            const int sh = logL - 1 - s, half = 1 << sh;
-            const double2* __restrict__ Ws = W + (L - (L >> s));
-            for (int b = tid; b < L / 2; b += FFT_THREADS) {
-                const int j = b & (half - 1);
-                const int i0 = ((b >> sh) << (sh + 1)) + j, i1 = i0 + half;
-                const double2 a = xs[i0], c = xs[i1];
-                xs[i0] = make_double2(a.x + c.x, a.y + c.y);
-                xs[i1] = cmul(make_double2(a.x - c.x, a.y - c.y), Ws[j]);
-            }
-            __syncthreads();
-        }
+        fft_dif_inplace(xs, L, logL, W, tid);
 #pragma unroll
         for (int k = 0; k < FFT_ACC; ++k) {
             const int p = tid + k * FFT_THREADS;
@@ -112,7 +184,7 @@ xcorr_spectrum_kernel(const double* __restrict__ X, const double* __restrict__ Y
                 const unsigned f = __brev((unsigned)p) >> (32 - logL);
                 const unsigned fm = (unsigned)(L - (int)f) & (unsigned)(L - 1);
                 const unsigned pm = __brev(fm) >> (32 - logL);
-                const double2 zf = xs[p], zm = xs[pm];
+                const double2 zf = xs[PADI(p)], zm = xs[PADI((int)pm)];
                 const double2 xh = make_double2(0.5 * (zf.x + zm.x), 0.5 * (zf.y - zm.y));       // X^(f)
                 const double2 yh = make_double2(0.5 * (zf.y + zm.y), -0.5 * (zf.x - zm.x));      // Y^(f)
                 acc[k].x += isc * (xh.x * yh.x + xh.y * yh.y);                                    // conj(X^) Y^
@@ -145,29 +217,16 @@ spectrum_to_diag_sums_kernel(const double2* __restrict__ partK, const double2* _
     for (int p = tid; p < L; p += FFT_THREADS) {
         double2 s = make_double2(0.0, 0.0);
         for (int c = 0; c < nparts; ++c) { const double2 v = part[(size_t)c * L + p]; s.x += v.x; s.y += v.y; }
-        xs[p] = s;
+        xs[PADI(p)] = s;
     }
     __syncthreads();
-    for (int s = 0; s < logL; ++s) {                   // radix-2 DIT inverse, bit-reversed in -> natural out
-        const int half = 1 << s;
-        const double2* __restrict__ Ws = W + (L - (2 << s));       // table of forward stage logL-1-s
-        for (int b = tid; b < L / 2; b += FFT_THREADS) {
-            const int j = b & (half - 1);
-            const int i0 = ((b >> s) << (s + 1)) + j, i1 = i0 + half;
-            const double2 w = Ws[j];
-            const double2 t = cmul(xs[i1], make_double2(w.x, -w.y));
-            const double2 a = xs[i0];
-            xs[i0] = make_double2(a.x + t.x, a.y + t.y);
-            xs[i1] = make_double2(a.x - t.x, a.y - t.y);
-        }
-        __syncthreads();
-    }
+    fft_dit_inverse_inplace(xs, L, logL, W, tid);
     const double inv = 1.0 / (double)L;
     double* out = blockIdx.x == 0 ? sK : sD;
     const bool anti = (blockIdx.x == 1) && antisym;
     for (int m = tid; m < n; m += FFT_THREADS) {
-        const double up = xs[m].x * inv;                           // col - row = m
-        const double lo = xs[(L - m) & (L - 1)].x * inv;           // row - col = m
+        const double up = xs[PADI(m)].x * inv;                         // col - row = m
+        const double lo = xs[PADI((L - m) & (L - 1))].x * inv;         // row - col = m
         double v;
         if (m == 0) v = anti ? 0.0 : up;
         else v = anti ? dirsign * (lo - up) : (up + lo);
@@ -186,37 +245,6 @@ spectrum_to_diag_sums_kernel(const double2* __restrict__ partK, const double2* _
 // product, inverse DIT, all in place in shared memory.  Replaces the four D-GEMMs of the step
 // (jnp.matmul at model_GP_solver_2d.py:112,119 and their transposes in the reverse pass).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fft_dif_inplace(double2* xs, int L, int logL, const double2* __restrict__ W, int tid) {
-    for (int s = 0; s < logL; ++s) {
-        const int sh = logL - 1 - s, half = 1 << sh;
-        const double2* __restrict__ Ws = W + (L - (L >> s));
-        for (int b = tid; b < L / 2; b += FFT_THREADS) {
-            const int j = b & (half - 1);
-            const int i0 = ((b >> sh) << (sh + 1)) + j, i1 = i0 + half;
-            const double2 a = xs[i0], c = xs[i1];
-            xs[i0] = make_double2(a.x + c.x, a.y + c.y);
-            xs[i1] = cmul(make_double2(a.x - c.x, a.y - c.y), Ws[j]);
-        }
-        __syncthreads();
-    }
-}
-__device__ __forceinline__ void fft_dit_inverse_inplace(double2* xs, int L, int logL, const double2* __restrict__ W, int tid) {
-    for (int s = 0; s < logL; ++s) {
-        const int half = 1 << s;
-        const double2* __restrict__ Ws = W + (L - (2 << s));
-        for (int b = tid; b < L / 2; b += FFT_THREADS) {
-            const int j = b & (half - 1);
-            const int i0 = ((b >> s) << (s + 1)) + j, i1 = i0 + half;
-            const double2 w = Ws[j];
-            const double2 t = cmul(xs[i1], make_double2(w.x, -w.y));
-            const double2 a = xs[i0];
-            xs[i0] = make_double2(a.x + t.x, a.y + t.y);
-            xs[i1] = make_double2(a.x - t.x, a.y - t.y);
-        }
-        __syncthreads();
-    }
-}
-
 // spec[p] = FFT(c)[brev(p)] / L  with  c[m] = t(m), c[L-m] = t(-m)
 __global__ void __launch_bounds__(FFT_THREADS, 1)
 toeplitz_spectrum_kernel(const double* __restrict__ tab, int n, int L, int logL, const double2* __restrict__ W,
@@ -228,12 +256,12 @@ toeplitz_spectrum_kernel(const double* __restrict__ tab, int n, int L, int logL,
         if (j < n) v = antisym ? dirsign * tab[j] : tab[j];                       // i - j = m >= 0
         else if (L - j < n) v = antisym ? -dirsign * tab[L - j] : tab[L - j];     // i - j = -(L - j)
         if (antisym && j == 0) v = 0.0;
-        xs[j] = make_double2(v, 0.0);
+        xs[PADI(j)] = make_double2(v, 0.0);
     }
     __syncthreads();
     fft_dif_inplace(xs, L, logL, W, tid);
     const double inv = 1.0 / (double)L;
-    for (int p = tid; p < L; p += FFT_THREADS) spec[p] = make_double2(xs[p].x * inv, xs[p].y * inv);
+    for (int p = tid; p < L; p += FFT_THREADS) { const double2 v = xs[PADI(p)]; spec[p] = make_double2(v.x * inv, v.y * inv); }
 }
 
 __global__ void __launch_bounds__(FFT_THREADS, 1)
@@ -249,16 +277,16 @@ toeplitz_apply_kernel(const double* __restrict__ X, int rows, int n, int ldx, co
         const double* x0 = X + (size_t)r0 * ldx;
         const double* x1 = X + (size_t)(two ? r1 : r0) * ldx;
         for (int j = tid; j < L; j += FFT_THREADS)
-            xs[j] = (j < n) ? make_double2(x0[j], two ? x1[j] : 0.0) : make_double2(0.0, 0.0);
+            xs[PADI(j)] = (j < n) ? make_double2(x0[j], two ? x1[j] : 0.0) : make_double2(0.0, 0.0);
         __syncthreads();
         fft_dif_inplace(xs, L, logL, W, tid);
-        for (int p = tid; p < L; p += FFT_THREADS) xs[p] = cmul(xs[p], spec[p]);
+        for (int p = tid; p < L; p += FFT_THREADS) { const int q = PADI(p); xs[q] = cmul(xs[q], spec[p]); }
         __syncthreads();
         fft_dit_inverse_inplace(xs, L, logL, W, tid);
         double* o0 = Out + (size_t)r0 * ldo;
         double* o1 = Out + (size_t)r1 * ldo;
         for (int j = tid; j < n; j += FFT_THREADS) {
-            const double2 v = xs[j];
+            const double2 v = xs[PADI(j)];
             o0[j] = alpha * v.x + (beta != 0.0 ? beta * o0[j] : 0.0);
             if (two) o1[j] = alpha * v.y + (beta != 0.0 ? beta * o1[j] : 0.0);
         }
@@ -288,7 +316,7 @@ static int ilog2(int L) { int l = 0; while ((1 << l) < L) ++l; return l; }
 int fft_init() {
     static int done = -1;
     if (done >= 0) return done;
-    const int bytes = FFT_MAX_L * (int)sizeof(double2);
+    const int bytes = (int)fft_smem_bytes(FFT_MAX_L);
     GPHM_CUDA_OK(cudaFuncSetAttribute(xcorr_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     GPHM_CUDA_OK(cudaFuncSetAttribute(spectrum_to_diag_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     GPHM_CUDA_OK(cudaFuncSetAttribute(toeplitz_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -309,7 +337,7 @@ int launch_xcorr_spectrum(const double* X, const double* Y, int rows, int cols, 
     if (L > FFT_MAX_L || L < 2 * cols) { set_last_error("xcorr: L=%d does not fit cols=%d", L, cols); return GPHM_EINVAL; }
     {
         LaunchScope scope(CAT_FFT, st, 0.0, 16.0 * rows * (double)cols);
-        xcorr_spectrum_kernel<<<fft_grid(), FFT_THREADS, (size_t)L * sizeof(double2), st>>>(
+        xcorr_spectrum_kernel<<<fft_grid(), FFT_THREADS, fft_smem_bytes(L), st>>>(
             X, Y, rows, cols, ldx, ldy, L, ilog2(L), reinterpret_cast<const double2*>(W), weight, accumulate ? 1 : 0,
             reinterpret_cast<double2*>(partial));
     }
@@ -323,7 +351,7 @@ int launch_spectrum_to_diag_sums(const double* partK, const double* partD, int L
     GPHM_TRY(fft_init());
     {
         LaunchScope scope(CAT_FFT, st);
-        spectrum_to_diag_sums_kernel<<<2, FFT_THREADS, (size_t)L * sizeof(double2), st>>>(
+        spectrum_to_diag_sums_kernel<<<2, FFT_THREADS, fft_smem_bytes(L), st>>>(
             reinterpret_cast<const double2*>(partK), reinterpret_cast<const double2*>(partD), fft_grid(), L, ilog2(L),
             reinterpret_cast<const double2*>(W), n, antisym ? 1 : 0, dirsign, addK, addK_scale, sK, sD);
     }
@@ -336,7 +364,7 @@ int launch_toeplitz_spectrum(const double* tab, int n, int L, const double* W, b
     GPHM_TRY(fft_init());
     {
         LaunchScope scope(CAT_FFT, st);
-        toeplitz_spectrum_kernel<<<1, FFT_THREADS, (size_t)L * sizeof(double2), st>>>(
+        toeplitz_spectrum_kernel<<<1, FFT_THREADS, fft_smem_bytes(L), st>>>(
             tab, n, L, ilog2(L), reinterpret_cast<const double2*>(W), antisym ? 1 : 0, dirsign, reinterpret_cast<double2*>(spec));
     }
     GPHM_LAUNCH_OK();
@@ -350,7 +378,7 @@ int launch_toeplitz_apply(const double* X, int rows, int n, int ldx, const doubl
     {
         LaunchScope scope(CAT_FFT, st, 0.0, 16.0 * rows * (double)n);
         const int grid = std::min(fft_grid() * 1, (rows + 1) / 2);
-        toeplitz_apply_kernel<<<grid, FFT_THREADS, (size_t)L * sizeof(double2), st>>>(
+        toeplitz_apply_kernel<<<grid, FFT_THREADS, fft_smem_bytes(L), st>>>(
             X, rows, n, ldx, reinterpret_cast<const double2*>(spec), L, ilog2(L), reinterpret_cast<const double2*>(W), alpha, beta,
             Out, ldo);
     }
