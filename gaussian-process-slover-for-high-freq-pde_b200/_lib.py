@@ -61,6 +61,7 @@ _SIGS = {
                                c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gphm_mg_theta_grad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gphm_plan_uses_fft": (c_int, [c_void_p, c_int]),
+    "gphm_mg_toeplitz_apply": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "gphm_transpose": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "gphm_mg_theta_grad_fft": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double,
                                        c_void_p, c_void_p, c_void_p]),

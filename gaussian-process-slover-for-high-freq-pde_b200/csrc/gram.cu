@@ -162,6 +162,19 @@ int launch_gram_general(int kid, int order, const double* x1, int n1, const doub
     return GPHM_OK;
 }
 
+int launch_toeplitz_table(int kid, int order, const double* x, int n, const double* theta, int Q, double* tabK, double* tabD,
+                          cudaStream_t st) {
+    if (Q > kMaxQ || Q < 1) { set_last_error("gram: Q=%d outside [1,%d]", Q, kMaxQ); return GPHM_EINVAL; }
+    if (n <= 0) return GPHM_OK;
+    int rc;
+    { LaunchScope scope(CAT_GRAM, st, 0.0, 24.0 * n);
+    rc = GPHM_DISPATCH_KID_ORDER(kid, order,
+        toeplitz_table_kernel<KID, ORDER><<<(n + 127) / 128, 128, 0, st>>>(x, n, theta, Q, tabK, tabD)); }
+    if (rc != 0) { set_last_error("gram: bad kernel id %d / order %d", kid, order); return GPHM_EINVAL; }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
 int launch_gram_toeplitz(int kid, int order, const double* x, int n, const double* theta, int Q, double jitter,
                          double dirsign, double* tabK, double* tabD, double* Kout, double* Dout, int ld,
                          cudaStream_t st) {

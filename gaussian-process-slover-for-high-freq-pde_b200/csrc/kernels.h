@@ -13,6 +13,8 @@ int launch_gram_toeplitz(int kid, int order, const double* x, int n, const doubl
                          double dirsign, double* tabK, double* tabD, double* Kout, double* Dout, int ld,
                          cudaStream_t st);
 
+int launch_toeplitz_table(int kid, int order, const double* x, int n, const double* theta, int Q, double* tabK, double* tabD,
+                          cudaStream_t st);
 int launch_kappa_pairs(int kid, int order, const double* x1, const double* x2, size_t np, const double* theta, int Q,
                        double* out, cudaStream_t st);
 

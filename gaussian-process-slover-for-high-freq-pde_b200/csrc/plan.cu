@@ -684,6 +684,21 @@ int gphm_plan_uses_fft(const gphm_plan* plan, int axis) {
     return plan->ax[axis].n > 0 && plan->ax[axis].fftL > 0 ? 1 : 0;
 }
 
+int gphm_mg_toeplitz_apply(gphm_plan* plan, int axis, int transposed, const double* d_X, int rows, double alpha, double beta,
+                           const double* d_small, double* d_out, void* stream) {
+    if (!plan || !d_X || !d_out || !d_small) { set_last_error("gphm_mg_toeplitz_apply: null pointer"); return GPHM_EINVAL; }
+    if (axis < 0 || axis > 1 || plan->ax[axis].n == 0 || plan->ax[axis].fftL == 0) { set_last_error("gphm_mg_toeplitz_apply: axis %d has no FFT path", axis); return GPHM_EINVAL; }
+    Axis& X = plan->ax[axis];
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool anti = deriv_order(*plan) == 1;
+    // the table is rebuilt here (n*Q evaluations): this rank may not have factored this axis itself
+    GPHM_TRY(launch_toeplitz_table(plan->d.kernel_id, deriv_order(*plan), X.x, X.n, theta_of(*plan, d_small, axis), plan->d.Q,
+                                   X.tabK, X.tabD, st));
+    GPHM_TRY(launch_toeplitz_spectrum(X.tabD, X.n, X.fftL, X.twid, anti, X.dirsign, X.specT, st));
+    return launch_toeplitz_apply(d_X, rows, X.n, X.n, X.specT, X.fftL, X.twid, (anti && transposed) ? -alpha : alpha, beta,
+                                 d_out, X.n, st);
+}
+
 int gphm_transpose(const double* d_in, int rows, int cols, double* d_out, void* stream) {
     if (rows <= 0 || cols <= 0) return GPHM_OK;
     if (!d_in || !d_out) { set_last_error("gphm_transpose: null pointer"); return GPHM_EINVAL; }

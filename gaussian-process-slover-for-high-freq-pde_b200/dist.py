@@ -1,5 +1,6 @@
 """Multi-GPU (one process per GPU) version of the 2-D step: U, the source term and the Adam state
-are sharded by row blocks; per-axis operators (Gram factors, derivative Grams) are replicated.
+are sharded by row blocks; the per-axis operators (Gram factors) are factored once per axis by one
+half of the ranks and broadcast.
 
 Why it shards: left-multiplications by axis-1 operators (K1^-1, D1) act on every
 column of the N1 x N2 field independently, right-multiplications by axis-2 operators (K2^-1, D2)
@@ -122,6 +123,13 @@ class CudaOps(object):
     def transpose(self, X, tag):
         out = self._buf(tag, (X.shape[1], X.shape[0]))
         _lib.check(self.lib.gphm_transpose(_lib.ptr(X), X.shape[0], X.shape[1], _lib.ptr(out), self._s()), "gphm_transpose")
+        return out
+
+    def toeplitz_rows(self, axis, transposed, X, alpha, beta, small, out):
+        """out[r] = alpha * D x_r (or D^T x_r) + beta * out[r] for every row of X, D the axis' Toeplitz derivative Gram."""
+        _lib.check(self.lib.gphm_mg_toeplitz_apply(self.plan, axis, int(transposed), _lib.ptr(X), X.shape[0], float(alpha),
+                                                   float(beta), _lib.ptr(small), _lib.ptr(out), self._s()),
+                   "gphm_mg_toeplitz_apply")
         return out
 
     def theta_grad_rows(self, axis, X, Y, G, r0, r1, beta, cD, small, out):
@@ -251,11 +259,12 @@ class ShardedSolver2D(object):
         return t
 
     # ---- factorisation: the two axes are independent, so rank halves take one axis each ----------
-    def _factor(self, small, skip_kinv):
+    def _factor(self, small, fft1, fft2):
         """Gram + Cholesky + L^-1 (+ K^-1) of both axes on every rank; returns [log|K1|, log|K2|].
         With P >= 2 ranks [0, P/2) factor axis 1 and ranks [P/2, P) axis 2, then each axis' D, Linv
         (and K^-1 when needed) is broadcast from the first rank of its half."""
         o = self.ops
+        skip_kinv = fft1 and fft2
         skip = 4 if skip_kinv else 0
         if self.P == 1:
             o.factor(small, 3 | skip)
@@ -266,7 +275,9 @@ class ShardedSolver2D(object):
         ld = o.logdets().clone()
         for axis, root in ((0, 0), (1, half)):
             src = dist.get_global_rank(self.group, root) if self.group is not None else root
-            for which in ((1, 2) if skip_kinv else (1, 2, 0)):
+            fft_axis = fft1 if axis == 0 else fft2       # FFT axes need neither D (Toeplitz table instead) nor K^-1
+            which_list = [2] + ([] if fft_axis else [1]) + ([] if skip_kinv else [0])
+            for which in which_list:
                 dist.broadcast(o.mat(axis, which), src=src, group=self.group)
             dist.broadcast(ld[axis:axis + 1], src=src, group=self.group)
         return ld
@@ -278,16 +289,24 @@ class ShardedSolver2D(object):
         N1, N2, h, w = self.N1, self.N2, self.h, self.w
         small, U_r = self.small, self.U
         fft1, fft2 = o.uses_fft(0), o.uses_fft(1)
-        ld = self._factor(small, fft1 and fft2)
+        ld = self._factor(small, fft1, fft2)
         D1, D2 = o.mat(0, 1), o.mat(1, 1)
         # forward
         Bt_r = o.apply_kinv(1, 1, U_r, "Bt_r")                           # U K2^-1            (R)
         U_c = self.r2c(U_r)
         A_c = o.apply_kinv(0, 0, U_c, "A_c")                             # K1^-1 U            (C)
-        Uxx_c = o.gemm(D1, A_c, False, False, c1, 0.0, o.new("Uxx_c", (N1, w)))
+        if fft1:      # Toeplitz D1: FFT convolution of this rank's columns
+            At = o.transpose(A_c, "At")
+            Uxx_c = o.transpose(o.toeplitz_rows(0, False, At, c1, 0.0, small, o.new("Uxx_t", (w, N1))), "Uxx_c")
+        else:
+            At = None
+            Uxx_c = o.gemm(D1, A_c, False, False, c1, 0.0, o.new("Uxx_c", (N1, w)))
         R_r = self.c2r(Uxx_c)
         A_r = self.c2r(A_c)
-        o.gemm(Bt_r, D2, False, True, 1.0, 1.0, R_r)                     # + Bt D2^T          (R)
+        if fft2:
+            o.toeplitz_rows(1, False, Bt_r, 1.0, 1.0, small, R_r)               # + Bt D2^T          (R)
+        else:
+            o.gemm(Bt_r, D2, False, True, 1.0, 1.0, R_r)
         red = torch.empty(3, dtype=DT, device=R_r.device)
         red[0:2] = o.residual(R_r, U_r, self.F, A_r, Bt_r, small)        # R_r <- G_r ; [eqgap, quad]
         G_r = R_r
@@ -306,7 +325,12 @@ class ShardedSolver2D(object):
         G_c = self.r2c(G_r)
         Bt_c = self.r2c(Bt_r)
         W_c = o.apply_kinv(0, 0, Bt_c, "W_c")
-        P_c = o.gemm(D1, G_c, True, False, c1, 0.0, o.new("P_c", (N1, w)))
+        if fft1:
+            Gt = o.transpose(G_c, "Gt")
+            P_c = o.transpose(o.toeplitz_rows(0, True, Gt, c1, 0.0, small, o.new("P_t", (w, N1))), "P_c")
+        else:
+            Gt = None
+            P_c = o.gemm(D1, G_c, True, False, c1, 0.0, o.new("P_c", (N1, w)))
         S1_c = o.apply_kinv(0, 0, P_c, "S1_c")
         V1_c = o.lincomb(1.0, S1_c, 0.5, W_c, "V1_c")
         lead = 1.0 if self.rank == 0 else 0.0                            # the K^-1 (log-det) term is added once
@@ -314,15 +338,17 @@ class ShardedSolver2D(object):
         gs.zero_()
         if fft1:      # uniform grid: diagonal sums by FFT over this rank's columns; Linv rows are split over ranks
             r0, r1 = self.rank * N1 // self.P, (self.rank + 1) * N1 // self.P
-            o.theta_grad_rows(0, o.transpose(V1_c, "V1t"), o.transpose(A_c, "At"), o.transpose(G_c, "Gt"), r0, r1,
-                              0.5 * self.logdet * N2, c1, small, gs[0:3 * Q])
+            o.theta_grad_rows(0, o.transpose(V1_c, "V1t"), At, Gt, r0, r1, 0.5 * self.logdet * N2, c1, small, gs[0:3 * Q])
         else:
             Kinv1 = o.mat(0, 0)
             o.gemm(V1_c, A_c, False, True, -1.0, lead * 0.5 * self.logdet * N2, Kinv1)      # Kbar1 partial
             Dbar1 = o.gemm(G_c, A_c, False, True, c1, 0.0, o.new("Dbar1", (N1, N1)))
             o.theta_grad(0, Kinv1, Dbar1, small, gs[0:3 * Q])
         # axis-2 work in R layout
-        P_r = o.gemm(G_r, D2, False, False, 1.0, 0.0, o.new("P_r", (h, N2)))
+        if fft2:
+            P_r = o.toeplitz_rows(1, True, G_r, 1.0, 0.0, small, o.new("P_r", (h, N2)))
+        else:
+            P_r = o.gemm(G_r, D2, False, False, 1.0, 0.0, o.new("P_r", (h, N2)))
         S2_r = o.apply_kinv(1, 1, P_r, "S2_r")
         W_r = self.c2r(W_c)
         S1_r = self.c2r(S1_c)

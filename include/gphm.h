@@ -202,6 +202,13 @@ GPHM_API int gphm_mg_theta_grad(gphm_plan* plan, int axis, const double* d_Kbar,
  * skips forming K^-1 (not needed on this path).                                                 */
 GPHM_API int gphm_plan_uses_fft(const gphm_plan* plan, int axis);
 GPHM_API int gphm_transpose(const double* d_in, int rows, int cols, double* d_out, void* stream);
+/* Uniform-grid derivative-Gram product without the Gram matrix: every row x of d_X (rows x n_axis)
+ * becomes alpha * D x (transposed = 0) or alpha * D^T x (transposed = 1), + beta * d_out row, by
+ * FFT circulant convolution with the axis' Toeplitz table, rebuilt from d_small (so the rank need
+ * not have factored this axis itself).
+ * (D A = rows of A^T; Bt D^T = rows of Bt; D^T G = rows of G^T with transposed = 1; G D = rows of G, transposed = 1.) */
+GPHM_API int gphm_mg_toeplitz_apply(gphm_plan* plan, int axis, int transposed, const double* d_X, int rows, double alpha,
+                           double beta, const double* d_small, double* d_out, void* stream);
 GPHM_API int gphm_mg_theta_grad_fft(gphm_plan* plan, int axis, const double* d_X, const double* d_Y, const double* d_G, int rows,
                            int linv_row0, int linv_row1, double beta, double cD, const double* d_small,
                            double* d_gtheta, void* stream);

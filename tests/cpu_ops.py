@@ -67,6 +67,13 @@ class CpuOps(object):
     def transpose(self, X, tag):
         return X.T.contiguous()
 
+    def toeplitz_rows(self, axis, transposed, X, alpha, beta, small, out):
+        # like the product, D comes from `small`, not from a (possibly un-broadcast) factorisation
+        _, D = O._gram_pair(self.kernel, self.x if axis == 0 else self.y, self._theta(small, axis), self.order, self.jitter)
+        res = alpha * (X @ (D if transposed else D.T))          # row x -> D^T x (transposed) or D x
+        out.copy_(res + (beta * out if beta != 0.0 else 0.0))
+        return out
+
     def theta_grad_rows(self, axis, X, Y, G, r0, r1, beta, cD, small, out):
         Li = self.m[(axis, 2)][r0:r1]
         self.theta_grad(axis, beta * (Li.T @ Li) - X.T @ Y, cD * (G.T @ Y), small, out)
