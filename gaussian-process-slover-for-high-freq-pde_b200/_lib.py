@@ -61,6 +61,10 @@ _SIGS = {
                                c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gphm_mg_theta_grad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gphm_plan_uses_fft": (c_int, [c_void_p, c_int]),
+    "gphm_plan_uses_gs": (c_int, [c_void_p, c_int]),
+    "gphm_toeplitz_work_bytes": (c_size_t, [c_int, c_int]),
+    "gphm_toeplitz_solve": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p]),
     "gphm_mg_toeplitz_apply": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "gphm_transpose": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "gphm_mg_theta_grad_fft": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double,

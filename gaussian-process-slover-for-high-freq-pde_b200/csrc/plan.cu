@@ -64,10 +64,12 @@ LaunchScope::~LaunchScope() {
 struct Axis {
     int n = 0, nblk = 0, fftL = 0;   // fftL: FFT length of the diagonal-sum path (0 = GEMM path)
     bool toeplitz = false;
+    bool gs = false;                 // K^-1 by Schur/Levinson + Gohberg-Semencul FFT products (no dense factorisation)
     double dirsign = 1.0;
     double *x = nullptr, *K = nullptr, *D = nullptr, *L = nullptr, *Linv = nullptr, *Kinv = nullptr, *Dbar = nullptr,
            *T = nullptr, *invdiag = nullptr, *ldpart = nullptr, *tabK = nullptr, *tabD = nullptr, *dspart = nullptr,
-           *sK = nullptr, *sD = nullptr, *sKinv = nullptr, *tgpart = nullptr, *twid = nullptr, *specK = nullptr, *specD = nullptr, *specT = nullptr;   // specT: spectrum of the Toeplitz D
+           *sK = nullptr, *sD = nullptr, *sKinv = nullptr, *tgpart = nullptr, *twid = nullptr, *specK = nullptr, *specD = nullptr, *specT = nullptr,   // specT: spectrum of the Toeplitz D
+           *gsg = nullptr, *gspec = nullptr;   // gsg = K^-1 e_0; gspec: four Gohberg-Semencul circulant spectra
 };
 
 }  // namespace gphm
@@ -83,6 +85,7 @@ struct gphm_plan {
     double *A = nullptr, *Bt = nullptr, *Tf = nullptr, *R = nullptr, *W = nullptr, *P = nullptr, *S1 = nullptr,
            *S2 = nullptr, *V1 = nullptr, *V2 = nullptr, *gU = nullptr;
     double *part = nullptr, *eb = nullptr, *gsmall = nullptr, *terms = nullptr;
+    double* gsS = nullptr;           // field-sized scratch of the Gohberg-Semencul K^-1 application
     int* status = nullptr;
     void* ws = nullptr;
     bool owns_ws = false;
@@ -144,7 +147,9 @@ size_t carve(gphm_plan& p, void* base) {
             c.take(X.dspart, ds);
             if (X.fftL > 0) { c.take(X.twid, 2 * (size_t)X.fftL); c.take(X.specK, 2 * (size_t)X.fftL * fft_grid()); c.take(X.specD, 2 * (size_t)X.fftL * fft_grid()); c.take(X.specT, 2 * (size_t)X.fftL); }
         } else c.take(X.tgpart, tg);
+        if (p.size_query || X.gs) { c.take(X.gsg, n); c.take(X.gspec, 8 * Lq); }
     }
+    if (p.size_query || p.ax[0].gs || p.ax[1].gs) c.take(p.gsS, nf);
     c.take(p.src, nf); c.take(p.base, nf); c.take(p.bvals, d.nb); c.take(p.xind, std::max(d.nb, 1));
     c.take(p.A, nf); c.take(p.Tf, nf); c.take(p.R, nf); c.take(p.P, nf); c.take(p.S1, nf); c.take(p.V1, nf);
     c.take(p.gU, nf);
@@ -180,6 +185,7 @@ void init_axes(gphm_plan& p, const double* hx, const double* hy) {
             X.toeplitz = !(p.d.force_general & 1) && uniform_grid(h[a], X.n);
             X.dirsign = (h[a][X.n - 1] >= h[a][0]) ? 1.0 : -1.0;
             X.fftL = (X.toeplitz && !(p.d.force_general & 2)) ? fft_length_for(X.n) : 0;
+            X.gs = X.fftL > 0 && !(p.d.force_general & (4 | 16)) && X.n <= toeplitz_inv_max_n();
         } else {
             X.toeplitz = !(p.d.force_general & 1);   // size query: assume the (larger) general layout below
         }
@@ -219,9 +225,39 @@ int invert_axis(gphm_plan& p, int a, bool with_kinv, cudaStream_t st) {
     return GPHM_OK;
 }
 
+// Uniform-grid axes a0 .. a0+count-1 without a dense factorisation: Toeplitz tables, Schur/Levinson
+// recursion for g = K^-1 e_0 and log|K|, Gohberg-Semencul spectra and the diagonal sums of K^-1.
+// Two axes of equal size share every launch (one CTA per axis).
+int factor_gs(gphm_plan& p, int a0, int count, const double* small, cudaStream_t st) {
+    const int order = deriv_order(p);
+    const bool need_D = (p.d.force_general & 8) != 0;      // derivative-Gram products by GEMM want the full D
+    for (int a = a0; a < a0 + count; ++a) {
+        Axis& X = p.ax[a];
+        const double* th = theta_of(p, small, a);
+        if (need_D)
+            GPHM_TRY(launch_gram_toeplitz(p.d.kernel_id, order, X.x, X.n, th, p.d.Q, p.d.jitter, X.dirsign, X.tabK, X.tabD,
+                                          X.K, X.D, X.n, st));
+        else
+            GPHM_TRY(launch_toeplitz_table(p.d.kernel_id, order, X.x, X.n, th, p.d.Q, X.tabK, X.tabD, st));
+    }
+    Axis& X0 = p.ax[a0];
+    const bool batched = count == 2 && p.ax[a0 + 1].n == X0.n;
+    for (int a = a0; a < a0 + (batched ? 1 : count); ++a) {
+        Axis& X = p.ax[a];
+        const int nsys = batched ? 2 : 1;
+        const Axis& Y = p.ax[batched ? a + 1 : a];
+        GPHM_TRY(launch_schur_levinson(X.tabK, Y.tabK - X.tabK, X.n, p.d.jitter, X.gsg, Y.gsg - X.gsg, X.ldpart,
+                                       Y.ldpart - X.ldpart, p.status + a, 1, nsys, st));
+        GPHM_TRY(launch_gs_prepare(X.gsg, Y.gsg - X.gsg, X.n, X.fftL, X.twid, X.gspec, Y.gspec - X.gspec, X.sKinv,
+                                   Y.sKinv - X.sKinv, nsys, st));
+    }
+    return GPHM_OK;
+}
+
 // Gram + Cholesky + L^-1 (+ K^-1) for one axis.
 int factor_axis(gphm_plan& p, int a, const double* small, bool with_kinv, cudaStream_t st) {
     Axis& X = p.ax[a];
+    if (X.gs) return factor_gs(p, a, 1, small, st);
     GPHM_TRY(gram_axis(p, a, small, st));
     GPHM_TRY(chol_factor(X.K, X.L, X.n, X.n, X.invdiag, X.ldpart, p.status + a, st));
     return invert_axis(p, a, with_kinv, st);
@@ -231,7 +267,8 @@ int factor_axis(gphm_plan& p, int a, const double* small, bool with_kinv, cudaSt
 int factor_both(gphm_plan& p, const double* small, bool kinv0, bool kinv1, cudaStream_t st) {
     Axis& X0 = p.ax[0];
     Axis& X1 = p.ax[1];
-    if (X0.n != X1.n) {
+    if (X0.gs && X1.gs) return factor_gs(p, 0, 2, small, st);
+    if (X0.n != X1.n || X0.gs || X1.gs) {
         GPHM_TRY(factor_axis(p, 0, small, kinv0, st));
         return factor_axis(p, 1, small, kinv1, st);
     }
@@ -243,11 +280,31 @@ int factor_both(gphm_plan& p, const double* small, bool kinv0, bool kinv1, cudaS
     return invert_axis(p, 1, kinv1, st);
 }
 
+// rows x n matrix Xm -> out = Xm K_a^-1 (every row v -> K^-1 v) by the Gohberg-Semencul formula:
+// four circulant convolutions per row.  tmp: rows x n scratch; out may not alias Xm.
+int apply_kinv_rows_gs(const Axis& X, const double* Xm, int rows, double* out, double* tmp, cudaStream_t st) {
+    const int n = X.n, L = X.fftL;
+    const size_t sp = 2 * (size_t)L;
+    GPHM_TRY(launch_toeplitz_apply(Xm, rows, n, n, X.gspec, L, X.twid, 1.0, 0.0, out, n, st));            // L(g)^T v
+    GPHM_TRY(launch_toeplitz_apply(Xm, rows, n, n, X.gspec + sp, L, X.twid, 1.0, 0.0, tmp, n, st));       // L(h)^T v
+    GPHM_TRY(launch_toeplitz_apply(out, rows, n, n, X.gspec + 2 * sp, L, X.twid, 1.0, 0.0, out, n, st));  // L(g) . / g0
+    GPHM_TRY(launch_toeplitz_apply(tmp, rows, n, n, X.gspec + 3 * sp, L, X.twid, 1.0, 1.0, out, n, st));  // - L(h) . / g0
+    return GPHM_OK;
+}
+
 // out = K_a^-1 X (side 0, X is n x cols) or X K_a^-1 (side 1, X is rows x n); tmp has X's shape.
 int apply_kinv(gphm_plan& p, int a, int side, const double* Xm, int rows, int cols, double* out, double* tmp,
                cudaStream_t st) {
     const Axis& X = p.ax[a];
     const int n = X.n;
+    if (X.gs) {
+        if ((side == 0 ? rows : cols) != n) { set_last_error("apply_kinv: operand %d x %d does not match n %d", rows, cols, n); return GPHM_EINVAL; }
+        if (side == 1) return apply_kinv_rows_gs(X, Xm, rows, out, tmp, st);
+        if ((size_t)rows * cols > (size_t)p.d.n1 * p.d.n2) { set_last_error("apply_kinv: %d x %d exceeds the plan's scratch", rows, cols); return GPHM_EINVAL; }
+        GPHM_TRY(launch_transpose(Xm, n, cols, p.gsS, st));             // columns -> rows
+        GPHM_TRY(apply_kinv_rows_gs(X, p.gsS, cols, tmp, out, st));     // `out` is scratch here
+        return launch_transpose(tmp, cols, n, out, st);
+    }
     if (side == 0) {
         if (rows != n) { set_last_error("apply_kinv: rows %d != n %d", rows, n); return GPHM_EINVAL; }
         GPHM_TRY(launch_dgemm(gemm_args(X.Linv, n, false, Xm, cols, false, tmp, cols, n, cols, n, 1.0, 0.0, KM_A_LOWER), st));
@@ -333,8 +390,9 @@ int logjoint_grad(gphm_plan& p, const double* U, const double* small, double* gU
         GPHM_TRY(launch_transpose(p.V1, n1, n2, V1t, st));
         GPHM_TRY(launch_transpose(p.A, n1, n2, At, st));
         GPHM_TRY(launch_transpose(G, n1, n2, Gt, st));
-        const bool fk = (d.force_general & 4) == 0;       // K^-1 sums as FFT autocorrelation of the rows of Linv
-        if (fk) GPHM_TRY(launch_xcorr_spectrum(X1.Linv, X1.Linv, n1, n1, n1, n1, X1.fftL, X1.twid, 0.5 * d.logdet * n2, false, X1.specK, st));
+        const bool fk = (d.force_general & 4) == 0 && !X1.gs;   // K^-1 sums as FFT autocorrelation of the rows of Linv
+        if (X1.gs) {}                                           // sKinv already holds them (factor_gs)
+        else if (fk) GPHM_TRY(launch_xcorr_spectrum(X1.Linv, X1.Linv, n1, n1, n1, n1, X1.fftL, X1.twid, 0.5 * d.logdet * n2, false, X1.specK, st));
         else GPHM_TRY(launch_diag_sums(X1.Kinv, nullptr, n1, n1, false, 1.0, X1.dspart, X1.sKinv, nullptr, st));
         GPHM_TRY(launch_xcorr_spectrum(V1t, At, n2, n1, n1, n1, X1.fftL, X1.twid, -1.0, fk, X1.specK, st));
         GPHM_TRY(launch_xcorr_spectrum(Gt, At, n2, n1, n1, n1, X1.fftL, X1.twid, c1, false, X1.specD, st));
@@ -349,8 +407,9 @@ int logjoint_grad(gphm_plan& p, const double* U, const double* small, double* gU
     // ---- axis 2: Kbar2 = ld/2*N1*K2^-1 - V2^T Bt,  Dbar2 = G^T Bt ----
     if (two) {
         if (X2.fftL > 0) {
-            const bool fk = (d.force_general & 4) == 0;
-            if (fk) GPHM_TRY(launch_xcorr_spectrum(X2.Linv, X2.Linv, n2, n2, n2, n2, X2.fftL, X2.twid, 0.5 * d.logdet * n1, false, X2.specK, st));
+            const bool fk = (d.force_general & 4) == 0 && !X2.gs;
+            if (X2.gs) {}
+            else if (fk) GPHM_TRY(launch_xcorr_spectrum(X2.Linv, X2.Linv, n2, n2, n2, n2, X2.fftL, X2.twid, 0.5 * d.logdet * n1, false, X2.specK, st));
             else GPHM_TRY(launch_diag_sums(X2.Kinv, nullptr, n2, n2, false, 1.0, X2.dspart, X2.sKinv, nullptr, st));
             GPHM_TRY(launch_xcorr_spectrum(p.V2, Bt, n1, n2, n2, n2, X2.fftL, X2.twid, -1.0, fk, X2.specK, st));
             GPHM_TRY(launch_xcorr_spectrum(G, Bt, n1, n2, n2, n2, X2.fftL, X2.twid, 1.0, false, X2.specD, st));
@@ -465,6 +524,38 @@ int gphm_potrf_inv(double* d_K, int n, double* d_L, double* d_Linv, double* d_lo
     GPHM_TRY(chol_factor(d_K, d_L, n, n, invdiag, ldpart, d_status, st));
     GPHM_TRY(trtri_lower(d_L, d_Linv, n, n, invdiag, T, st));
     GPHM_TRY(launch_sum_scaled(ldpart, nblk, 2.0, d_logdet, st));
+    return GPHM_OK;
+}
+
+size_t gphm_toeplitz_work_bytes(int n, int rows) {
+    const int L = n > 0 ? fft_length_for(n) : 0;
+    if (n <= 0 || rows < 0 || L == 0 || n > toeplitz_inv_max_n()) return 0;
+    Carver c(nullptr);
+    double* p;
+    c.take(p, 2 * (size_t)L); c.take(p, 8 * (size_t)L); c.take(p, 1); c.take(p, (size_t)std::max(rows, 1) * n);
+    return c.off;
+}
+
+int gphm_toeplitz_solve(const double* d_t, int n, const double* d_B, int rows, double* d_X, double* d_g, double* d_sKinv,
+                        double* d_logdet, int* d_status, void* d_work, void* stream) {
+    if (!d_t || !d_g || !d_sKinv || !d_logdet || !d_status || !d_work || (rows > 0 && (!d_B || !d_X))) { set_last_error("gphm_toeplitz_solve: null pointer"); return GPHM_EINVAL; }
+    const int L = n > 0 ? fft_length_for(n) : 0;
+    if (n <= 0 || rows < 0 || L == 0 || n > toeplitz_inv_max_n()) { set_last_error("gphm_toeplitz_solve: n=%d outside [1,%d]", n, std::min(toeplitz_inv_max_n(), 4096)); return GPHM_EINVAL; }
+    if (rows > 0 && d_B == d_X) { set_last_error("gphm_toeplitz_solve: d_X may not alias d_B"); return GPHM_EINVAL; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Carver c(d_work);
+    double *twid, *spec, *hld, *tmp;
+    c.take(twid, 2 * (size_t)L); c.take(spec, 8 * (size_t)L); c.take(hld, 1); c.take(tmp, (size_t)std::max(rows, 1) * n);
+    GPHM_CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+    GPHM_TRY(launch_twiddle_init(twid, L, st));
+    GPHM_TRY(launch_schur_levinson(d_t, 0, n, 0.0, d_g, 0, hld, 0, d_status, 0, 1, st));
+    GPHM_TRY(launch_gs_prepare(d_g, 0, n, L, twid, spec, 0, d_sKinv, 0, 1, st));
+    GPHM_TRY(launch_sum_scaled(hld, 1, 2.0, d_logdet, st));
+    if (rows > 0) {
+        Axis X;
+        X.n = n; X.fftL = L; X.twid = twid; X.gspec = spec;
+        GPHM_TRY(apply_kinv_rows_gs(X, d_B, rows, d_X, tmp, st));
+    }
     return GPHM_OK;
 }
 
@@ -684,6 +775,11 @@ int gphm_plan_uses_fft(const gphm_plan* plan, int axis) {
     return plan->ax[axis].n > 0 && plan->ax[axis].fftL > 0 ? 1 : 0;
 }
 
+int gphm_plan_uses_gs(const gphm_plan* plan, int axis) {
+    if (!plan || axis < 0 || axis > 1) return 0;
+    return plan->ax[axis].n > 0 && plan->ax[axis].gs ? 1 : 0;
+}
+
 int gphm_mg_toeplitz_apply(gphm_plan* plan, int axis, int transposed, const double* d_X, int rows, double alpha, double beta,
                            const double* d_small, double* d_out, void* stream) {
     if (!plan || !d_X || !d_out || !d_small) { set_last_error("gphm_mg_toeplitz_apply: null pointer"); return GPHM_EINVAL; }
@@ -716,11 +812,14 @@ int gphm_mg_theta_grad_fft(gphm_plan* plan, int axis, const double* d_X, const d
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int order = deriv_order(*plan);
     // rows == 0 / empty Linv range still have to define the spectra: weight 0 passes over row 0 of Linv
-    GPHM_TRY(launch_xcorr_spectrum(X.Linv + (size_t)linv_row0 * n, X.Linv + (size_t)linv_row0 * n, linv_row1 - linv_row0, n, n, n,
-                                   X.fftL, X.twid, beta, false, X.specK, st));
-    GPHM_TRY(launch_xcorr_spectrum(d_X, d_Y, rows, n, n, n, X.fftL, X.twid, -1.0, true, X.specK, st));
+    const bool gs_lead = X.gs && linv_row0 == 0 && linv_row1 > 0;     // GS axes: the rank owning row 0 adds the K^-1 sums
+    if (!X.gs)
+        GPHM_TRY(launch_xcorr_spectrum(X.Linv + (size_t)linv_row0 * n, X.Linv + (size_t)linv_row0 * n, linv_row1 - linv_row0, n, n, n,
+                                       X.fftL, X.twid, beta, false, X.specK, st));
+    GPHM_TRY(launch_xcorr_spectrum(d_X, d_Y, rows, n, n, n, X.fftL, X.twid, -1.0, !X.gs, X.specK, st));
     GPHM_TRY(launch_xcorr_spectrum(d_G, d_Y, rows, n, n, n, X.fftL, X.twid, cD, false, X.specD, st));
-    GPHM_TRY(launch_spectrum_to_diag_sums(X.specK, X.specD, X.fftL, X.twid, n, order == 1, X.dirsign, nullptr, 0.0, X.sK, X.sD, st));
+    GPHM_TRY(launch_spectrum_to_diag_sums(X.specK, X.specD, X.fftL, X.twid, n, order == 1, X.dirsign, gs_lead ? X.sKinv : nullptr,
+                                          gs_lead ? beta : 0.0, X.sK, X.sD, st));
     return launch_theta_grad_toeplitz(plan->d.kernel_id, order, X.x, n, theta_of(*plan, d_small, axis), plan->d.Q, X.sK, X.sD,
                                       d_gtheta, st);
 }

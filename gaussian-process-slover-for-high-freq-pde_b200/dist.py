@@ -120,6 +120,9 @@ class CudaOps(object):
     def uses_fft(self, axis):
         return bool(self.lib.gphm_plan_uses_fft(self.plan, axis))
 
+    def uses_gs(self, axis):
+        return bool(self.lib.gphm_plan_uses_gs(self.plan, axis))
+
     def transpose(self, X, tag):
         out = self._buf(tag, (X.shape[1], X.shape[0]))
         _lib.check(self.lib.gphm_transpose(_lib.ptr(X), X.shape[0], X.shape[1], _lib.ptr(out), self._s()), "gphm_transpose")
@@ -266,7 +269,9 @@ class ShardedSolver2D(object):
         o = self.ops
         skip_kinv = fft1 and fft2
         skip = 4 if skip_kinv else 0
-        if self.P == 1:
+        gs = getattr(o, "uses_gs", None)
+        if self.P == 1 or (gs is not None and gs(0) and gs(1)):
+            # uniform grids: the Toeplitz inverse generators cost O(n^2) - every rank computes both, no broadcast
             o.factor(small, 3 | skip)
             return o.logdets()
         half = self.P // 2
@@ -290,7 +295,8 @@ class ShardedSolver2D(object):
         small, U_r = self.small, self.U
         fft1, fft2 = o.uses_fft(0), o.uses_fft(1)
         ld = self._factor(small, fft1, fft2)
-        D1, D2 = o.mat(0, 1), o.mat(1, 1)
+        D1 = None if fft1 else o.mat(0, 1)
+        D2 = None if fft2 else o.mat(1, 1)
         # forward
         Bt_r = o.apply_kinv(1, 1, U_r, "Bt_r")                           # U K2^-1            (R)
         U_c = self.r2c(U_r)

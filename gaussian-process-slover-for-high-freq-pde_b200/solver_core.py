@@ -227,3 +227,25 @@ def solve_spd(K, B):
     """K^-1 B through libgphm's Cholesky + L^-1 (the reference's jnp.linalg.solve call sites)."""
     _, Linv, _, _ = potrf_inv(K)
     return dgemm(Linv, dgemm(Linv, B), transA=True)
+
+
+def toeplitz_solve(t, B=None):
+    """(X, g, sKinv, logdet, status) for the SPD Toeplitz matrix with first column t: X[r] = K^-1 B[r]
+    for every row of B (None: no right-hand sides), g = K^-1 e_0, sKinv = diagonal sums of K^-1."""
+    lib = _lib.load()
+    t = as_dev(t).reshape(-1).contiguous()
+    n = t.numel()
+    Bd = None if B is None else as_dev(B).reshape(-1, n).contiguous()
+    rows = 0 if Bd is None else Bd.shape[0]
+    X = None if Bd is None else torch.empty_like(Bd)
+    g, sK = torch.empty_like(t), torch.empty_like(t)
+    logdet = torch.empty(1, dtype=DT, device=t.device)
+    status = torch.zeros(1, dtype=torch.int32, device=t.device)
+    nbytes = lib.gphm_toeplitz_work_bytes(n, rows)
+    if nbytes == 0:
+        raise ValueError("toeplitz_solve: n=%d not supported (1 <= n <= 4096)" % n)
+    work = torch.empty(nbytes, dtype=torch.uint8, device=t.device)
+    _lib.check(lib.gphm_toeplitz_solve(_lib.ptr(t), n, _lib.ptr(Bd), rows, _lib.ptr(X), _lib.ptr(g), _lib.ptr(sK),
+                                       _lib.ptr(logdet), _lib.ptr(status), _lib.ptr(work), _lib.stream_ptr()),
+               "gphm_toeplitz_solve")
+    return X, g, sK, logdet, status

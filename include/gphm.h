@@ -64,7 +64,10 @@ typedef struct gphm_problem_desc {
     int force_general;   /* bit 0: never use the Toeplitz fast path even on uniform grids;
                             bit 1: Toeplitz Grams, but Kbar/Dbar by GEMM + direct diagonal sums (no FFT);
                             bit 2: FFT diagonal sums, but K^-1 by GEMM + direct sums;
-                            bit 3: derivative-Gram products D*A, D^T*G by GEMM, not Toeplitz FFT */
+                            bit 3: derivative-Gram products D*A, D^T*G by GEMM, not Toeplitz FFT;
+                            bit 4: K^-1 by blocked Cholesky + triangular GEMMs even on uniform grids
+                                   (default there: Schur/Levinson recursion + Gohberg-Semencul FFT
+                                   products, no dense factorisation) */
     double llk_weight;   /* trick_paras['llk_weight'] */
     double logdet;       /* trick_paras['logdet'] (True -> 1.0) */
     double beta;         /* advection speed, trick_paras['beta'] (ignored otherwise) */
@@ -113,6 +116,17 @@ GPHM_API int gphm_dgemm(int transA, int transB, int M, int N, int K, double alph
 GPHM_API size_t gphm_potrf_work_bytes(int n);
 GPHM_API int gphm_potrf_inv(double* d_K, int n, double* d_L, double* d_Linv, double* d_logdet, int* d_status,
                    void* d_work, void* stream);
+/* The same solve / slogdet pair for a symmetric positive definite TOEPLITZ matrix given by its first
+ * column d_t (n entries, jitter already added) - what K is on the uniform grids of every reference
+ * config (np.linspace, model_GP_solver_2d.py:360-362).  No dense factorisation: Schur/Levinson
+ * recursion for d_g = K^-1 e_0 (n) and log|K|, then each of the `rows` right-hand sides (rows of
+ * d_B, rows x n) is solved by the Gohberg-Semencul formula as four FFT convolutions -> d_X.
+ * d_sKinv (n) gets the diagonal sums of K^-1 (d > 0: both triangles) that the theta-gradient of
+ * log|K| needs.  n <= 4096; d_status: 0 = SPD, else 1 + first step with a non-positive prediction
+ * error; d_work holds gphm_toeplitz_work_bytes(n, rows) bytes; d_X may not alias d_B.             */
+GPHM_API size_t gphm_toeplitz_work_bytes(int n, int rows);
+GPHM_API int gphm_toeplitz_solve(const double* d_t, int n, const double* d_B, int rows, double* d_X, double* d_g,
+                        double* d_sKinv, double* d_logdet, int* d_status, void* d_work, void* stream);
 
 /* ---- plan: one solver instance ---------------------------------------------------------------
  * Host inputs are copied to the device once.  h_x (n1), h_y (n2; NULL when dim == 1),
@@ -201,6 +215,12 @@ GPHM_API int gphm_mg_theta_grad(gphm_plan* plan, int axis, const double* d_Kbar,
  * Dbar = cD * G^T Y.  Needs gphm_plan_uses_fft(plan, axis).  gphm_plan_factor: axis_mask bit 2
  * skips forming K^-1 (not needed on this path).                                                 */
 GPHM_API int gphm_plan_uses_fft(const gphm_plan* plan, int axis);
+/* 1 when the axis' K^-1 (jnp.linalg.solve / slogdet, model_GP_solver_2d.py:104-105,158-161) is applied through
+ * the Toeplitz inverse generator (Schur/Levinson + Gohberg-Semencul): gphm_plan_factor is then O(n^2) and
+ * local to every rank (nothing to broadcast), gphm_plan_matrix has no L / Linv / K^-1 to return, and
+ * gphm_mg_theta_grad_fft takes the K^-1 diagonal sums from the generator on the rank whose
+ * linv_row0 == 0 (the Linv row range only selects that rank).                                   */
+GPHM_API int gphm_plan_uses_gs(const gphm_plan* plan, int axis);
 GPHM_API int gphm_transpose(const double* d_in, int rows, int cols, double* d_out, void* stream);
 /* Uniform-grid derivative-Gram product without the Gram matrix: every row x of d_X (rows x n_axis)
  * becomes alpha * D x (transposed = 0) or alpha * D^T x (transposed = 1), + beta * d_out row, by

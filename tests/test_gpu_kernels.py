@@ -94,6 +94,41 @@ def test_cholesky_flags_non_spd(gphm):
     assert int(status) == 151                       # 1 + index of the first bad pivot
 
 
+@pytest.mark.parametrize("n", [1, 2, 7, 255, 256, 257, 400, 1024, 2047, 4096])
+@pytest.mark.parametrize("kernel", ["Matern52_Cos_1d", "SE_Cos_1d"])
+def test_toeplitz_solve_matches_cholesky(gphm, oracle, kernel, n):
+    """gphm_toeplitz_solve (Schur/Levinson + Gohberg-Semencul FFT products, no dense factorisation)
+    against torch's Cholesky on the same Gram matrix (cond(K) 4e6 .. 5e7).  Two stable FP64
+    algorithms agree to ~cond(K)*eps: bounds 2e-8 on the solution / generator / K^-1 diagonal
+    sums, 1e-9 relative on log|K|."""
+    x = torch.linspace(0, 1, n, dtype=DT) * 2 * math.pi
+    K = oracle.gram(kernel, x, x, theta_state(30, 20.0), 0, 1e-6)
+    B = torch.stack([torch.sin(3 * x) + 0.2 * torch.cos(17 * x), torch.cos(5 * x) * x, torch.ones(n, dtype=DT)])
+    X, g, sK, logdet, status = gphm.solver_core.toeplitz_solve(K[:, 0], B)
+    assert int(status) == 0
+    L = torch.linalg.cholesky(K)
+    Kinv = torch.cholesky_inverse(L)
+    assert rel(X, torch.cholesky_solve(B.T.contiguous(), L).T) <= 2e-8
+    assert rel(g, Kinv[:, 0]) <= 2e-8
+    assert rel(sK, oracle._diag_sums(Kinv)) <= 2e-8
+    want_ld = float(2.0 * torch.log(torch.diagonal(L)).sum())
+    assert abs(float(logdet) - want_ld) <= 1e-9 * max(1.0, abs(want_ld))
+    # residual check against the matrix itself (independent of any second solver)
+    assert rel(X.cpu() @ K, B) <= 1e-7
+
+
+def test_toeplitz_solve_flags_non_spd(gphm):
+    t = torch.zeros(300, dtype=DT)
+    t[0], t[1] = 1.0, 0.8                  # tridiagonal Toeplitz with 2*0.8 > 1: indefinite for n = 300
+    _, _, _, _, status = gphm.solver_core.toeplitz_solve(t)
+    assert int(status) > 0
+    t[1] = 0.3
+    _, _, _, _, status = gphm.solver_core.toeplitz_solve(t)
+    assert int(status) == 0
+    with pytest.raises(ValueError):
+        gphm.solver_core.toeplitz_solve(torch.ones(5000, dtype=DT))
+
+
 def test_adam_matches_oracle(gphm, oracle):
     lib = gphm._lib.load()
     g = torch.Generator().manual_seed(0)

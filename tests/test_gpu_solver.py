@@ -15,6 +15,11 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 TOL = 1e-6            # north_star: loss and gradients within 1e-6 relative in FP64
 
 
+def gphm_uses_gs(model):
+    lib, plan = model.core.lib, model.core.plan
+    return bool(lib.gphm_plan_uses_gs(plan, 0)) and bool(lib.gphm_plan_uses_gs(plan, 1))
+
+
 def trick(equation, kernel, Q, freq_scale, N, llk=200.0, lr=0.01, **kw):
     d = {"equation": equation, "kernel": kernel, "Q": Q, "freq_scale": freq_scale, "N_col": N, "llk_weight": llk,
          "lr": lr, "logdet": True, "nepoch": 100, "tol": -1, "num_fold": 1, "num_u_trick": 1, "other_paras": ""}
@@ -22,13 +27,13 @@ def trick(equation, kernel, Q, freq_scale, N, llk=200.0, lr=0.01, **kw):
     return d
 
 
-def make_2d(gphm, oracle, equation, kernel, N1, N2, Q, fs, scale, beta=1.0, uniform=True, llk=200.0, M=40):
+def make_2d(gphm, oracle, equation, kernel, N1, N2, Q, fs, scale, beta=1.0, uniform=True, llk=200.0, M=40, mode=0):
     O = oracle
     p, (xt, yt), ut = O.make_problem_2d(equation, kernel, N1, scale, llk_weight=llk, beta=beta, M=M, N2=N2)
     if not uniform:
         p.x, p.y = nonuniform_grid(N1, scale, 1), nonuniform_grid(N2, scale, 2)
     cls = gphm.GP_solver_2d_single_advection if equation.startswith("advection") else gphm.GP_solver_2d_single
-    tp = trick(equation, kernel, Q, fs, N1, llk=llk, beta=beta)
+    tp = trick(equation, kernel, Q, fs, N1, llk=llk, beta=beta, force_general=mode)
     model = cls(p.bvals.numpy(), (p.x.numpy(), p.y.numpy()), p.src.numpy(), 1e-6, (xt.numpy(), yt.numpy()), ut.numpy(), tp)
     return p, model, (xt, yt), ut
 
@@ -68,8 +73,22 @@ CASES_2D = [
 def test_logjoint_grad_2d_parity(gphm, oracle, equation, kernel, N1, N2, Q, fs, scale, beta, uniform):
     p, model, _, _ = make_2d(gphm, oracle, equation, kernel, N1, N2, Q, fs, scale, beta, uniform)
     assert bool(model.core.lib.gphm_plan_uses_toeplitz(model.core.plan, 0)) == uniform
+    assert bool(model.core.lib.gphm_plan_uses_gs(model.core.plan, 0)) == uniform
+    assert bool(model.core.lib.gphm_plan_uses_gs(model.core.plan, 1)) == uniform
     check_terms_and_grads(oracle, p, model, oracle.state_S1(p, Q=Q, freq_scale=fs))
     check_terms_and_grads(oracle, p, model, oracle.init_params_2d(N1, N2, Q, fs))
+
+
+@pytest.mark.parametrize("equation,kernel,N1,N2,Q,fs,scale,beta,uniform", [c for c in CASES_2D if c[-1]][:7])
+@pytest.mark.parametrize("mode", [16, 16 | 8])
+def test_logjoint_grad_2d_parity_cholesky_path(gphm, oracle, mode, equation, kernel, N1, N2, Q, fs, scale, beta, uniform):
+    """Uniform grids default to the Toeplitz inverse generator (Schur/Levinson + Gohberg-Semencul);
+    force_general bit 4 keeps the blocked Cholesky + triangular-GEMM path (what larger-than-4096 or
+    non-uniform axes use), bit 3 additionally the derivative-Gram GEMMs: same parity bound."""
+    p, model, _, _ = make_2d(gphm, oracle, equation, kernel, N1, N2, Q, fs, scale, beta, uniform, mode=mode)
+    lib = model.core.lib
+    assert not lib.gphm_plan_uses_gs(model.core.plan, 0) and not lib.gphm_plan_uses_gs(model.core.plan, 1)
+    check_terms_and_grads(oracle, p, model, oracle.state_S1(p, Q=Q, freq_scale=fs))
 
 
 def test_logjoint_grad_2d_golden_final_state(gphm, oracle):
@@ -224,16 +243,25 @@ def test_properties_at_scale(gphm, oracle, N):
         assert float((gch.reshape(-1) - want[path].reshape(-1)).norm()) <= TOL * float(want[path].norm()), path
     loss2, grads2 = model.value_and_grad(s1)
     assert float(loss2) == float(loss) and all(torch.equal(a, b) for (_, a), (_, b) in zip(tree_flatten(grads), tree_flatten(grads2)))
-    # the theta-gradient paths agree: FFT diagonal sums (default), K^-1 by GEMM (4), GEMM + direct sums (2), general (1)
-    for mode in (8, 4, 2, 1):
+    # the paths agree: Toeplitz inverse generator + FFT products (default), Cholesky + FFT diagonal sums (16),
+    # derivative-Gram GEMMs (8), K^-1 by GEMM (4), GEMM + direct sums (2), general (1).  Default vs the rest are two
+    # different stable factorisations of a matrix with cond(K) ~ 1e7: they agree to ~cond*eps (5e-7), not to 1e-7.
+    assert gphm_uses_gs(model)
+    for mode in (16, 8, 4, 2, 1):
         tp = trick("poisson_2d-sin_add_cos", "Matern52_Cos_1d", 30, 20.0, N, force_general=mode)
         gen = gphm.GP_solver_2d_single(p.bvals.numpy(), (p.x.numpy(), p.y.numpy()), p.src.numpy(), 1e-6,
                                        (p.x.numpy()[:5], p.y.numpy()[:5]), np.zeros((5, 5)), tp)
         assert bool(gen.core.lib.gphm_plan_uses_toeplitz(gen.core.plan, 0)) == (mode != 1)
+        assert gphm_uses_gs(gen) == (mode == 8)
         lg, gg = gen.value_and_grad(s1)
+        if mode == 16:
+            ref_loss, ref_grads = lg, gg            # the Cholesky-family reference for the remaining modes
         assert abs(float(lg) - float(loss)) <= 1e-9 * abs(float(loss))
         for (path, a), (_, b) in zip(tree_flatten(gg), tree_flatten(grads)):
-            assert float((a - b).norm()) <= 1e-7 * float(b.norm()), (mode, path)
+            assert float((a - b).norm()) <= 5e-7 * float(b.norm()), (mode, path)
+        if mode in (4, 2, 1):
+            for (path, a), (_, b) in zip(tree_flatten(gg), tree_flatten(ref_grads)):
+                assert float((a - b).norm()) <= 1e-7 * float(b.norm()), (mode, path)
     # central difference along dL/dU reproduces |g|^2 (the Poisson loss is quadratic in U)
     gU = grads["U"]
     eps = 1e-3 / float(gU.abs().max())
