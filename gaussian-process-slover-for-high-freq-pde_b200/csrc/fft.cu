@@ -52,6 +52,7 @@ xcorr_spectrum_kernel(const double* __restrict__ X, const double* __restrict__ Y
                       double2* __restrict__ partial) {
     extern __shared__ double2 xs[];
     const int tid = threadIdx.x;
+    fft_load_twiddles(xs, L, logL, W, tid);
     double2 acc[FFT_ACC];
 #pragma unroll
     for (int k = 0; k < FFT_ACC; ++k) acc[k] = make_double2(0.0, 0.0);
@@ -117,6 +118,17 @@ xcorr_spectrum_kernel(const double* __restrict__ X, const double* __restrict__ Y
     }
 }
 
+// part[0][p] <- sum_c part[c][p] in a fixed order (deterministic); blockIdx.y selects the K / D spectra
+__global__ void __launch_bounds__(256)
+reduce_partial_spectra_kernel(double2* __restrict__ partK, double2* __restrict__ partD, int nparts, int L) {
+    double2* part = blockIdx.y == 0 ? partK : partD;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= L) return;
+    double2 s = part[p];
+    for (int c = 1; c < nparts; ++c) { const double2 v = part[(size_t)c * L + p]; s.x += v.x; s.y += v.y; }
+    part[p] = s;
+}
+
 // blockIdx.x = 0: K spectrum -> sK (symmetric sums); 1: D spectrum -> sD (symmetric or antisymmetric)
 __global__ void __launch_bounds__(FFT_THREADS, 1)
 spectrum_to_diag_sums_kernel(const double2* __restrict__ partK, const double2* __restrict__ partD, int nparts, int L,
@@ -125,6 +137,7 @@ spectrum_to_diag_sums_kernel(const double2* __restrict__ partK, const double2* _
                              double* __restrict__ sK, double* __restrict__ sD) {
     extern __shared__ double2 xs[];
     const int tid = threadIdx.x;
+    fft_load_twiddles(xs, L, logL, W, tid);
     const double2* part = blockIdx.x == 0 ? partK : partD;
     for (int p = tid; p < L; p += FFT_THREADS) {
         double2 s = make_double2(0.0, 0.0);
@@ -163,6 +176,7 @@ toeplitz_spectrum_kernel(const double* __restrict__ tab, int n, int L, int logL,
                          int antisym, double dirsign, double2* __restrict__ spec) {
     extern __shared__ double2 xs[];
     const int tid = threadIdx.x;
+    fft_load_twiddles(xs, L, logL, W, tid);
     for (int j = tid; j < L; j += FFT_THREADS) {
         double v = 0.0;
         if (j < n) v = antisym ? dirsign * tab[j] : tab[j];                       // i - j = m >= 0
@@ -182,6 +196,7 @@ toeplitz_apply_kernel(const double* __restrict__ X, int rows, int n, int ldx, co
                       int ldo) {
     extern __shared__ double2 xs[];
     const int tid = threadIdx.x;
+    fft_load_twiddles(xs, L, logL, W, tid);
     const int npairs = (rows + 1) / 2;
     for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
         const int r0 = 2 * pr, r1 = r0 + 1;
@@ -261,10 +276,16 @@ int launch_spectrum_to_diag_sums(const double* partK, const double* partD, int L
                                  double dirsign, const double* addK, double addK_scale, double* sK, double* sD,
                                  cudaStream_t st) {
     GPHM_TRY(fft_init());
+    {   // sum the per-CTA partial spectra with the whole GPU first (148 x L complex values each)
+        LaunchScope scope(CAT_FFT, st, 0.0, 2.0 * 16.0 * fft_grid() * (double)L);
+        reduce_partial_spectra_kernel<<<dim3((L + 255) / 256, 2), 256, 0, st>>>(
+            reinterpret_cast<double2*>(const_cast<double*>(partK)), reinterpret_cast<double2*>(const_cast<double*>(partD)), fft_grid(), L);
+    }
+    GPHM_LAUNCH_OK();
     {
         LaunchScope scope(CAT_FFT, st);
         spectrum_to_diag_sums_kernel<<<2, FFT_THREADS, fft_smem_bytes(L), st>>>(
-            reinterpret_cast<const double2*>(partK), reinterpret_cast<const double2*>(partD), fft_grid(), L, ilog2(L),
+            reinterpret_cast<const double2*>(partK), reinterpret_cast<const double2*>(partD), 1, L, ilog2(L),
             reinterpret_cast<const double2*>(W), n, antisym ? 1 : 0, dirsign, addK, addK_scale, sK, sD);
     }
     GPHM_LAUNCH_OK();
@@ -287,6 +308,8 @@ int launch_toeplitz_apply(const double* X, int rows, int n, int ldx, const doubl
                           double beta, double* Out, int ldo, cudaStream_t st) {
     GPHM_TRY(fft_init());
     if (rows <= 0) return GPHM_OK;
+    if (toeplitz_fused_supported(L) && L >= 2 * n)
+        return launch_toeplitz_apply_fused(X, rows, n, ldx, spec, L, W, alpha, beta, nullptr, 0, Out, ldo, st);
     {
         LaunchScope scope(CAT_FFT, st, 0.0, 16.0 * rows * (double)n);
         const int grid = std::min(fft_grid() * 1, (rows + 1) / 2);

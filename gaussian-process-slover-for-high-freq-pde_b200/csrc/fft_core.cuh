@@ -1,5 +1,15 @@
 // In-place shared-memory FFT building blocks shared by fft.cu and toeplitz_inv.cu (FP64 complex,
 // power-of-two lengths up to FFT_MAX_L, register-blocked radix-8 passes on a padded layout).
+//
+// Twiddles: a radix-8 pass that fuses the radix-2 stages s, s+1, s+2 (butterfly j of q = L >> (s+3))
+// needs  exp(-2 pi i (j + m q) 2^(s+t) / L)  = w_t[j] * W8^m / W4^m / 1  with only three table values
+//   w1 = T_s[j],  w2 = T_{s+1}[j],  w4 = T_{s+2}[j]          (T_s[j] = exp(-2 pi i j 2^s / L))
+// and the constants W8^m.  The 3*q values per pass (56 KB for L = 8192, all passes) are staged once
+// per CTA in shared memory behind the data (the full per-stage tables - 128 KB, seven gathers per
+// butterfly through an L1 that the 144 KB data buffer leaves ~100 KB of - were the bottleneck:
+// long-scoreboard stalls).  Forward = DIF (natural in, bit-reversed out), passes (8,8,...,tail);
+// inverse = DIT (bit-reversed in, natural out), passes (head,8,...,8); the inverse pass at stage s
+// uses the table of the forward pass at stage logL-3-s.  The tail/head pass has q = 1: constants only.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -12,86 +22,369 @@ constexpr int FFT_ACC = FFT_MAX_L / FFT_THREADS;      // spectrum bins per threa
 // shared-memory layout: one pad slot per 8 complex values, so that the 8 lanes of a quarter-warp
 // always hit 8 different 16-byte bank groups for every stride the passes use
 __device__ __forceinline__ int PADI(int i) { return i + (i >> 3); }
-inline size_t fft_smem_bytes(int L) { return (size_t)(L + (L >> 3) + 1) * sizeof(double2); }
+__host__ __device__ inline int fft_data_slots(int L) { return L + (L >> 3) + 1; }
+// entries of the compact twiddle table: 3 * sum over radix-8 passes of q_p = L >> (3p+3)
+__host__ __device__ inline int fft_twiddle_slots(int L) {
+    int logL = 0;
+    while ((1 << logL) < L) ++logL;
+    int n = 0;
+    for (int s = 0; logL - s >= 3; s += 3) n += 3 * (L >> (s + 3));
+    return n;
+}
+inline size_t fft_smem_bytes(int L) { return (size_t)(fft_data_slots(L) + fft_twiddle_slots(L)) * sizeof(double2); }
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {      // a * conj(b)
+    return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 
-// K radix-2 DIF stages s..s+K-1 fused in registers: each thread owns the 2^K points
-// base + m*q (q = L >> (s+K)) of one sub-transform.
-template <int K>
-__device__ __forceinline__ void dif_pass(double2* xs, int L, int logL, int s, const double2* __restrict__ W, int tid) {
-    constexpr int R = 1 << K;
-    const int lq = logL - s - K, q = 1 << lq;
-    for (int b = tid; b < (L >> K); b += FFT_THREADS) {
-        const int j = b & (q - 1);
-        const int base = ((b >> lq) << (lq + K)) + j;
-        double2 e[R];
-#pragma unroll
-        for (int m = 0; m < R; ++m) e[m] = xs[PADI(base + m * q)];
-#pragma unroll
-        for (int t = 0; t < K; ++t) {
-            const int span = R >> (t + 1);
-            const double2* __restrict__ Ws = W + (L - (L >> (s + t)));
-#pragma unroll
-            for (int m = 0; m < R; ++m) {
-                if (m & span) continue;
-                const double2 a = e[m], c = e[m + span];
-                e[m] = make_double2(a.x + c.x, a.y + c.y);
-                e[m + span] = cmul(make_double2(a.x - c.x, a.y - c.y), Ws[j + (m & (span - 1)) * q]);
-            }
+// Shared-memory twiddle table behind the data buffer; W is the global per-stage table built by
+// twiddle_init_kernel:  W[(L - (L >> s)) + j] = T_s[j],  j < L >> (s+1).   Ends with a barrier.
+__device__ __forceinline__ double2* fft_twiddles(double2* xs, int L) { return xs + fft_data_slots(L); }
+__device__ __forceinline__ void fft_load_twiddles(double2* xs, int L, int logL, const double2* __restrict__ W, int tid) {
+    double2* tw = fft_twiddles(xs, L);
+    for (int s = 0; logL - s >= 3; s += 3) {
+        const int q = L >> (s + 3);
+        for (int i = tid; i < 3 * q; i += FFT_THREADS) {
+            const int t = i / q, j = i - t * q;
+            tw[i] = W[(L - (L >> (s + t))) + j];
         }
-#pragma unroll
-        for (int m = 0; m < R; ++m) xs[PADI(base + m * q)] = e[m];
+        tw += 3 * q;
     }
     __syncthreads();
 }
 
-// K radix-2 inverse DIT stages s..s+K-1 (half-spans 2^s .. 2^(s+K-1)) fused in registers.
-template <int K>
-__device__ __forceinline__ void dit_pass(double2* xs, int L, int logL, int s, const double2* __restrict__ W, int tid) {
-    constexpr int R = 1 << K;
+constexpr double kRsqrt2 = 0.70710678118654752440;
+
+// One radix-8 DIF butterfly: e[0..7] are the points base + m*q; output slot m holds frequency
+// brev3(m) of the 8-point sub-transform, twiddled for the next pass.
+__device__ __forceinline__ void bfly8_dif(double2 (&e)[8], double2 w1, double2 w2, double2 w4) {
+    // stage 0: span 4, twiddle w1 * W8^m
+    {
+        const double2 d0 = csub(e[0], e[4]), d1 = csub(e[1], e[5]), d2 = csub(e[2], e[6]), d3 = csub(e[3], e[7]);
+        e[0] = cadd(e[0], e[4]); e[1] = cadd(e[1], e[5]); e[2] = cadd(e[2], e[6]); e[3] = cadd(e[3], e[7]);
+        e[4] = cmul(d0, w1);
+        e[5] = cmul(make_double2((d1.x + d1.y) * kRsqrt2, (d1.y - d1.x) * kRsqrt2), w1);
+        e[6] = cmul(make_double2(d2.y, -d2.x), w1);
+        e[7] = cmul(make_double2((d3.y - d3.x) * kRsqrt2, -(d3.x + d3.y) * kRsqrt2), w1);
+    }
+    // stage 1: span 2 inside each half, twiddle w2 * W4^m
+#pragma unroll
+    for (int h = 0; h < 8; h += 4) {
+        const double2 d0 = csub(e[h], e[h + 2]), d1 = csub(e[h + 1], e[h + 3]);
+        e[h] = cadd(e[h], e[h + 2]); e[h + 1] = cadd(e[h + 1], e[h + 3]);
+        e[h + 2] = cmul(d0, w2);
+        e[h + 3] = cmul(make_double2(d1.y, -d1.x), w2);
+    }
+    // stage 2: span 1, twiddle w4
+#pragma unroll
+    for (int h = 0; h < 8; h += 2) {
+        const double2 d = csub(e[h], e[h + 1]);
+        e[h] = cadd(e[h], e[h + 1]);
+        e[h + 1] = cmul(d, w4);
+    }
+}
+
+// One radix-8 inverse DIT butterfly (conjugate twiddles): stages span 1 (u1), span 2 (u2 * W4^m), span 4 (u4 * W8^m).
+__device__ __forceinline__ void bfly8_dit_inv(double2 (&e)[8], double2 u1, double2 u2, double2 u4) {
+#pragma unroll
+    for (int h = 0; h < 8; h += 2) {
+        const double2 t = cmulc(e[h + 1], u1);
+        const double2 a = e[h];
+        e[h] = cadd(a, t); e[h + 1] = csub(a, t);
+    }
+#pragma unroll
+    for (int h = 0; h < 8; h += 4) {
+        const double2 t0 = cmulc(e[h + 2], u2);
+        const double2 v = cmulc(e[h + 3], u2);
+        const double2 t1 = make_double2(-v.y, v.x);                 // * conj(W4) = * (+i)
+        const double2 a0 = e[h], a1 = e[h + 1];
+        e[h] = cadd(a0, t0); e[h + 2] = csub(a0, t0);
+        e[h + 1] = cadd(a1, t1); e[h + 3] = csub(a1, t1);
+    }
+    {
+        const double2 t0 = cmulc(e[4], u4);
+        const double2 v1 = cmulc(e[5], u4), v2 = cmulc(e[6], u4), v3 = cmulc(e[7], u4);
+        const double2 t1 = make_double2((v1.x - v1.y) * kRsqrt2, (v1.x + v1.y) * kRsqrt2);      // * (1+i)/sqrt2
+        const double2 t2 = make_double2(-v2.y, v2.x);                                           // * i
+        const double2 t3 = make_double2(-(v3.x + v3.y) * kRsqrt2, (v3.x - v3.y) * kRsqrt2);     // * (-1+i)/sqrt2
+        const double2 a0 = e[0], a1 = e[1], a2 = e[2], a3 = e[3];
+        e[0] = cadd(a0, t0); e[4] = csub(a0, t0);
+        e[1] = cadd(a1, t1); e[5] = csub(a1, t1);
+        e[2] = cadd(a2, t2); e[6] = csub(a2, t2);
+        e[3] = cadd(a3, t3); e[7] = csub(a3, t3);
+    }
+}
+
+// Radix-8 DIF pass over stages s..s+2; tw = this pass' compact table [w1 | w2 | w4], q entries each.
+__device__ __forceinline__ void dif_pass8(double2* xs, int L, int logL, int s, const double2* tw, int tid) {
+    const int lq = logL - s - 3, q = 1 << lq;
+    for (int b = tid; b < (L >> 3); b += FFT_THREADS) {
+        const int j = b & (q - 1);
+        const int base = ((b >> lq) << (lq + 3)) + j;
+        double2 e[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) e[m] = xs[PADI(base + m * q)];
+        bfly8_dif(e, tw[j], tw[q + j], tw[2 * q + j]);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) xs[PADI(base + m * q)] = e[m];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void dit_pass8(double2* xs, int L, int logL, int s, const double2* tw, int tid) {
     const int q = 1 << s;
-    for (int b = tid; b < (L >> K); b += FFT_THREADS) {
+    for (int b = tid; b < (L >> 3); b += FFT_THREADS) {
         const int j = b & (q - 1);
-        const int base = ((b >> s) << (s + K)) + j;
-        double2 e[R];
+        const int base = ((b >> s) << (s + 3)) + j;
+        double2 e[8];
 #pragma unroll
-        for (int m = 0; m < R; ++m) e[m] = xs[PADI(base + m * q)];
+        for (int m = 0; m < 8; ++m) e[m] = xs[PADI(base + m * q)];
+        bfly8_dit_inv(e, tw[2 * q + j], tw[q + j], tw[j]);          // table of the forward pass at stage logL-3-s
 #pragma unroll
-        for (int t = 0; t < K; ++t) {
-            const int span = 1 << t;
-            const double2* __restrict__ Ws = W + (L - (2 << (s + t)));      // table of forward stage logL-1-(s+t)
-#pragma unroll
-            for (int m = 0; m < R; ++m) {
-                if (m & span) continue;
-                const double2 w = Ws[j + (m & (span - 1)) * q];
-                const double2 tt = cmul(e[m + span], make_double2(w.x, -w.y));
-                const double2 a = e[m];
-                e[m] = make_double2(a.x + tt.x, a.y + tt.y);
-                e[m + span] = make_double2(a.x - tt.x, a.y - tt.y);
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < R; ++m) xs[PADI(base + m * q)] = e[m];
+        for (int m = 0; m < 8; ++m) xs[PADI(base + m * q)] = e[m];
     }
     __syncthreads();
 }
 
-// natural order in -> bit-reversed order out
-__device__ __forceinline__ void fft_dif_inplace(double2* xs, int L, int logL, const double2* __restrict__ W, int tid) {
+// Tail (forward) / head (inverse) pass of 2^K points with unit stride: every twiddle is a constant.
+template <int K>
+__device__ __forceinline__ void unit_pass(double2* xs, int L, bool inverse, int tid) {
+    constexpr int R = 1 << K;
+    for (int b = tid; b < (L >> K); b += FFT_THREADS) {
+        const int base = b << K;
+        double2 e[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) e[m] = xs[PADI(base + m)];
+        if (K == 1) {
+            const double2 a = e[0], c = e[1];
+            e[0] = cadd(a, c); e[1] = csub(a, c);
+        } else if (!inverse) {   // K == 2, DIF: span 2 (twiddle W4^m), then span 1
+            const double2 d0 = csub(e[0], e[2]), d1 = csub(e[1], e[3]);
+            const double2 s0 = cadd(e[0], e[2]), s1 = cadd(e[1], e[3]);
+            const double2 r1 = make_double2(d1.y, -d1.x);
+            e[0] = cadd(s0, s1); e[1] = csub(s0, s1); e[2] = cadd(d0, r1); e[3] = csub(d0, r1);
+        } else {                 // K == 2, inverse DIT: span 1, then span 2 (twiddle conj W4^m)
+            const double2 a0 = cadd(e[0], e[1]), a1 = csub(e[0], e[1]);
+            const double2 b0 = cadd(e[2], e[3]), v = csub(e[2], e[3]);
+            const double2 b1 = make_double2(-v.y, v.x);
+            e[0] = cadd(a0, b0); e[2] = csub(a0, b0); e[1] = cadd(a1, b1); e[3] = csub(a1, b1);
+        }
+#pragma unroll
+        for (int m = 0; m < R; ++m) xs[PADI(base + m)] = e[m];
+    }
+    __syncthreads();
+}
+
+// natural order in -> bit-reversed order out.  Needs fft_load_twiddles(xs, L, ...) once per CTA.
+__device__ __forceinline__ void fft_dif_inplace(double2* xs, int L, int logL, const double2* __restrict__, int tid) {
+    const double2* tw = fft_twiddles(xs, L);
     int s = 0;
-    for (; logL - s >= 3; s += 3) dif_pass<3>(xs, L, logL, s, W, tid);
-    if (logL - s == 2) dif_pass<2>(xs, L, logL, s, W, tid);
-    else if (logL - s == 1) dif_pass<1>(xs, L, logL, s, W, tid);
+    for (; logL - s >= 3; s += 3) { dif_pass8(xs, L, logL, s, tw, tid); tw += 3 * (L >> (s + 3)); }
+    if (logL - s == 2) unit_pass<2>(xs, L, false, tid);
+    else if (logL - s == 1) unit_pass<1>(xs, L, false, tid);
 }
 // bit-reversed order in -> natural order out (unscaled inverse)
-__device__ __forceinline__ void fft_dit_inverse_inplace(double2* xs, int L, int logL, const double2* __restrict__ W, int tid) {
-    int s = 0;
-    for (; logL - s >= 3; s += 3) dit_pass<3>(xs, L, logL, s, W, tid);
-    if (logL - s == 2) dit_pass<2>(xs, L, logL, s, W, tid);
-    else if (logL - s == 1) dit_pass<1>(xs, L, logL, s, W, tid);
+__device__ __forceinline__ void fft_dit_inverse_inplace(double2* xs, int L, int logL, const double2* __restrict__, int tid) {
+    const int r = logL % 3;
+    if (r == 2) unit_pass<2>(xs, L, true, tid);
+    else if (r == 1) unit_pass<1>(xs, L, true, tid);
+    // inverse pass at stage s pairs with the forward pass at stage logL-3-s: walk the table backwards
+    const double2* tw = fft_twiddles(xs, L) + fft_twiddle_slots(L);
+    for (int s = r; s + 3 <= logL; s += 3) {
+        tw -= 3 * (1 << s);
+        dit_pass8(xs, L, logL, s, tw, tid);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Fused pipeline pieces (toeplitz_fused.cu): the same transforms with fewer shared-memory sweeps.
+//   pass structure  forward: np8 radix-8 passes (stages 0 .. 3 np8 - 1), then a unit-stride tail
+//   of KT = logL - 3 np8 in {1,2,3} stages whose twiddles are constants; inverse: head, np8 passes.
+//   dif_first          global load (zero padded) fused into the first forward pass
+//   mid_fused          forward tail + pointwise functor + inverse head in registers
+//   dit_last           last inverse pass fused into the global store (only indices < L/2 are live)
+//   dit_last_dif_first last inverse pass + truncation to n + first forward pass of the next
+//                      convolution in registers (both touch the points j + m L/8)
+// A convolution costs 2 np8 + 1 sweeps instead of 2 (np8 + 1) + 3.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int fft_tail_stages(int logL) { return logL % 3 == 0 ? 3 : logL % 3; }
+
+__device__ __forceinline__ void bfly8_dif_unit(double2 (&e)[8]) {      // bfly8_dif with w1 = w2 = w4 = 1
+    {
+        const double2 d0 = csub(e[0], e[4]), d1 = csub(e[1], e[5]), d2 = csub(e[2], e[6]), d3 = csub(e[3], e[7]);
+        e[0] = cadd(e[0], e[4]); e[1] = cadd(e[1], e[5]); e[2] = cadd(e[2], e[6]); e[3] = cadd(e[3], e[7]);
+        e[4] = d0;
+        e[5] = make_double2((d1.x + d1.y) * kRsqrt2, (d1.y - d1.x) * kRsqrt2);
+        e[6] = make_double2(d2.y, -d2.x);
+        e[7] = make_double2((d3.y - d3.x) * kRsqrt2, -(d3.x + d3.y) * kRsqrt2);
+    }
+#pragma unroll
+    for (int h = 0; h < 8; h += 4) {
+        const double2 d0 = csub(e[h], e[h + 2]), d1 = csub(e[h + 1], e[h + 3]);
+        e[h] = cadd(e[h], e[h + 2]); e[h + 1] = cadd(e[h + 1], e[h + 3]);
+        e[h + 2] = d0;
+        e[h + 3] = make_double2(d1.y, -d1.x);
+    }
+#pragma unroll
+    for (int h = 0; h < 8; h += 2) {
+        const double2 d = csub(e[h], e[h + 1]);
+        e[h] = cadd(e[h], e[h + 1]);
+        e[h + 1] = d;
+    }
+}
+
+__device__ __forceinline__ void bfly8_dit_inv_unit(double2 (&e)[8]) {
+#pragma unroll
+    for (int h = 0; h < 8; h += 2) {
+        const double2 a = e[h], t = e[h + 1];
+        e[h] = cadd(a, t); e[h + 1] = csub(a, t);
+    }
+#pragma unroll
+    for (int h = 0; h < 8; h += 4) {
+        const double2 t0 = e[h + 2], v = e[h + 3];
+        const double2 t1 = make_double2(-v.y, v.x);
+        const double2 a0 = e[h], a1 = e[h + 1];
+        e[h] = cadd(a0, t0); e[h + 2] = csub(a0, t0);
+        e[h + 1] = cadd(a1, t1); e[h + 3] = csub(a1, t1);
+    }
+    {
+        const double2 t0 = e[4], v1 = e[5], v2 = e[6], v3 = e[7];
+        const double2 t1 = make_double2((v1.x - v1.y) * kRsqrt2, (v1.x + v1.y) * kRsqrt2);
+        const double2 t2 = make_double2(-v2.y, v2.x);
+        const double2 t3 = make_double2(-(v3.x + v3.y) * kRsqrt2, (v3.x - v3.y) * kRsqrt2);
+        const double2 a0 = e[0], a1 = e[1], a2 = e[2], a3 = e[3];
+        e[0] = cadd(a0, t0); e[4] = csub(a0, t0);
+        e[1] = cadd(a1, t1); e[5] = csub(a1, t1);
+        e[2] = cadd(a2, t2); e[6] = csub(a2, t2);
+        e[3] = cadd(a3, t3); e[7] = csub(a3, t3);
+    }
+}
+
+template <int KT>
+__device__ __forceinline__ void unit_fwd(double2 (&e)[1 << KT]) {
+    if constexpr (KT == 1) {
+        const double2 a = e[0], c = e[1];
+        e[0] = cadd(a, c); e[1] = csub(a, c);
+    } else if constexpr (KT == 2) {
+        const double2 d0 = csub(e[0], e[2]), d1 = csub(e[1], e[3]);
+        const double2 s0 = cadd(e[0], e[2]), s1 = cadd(e[1], e[3]);
+        const double2 r1 = make_double2(d1.y, -d1.x);
+        e[0] = cadd(s0, s1); e[1] = csub(s0, s1); e[2] = cadd(d0, r1); e[3] = csub(d0, r1);
+    } else {
+        bfly8_dif_unit(e);
+    }
+}
+template <int KT>
+__device__ __forceinline__ void unit_inv(double2 (&e)[1 << KT]) {
+    if constexpr (KT == 1) {
+        const double2 a = e[0], c = e[1];
+        e[0] = cadd(a, c); e[1] = csub(a, c);
+    } else if constexpr (KT == 2) {
+        const double2 a0 = cadd(e[0], e[1]), a1 = csub(e[0], e[1]);
+        const double2 b0 = cadd(e[2], e[3]), v = csub(e[2], e[3]);
+        const double2 b1 = make_double2(-v.y, v.x);
+        e[0] = cadd(a0, b0); e[2] = csub(a0, b0); e[1] = cadd(a1, b1); e[3] = csub(a1, b1);
+    } else {
+        bfly8_dit_inv_unit(e);
+    }
+}
+
+// First forward pass (stage 0, q = L/8) with the input taken from ld(index); indices >= L/2 are zero padding.
+template <class Load>
+__device__ __forceinline__ void dif_first(double2* xs, int L, const double2* tw, int tid, Load ld) {
+    const int q = L >> 3;
+    for (int j = tid; j < q; j += FFT_THREADS) {
+        double2 e[8];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) e[m] = ld(j + m * q);
+#pragma unroll
+        for (int m = 4; m < 8; ++m) e[m] = make_double2(0.0, 0.0);
+        bfly8_dif(e, tw[j], tw[q + j], tw[2 * q + j]);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) xs[PADI(j + m * q)] = e[m];
+    }
+    __syncthreads();
+}
+
+// Forward passes 1 .. np8-1 (after dif_first).
+__device__ __forceinline__ void dif_middle(double2* xs, int L, int logL, int np8, int tid) {
+    const double2* tw = fft_twiddles(xs, L) + 3 * (L >> 3);
+    for (int p = 1; p < np8; ++p) { dif_pass8(xs, L, logL, 3 * p, tw, tid); tw += 3 * (L >> (3 * p + 3)); }
+}
+// Inverse passes at stages KT, KT+3, ..., logL-6 (all but the last one).
+__device__ __forceinline__ void dit_middle(double2* xs, int L, int logL, int np8, int KT, int tid) {
+    const double2* tw = fft_twiddles(xs, L);
+    for (int p = 0; p < np8; ++p) tw += 3 * (L >> (3 * p + 3));
+    for (int p = np8 - 1; p >= 1; --p) {          // inverse stage s = logL - 3 - 3p pairs with forward pass p
+        tw -= 3 * (L >> (3 * p + 3));
+        dit_pass8(xs, L, logL, logL - 3 - 3 * p, tw, tid);
+    }
+}
+
+// Forward tail + functor + inverse head on groups of 2^KT contiguous (bit-reversed-order) bins.
+// f(slot, p, v): slot = static register slot (0 .. 15) of this thread, p = bin position, v = spectrum value.
+template <int KT, class F>
+__device__ __forceinline__ void mid_fused(double2* xs, int L, int tid, F f) {
+    constexpr int R = 1 << KT;
+    constexpr int MAXG = FFT_MAX_L / (R * FFT_THREADS);
+#pragma unroll
+    for (int i = 0; i < MAXG; ++i) {
+        const int g = tid + i * FFT_THREADS;
+        if (g < (L >> KT)) {
+            const int base = g << KT;
+            double2 e[R];
+#pragma unroll
+            for (int m = 0; m < R; ++m) e[m] = xs[PADI(base + m)];
+            unit_fwd<KT>(e);
+#pragma unroll
+            for (int m = 0; m < R; ++m) e[m] = f(i * R + m, base + m, e[m]);
+            unit_inv<KT>(e);
+#pragma unroll
+            for (int m = 0; m < R; ++m) xs[PADI(base + m)] = e[m];
+        }
+    }
+    __syncthreads();
+}
+
+// Last inverse pass (stage logL-3, q = L/8); st(index, value) for the live half (index < L/2).
+template <class Store>
+__device__ __forceinline__ void dit_last(double2* xs, int L, const double2* tw, int tid, Store st) {
+    const int q = L >> 3;
+    for (int j = tid; j < q; j += FFT_THREADS) {
+        double2 e[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) e[m] = xs[PADI(j + m * q)];
+        bfly8_dit_inv(e, tw[2 * q + j], tw[q + j], tw[j]);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) st(j + m * q, e[m]);
+    }
+    __syncthreads();
+}
+
+// Last inverse pass, truncation to the first n entries, first forward pass of the next convolution.
+__device__ __forceinline__ void dit_last_dif_first(double2* xs, int L, const double2* tw, int tid, int n) {
+    const int q = L >> 3;
+    for (int j = tid; j < q; j += FFT_THREADS) {
+        double2 e[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) e[m] = xs[PADI(j + m * q)];
+        const double2 w1 = tw[j], w2 = tw[q + j], w4 = tw[2 * q + j];
+        bfly8_dit_inv(e, w4, w2, w1);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) if (j + m * q >= n) e[m] = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int m = 4; m < 8; ++m) e[m] = make_double2(0.0, 0.0);
+        bfly8_dif(e, w1, w2, w4);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) xs[PADI(j + m * q)] = e[m];
+    }
+    __syncthreads();
 }
 
 }  // namespace gphm

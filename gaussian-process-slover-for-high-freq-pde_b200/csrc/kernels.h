@@ -82,6 +82,14 @@ int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitt
 int launch_gs_prepare(const double* g, long long sG, int n, int L, const double* W, double* spec, long long sSpec,
                       double* sKinv, long long sS, int nsys, cudaStream_t st);
 
+// ---- toeplitz_fused.cu ---------------------------------------------------------------------
+bool toeplitz_fused_supported(int L);   // L >= 16: fused-sweep kernels; smaller sizes use the plain ones in fft.cu
+int launch_toeplitz_apply_fused(const double* X, int rows, int n, int ldx, const double* spec, int L, const double* W,
+                                double alpha, double beta, const double* Add, int lda, double* Out, int ldo, cudaStream_t st);
+// Out[r] = alpha * K^-1 X[r] + beta * Add[r] for every row, K^-1 through the four spectra of launch_gs_prepare
+int launch_gs_apply_fused(const double* X, int rows, int n, int ldx, const double* gspec, int L, const double* W, double alpha,
+                          double beta, const double* Add, int lda, double* Out, int ldo, cudaStream_t st);
+
 // ---- elemwise.cu ---------------------------------------------------------------------------
 struct LossConsts { int dim, eq_type, n1, n2, nb, Q; double llk_weight, logdet, c1; };
 constexpr int kRedBlocks = 592;         // 148 SMs x 4

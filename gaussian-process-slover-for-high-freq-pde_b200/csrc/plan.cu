@@ -285,6 +285,8 @@ int factor_both(gphm_plan& p, const double* small, bool kinv0, bool kinv1, cudaS
 int apply_kinv_rows_gs(const Axis& X, const double* Xm, int rows, double* out, double* tmp, cudaStream_t st) {
     const int n = X.n, L = X.fftL;
     const size_t sp = 2 * (size_t)L;
+    if (toeplitz_fused_supported(L))
+        return launch_gs_apply_fused(Xm, rows, n, n, X.gspec, L, X.twid, 1.0, 0.0, nullptr, 0, out, n, st);
     GPHM_TRY(launch_toeplitz_apply(Xm, rows, n, n, X.gspec, L, X.twid, 1.0, 0.0, out, n, st));            // L(g)^T v
     GPHM_TRY(launch_toeplitz_apply(Xm, rows, n, n, X.gspec + sp, L, X.twid, 1.0, 0.0, tmp, n, st));       // L(h)^T v
     GPHM_TRY(launch_toeplitz_apply(out, rows, n, n, X.gspec + 2 * sp, L, X.twid, 1.0, 0.0, out, n, st));  // L(g) . / g0
@@ -317,10 +319,105 @@ int apply_kinv(gphm_plan& p, int a, int side, const double* Xm, int rows, int co
     return GPHM_OK;
 }
 
+// Uniform grids, every axis on the Toeplitz inverse generator: the whole iteration is FFT work.
+// Four K^-1 applications instead of five: with P1 = c1 D1^T G and P2 = G D2,
+//   V1 = S1 + W/2 = K1^-1 (P1 + Bt/2),   V2 = S2 + W/2 = (P2 + A/2) K2^-1,   dU = V1 + V2 + ...
+// and axis-1 operands stay transposed (rows = columns of the field) from U^T to the diagonal sums.
+int logjoint_grad_gs(gphm_plan& p, const double* U, const double* small, double* gU, double* gsmall, double* terms,
+                     int flags, cudaStream_t st) {
+    const gphm_problem_desc& d = p.d;
+    const bool two = d.dim == 2, fwd_only = (flags & GPHM_FORWARD_ONLY) != 0;
+    const int n1 = d.n1, n2 = d.n2, Q = d.Q;
+    const size_t nf = (size_t)n1 * n2;
+    const double c1 = coef_c1(p);
+    const int order = deriv_order(p);
+    const bool anti = order == 1;
+    Axis& X1 = p.ax[0];
+    Axis& X2 = p.ax[1];
+    GPHM_TRY(factor_gs(p, 0, two ? 2 : 1, small, st));
+    GPHM_TRY(launch_toeplitz_spectrum(X1.tabD, n1, X1.fftL, X1.twid, anti, X1.dirsign, X1.specT, st));
+    if (two) GPHM_TRY(launch_toeplitz_spectrum(X2.tabD, n2, X2.fftL, X2.twid, anti, X2.dirsign, X2.specT, st));
+    auto gs1 = [&](const double* Xr, double* out) {       // rows of length n1 (columns of the field)
+        return launch_gs_apply_fused(Xr, n2, n1, n1, X1.gspec, X1.fftL, X1.twid, 1.0, 0.0, nullptr, 0, out, n1, st);
+    };
+    auto gs2 = [&](const double* Xr, double* out) {       // rows of length n2
+        return launch_gs_apply_fused(Xr, n1, n2, n2, X2.gspec, X2.fftL, X2.twid, 1.0, 0.0, nullptr, 0, out, n2, st);
+    };
+    auto d1 = [&](const double* Xr, double alpha, double beta, const double* add, double* out) {
+        return launch_toeplitz_apply_fused(Xr, n2, n1, n1, X1.specT, X1.fftL, X1.twid, alpha, beta, add, n1, out, n1, st);
+    };
+    auto d2 = [&](const double* Xr, double alpha, double beta, const double* add, double* out) {
+        return launch_toeplitz_apply_fused(Xr, n1, n2, n2, X2.specT, X2.fftL, X2.twid, alpha, beta, add, n2, out, n2, st);
+    };
+    // ---- forward ----
+    const double* Ut = U;                                  // 1-D: the field is one row already
+    if (two) { GPHM_TRY(launch_transpose(U, n1, n2, p.Tf, st)); Ut = p.Tf; }
+    double* At = p.P;
+    GPHM_TRY(gs1(Ut, At));                                 // A^T = (K1^-1 U)^T
+    const double* Bt = U;
+    const double* A = At;
+    if (two) {
+        GPHM_TRY(gs2(U, p.Bt)); Bt = p.Bt;                 // Bt = U K2^-1
+        GPHM_TRY(d1(At, c1, 0.0, nullptr, p.Tf));          // (c1 D1 A)^T
+        GPHM_TRY(launch_transpose(p.Tf, n2, n1, p.R, st));
+        GPHM_TRY(d2(Bt, 1.0, 1.0, nullptr, p.R));          // + Bt D2^T
+        GPHM_TRY(launch_transpose(At, n2, n1, p.A, st)); A = p.A;
+    } else {
+        GPHM_TRY(d1(At, c1, 0.0, nullptr, p.R));
+    }
+    GPHM_TRY(launch_residual(p.R, U, p.src, A, Bt, nf, d.eq_type, p.has_base ? p.base : nullptr, small, Q, p.part, st));    // R <- G
+    const LossConsts lc = loss_consts(p);
+    GPHM_TRY(launch_finalize(lc, U, p.bvals, p.xind, p.part, X1.ldpart, X1.nblk, two ? X2.ldpart : nullptr,
+                             two ? X2.nblk : 0, small, p.eb, terms, fwd_only ? nullptr : gsmall, p.status, st));
+    if (fwd_only) return GPHM_OK;
+    // ---- backward ----
+    const double* G = p.R;
+    const double* Gt = G;
+    const double *V1t, *V2 = nullptr;
+    if (two) {
+        GPHM_TRY(launch_transpose(G, n1, n2, p.S1, st)); Gt = p.S1;
+        GPHM_TRY(launch_transpose(Bt, n1, n2, p.Tf, st));                       // Bt^T
+        GPHM_TRY(d1(Gt, anti ? -c1 : c1, 0.5, nullptr, p.Tf));                  // (c1 D1^T G + Bt/2)^T
+        GPHM_TRY(gs1(p.Tf, p.W)); V1t = p.W;                                    // V1^T
+        GPHM_TRY(launch_transpose(p.W, n2, n1, p.V1, st));
+        GPHM_TRY(d2(G, anti ? -1.0 : 1.0, 0.5, nullptr, p.A));                  // G D2 + A/2  (A is free after the residual)
+        GPHM_TRY(gs2(p.A, p.V2)); V2 = p.V2;
+        GPHM_TRY(launch_grad_u(lc, p.has_base ? p.base : nullptr, U, G, p.V1, p.V2, nullptr, p.eb, p.xind, small, gU, nullptr,
+                               nullptr, st));
+    } else {
+        GPHM_TRY(d1(G, anti ? -c1 : c1, 0.5, U, p.Tf));                         // D^T g + u/2
+        GPHM_TRY(gs1(p.Tf, p.V1)); V1t = p.V1;                                  // s + a/2
+        GPHM_TRY(launch_lincomb(p.S1, 0.5, At, 0.0, nullptr, nf, st));
+        GPHM_TRY(launch_grad_u(lc, p.has_base ? p.base : nullptr, U, G, p.V1, p.S1, nullptr, p.eb, p.xind, small, gU, nullptr,
+                               nullptr, st));
+    }
+    // diagonal sums of Kbar_a = ld/2 N_b K_a^-1 - V_a (.)^T and Dbar_a by row cross-correlations
+    GPHM_TRY(launch_xcorr_spectrum(V1t, At, n2, n1, n1, n1, X1.fftL, X1.twid, -1.0, false, X1.specK, st));
+    GPHM_TRY(launch_xcorr_spectrum(Gt, At, n2, n1, n1, n1, X1.fftL, X1.twid, c1, false, X1.specD, st));
+    GPHM_TRY(launch_spectrum_to_diag_sums(X1.specK, X1.specD, X1.fftL, X1.twid, n1, anti, X1.dirsign, X1.sKinv,
+                                          0.5 * d.logdet * n2, X1.sK, X1.sD, st));
+    if (two) {
+        GPHM_TRY(launch_xcorr_spectrum(V2, Bt, n1, n2, n2, n2, X2.fftL, X2.twid, -1.0, false, X2.specK, st));
+        GPHM_TRY(launch_xcorr_spectrum(G, Bt, n1, n2, n2, n2, X2.fftL, X2.twid, 1.0, false, X2.specD, st));
+        GPHM_TRY(launch_spectrum_to_diag_sums(X2.specK, X2.specD, X2.fftL, X2.twid, n2, anti, X2.dirsign, X2.sKinv,
+                                              0.5 * d.logdet * n1, X2.sK, X2.sD, st));
+    }
+    for (int a = 0; a < (two ? 2 : 1); ++a) {
+        Axis& X = p.ax[a];
+        GPHM_TRY(launch_theta_grad_toeplitz(d.kernel_id, order, X.x, X.n, theta_of(p, small, a), Q, X.sK, X.sD,
+                                            gsmall + (size_t)a * 3 * Q, st));
+    }
+    if (!two) GPHM_CUDA_OK(cudaMemsetAsync(gsmall + 3 * Q, 0, sizeof(double) * 3 * Q, st));
+    return GPHM_OK;
+}
+
 int logjoint_grad(gphm_plan& p, const double* U, const double* small, double* gU, double* gsmall, double* terms,
                   int flags, cudaStream_t st) {
     const gphm_problem_desc& d = p.d;
     const bool two = d.dim == 2, fwd_only = (flags & GPHM_FORWARD_ONLY) != 0;
+    if (p.ax[0].gs && (!two || p.ax[1].gs) && !(d.force_general & 8) && toeplitz_fused_supported(p.ax[0].fftL) &&
+        (!two || toeplitz_fused_supported(p.ax[1].fftL)))
+        return logjoint_grad_gs(p, U, small, gU, gsmall, terms, flags, st);
     const int n1 = d.n1, n2 = d.n2, Q = d.Q;
     const size_t nf = (size_t)n1 * n2;
     const double c1 = coef_c1(p);

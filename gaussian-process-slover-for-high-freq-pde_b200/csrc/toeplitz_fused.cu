@@ -1,0 +1,181 @@
+// Row-wise Toeplitz products on uniform grids with fused shared-memory sweeps (FP64).
+//
+//   toeplitz_apply_fused_kernel   Out[r] = alpha * T X[r] (+ beta * Out[r]): one circulant convolution
+//       per row (derivative-Gram products D A, D^T G, Bt D^T, G D; jnp.matmul at
+//       model_GP_solver_2d.py:112,119 and their reverse pass).
+//   gs_apply_fused_kernel         Out[r] = alpha * K^-1 X[r] (+ beta * Add[r]): the Gohberg-Semencul
+//       formula  K^-1 v = ( L(g) [L(g)^T v]_n - L(h) [L(h)^T v]_n ) / g0  (jnp.linalg.solve,
+//       :104-105, and the solve-VJPs) as ONE pass over the row pair:
+//           Z = F z;  Q1 = F [F^-1 (conj G . Z)]_n;  Q2 = F [F^-1 (conj H . Z)]_n;
+//           out = F^-1 ( G' . Q1 + H' . Q2 )            (G' = G/(L g0), H' = -H/(L g0))
+//       six transforms; Z and then G'.Q1 wait in registers (16 complex values per thread).
+// Two real rows ride in one complex transform (every operator here is real).  Transforms run in
+// place in shared memory with the pass structure of fft_core.cuh: the global load is fused into
+// the first pass, the spectrum product into the tail/head pass, the truncation between two
+// convolutions into one register butterfly, the global store into the last pass - 2 np8 + 1
+// sweeps per convolution (9 for L = 8192) instead of 12, and 24 instead of 48 for K^-1.
+#include <algorithm>
+#include "common.cuh"
+#include "kernels.h"
+#include "fft_core.cuh"
+
+namespace gphm {
+
+namespace {
+
+struct RowPairIO {
+    const double* x0; const double* x1; double* o0; double* o1; const double* a0; const double* a1;
+    int n; bool two; double alpha, beta;
+    __device__ __forceinline__ double2 load(int idx) const {
+        if (idx >= n) return make_double2(0.0, 0.0);
+        return make_double2(x0[idx], two ? x1[idx] : 0.0);
+    }
+    __device__ __forceinline__ void store(int idx, double2 v) const {
+        if (idx >= n) return;
+        double r0 = alpha * v.x, r1 = alpha * v.y;
+        if (beta != 0.0) { r0 += beta * a0[idx]; if (two) r1 += beta * a1[idx]; }
+        o0[idx] = r0;
+        if (two) o1[idx] = r1;
+    }
+};
+
+__device__ __forceinline__ RowPairIO row_pair(const double* X, int ldx, double* Out, int ldo, const double* Add, int lda,
+                                              int rows, int n, int pr, double alpha, double beta) {
+    RowPairIO io;
+    const int r0 = 2 * pr, r1 = r0 + 1;
+    io.two = r1 < rows;
+    io.x0 = X + (size_t)r0 * ldx; io.x1 = X + (size_t)(io.two ? r1 : r0) * ldx;
+    io.o0 = Out + (size_t)r0 * ldo; io.o1 = Out + (size_t)(io.two ? r1 : r0) * ldo;
+    io.a0 = Add ? Add + (size_t)r0 * lda : io.o0; io.a1 = Add ? Add + (size_t)(io.two ? r1 : r0) * lda : io.o1;
+    io.n = n; io.alpha = alpha; io.beta = beta;
+    return io;
+}
+
+}  // namespace
+
+template <int KT>
+__global__ void __launch_bounds__(FFT_THREADS, 1)
+toeplitz_apply_fused_kernel(const double* X, int rows, int n, int ldx, const double2* __restrict__ spec, int L,
+                            int logL, const double2* __restrict__ W, double alpha, double beta, const double* Add, int lda,
+                            double* Out, int ldo) {
+    extern __shared__ double2 xs[];
+    const int tid = threadIdx.x;
+    fft_load_twiddles(xs, L, logL, W, tid);
+    const int np8 = (logL - KT) / 3;
+    const double2* tw0 = fft_twiddles(xs, L);
+    const int npairs = (rows + 1) / 2;
+    for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
+        const RowPairIO io = row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr, alpha, beta);
+        dif_first(xs, L, tw0, tid, [&](int idx) { return io.load(idx); });
+        dif_middle(xs, L, logL, np8, tid);
+        mid_fused<KT>(xs, L, tid, [&](int, int p, double2 v) { return cmul(v, spec[p]); });
+        dit_middle(xs, L, logL, np8, KT, tid);
+        dit_last(xs, L, tw0, tid, [&](int idx, double2 v) { io.store(idx, v); });
+    }
+}
+
+// spec: the four Gohberg-Semencul spectra of gs_prepare_kernel, L complex values each.
+template <int KT>
+__global__ void __launch_bounds__(FFT_THREADS, 1)
+gs_apply_fused_kernel(const double* X, int rows, int n, int ldx, const double2* __restrict__ spec, int L,
+                      int logL, const double2* __restrict__ W, double alpha, double beta, const double* Add, int lda,
+                      double* Out, int ldo) {
+    extern __shared__ double2 xs[];
+    const int tid = threadIdx.x;
+    fft_load_twiddles(xs, L, logL, W, tid);
+    const int np8 = (logL - KT) / 3;
+    const double2* tw0 = fft_twiddles(xs, L);
+    const double2* __restrict__ sGt = spec;             // conj(G)/L
+    const double2* __restrict__ sHt = spec + L;         // conj(H)/L
+    const double2* __restrict__ sG = spec + 2 * (size_t)L;   //  G/(L g0)
+    const double2* __restrict__ sH = spec + 3 * (size_t)L;   // -H/(L g0)
+    const int npairs = (rows + 1) / 2;
+    double2 stash[FFT_ACC];
+    for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
+        const RowPairIO io = row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr, alpha, beta);
+        dif_first(xs, L, tw0, tid, [&](int idx) { return io.load(idx); });
+        dif_middle(xs, L, logL, np8, tid);
+        mid_fused<KT>(xs, L, tid, [&](int slot, int p, double2 v) { stash[slot] = v; return cmul(v, sGt[p]); });   // Z kept
+        dit_middle(xs, L, logL, np8, KT, tid);
+        dit_last_dif_first(xs, L, tw0, tid, n);                                   // [L(g)^T v]_n
+        dif_middle(xs, L, logL, np8, tid);
+        mid_fused<KT>(xs, L, tid, [&](int slot, int p, double2 v) {
+            const double2 z = stash[slot];
+            stash[slot] = cmul(v, sG[p]);                                         // G'.Q1 kept
+            return cmul(z, sHt[p]);
+        });
+        dit_middle(xs, L, logL, np8, KT, tid);
+        dit_last_dif_first(xs, L, tw0, tid, n);                                   // [L(h)^T v]_n
+        dif_middle(xs, L, logL, np8, tid);
+        mid_fused<KT>(xs, L, tid, [&](int slot, int p, double2 v) {
+            const double2 a = stash[slot], b = cmul(v, sH[p]);
+            return make_double2(a.x + b.x, a.y + b.y);
+        });
+        dit_middle(xs, L, logL, np8, KT, tid);
+        dit_last(xs, L, tw0, tid, [&](int idx, double2 v) { io.store(idx, v); });
+    }
+}
+
+static int ilog2f(int L) { int l = 0; while ((1 << l) < L) ++l; return l; }
+
+int toeplitz_fused_init() {
+    static int done = -1;
+    if (done >= 0) return done;
+    const int bytes = (int)fft_smem_bytes(FFT_MAX_L);
+    GPHM_CUDA_OK(cudaFuncSetAttribute(toeplitz_apply_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    GPHM_CUDA_OK(cudaFuncSetAttribute(toeplitz_apply_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    GPHM_CUDA_OK(cudaFuncSetAttribute(toeplitz_apply_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    GPHM_CUDA_OK(cudaFuncSetAttribute(gs_apply_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    GPHM_CUDA_OK(cudaFuncSetAttribute(gs_apply_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    GPHM_CUDA_OK(cudaFuncSetAttribute(gs_apply_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done = GPHM_OK;
+    return done;
+}
+
+bool toeplitz_fused_supported(int L) { return L >= 16 && L <= FFT_MAX_L; }
+
+// Out[r] = alpha * T X[r] + beta * Add[r] (Add == NULL: beta * Out[r]).  Out may alias X or Add (each CTA
+// reads its row pair completely before it writes it).
+int launch_toeplitz_apply_fused(const double* X, int rows, int n, int ldx, const double* spec, int L, const double* W,
+                                double alpha, double beta, const double* Add, int lda, double* Out, int ldo, cudaStream_t st) {
+    GPHM_TRY(toeplitz_fused_init());
+    if (rows <= 0) return GPHM_OK;
+    if (!toeplitz_fused_supported(L) || L < 2 * n) { set_last_error("toeplitz_apply_fused: L=%d does not fit n=%d", L, n); return GPHM_EINVAL; }
+    const int logL = ilog2f(L), KT = fft_tail_stages(logL);
+    const int grid = std::min(fft_grid(), (rows + 1) / 2);
+    const size_t smem = fft_smem_bytes(L);
+    auto sp = reinterpret_cast<const double2*>(spec);
+    auto w = reinterpret_cast<const double2*>(W);
+    {
+        LaunchScope scope(CAT_FFT, st, 0.0, 16.0 * rows * (double)n);
+        if (KT == 1) toeplitz_apply_fused_kernel<1><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
+        else if (KT == 2) toeplitz_apply_fused_kernel<2><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
+        else toeplitz_apply_fused_kernel<3><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
+    }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+// Out[r] = alpha * K^-1 X[r] + beta * Add[r]  (Add may be NULL when beta == 0; Out may alias X or Add).
+int launch_gs_apply_fused(const double* X, int rows, int n, int ldx, const double* gspec, int L, const double* W, double alpha,
+                          double beta, const double* Add, int lda, double* Out, int ldo, cudaStream_t st) {
+    GPHM_TRY(toeplitz_fused_init());
+    if (rows <= 0) return GPHM_OK;
+    if (!toeplitz_fused_supported(L) || L < 2 * n) { set_last_error("gs_apply_fused: L=%d does not fit n=%d", L, n); return GPHM_EINVAL; }
+    if (beta != 0.0 && !Add) { set_last_error("gs_apply_fused: beta without Add"); return GPHM_EINVAL; }
+    const int logL = ilog2f(L), KT = fft_tail_stages(logL);
+    const int grid = std::min(fft_grid(), (rows + 1) / 2);
+    const size_t smem = fft_smem_bytes(L);
+    auto sp = reinterpret_cast<const double2*>(gspec);
+    auto w = reinterpret_cast<const double2*>(W);
+    {
+        LaunchScope scope(CAT_FFT, st, 0.0, 16.0 * rows * (double)n);
+        if (KT == 1) gs_apply_fused_kernel<1><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
+        else if (KT == 2) gs_apply_fused_kernel<2><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
+        else gs_apply_fused_kernel<3><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
+    }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+}  // namespace gphm

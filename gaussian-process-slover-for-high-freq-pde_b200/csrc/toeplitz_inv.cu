@@ -166,6 +166,7 @@ gs_prepare_kernel(const double* __restrict__ g, long long sG, int n, int L, int 
     g += blockIdx.x * sG; spec += blockIdx.x * sSpec; sKinv += blockIdx.x * sS;
     extern __shared__ double2 xs[];
     const int tid = threadIdx.x;
+    fft_load_twiddles(xs, L, logL, W, tid);
     const double g0 = g[0];
     const double wsc = exp2(-ceil(log2((double)n)));       // keeps u_p = (n-p) c_p at c's magnitude inside the shared FFT
     const double invL = 1.0 / (double)L, ig0 = 1.0 / g0;

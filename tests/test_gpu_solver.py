@@ -173,16 +173,23 @@ def test_golden_1d_training_run(gphm, oracle):
     assert rel(model.params["u"], g["u"]) <= 1e-5
 
 
-def test_golden_2d_training_run(gphm, oracle):
-    """2-D shipped run.  Trajectories are chaotic (cond(K) ~ 4e6): exact at step 0,
-    1e-7 through step 5, 1e-4 / 1e-3 through step 95, final rel-L2 error within 5 %."""
+@pytest.mark.parametrize("mode,tol5", [(16, 1e-7), (0, 5e-7)])
+def test_golden_2d_training_run(gphm, oracle, mode, tol5):
+    """2-D shipped run.  Trajectories are chaotic (cond(K) ~ 4e6; Adam's first updates are
+    +-lr*sign(g), so rounding-level gradient differences move individual entries by O(lr)): exact at
+    step 0, then 1e-7 through step 5 on the Cholesky path (the factorisation family of the reference's
+    LU) and 5e-7 on the default Toeplitz-generator path (a different stable algorithm: same bound on
+    the single-step gradients, different rounding), 1e-4 / 1e-3 through step 95, final rel-L2 error
+    within 5 %."""
     g = np.load(os.path.join(GOLD, "poisson_2d_sin_sin_matern52cos_e100.npz"))
     cfg = gphm.model_GP_solver_2d.make_config("poisson_2d-sin_sin", "Matern52_Cos_1d", 100, config_dir="/nonexistent")
+    cfg["force_general"] = mode
     model = gphm.GP_solver_2d_single(*_args2d(gphm, cfg), cfg)
+    assert gphm_uses_gs(model) == (mode == 0)
     log, _, min_err = model.train(100)
     ll, ee = np.array(log["loss_list"]), np.array(log["err_list"])
     assert abs(ll[0] - g["log_loss_list"][0]) <= 1e-12 * abs(ll[0])
-    assert abs(ll[1] - g["log_loss_list"][1]) <= 1e-7 * abs(ll[1]) and abs(ee[1] - g["log_err_list"][1]) <= 1e-7
+    assert abs(ll[1] - g["log_loss_list"][1]) <= tol5 * abs(ll[1]) and abs(ee[1] - g["log_err_list"][1]) <= tol5
     assert np.allclose(ll, g["log_loss_list"], rtol=1e-4) and np.allclose(ee, g["log_err_list"], rtol=1e-3)
     assert abs(ee[-1] - 0.46758844) <= 0.05 * 0.46758844
 
