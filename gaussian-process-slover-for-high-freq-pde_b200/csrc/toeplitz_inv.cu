@@ -43,58 +43,69 @@ int toeplitz_inv_max_n() { return SCHUR_MAX_N; }
 //                                kappa_k = -beta[k] / alpha[k-1] into one thread)
 //   a[j]   = A_{k-1}[j],  bS[j] = B_{k-1}[j-1]                   (non-zero for j <= k)
 // Step k:  alpha_k = alS + kappa be,  beta_k = be + kappa alS,  A_k = a + kappa bS,  B_k = bS + kappa a,
-// then the two shifted sequences move up by one position (in-thread, warp shuffle, and one value
-// per warp through shared memory).  kappa_{k+1} is produced by its owner before the step's only
-// barrier, except when its operand crosses a warp boundary (every 256th step: one more barrier).
+// then the two shifted sequences move up by one position.  The shift costs no register moves: the
+// loop is unrolled by 8 and at unrolled slot I the logical entry i of a shifted array lives in the
+// physical register (i - I) mod 8, updates are in place, and only the entry that leaves the thread
+// travels (warp shuffle; one value per warp through shared memory, patched after the barrier).
+// kappa_{k+1} is produced by its owner (its operands are always physical register 0 / slot I+1)
+// before the step's only barrier, except when the operand crosses a warp boundary (every 256th
+// step: one more barrier).  Warps whose generator entries are all dead / lattice entries all
+// zero skip that half of the update (warp-uniform branches).
 template <int I>
-__device__ __forceinline__ void schur_step(int k, int n, int tid, int lane, int warp, double (&alS)[SCHUR_EPT],
-                                           double (&be)[SCHUR_EPT], double (&a)[SCHUR_EPT], double (&bS)[SCHUR_EPT],
+__device__ __forceinline__ void schur_step(int k, int n, int tid, int lane, int warp, double (&A)[SCHUR_EPT],
+                                           double (&be)[SCHUR_EPT], double (&a)[SCHUR_EPT], double (&B)[SCHUR_EPT],
                                            double* kap, double (*bndA)[32], double (*bndB)[32]) {
+    constexpr int E = SCHUR_EPT;
+    constexpr int I1 = (I + 1) % E;
+    constexpr int OUT = (E - 1 - I) % E;       // physical slot of logical entry E-1 (leaves the thread)
     const double kp = kap[k];
-    const int wlo = warp * 32 * SCHUR_EPT, whi = wlo + 32 * SCHUR_EPT - 1;
-    const bool gen = whi >= k;             // warp still holds live generator entries
-    const bool lat = wlo <= k + 1;         // warp holds non-zero lattice entries
-    double nal[SCHUR_EPT], nb[SCHUR_EPT];
+    const int wlo = warp * 32 * E, whi = wlo + 32 * E - 1;
+    const int owner = (k + 1) / E;
+    const bool cross = (I1 == 0) && ((owner & 31) == 0);      // kappa_{k+1}'s alpha comes from the previous warp
+    if (whi >= k) {                            // warp still holds live generator entries
 #pragma unroll
-    for (int i = 0; i < SCHUR_EPT; ++i) { nal[i] = alS[i]; nb[i] = bS[i]; }
-    if (gen) {
-#pragma unroll
-        for (int i = 0; i < SCHUR_EPT; ++i) { nal[i] = fma(kp, be[i], alS[i]); be[i] = fma(kp, alS[i], be[i]); }
+        for (int ii = 0; ii < E; ++ii) {
+            const int i = (I + ii) % E;        // start with the entry that defines kappa_{k+1}
+            const int ph = (i - I + E) % E;
+            const double al = A[ph], b = be[i];
+            A[ph] = fma(kp, b, al);
+            be[i] = fma(kp, al, b);
+            if (ii == 1 && I1 != 0) { if (tid == owner && k + 1 < n) kap[k + 1] = -be[I1] * __drcp_rn(A[0]); }
+        }
     }
-    if (lat) {
+    if (wlo <= k + 1) {                        // warp holds non-zero lattice entries
 #pragma unroll
-        for (int i = 0; i < SCHUR_EPT; ++i) { nb[i] = fma(kp, a[i], bS[i]); a[i] = fma(kp, bS[i], a[i]); }
+        for (int i = 0; i < E; ++i) {
+            const int ph = (i - I + E) % E;
+            const double bs = B[ph], av = a[i];
+            B[ph] = fma(kp, av, bs);
+            a[i] = fma(kp, bs, av);
+        }
     }
-    const double upA = __shfl_up_sync(0xffffffffu, nal[SCHUR_EPT - 1], 1);
-    const double upB = __shfl_up_sync(0xffffffffu, nb[SCHUR_EPT - 1], 1);
-    if (lane == 31) { bndA[k & 1][warp] = nal[SCHUR_EPT - 1]; bndB[k & 1][warp] = nb[SCHUR_EPT - 1]; }
-#pragma unroll
-    for (int i = SCHUR_EPT - 1; i > 0; --i) { alS[i] = nal[i - 1]; bS[i] = nb[i - 1]; }
-    alS[0] = upA; bS[0] = upB;             // lane 0 is patched after the barrier
-    // kappa_{k+1} = -beta_k[k+1] / alpha_k[k]: position k+1 = SCHUR_EPT*owner + I1
-    constexpr int I1 = (I + 1) % SCHUR_EPT;
-    const int owner = (k + 1) / SCHUR_EPT;
-    const bool cross = (I1 == 0) && ((owner & 31) == 0);      // operand comes from the previous warp
-    if (tid == owner && !cross && k + 1 < n) kap[k + 1] = -be[I1] / alS[I1];
+    const double outA = A[OUT], outB = B[OUT];
+    const double upA = __shfl_up_sync(0xffffffffu, outA, 1);
+    const double upB = __shfl_up_sync(0xffffffffu, outB, 1);
+    if (lane == 31) { bndA[k & 1][warp] = outA; bndB[k & 1][warp] = outB; }
+    A[OUT] = upA; B[OUT] = upB;                // becomes logical entry 0 of the next step; lane 0 is patched below
+    if (I1 == 0 && !cross) { if (tid == owner && k + 1 < n) kap[k + 1] = -be[0] * __drcp_rn(A[OUT]); }
     __syncthreads();
     if (lane == 0) {
-        if (warp > 0) { alS[0] = bndA[k & 1][warp - 1]; bS[0] = bndB[k & 1][warp - 1]; }
-        else { alS[0] = 0.0; bS[0] = 0.0; }
+        if (warp > 0) { A[OUT] = bndA[k & 1][warp - 1]; B[OUT] = bndB[k & 1][warp - 1]; }
+        else { A[OUT] = 0.0; B[OUT] = 0.0; }
     }
     if (cross) {                                               // uniform in k
-        if (tid == owner && k + 1 < n) kap[k + 1] = -be[0] / alS[0];
+        if (tid == owner && k + 1 < n) kap[k + 1] = -be[0] * __drcp_rn(A[OUT]);
         __syncthreads();
     }
 }
 
 template <int I>
-__device__ __forceinline__ void schur_steps(int kb, int n, int tid, int lane, int warp, double (&alS)[SCHUR_EPT],
-                                            double (&be)[SCHUR_EPT], double (&a)[SCHUR_EPT], double (&bS)[SCHUR_EPT],
+__device__ __forceinline__ void schur_steps(int kb, int n, int tid, int lane, int warp, double (&A)[SCHUR_EPT],
+                                            double (&be)[SCHUR_EPT], double (&a)[SCHUR_EPT], double (&B)[SCHUR_EPT],
                                             double* kap, double (*bndA)[32], double (*bndB)[32]) {
     if constexpr (I < SCHUR_EPT) {
-        const int k = kb + I;
-        if (k >= 1 && k < n) schur_step<I>(k, n, tid, lane, warp, alS, be, a, bS, kap, bndA, bndB);
-        schur_steps<I + 1>(kb, n, tid, lane, warp, alS, be, a, bS, kap, bndA, bndB);
+        if (kb + I < n) schur_step<I>(kb + I, n, tid, lane, warp, A, be, a, B, kap, bndA, bndB);
+        schur_steps<I + 1>(kb, n, tid, lane, warp, A, be, a, B, kap, bndA, bndB);
     }
 }
 
@@ -109,22 +120,24 @@ schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, dou
     __shared__ int bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int j0 = tid * SCHUR_EPT;
-    double alS[SCHUR_EPT], be[SCHUR_EPT], a[SCHUR_EPT], bS[SCHUR_EPT];
+    double A[SCHUR_EPT], be[SCHUR_EPT], a[SCHUR_EPT], B[SCHUR_EPT];
     const double r0 = tab[0] + jitter;
+    // State "before step 0": unshifted alpha_0 = r, beta_0 = (0, r_1, ...), A_0 = B_0 = 1.  Step 0 runs with
+    // kappa_0 = 0: it changes no value and performs the first shift, so that every step is identical.
 #pragma unroll
     for (int i = 0; i < SCHUR_EPT; ++i) {
         const int j = j0 + i;
         const double rj = (j < n) ? (j == 0 ? r0 : tab[j]) : 0.0;
-        const double rm = (j >= 1 && j - 1 < n) ? (j == 1 ? r0 : tab[j - 1]) : 0.0;
-        be[i] = (j == 0) ? 0.0 : rj;       // beta_0 = (0, r_1, r_2, ...)
-        alS[i] = rm;                        // alpha_0 shifted: alpha_0[j-1]
-        a[i] = (j == 0) ? 1.0 : 0.0;       // A_0 = 1
-        bS[i] = (j == 1) ? 1.0 : 0.0;      // B_0 = 1, shifted
+        A[i] = rj;
+        be[i] = (j == 0) ? 0.0 : rj;
+        a[i] = (j == 0) ? 1.0 : 0.0;
+        B[i] = (j == 0) ? 1.0 : 0.0;
     }
-    if (tid == 0) { bad = 0x7fffffff; kap[0] = 0.0; if (n > 1) kap[1] = -be[1] / alS[1]; }
+    if (tid == 0) { bad = 0x7fffffff; kap[0] = 0.0; }
     __syncthreads();
-    for (int kb = 0; kb < n; kb += SCHUR_EPT)            // steps k = 1 .. n-1; the position inside a thread is static per slot
-        schur_steps<0>(kb, n, tid, lane, warp, alS, be, a, bS, kap, bndA, bndB);
+    for (int kb = 0; kb < n; kb += SCHUR_EPT)             // the position inside a thread is static per unrolled slot
+        schur_steps<0>(kb, n, tid, lane, warp, A, be, a, B, kap, bndA, bndB);
+    // After the last step (k = n-1, slot I = (n-1) % 8) logical entry i of A_{n-1} is a[i] (a does not shift).
     // E_{n-1} = r0 * prod (1 - kappa_k^2);  log|K| = n log r0 + sum_k (n - k) log(1 - kappa_k^2)
     double prod = 1.0, lsum = 0.0;
 #pragma unroll
