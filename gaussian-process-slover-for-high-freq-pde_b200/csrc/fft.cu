@@ -309,7 +309,7 @@ int launch_toeplitz_apply(const double* X, int rows, int n, int ldx, const doubl
     GPHM_TRY(fft_init());
     if (rows <= 0) return GPHM_OK;
     if (toeplitz_fused_supported(L) && L >= 2 * n)
-        return launch_toeplitz_apply_fused(X, rows, n, ldx, spec, L, W, alpha, beta, nullptr, 0, Out, ldo, st);
+        return launch_toeplitz_apply_fused(X, rows, n, ldx, spec, L, W, alpha, beta, nullptr, 0, Out, ldo, nullptr, st);
     {
         LaunchScope scope(CAT_FFT, st, 0.0, 16.0 * rows * (double)n);
         const int grid = std::min(fft_grid() * 1, (rows + 1) / 2);

@@ -352,17 +352,22 @@ __device__ __forceinline__ void mid_fused(double2* xs, int L, int tid, F f) {
     __syncthreads();
 }
 
-// Last inverse pass (stage logL-3, q = L/8); st(index, value) for the live half (index < L/2).
-template <class Store>
-__device__ __forceinline__ void dit_last(double2* xs, int L, const double2* tw, int tid, Store st) {
+// Last inverse pass (stage logL-3, q = L/8); st(index, value, addend) for the live half (index < L/2).
+// The addends pre(index) are fetched before the butterfly so that their global-memory latency
+// hides behind it (the stores may alias the addend, so the compiler cannot hoist the loads itself).
+template <class Pre, class Store>
+__device__ __forceinline__ void dit_last(double2* xs, int L, const double2* tw, int tid, Pre pre, Store st) {
     const int q = L >> 3;
     for (int j = tid; j < q; j += FFT_THREADS) {
+        double2 add[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) add[m] = pre(j + m * q);
         double2 e[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m) e[m] = xs[PADI(j + m * q)];
         bfly8_dit_inv(e, tw[2 * q + j], tw[q + j], tw[j]);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) st(j + m * q, e[m]);
+        for (int m = 0; m < 4; ++m) st(j + m * q, e[m], add[m]);
     }
     __syncthreads();
 }

@@ -84,8 +84,12 @@ int launch_gs_prepare(const double* g, long long sG, int n, int L, const double*
 
 // ---- toeplitz_fused.cu ---------------------------------------------------------------------
 bool toeplitz_fused_supported(int L);   // L >= 16: fused-sweep kernels; smaller sizes use the plain ones in fft.cu
+// SpecOut (optional): ceil(rows/2) x L complex, the transform of every packed row pair of X (for launch_xcorr_pairs)
 int launch_toeplitz_apply_fused(const double* X, int rows, int n, int ldx, const double* spec, int L, const double* W,
-                                double alpha, double beta, const double* Add, int lda, double* Out, int ldo, cudaStream_t st);
+                                double alpha, double beta, const double* Add, int lda, double* Out, int ldo, double* SpecOut,
+                                cudaStream_t st);
+int launch_xcorr_pairs(const double* X, int rows, int n, int ldx, const double* SpecY, int L, const double* W, double weight,
+                       double* partial, cudaStream_t st);
 // Out[r] = alpha * K^-1 X[r] + beta * Add[r] for every row, K^-1 through the four spectra of launch_gs_prepare
 int launch_gs_apply_fused(const double* X, int rows, int n, int ldx, const double* gspec, int L, const double* W, double alpha,
                           double beta, const double* Add, int lda, double* Out, int ldo, cudaStream_t st);

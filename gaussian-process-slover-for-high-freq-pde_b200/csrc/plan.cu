@@ -69,7 +69,8 @@ struct Axis {
     double *x = nullptr, *K = nullptr, *D = nullptr, *L = nullptr, *Linv = nullptr, *Kinv = nullptr, *Dbar = nullptr,
            *T = nullptr, *invdiag = nullptr, *ldpart = nullptr, *tabK = nullptr, *tabD = nullptr, *dspart = nullptr,
            *sK = nullptr, *sD = nullptr, *sKinv = nullptr, *tgpart = nullptr, *twid = nullptr, *specK = nullptr, *specD = nullptr, *specT = nullptr,   // specT: spectrum of the Toeplitz D
-           *gsg = nullptr, *gspec = nullptr;   // gsg = K^-1 e_0; gspec: four Gohberg-Semencul circulant spectra
+           *gsg = nullptr, *gspec = nullptr,   // gsg = K^-1 e_0; gspec: four Gohberg-Semencul circulant spectra
+           *specY = nullptr;                   // transforms of the packed row pairs of A^T (axis 1) / Bt (axis 2)
 };
 
 }  // namespace gphm
@@ -147,7 +148,10 @@ size_t carve(gphm_plan& p, void* base) {
             c.take(X.dspart, ds);
             if (X.fftL > 0) { c.take(X.twid, 2 * (size_t)X.fftL); c.take(X.specK, 2 * (size_t)X.fftL * fft_grid()); c.take(X.specD, 2 * (size_t)X.fftL * fft_grid()); c.take(X.specT, 2 * (size_t)X.fftL); }
         } else c.take(X.tgpart, tg);
-        if (p.size_query || X.gs) { c.take(X.gsg, n); c.take(X.gspec, 8 * Lq); }
+        if (p.size_query || X.gs) {
+            const size_t other = (d.dim == 2) ? (a == 0 ? (size_t)d.n2 : (size_t)d.n1) : 1;      // rows this axis' operators act on
+            c.take(X.gsg, n); c.take(X.gspec, 8 * Lq); c.take(X.specY, 2 * Lq * ((other + 1) / 2));
+        }
     }
     if (p.size_query || p.ax[0].gs || p.ax[1].gs) c.take(p.gsS, nf);
     c.take(p.src, nf); c.take(p.base, nf); c.take(p.bvals, d.nb); c.take(p.xind, std::max(d.nb, 1));
@@ -343,11 +347,11 @@ int logjoint_grad_gs(gphm_plan& p, const double* U, const double* small, double*
     auto gs2 = [&](const double* Xr, double* out) {       // rows of length n2
         return launch_gs_apply_fused(Xr, n1, n2, n2, X2.gspec, X2.fftL, X2.twid, 1.0, 0.0, nullptr, 0, out, n2, st);
     };
-    auto d1 = [&](const double* Xr, double alpha, double beta, const double* add, double* out) {
-        return launch_toeplitz_apply_fused(Xr, n2, n1, n1, X1.specT, X1.fftL, X1.twid, alpha, beta, add, n1, out, n1, st);
+    auto d1 = [&](const double* Xr, double alpha, double beta, const double* add, double* out, double* spec_out = nullptr) {
+        return launch_toeplitz_apply_fused(Xr, n2, n1, n1, X1.specT, X1.fftL, X1.twid, alpha, beta, add, n1, out, n1, spec_out, st);
     };
-    auto d2 = [&](const double* Xr, double alpha, double beta, const double* add, double* out) {
-        return launch_toeplitz_apply_fused(Xr, n1, n2, n2, X2.specT, X2.fftL, X2.twid, alpha, beta, add, n2, out, n2, st);
+    auto d2 = [&](const double* Xr, double alpha, double beta, const double* add, double* out, double* spec_out = nullptr) {
+        return launch_toeplitz_apply_fused(Xr, n1, n2, n2, X2.specT, X2.fftL, X2.twid, alpha, beta, add, n2, out, n2, spec_out, st);
     };
     // ---- forward ----
     const double* Ut = U;                                  // 1-D: the field is one row already
@@ -358,12 +362,12 @@ int logjoint_grad_gs(gphm_plan& p, const double* U, const double* small, double*
     const double* A = At;
     if (two) {
         GPHM_TRY(gs2(U, p.Bt)); Bt = p.Bt;                 // Bt = U K2^-1
-        GPHM_TRY(d1(At, c1, 0.0, nullptr, p.Tf));          // (c1 D1 A)^T
+        GPHM_TRY(d1(At, c1, 0.0, nullptr, p.Tf, X1.specY));   // (c1 D1 A)^T; keeps the transforms of A^T's rows
         GPHM_TRY(launch_transpose(p.Tf, n2, n1, p.R, st));
-        GPHM_TRY(d2(Bt, 1.0, 1.0, nullptr, p.R));          // + Bt D2^T
+        GPHM_TRY(d2(Bt, 1.0, 1.0, nullptr, p.R, X2.specY));   // + Bt D2^T; keeps the transforms of Bt's rows
         GPHM_TRY(launch_transpose(At, n2, n1, p.A, st)); A = p.A;
     } else {
-        GPHM_TRY(d1(At, c1, 0.0, nullptr, p.R));
+        GPHM_TRY(d1(At, c1, 0.0, nullptr, p.R, X1.specY));
     }
     GPHM_TRY(launch_residual(p.R, U, p.src, A, Bt, nf, d.eq_type, p.has_base ? p.base : nullptr, small, Q, p.part, st));    // R <- G
     const LossConsts lc = loss_consts(p);
@@ -392,13 +396,14 @@ int logjoint_grad_gs(gphm_plan& p, const double* U, const double* small, double*
                                nullptr, st));
     }
     // diagonal sums of Kbar_a = ld/2 N_b K_a^-1 - V_a (.)^T and Dbar_a by row cross-correlations
-    GPHM_TRY(launch_xcorr_spectrum(V1t, At, n2, n1, n1, n1, X1.fftL, X1.twid, -1.0, false, X1.specK, st));
-    GPHM_TRY(launch_xcorr_spectrum(Gt, At, n2, n1, n1, n1, X1.fftL, X1.twid, c1, false, X1.specD, st));
+    // (one transform per row PAIR against the stored transforms of A^T / Bt)
+    GPHM_TRY(launch_xcorr_pairs(V1t, n2, n1, n1, X1.specY, X1.fftL, X1.twid, -1.0, X1.specK, st));
+    GPHM_TRY(launch_xcorr_pairs(Gt, n2, n1, n1, X1.specY, X1.fftL, X1.twid, c1, X1.specD, st));
     GPHM_TRY(launch_spectrum_to_diag_sums(X1.specK, X1.specD, X1.fftL, X1.twid, n1, anti, X1.dirsign, X1.sKinv,
                                           0.5 * d.logdet * n2, X1.sK, X1.sD, st));
     if (two) {
-        GPHM_TRY(launch_xcorr_spectrum(V2, Bt, n1, n2, n2, n2, X2.fftL, X2.twid, -1.0, false, X2.specK, st));
-        GPHM_TRY(launch_xcorr_spectrum(G, Bt, n1, n2, n2, n2, X2.fftL, X2.twid, 1.0, false, X2.specD, st));
+        GPHM_TRY(launch_xcorr_pairs(V2, n1, n2, n2, X2.specY, X2.fftL, X2.twid, -1.0, X2.specK, st));
+        GPHM_TRY(launch_xcorr_pairs(G, n1, n2, n2, X2.specY, X2.fftL, X2.twid, 1.0, X2.specD, st));
         GPHM_TRY(launch_spectrum_to_diag_sums(X2.specK, X2.specD, X2.fftL, X2.twid, n2, anti, X2.dirsign, X2.sKinv,
                                               0.5 * d.logdet * n1, X2.sK, X2.sD, st));
     }

@@ -30,12 +30,14 @@ struct RowPairIO {
         if (idx >= n) return make_double2(0.0, 0.0);
         return make_double2(x0[idx], two ? x1[idx] : 0.0);
     }
-    __device__ __forceinline__ void store(int idx, double2 v) const {
+    __device__ __forceinline__ double2 addend(int idx) const {
+        if (beta == 0.0 || idx >= n) return make_double2(0.0, 0.0);
+        return make_double2(a0[idx], two ? a1[idx] : 0.0);
+    }
+    __device__ __forceinline__ void store(int idx, double2 v, double2 add) const {
         if (idx >= n) return;
-        double r0 = alpha * v.x, r1 = alpha * v.y;
-        if (beta != 0.0) { r0 += beta * a0[idx]; if (two) r1 += beta * a1[idx]; }
-        o0[idx] = r0;
-        if (two) o1[idx] = r1;
+        o0[idx] = fma(beta, add.x, alpha * v.x);
+        if (two) o1[idx] = fma(beta, add.y, alpha * v.y);
     }
 };
 
@@ -57,7 +59,7 @@ template <int KT>
 __global__ void __launch_bounds__(FFT_THREADS, 1)
 toeplitz_apply_fused_kernel(const double* X, int rows, int n, int ldx, const double2* __restrict__ spec, int L,
                             int logL, const double2* __restrict__ W, double alpha, double beta, const double* Add, int lda,
-                            double* Out, int ldo) {
+                            double* Out, int ldo, double2* __restrict__ SpecOut) {
     extern __shared__ double2 xs[];
     const int tid = threadIdx.x;
     fft_load_twiddles(xs, L, logL, W, tid);
@@ -68,9 +70,10 @@ toeplitz_apply_fused_kernel(const double* X, int rows, int n, int ldx, const dou
         const RowPairIO io = row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr, alpha, beta);
         dif_first(xs, L, tw0, tid, [&](int idx) { return io.load(idx); });
         dif_middle(xs, L, logL, np8, tid);
-        mid_fused<KT>(xs, L, tid, [&](int, int p, double2 v) { return cmul(v, spec[p]); });
+        double2* so = SpecOut ? SpecOut + (size_t)pr * L : nullptr;      // spectrum of the packed row pair, kept for the diagonal sums
+        mid_fused<KT>(xs, L, tid, [&](int, int p, double2 v) { if (so) so[p] = v; return cmul(v, spec[p]); });
         dit_middle(xs, L, logL, np8, KT, tid);
-        dit_last(xs, L, tw0, tid, [&](int idx, double2 v) { io.store(idx, v); });
+        dit_last(xs, L, tw0, tid, [&](int idx) { return io.addend(idx); }, [&](int idx, double2 v, double2 add) { io.store(idx, v, add); });
     }
 }
 
@@ -112,7 +115,67 @@ gs_apply_fused_kernel(const double* X, int rows, int n, int ldx, const double2* 
             return make_double2(a.x + b.x, a.y + b.y);
         });
         dit_middle(xs, L, logL, np8, KT, tid);
-        dit_last(xs, L, tw0, tid, [&](int idx, double2 v) { io.store(idx, v); });
+        dit_last(xs, L, tw0, tid, [&](int idx) { return io.addend(idx); }, [&](int idx, double2 v, double2 add) { io.store(idx, v, add); });
+    }
+}
+
+// partial[blockIdx.x][p] = weight * sum over the CTA's row pairs of conj(Zx)(p) * Zy(p), where Zx is the
+// transform of the packed pair (x_2r + i x_2r+1) computed here and Zy the stored transform of the
+// matching packed pair of Y (SpecOut of toeplitz_apply_fused_kernel).  conj(Zx) Zy = conj(X0) Y0 +
+// conj(X1) Y1 + i (conj(X0) Y1 - conj(X1) Y0): the cross term transforms back to a purely imaginary
+// sequence, so the real part of the inverse transform of the sum is exactly the sum over ROWS of the
+// cross-correlations - one transform per row pair and no spectrum separation.
+template <int KT>
+__global__ void __launch_bounds__(FFT_THREADS, 1)
+xcorr_pairs_kernel(const double* __restrict__ X, int rows, int n, int ldx, const double2* __restrict__ SpecY, int L, int logL,
+                   const double2* __restrict__ W, double weight, double2* __restrict__ partial) {
+    extern __shared__ double2 xs[];
+    const int tid = threadIdx.x;
+    fft_load_twiddles(xs, L, logL, W, tid);
+    const int np8 = (logL - KT) / 3;
+    const double2* tw0 = fft_twiddles(xs, L);
+    const int npairs = (rows + 1) / 2;
+    constexpr int R = 1 << KT;
+    constexpr int MAXG = FFT_MAX_L / (R * FFT_THREADS);
+    double2 acc[FFT_ACC];
+#pragma unroll
+    for (int k = 0; k < FFT_ACC; ++k) acc[k] = make_double2(0.0, 0.0);
+    for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
+        const int r0 = 2 * pr;
+        const bool two = r0 + 1 < rows;
+        const double* x0 = X + (size_t)r0 * ldx;
+        const double* x1 = X + (size_t)(two ? r0 + 1 : r0) * ldx;
+        const double2* __restrict__ sy = SpecY + (size_t)pr * L;
+        dif_first(xs, L, tw0, tid, [&](int idx) { return idx < n ? make_double2(x0[idx], two ? x1[idx] : 0.0) : make_double2(0.0, 0.0); });
+        dif_middle(xs, L, logL, np8, tid);
+#pragma unroll
+        for (int i = 0; i < MAXG; ++i) {                       // forward tail in registers + accumulation
+            const int g = tid + i * FFT_THREADS;
+            if (g < (L >> KT)) {
+                const int base = g << KT;
+                double2 y[R], e[R];
+#pragma unroll
+                for (int m = 0; m < R; ++m) y[m] = sy[base + m];
+#pragma unroll
+                for (int m = 0; m < R; ++m) e[m] = xs[PADI(base + m)];
+                unit_fwd<KT>(e);
+#pragma unroll
+                for (int m = 0; m < R; ++m) {
+                    acc[i * R + m].x += e[m].x * y[m].x + e[m].y * y[m].y;
+                    acc[i * R + m].y += e[m].x * y[m].y - e[m].y * y[m].x;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    double2* out = partial + (size_t)blockIdx.x * L;
+#pragma unroll
+    for (int i = 0; i < MAXG; ++i) {
+        const int g = tid + i * FFT_THREADS;
+        if (g < (L >> KT)) {
+#pragma unroll
+            for (int m = 0; m < R; ++m) out[(g << KT) + m] = make_double2(weight * acc[i * R + m].x, weight * acc[i * R + m].y);
+        }
     }
 }
 
@@ -125,6 +188,9 @@ int toeplitz_fused_init() {
     GPHM_CUDA_OK(cudaFuncSetAttribute(toeplitz_apply_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     GPHM_CUDA_OK(cudaFuncSetAttribute(toeplitz_apply_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     GPHM_CUDA_OK(cudaFuncSetAttribute(toeplitz_apply_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    GPHM_CUDA_OK(cudaFuncSetAttribute(xcorr_pairs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    GPHM_CUDA_OK(cudaFuncSetAttribute(xcorr_pairs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    GPHM_CUDA_OK(cudaFuncSetAttribute(xcorr_pairs_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     GPHM_CUDA_OK(cudaFuncSetAttribute(gs_apply_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     GPHM_CUDA_OK(cudaFuncSetAttribute(gs_apply_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     GPHM_CUDA_OK(cudaFuncSetAttribute(gs_apply_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -137,7 +203,8 @@ bool toeplitz_fused_supported(int L) { return L >= 16 && L <= FFT_MAX_L; }
 // Out[r] = alpha * T X[r] + beta * Add[r] (Add == NULL: beta * Out[r]).  Out may alias X or Add (each CTA
 // reads its row pair completely before it writes it).
 int launch_toeplitz_apply_fused(const double* X, int rows, int n, int ldx, const double* spec, int L, const double* W,
-                                double alpha, double beta, const double* Add, int lda, double* Out, int ldo, cudaStream_t st) {
+                                double alpha, double beta, const double* Add, int lda, double* Out, int ldo, double* SpecOut,
+                                cudaStream_t st) {
     GPHM_TRY(toeplitz_fused_init());
     if (rows <= 0) return GPHM_OK;
     if (!toeplitz_fused_supported(L) || L < 2 * n) { set_last_error("toeplitz_apply_fused: L=%d does not fit n=%d", L, n); return GPHM_EINVAL; }
@@ -146,11 +213,12 @@ int launch_toeplitz_apply_fused(const double* X, int rows, int n, int ldx, const
     const size_t smem = fft_smem_bytes(L);
     auto sp = reinterpret_cast<const double2*>(spec);
     auto w = reinterpret_cast<const double2*>(W);
+    auto so = reinterpret_cast<double2*>(SpecOut);
     {
         LaunchScope scope(CAT_FFT, st, 0.0, 16.0 * rows * (double)n);
-        if (KT == 1) toeplitz_apply_fused_kernel<1><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
-        else if (KT == 2) toeplitz_apply_fused_kernel<2><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
-        else toeplitz_apply_fused_kernel<3><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
+        if (KT == 1) toeplitz_apply_fused_kernel<1><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo, so);
+        else if (KT == 2) toeplitz_apply_fused_kernel<2><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo, so);
+        else toeplitz_apply_fused_kernel<3><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo, so);
     }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
@@ -173,6 +241,26 @@ int launch_gs_apply_fused(const double* X, int rows, int n, int ldx, const doubl
         if (KT == 1) gs_apply_fused_kernel<1><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
         else if (KT == 2) gs_apply_fused_kernel<2><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
         else gs_apply_fused_kernel<3><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
+    }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+// partial[fft_grid()][L] = weight * sum over row pairs of conj(FFT(packed X pair)) * SpecY[pair]  (every CTA writes its slot)
+int launch_xcorr_pairs(const double* X, int rows, int n, int ldx, const double* SpecY, int L, const double* W, double weight,
+                       double* partial, cudaStream_t st) {
+    GPHM_TRY(toeplitz_fused_init());
+    if (!toeplitz_fused_supported(L) || L < 2 * n) { set_last_error("xcorr_pairs: L=%d does not fit n=%d", L, n); return GPHM_EINVAL; }
+    const int logL = ilog2f(L), KT = fft_tail_stages(logL);
+    const size_t smem = fft_smem_bytes(L);
+    auto sy = reinterpret_cast<const double2*>(SpecY);
+    auto w = reinterpret_cast<const double2*>(W);
+    auto pt = reinterpret_cast<double2*>(partial);
+    {
+        LaunchScope scope(CAT_FFT, st, 0.0, 8.0 * rows * (double)n + 8.0 * rows * (double)L);
+        if (KT == 1) xcorr_pairs_kernel<1><<<fft_grid(), FFT_THREADS, smem, st>>>(X, rows, n, ldx, sy, L, logL, w, weight, pt);
+        else if (KT == 2) xcorr_pairs_kernel<2><<<fft_grid(), FFT_THREADS, smem, st>>>(X, rows, n, ldx, sy, L, logL, w, weight, pt);
+        else xcorr_pairs_kernel<3><<<fft_grid(), FFT_THREADS, smem, st>>>(X, rows, n, ldx, sy, L, logL, w, weight, pt);
     }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
