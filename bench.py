@@ -6,8 +6,9 @@
 
 Workload (N=1 and N>1): 2-D multi-scale Poisson `poisson_2d-sin_add_cos` on a 4096^2 collocation
 grid, Matern52_Cos_1d, Q=30, FP64, reference initial state.  A "step" is one full
-iteration: Gram build + Cholesky + K^-1 applications + Kronecker contractions + reductions +
-hand-derived backward + Adam on every leaf.  One JSON line is printed by rank 0.
+iteration: Gram tables + K^-1 (Schur/Levinson generator + Gohberg-Semencul FFT applications on the
+uniform grid; blocked Cholesky + DMMA GEMMs on general grids) + Kronecker contractions + reductions
++ hand-derived backward + Adam on every leaf.  One JSON line is printed by rank 0.
 N>1 shards the same problem (strong scaling): U row/column blocks per rank, NCCL all-to-all.
 """
 import argparse
@@ -44,6 +45,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="profiling runs only")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
     ap.add_argument("--no-peak", action="store_true", help="profiling runs only: skip the cuBLAS DGEMM denominator")
+    ap.add_argument("--no-general", action="store_true", help="skip the short dense-path (Cholesky + DGEMM) measurement")
     return ap.parse_args()
 
 
@@ -239,8 +241,9 @@ def run_ours(args, rank, world, local):
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    cat_ms = (ctypes.c_double * 6)(); cat_fl = (ctypes.c_double * 6)(); cat_by = (ctypes.c_double * 6)()
-    cat_n = (ctypes.c_longlong * 6)()
+    NF = 8
+    cat_ms = (ctypes.c_double * NF)(); cat_fl = (ctypes.c_double * NF)(); cat_by = (ctypes.c_double * NF)()
+    cat_n = (ctypes.c_longlong * NF)()
     lib.gphm_profile_stop(cat_ms, cat_fl, cat_by, cat_n)
     launches = lib.gphm_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
@@ -265,7 +268,7 @@ def run_ours(args, rank, world, local):
         hcount = torch.zeros(1, dtype=torch.int64).pin_memory()
         hterms = torch.zeros(8, dtype=torch.float64).pin_memory()
         host[0].copy_(st.U.cpu()); hs[0].copy_(st.small.cpu())
-        e2e_steps = min(args.steps, 5)
+        e2e_steps = min(args.steps, 10)
         core.step_host(host[0], hs[0], host[1], host[2], hs[1], hs[2], hcount, hterms, LR)       # warm
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -275,38 +278,108 @@ def run_ours(args, rank, world, local):
         h2d = 8 * (3 * nf + 3 * ns) + 8
         e2e = {"value": e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d + 64,
                "steps": e2e_steps, "api": "gphm_step_host (pinned host params + opt_state in, updated out)"}
-    elif world > 1:
-        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "note": "host-buffer entry point is single-GPU; see the N=1 line"}
+    elif world > 1 and not args.no_e2e:
+        # every rank moves ITS row block of the params and Adam state host -> device before, and device -> host after, each step
+        import torch.distributed as dist
+        blocks = [solver.U, solver.mU, solver.vU, solver.small, solver.msmall, solver.vsmall]
+        hostb = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in blocks]
+        for h, t in zip(hostb, blocks):
+            h.copy_(t.cpu())
+        hloss = torch.zeros(1, dtype=torch.float64).pin_memory()
+
+        def host_step():
+            for h, t in zip(hostb, blocks):
+                t.copy_(h, non_blocking=True)
+            solver.step()
+            for h, t in zip(hostb, blocks):
+                h.copy_(t, non_blocking=True)
+            hloss.copy_(solver.last_loss().reshape(1), non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_steps = min(args.steps, 10)
+        host_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host_step()
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        per_rank = sum(t.numel() * t.element_size() for t in blocks)
+        e2e = {"value": e2e_steps / float(tt), "unit": UNIT, "h2d_bytes_per_step": per_rank * world,
+               "d2h_bytes_per_step": per_rank * world + 8 * world, "steps": e2e_steps,
+               "api": "ShardedSolver2D.step with every rank's row block of params + Adam state copied from / to pinned host memory"}
 
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel (DGEMM on the FP64 DMMA pipe) ----
+    # ---- roofline of the dominant kernel ----
     peaks = measured_peaks()
     burst = sustained = None
     if not args.no_peak:
         burst, sustained = measure_fp64_peak(device)
-    gemm_ms, gemm_fl = cat_ms[1], cat_fl[1]
-    achieved = gemm_fl / gemm_ms / 1e9 if gemm_ms > 0 else None
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "dgemm_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    except Exception:
-        pass
-    roofline = {"bound": "tensor", "kernel": "dgemm_kernel (FP64 DMMA.8x8x4; tcgen05 has no f64 kind)",
-                "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
-                "frac": (achieved / sustained) if (achieved and sustained) else None, "traffic": traffic,
-                "peak_source": "cuBLAS DGEMM 8192^3 measured in this run, sustained over %d back-to-back calls "
-                               "(burst %.1f); MEASURED_PEAKS.json has no FP64 entry (bf16 %.0f TFLOP/s, HBM %.0f GB/s)"
-                               % (40, burst or 0.0, peaks.get("bf16_tflops", 0.0), peaks.get("hbm_gbs", 0.0)),
-                "launches_per_step": cat_n[1] / args.steps, "ms_per_step": gemm_ms / args.steps,
-                "flops_issued_per_step": gemm_fl / args.steps,
-                "step_tflops_of_28N3": flops_per_iter(n) / ms_step / 1e9,
-                "step_frac_of_peak": (flops_per_iter(n) / ms_step / 1e9 / sustained) if sustained else None,
-                "by_family_ms_per_step": {"gram": cat_ms[0] / args.steps, "dgemm": cat_ms[1] / args.steps,
-                                          "chol_diag": cat_ms[2] / args.steps, "reduce_elementwise": cat_ms[3] / args.steps,
-                                          "adam": cat_ms[4] / args.steps, "fft_diag_sums": cat_ms[5] / args.steps}}
+    fam = ("gram", "dgemm", "factor_serial", "reduce_elementwise", "adam", "fft_diag_sums", "gs_kinv_apply", "toeplitz_products")
+    by_family = {name: cat_ms[i] / args.steps for i, name in enumerate(fam)}
+    peak_source = ("FP64 pipe: cuBLAS DGEMM 8192^3 measured in this run, sustained over %d back-to-back calls (burst %.1f); "
+                   "MEASURED_PEAKS.json has no FP64 entry (bf16 %.0f TFLOP/s, HBM %.0f GB/s)"
+                   % (40, burst or 0.0, peaks.get("bf16_tflops", 0.0), peaks.get("hbm_gbs", 0.0)))
+
+    def family_roofline(idx, kernel, traffic_file, note):
+        ms, fl = cat_ms[idx], cat_fl[idx]
+        ach = fl / ms / 1e9 if ms > 0 else None
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", traffic_file)) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        return {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": sustained, "unit": "TFLOP/s",
+                "frac": (ach / sustained) if (ach and sustained) else None, "traffic": traffic, "note": note,
+                "peak_source": peak_source, "launches_per_step": cat_n[idx] / args.steps, "ms_per_step": ms / args.steps,
+                "flops_per_step": fl / args.steps,
+                "algorithmic_bytes_per_launch": (cat_by[idx] / cat_n[idx]) if cat_n[idx] else None,
+                "hbm_gbs_algorithmic": (cat_by[idx] / ms / 1e6) if ms > 0 else None}
+
+    if cat_ms[6] >= cat_ms[1]:
+        roofline = family_roofline(
+            6, "gs_apply_fused_kernel (K^-1 rows by Gohberg-Semencul: six length-2N FP64 FFTs per row pair in shared memory)",
+            "gs_apply_traffic.json",
+            "compute-bound by the roofline model (24 FLOP/B algorithmic intensity vs 5.4 FLOP/B machine balance); FLOPs = "
+            "5 L log2 L per complex transform + spectrum products; FP64 FMA pipe (same peak rate as the FP64 DMMA pipe; "
+            "tcgen05 has no f64 kind); the binding on-chip resource is shared-memory bandwidth (ncu: see profiles/)")
+    else:
+        roofline = family_roofline(1, "dgemm_kernel (FP64 DMMA.8x8x4; tcgen05 has no f64 kind)", "dgemm_traffic.json",
+                                   "FLOPs issued by the triangular / full GEMM launches of the step")
+    roofline["step_tflops_of_28N3"] = flops_per_iter(n) / ms_step / 1e9
+    roofline["step_frac_of_peak"] = (flops_per_iter(n) / ms_step / 1e9 / sustained) if sustained else None
+    roofline["by_family_ms_per_step"] = by_family
+    # the dense path (general grids, axes longer than 4096): same workload with the Toeplitz inverse generator and the
+    # FFT products switched off, a few steps, to report the DGEMM kernel against the same FP64 peak
+    if world == 1 and not args.no_general:
+        del st
+        core = None
+        torch.cuda.empty_cache()
+        core2 = G.solver_core.SolverCore(2, KERNEL, "poisson", X_col[0], X_col[1], src, bvals, None, LLK, 1.0, 1.0, 1e-6, Q,
+                                         force_general=16 | 8)
+        st2 = core2.new_state(model_init(_M))
+        core2.step_inplace(st2, LR)
+        torch.cuda.synchronize()
+        lib.gphm_profile_start()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        gsteps = 3
+        for _ in range(gsteps):
+            core2.step_inplace(st2, LR)
+        g1.record()
+        torch.cuda.synchronize()
+        ms2 = (ctypes.c_double * NF)(); fl2 = (ctypes.c_double * NF)(); by2 = (ctypes.c_double * NF)(); n2_ = (ctypes.c_longlong * NF)()
+        lib.gphm_profile_stop(ms2, fl2, by2, n2_)
+        ach2 = fl2[1] / ms2[1] / 1e9 if ms2[1] > 0 else None
+        roofline["general_path"] = {
+            "what": "same workload, force_general = 16|8: blocked Cholesky + triangular DMMA GEMMs for K^-1, GEMMs for the "
+                    "derivative-Gram contractions (the path of non-uniform grids)",
+            "ms_per_step": g0.elapsed_time(g1) / gsteps, "dgemm_ms_per_step": ms2[1] / gsteps,
+            "dgemm_tflops": ach2, "dgemm_frac_of_fp64_peak": (ach2 / sustained) if (ach2 and sustained) else None,
+            "dgemm_launches_per_step": n2_[1] / gsteps}
+        del st2, core2
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

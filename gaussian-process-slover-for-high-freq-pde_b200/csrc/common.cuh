@@ -30,7 +30,9 @@ void set_last_error(const char* fmt, ...);
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 
 // Launch accounting / optional CUDA-event profiling per kernel family (gphm_profile_* in gphm.h).
-enum : int { CAT_GRAM = 0, CAT_DGEMM = 1, CAT_CHOL_DIAG = 2, CAT_ELEMWISE = 3, CAT_ADAM = 4, CAT_FFT = 5, CAT_COUNT = 6 };
+enum : int { CAT_GRAM = 0, CAT_DGEMM = 1, CAT_CHOL_DIAG = 2, CAT_ELEMWISE = 3, CAT_ADAM = 4, CAT_FFT = 5, CAT_GS_APPLY = 6,
+              CAT_TOEPLITZ_APPLY = 7, CAT_COUNT = 8 };
+inline double fft_flops(int L) { double l = 0; for (int t = 1; t < L; t <<= 1) l += 1.0; return 5.0 * L * l; }   // per complex transform
 bool profiling_enabled();
 struct LaunchScope {
     int cat; cudaStream_t st; int slot;

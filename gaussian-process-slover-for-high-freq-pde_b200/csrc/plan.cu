@@ -94,6 +94,8 @@ struct gphm_plan {
     // device staging for gphm_step_host (allocated on first use)
     double* hs = nullptr;
     long long* hs_count = nullptr;
+    cudaStream_t hs_stream = nullptr;     // second copy stream: the Adam moments travel while the gradient is computed
+    cudaEvent_t hs_ev_u = nullptr, hs_ev_mv = nullptr;
 };
 
 namespace {
@@ -724,6 +726,9 @@ void gphm_plan_destroy(gphm_plan* plan) {
     if (plan->owns_ws && plan->ws) cudaFree(plan->ws);
     if (plan->hs) cudaFree(plan->hs);
     if (plan->hs_count) cudaFree(plan->hs_count);
+    if (plan->hs_stream) cudaStreamDestroy(plan->hs_stream);
+    if (plan->hs_ev_u) cudaEventDestroy(plan->hs_ev_u);
+    if (plan->hs_ev_mv) cudaEventDestroy(plan->hs_ev_mv);
     delete plan;
 }
 
@@ -794,17 +799,29 @@ int gphm_step_host(gphm_plan* plan, double* h_U, double* h_small, double* h_mU, 
     if (!plan->hs) {
         GPHM_CUDA_OK(cudaMalloc(&plan->hs, sizeof(double) * (3 * nfp + 3 * nsp + 32)));
         GPHM_CUDA_OK(cudaMalloc(&plan->hs_count, sizeof(long long)));
+        GPHM_CUDA_OK(cudaStreamCreateWithFlags(&plan->hs_stream, cudaStreamNonBlocking));
+        GPHM_CUDA_OK(cudaEventCreateWithFlags(&plan->hs_ev_u, cudaEventDisableTiming));
+        GPHM_CUDA_OK(cudaEventCreateWithFlags(&plan->hs_ev_mv, cudaEventDisableTiming));
     }
     double *U = plan->hs, *mU = U + nfp, *vU = mU + nfp, *sm = vU + nfp, *msm = sm + nsp, *vsm = msm + nsp,
            *terms = vsm + nsp;
-    GPHM_CUDA_OK(cudaMemcpyAsync(U, h_U, sizeof(double) * nf, cudaMemcpyHostToDevice, st));
-    GPHM_CUDA_OK(cudaMemcpyAsync(mU, h_mU, sizeof(double) * nf, cudaMemcpyHostToDevice, st));
-    GPHM_CUDA_OK(cudaMemcpyAsync(vU, h_vU, sizeof(double) * nf, cudaMemcpyHostToDevice, st));
+    // params first (the gradient needs only them); the Adam moments follow on a second stream and
+    // overlap the log-joint + gradient kernels - they are first touched by the Adam update.
     GPHM_CUDA_OK(cudaMemcpyAsync(sm, h_small, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
     GPHM_CUDA_OK(cudaMemcpyAsync(msm, h_msmall, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
     GPHM_CUDA_OK(cudaMemcpyAsync(vsm, h_vsmall, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
     GPHM_CUDA_OK(cudaMemcpyAsync(plan->hs_count, h_count, sizeof(long long), cudaMemcpyHostToDevice, st));
-    GPHM_TRY(gphm_step(plan, U, sm, mU, vU, msm, vsm, plan->hs_count, lr, terms, stream));
+    GPHM_CUDA_OK(cudaMemcpyAsync(U, h_U, sizeof(double) * nf, cudaMemcpyHostToDevice, st));
+    GPHM_CUDA_OK(cudaEventRecord(plan->hs_ev_u, st));
+    GPHM_CUDA_OK(cudaStreamWaitEvent(plan->hs_stream, plan->hs_ev_u, 0));
+    GPHM_CUDA_OK(cudaMemcpyAsync(mU, h_mU, sizeof(double) * nf, cudaMemcpyHostToDevice, plan->hs_stream));
+    GPHM_CUDA_OK(cudaMemcpyAsync(vU, h_vU, sizeof(double) * nf, cudaMemcpyHostToDevice, plan->hs_stream));
+    GPHM_CUDA_OK(cudaEventRecord(plan->hs_ev_mv, plan->hs_stream));
+    GPHM_TRY(logjoint_grad(*plan, U, sm, plan->gU, plan->gsmall, terms, 0, st));
+    GPHM_CUDA_OK(cudaStreamWaitEvent(st, plan->hs_ev_mv, 0));
+    GPHM_TRY(launch_adam(U, plan->gU, mU, vU, nf, plan->hs_count, lr, st));
+    GPHM_TRY(launch_adam(sm, plan->gsmall, msm, vsm, ns, plan->hs_count, lr, st));
+    GPHM_TRY(launch_count_inc(plan->hs_count, st));
     GPHM_CUDA_OK(cudaMemcpyAsync(h_U, U, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
     GPHM_CUDA_OK(cudaMemcpyAsync(h_mU, mU, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
     GPHM_CUDA_OK(cudaMemcpyAsync(h_vU, vU, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));

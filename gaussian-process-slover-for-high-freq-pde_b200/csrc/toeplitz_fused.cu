@@ -215,7 +215,9 @@ int launch_toeplitz_apply_fused(const double* X, int rows, int n, int ldx, const
     auto w = reinterpret_cast<const double2*>(W);
     auto so = reinterpret_cast<double2*>(SpecOut);
     {
-        LaunchScope scope(CAT_FFT, st, 0.0, 16.0 * rows * (double)n);
+        const double pairs = (rows + 1) / 2;
+        LaunchScope scope(CAT_TOEPLITZ_APPLY, st, pairs * (2.0 * fft_flops(L) + 6.0 * L),
+                          (beta != 0.0 ? 24.0 : 16.0) * rows * (double)n + (SpecOut ? 16.0 * pairs * L : 0.0));
         if (KT == 1) toeplitz_apply_fused_kernel<1><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo, so);
         else if (KT == 2) toeplitz_apply_fused_kernel<2><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo, so);
         else toeplitz_apply_fused_kernel<3><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo, so);
@@ -237,7 +239,8 @@ int launch_gs_apply_fused(const double* X, int rows, int n, int ldx, const doubl
     auto sp = reinterpret_cast<const double2*>(gspec);
     auto w = reinterpret_cast<const double2*>(W);
     {
-        LaunchScope scope(CAT_FFT, st, 0.0, 16.0 * rows * (double)n);
+        const double pairs = (rows + 1) / 2;
+        LaunchScope scope(CAT_GS_APPLY, st, pairs * (6.0 * fft_flops(L) + 18.0 * L), (beta != 0.0 ? 24.0 : 16.0) * rows * (double)n);
         if (KT == 1) gs_apply_fused_kernel<1><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
         else if (KT == 2) gs_apply_fused_kernel<2><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
         else gs_apply_fused_kernel<3><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
@@ -257,7 +260,8 @@ int launch_xcorr_pairs(const double* X, int rows, int n, int ldx, const double* 
     auto w = reinterpret_cast<const double2*>(W);
     auto pt = reinterpret_cast<double2*>(partial);
     {
-        LaunchScope scope(CAT_FFT, st, 0.0, 8.0 * rows * (double)n + 8.0 * rows * (double)L);
+        const double pairs = (rows + 1) / 2;
+        LaunchScope scope(CAT_FFT, st, pairs * (fft_flops(L) + 8.0 * L), 8.0 * rows * (double)n + 16.0 * pairs * L);
         if (KT == 1) xcorr_pairs_kernel<1><<<fft_grid(), FFT_THREADS, smem, st>>>(X, rows, n, ldx, sy, L, logL, w, weight, pt);
         else if (KT == 2) xcorr_pairs_kernel<2><<<fft_grid(), FFT_THREADS, smem, st>>>(X, rows, n, ldx, sy, L, logL, w, weight, pt);
         else xcorr_pairs_kernel<3><<<fft_grid(), FFT_THREADS, smem, st>>>(X, rows, n, ldx, sy, L, logL, w, weight, pt);

@@ -83,9 +83,12 @@ GPHM_API const char* gphm_last_error(void);
  * gphm_launch_count: kernels launched by this library in this process so far.
  * gphm_profile_start/stop: while enabled every launch is bracketed by CUDA events on its stream;
  * stop synchronises the device and returns, per kernel family (index: 0 Gram builders, 1 DGEMM,
- * 2 Cholesky diagonal-block, 3 reductions/element-wise, 4 Adam, 5 FFT diagonal sums), the summed
- * device time in ms, the FLOPs issued (DGEMM only), algorithmic bytes (Gram, FFT) and launch
- * counts (arrays of 6).                                                                        */
+ * 2 serial factorisation chain (Cholesky diagonal blocks / Schur-Levinson recursion), 3 reductions
+ * and element-wise, 4 Adam, 5 FFT diagonal sums and spectra, 6 Gohberg-Semencul K^-1 application,
+ * 7 Toeplitz derivative-Gram products), the summed device time in ms, the FLOPs (issued for DGEMM;
+ * 5 L log2 L per complex transform + the spectrum products for the FFT kernels), algorithmic bytes
+ * and launch counts (arrays of GPHM_PROFILE_FAMILIES = 8).                                     */
+#define GPHM_PROFILE_FAMILIES 8
 GPHM_API long long gphm_launch_count(void);
 GPHM_API int gphm_profile_start(void);
 GPHM_API int gphm_profile_stop(double* ms, double* flops, double* bytes, long long* launches);
