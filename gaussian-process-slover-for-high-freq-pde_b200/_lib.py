@@ -69,6 +69,10 @@ _SIGS = {
     "gphm_transpose": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "gphm_mg_theta_grad_fft": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double,
                                        c_void_p, c_void_p, c_void_p]),
+    "gphm_mg_toeplitz_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_double, c_double, c_void_p, c_void_p, c_int,
+                                      c_void_p]),
+    "gphm_mg_theta_grad_pairs": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_void_p,
+                                         c_void_p, c_void_p]),
     "gphm_lincomb": (c_int, [c_void_p, c_double, c_void_p, c_double, c_void_p, c_size_t, c_void_p]),
 }
 

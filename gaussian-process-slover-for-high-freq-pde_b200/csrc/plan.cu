@@ -257,6 +257,11 @@ int factor_gs(gphm_plan& p, int a0, int count, const double* small, cudaStream_t
         GPHM_TRY(launch_gs_prepare(X.gsg, Y.gsg - X.gsg, X.n, X.fftL, X.twid, X.gspec, Y.gspec - X.gspec, X.sKinv,
                                    Y.sKinv - X.sKinv, nsys, st));
     }
+    if (!need_D)     // spectrum of the Toeplitz derivative Gram (FFT products)
+        for (int a = a0; a < a0 + count; ++a) {
+            Axis& X = p.ax[a];
+            GPHM_TRY(launch_toeplitz_spectrum(X.tabD, X.n, X.fftL, X.twid, order == 1, X.dirsign, X.specT, st));
+        }
     return GPHM_OK;
 }
 
@@ -340,9 +345,7 @@ int logjoint_grad_gs(gphm_plan& p, const double* U, const double* small, double*
     const bool anti = order == 1;
     Axis& X1 = p.ax[0];
     Axis& X2 = p.ax[1];
-    GPHM_TRY(factor_gs(p, 0, two ? 2 : 1, small, st));
-    GPHM_TRY(launch_toeplitz_spectrum(X1.tabD, n1, X1.fftL, X1.twid, anti, X1.dirsign, X1.specT, st));
-    if (two) GPHM_TRY(launch_toeplitz_spectrum(X2.tabD, n2, X2.fftL, X2.twid, anti, X2.dirsign, X2.specT, st));
+    GPHM_TRY(factor_gs(p, 0, two ? 2 : 1, small, st));       // includes the spectra of D1, D2
     auto gs1 = [&](const double* Xr, double* out) {       // rows of length n1 (columns of the field)
         return launch_gs_apply_fused(Xr, n2, n1, n1, X1.gspec, X1.fftL, X1.twid, 1.0, 0.0, nullptr, 0, out, n1, st);
     };
@@ -914,6 +917,40 @@ int gphm_mg_toeplitz_apply(gphm_plan* plan, int axis, int transposed, const doub
                                  d_out, X.n, st);
 }
 
+int gphm_mg_toeplitz_rows(gphm_plan* plan, int axis, int transposed, const double* d_X, int rows, double alpha, double beta,
+                          const double* d_add, double* d_out, int keep_spectrum, void* stream) {
+    if (!plan || !d_X || !d_out) { set_last_error("gphm_mg_toeplitz_rows: null pointer"); return GPHM_EINVAL; }
+    if (axis < 0 || axis > 1 || plan->ax[axis].n == 0 || !plan->ax[axis].gs || (plan->d.force_general & 8) ||
+        !toeplitz_fused_supported(plan->ax[axis].fftL)) {
+        set_last_error("gphm_mg_toeplitz_rows: axis %d is not on the Toeplitz inverse-generator path", axis);
+        return GPHM_EINVAL;
+    }
+    Axis& X = plan->ax[axis];
+    const size_t other = plan->d.dim == 2 ? (axis == 0 ? (size_t)plan->d.n2 : (size_t)plan->d.n1) : 1;
+    if (rows < 0 || (keep_spectrum && (size_t)rows > other)) { set_last_error("gphm_mg_toeplitz_rows: %d rows exceed the plan's spectrum store", rows); return GPHM_EINVAL; }
+    const bool anti = deriv_order(*plan) == 1;
+    return launch_toeplitz_apply_fused(d_X, rows, X.n, X.n, X.specT, X.fftL, X.twid, (anti && transposed) ? -alpha : alpha, beta,
+                                       d_add, X.n, d_out, X.n, keep_spectrum ? X.specY : nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int gphm_mg_theta_grad_pairs(gphm_plan* plan, int axis, const double* d_V, const double* d_G, int rows, int lead, double beta,
+                             double cD, const double* d_small, double* d_gtheta, void* stream) {
+    if (!plan || !d_V || !d_G || !d_small || !d_gtheta) { set_last_error("gphm_mg_theta_grad_pairs: null pointer"); return GPHM_EINVAL; }
+    if (axis < 0 || axis > 1 || plan->ax[axis].n == 0 || !plan->ax[axis].gs || !toeplitz_fused_supported(plan->ax[axis].fftL)) {
+        set_last_error("gphm_mg_theta_grad_pairs: axis %d is not on the Toeplitz inverse-generator path", axis);
+        return GPHM_EINVAL;
+    }
+    Axis& X = plan->ax[axis];
+    const int n = X.n, order = deriv_order(*plan);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GPHM_TRY(launch_xcorr_pairs(d_V, rows, n, n, X.specY, X.fftL, X.twid, -1.0, X.specK, st));
+    GPHM_TRY(launch_xcorr_pairs(d_G, rows, n, n, X.specY, X.fftL, X.twid, cD, X.specD, st));
+    GPHM_TRY(launch_spectrum_to_diag_sums(X.specK, X.specD, X.fftL, X.twid, n, order == 1, X.dirsign, lead ? X.sKinv : nullptr,
+                                          lead ? beta : 0.0, X.sK, X.sD, st));
+    return launch_theta_grad_toeplitz(plan->d.kernel_id, order, X.x, n, theta_of(*plan, d_small, axis), plan->d.Q, X.sK, X.sD,
+                                      d_gtheta, st);
+}
+
 int gphm_transpose(const double* d_in, int rows, int cols, double* d_out, void* stream) {
     if (rows <= 0 || cols <= 0) return GPHM_OK;
     if (!d_in || !d_out) { set_last_error("gphm_transpose: null pointer"); return GPHM_EINVAL; }
@@ -977,7 +1014,7 @@ int gphm_mg_boundary(const double* d_U, const int* d_bidx, const double* d_bvals
 int gphm_mg_grad_u(gphm_plan* plan, const double* d_U, const double* d_G, const double* d_W, const double* d_S1,
                    const double* d_S2, size_t n_local, const int* d_bidx, const double* d_eb, int nseg0, int nb_local,
                    const double* d_small, double* d_gU, double* d_V2, void* stream) {
-    if (!plan || !d_U || !d_G || !d_W || !d_S1 || !d_S2 || !d_small || !d_gU || !d_V2) { set_last_error("gphm_mg_grad_u: null pointer"); return GPHM_EINVAL; }
+    if (!plan || !d_U || !d_G || !d_W || !d_S1 || !d_small || !d_gU) { set_last_error("gphm_mg_grad_u: null pointer"); return GPHM_EINVAL; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     GPHM_TRY(launch_grad_u_local(n_local, plan->d.eq_type == GPHM_EQ_ALLENCAHN, d_U, d_G, d_W, d_S1, d_S2, d_gU, nullptr, d_V2, st));
     if (nb_local > 0)

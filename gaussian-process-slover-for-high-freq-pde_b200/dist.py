@@ -9,7 +9,8 @@ axis-1 work on column blocks ("C" layout, N1 x w, w = N2/P), and the only data-p
 the block transpose between the two layouts (NCCL all-to-all, N1*N2*8/P bytes per rank), seven
 times per step.  Scalars (loss terms, 6Q theta-gradients) use one small all-reduce each.
 
-    R->C : U, G, Bt            C->R : c1*D1*A, A, W, S1
+    R->C : U, G, Bt            C->R : c1*D1*A, A, W, S1          (general grids: 7 exchanges)
+    R->Ct: [U], [G, Bt]        Ct->R: [c1*D1*A, A], [V1]         (uniform grids, all-FFT step: 4 exchanges)
 
 The numerical pieces are calls into libgphm through the `ops` object (CudaOps below).  The step
 logic itself is backend-agnostic so that tests can drive it with a CPU stand-in over gloo.
@@ -141,6 +142,32 @@ class CudaOps(object):
                                                    float(beta), float(cD), _lib.ptr(small), _lib.ptr(out), self._s()),
                    "gphm_mg_theta_grad_fft")
 
+    def kinv_rows(self, axis, X, tag):
+        """Every row of X (rows x n_axis) times K_axis^-1."""
+        out, tmp = self._buf(tag, X.shape), self._buf("kinv_tmp", X.shape)
+        _lib.check(self.lib.gphm_apply_kinv(self.plan, axis, 1, _lib.ptr(X), X.shape[0], X.shape[1], _lib.ptr(out),
+                                            _lib.ptr(tmp), self._s()), "gphm_apply_kinv")
+        return out
+
+    def toeplitz_rows_add(self, axis, transposed, X, alpha, beta, add, out, keep):
+        """out[r] = alpha * D x_r (D^T x_r) + beta * add[r]; keep: the plan stores the transforms of X's rows."""
+        _lib.check(self.lib.gphm_mg_toeplitz_rows(self.plan, axis, int(transposed), _lib.ptr(X), X.shape[0], float(alpha),
+                                                  float(beta), _lib.ptr(add), _lib.ptr(out), int(keep), self._s()),
+                   "gphm_mg_toeplitz_rows")
+        return out
+
+    def theta_grad_pairs(self, axis, V, G, lead, beta, cD, small, out):
+        _lib.check(self.lib.gphm_mg_theta_grad_pairs(self.plan, axis, _lib.ptr(V), _lib.ptr(G), V.shape[0], int(lead),
+                                                     float(beta), float(cD), _lib.ptr(small), _lib.ptr(out), self._s()),
+                   "gphm_mg_theta_grad_pairs")
+
+    def grad_u_sum(self, U, G, V1, V2, bidx, eb, nseg0, small):
+        gU = self._buf("gU", U.shape)
+        _lib.check(self.lib.gphm_mg_grad_u(self.plan, _lib.ptr(U), _lib.ptr(G), _lib.ptr(V1), _lib.ptr(V2), None,
+                                           U.numel(), _lib.ptr(bidx), _lib.ptr(eb), nseg0, bidx.numel(), _lib.ptr(small),
+                                           _lib.ptr(gU), None, self._s()), "gphm_mg_grad_u")
+        return gU
+
     def adam(self, p, g, m, v, count, lr):
         _lib.check(self.lib.gphm_adam_update(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), p.numel(), _lib.ptr(count),
                                              float(lr), self._s()), "gphm_adam_update")
@@ -170,7 +197,7 @@ class ShardedSolver2D(object):
     construct it with identical arguments; `step()` is collective."""
 
     def __init__(self, kernel_name, eq_name, x, y, src, bvals, llk_weight, logdet, beta, jitter, Q, lr, ops=None,
-                 group=None):
+                 group=None, force_general=0):
         import numpy as np
         self.group = group
         self.P = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -187,7 +214,8 @@ class ShardedSolver2D(object):
         self.c1 = float(beta) if eq_name == "advection" else 1.0
         if ops is None:
             from .solver_core import SolverCore
-            core = SolverCore(2, kernel_name, eq_name, x, y, src, bvals, None, llk_weight, logdet, beta, jitter, Q)
+            core = SolverCore(2, kernel_name, eq_name, x, y, src, bvals, None, llk_weight, logdet, beta, jitter, Q,
+                              force_general=force_general)
             ops = CudaOps(core)
         self.ops = ops
         r0 = self.rank * self.h
@@ -256,6 +284,23 @@ class ShardedSolver2D(object):
         recv = self._a2a(X.contiguous().reshape(P, h, w))               # chunk s = my rows, columns of rank s
         return recv.transpose(0, 1).reshape(h, self.N2).contiguous()
 
+    def r2ct(self, Xs):
+        """Row blocks (h, N2) -> TRANSPOSED column blocks (w, N1): row j holds column rank*w + j of the field.
+        Several arrays travel in one all-to-all."""
+        P, h, w, k = self.P, self.h, self.w, len(Xs)
+        send = torch.stack(Xs).reshape(k, h, P, w).permute(2, 0, 3, 1).contiguous()       # [dest][array][j][i]
+        recv = self._a2a(send)                                                            # [src][array][j][i]
+        out = recv.permute(1, 2, 0, 3).reshape(k, w, self.N1).contiguous()
+        return [out[a] for a in range(k)]
+
+    def ct2r(self, Ys):
+        """Transposed column blocks (w, N1) -> row blocks (h, N2)."""
+        P, h, w, k = self.P, self.h, self.w, len(Ys)
+        send = torch.stack(Ys).reshape(k, w, P, h).permute(2, 0, 3, 1).contiguous()       # [dest][array][i][j]
+        recv = self._a2a(send)                                                            # [src][array][i][j]
+        out = recv.permute(1, 2, 0, 3).reshape(k, h, self.N2).contiguous()
+        return [out[a] for a in range(k)]
+
     def _allreduce(self, t):
         if self.P > 1:
             dist.all_reduce(t, group=self.group)
@@ -288,8 +333,58 @@ class ShardedSolver2D(object):
         return ld
 
     # ---- one iteration ---------------------------------------------------------------------------
+    def value_and_grad_fft(self):
+        """All-FFT step (both axes on the Toeplitz inverse generator): four K^-1 applications
+        (V1 = K1^-1 (c1 D1^T G + Bt/2), V2 = (G D2 + A/2) K2^-1, dU = V1 + V2 + ...), axis-1 operands
+        kept as transposed column blocks, four all-to-alls:  [U] R->Ct, [c1 D1 A, A] Ct->R, [G, Bt] R->Ct, [V1] Ct->R."""
+        o, Q, c1 = self.ops, self.Q, self.c1
+        N1, N2 = self.N1, self.N2
+        small, U_r = self.small, self.U
+        o.factor(small, 3)                          # O(n^2) generators + spectra, local to every rank
+        ld = o.logdets()
+        (U_ct,) = self.r2ct([U_r])
+        At = o.kinv_rows(0, U_ct, "At")                                           # (K1^-1 U)^T      (Ct)
+        Bt_r = o.kinv_rows(1, U_r, "Bt_r")                                        # U K2^-1          (R)
+        Rt = o.toeplitz_rows_add(0, False, At, c1, 0.0, None, o.new("Rt", At.shape), True)      # (c1 D1 A)^T
+        R_r, A_r = self.ct2r([Rt, At])
+        o.toeplitz_rows_add(1, False, Bt_r, 1.0, 1.0, R_r, R_r, True)             # + Bt D2^T
+        red = torch.empty(3, dtype=DT, device=R_r.device)
+        red[0:2] = o.residual(R_r, U_r, self.F, A_r, Bt_r, small)                 # R_r <- G_r ; [eqgap, quad]
+        G_r = R_r
+        eb, bg = o.boundary(U_r, self.bidx, self.bvals)
+        red[2:3] = bg
+        self._allreduce(red)
+        eq, quad, bgap = red[0], red[1], red[2]
+        tau, v = small[6 * Q], small[6 * Q + 1]
+        loss = (0.5 * self.logdet * (N2 * ld[0] + N1 * ld[1]) + 0.5 * quad
+                - self.llk_weight * (0.5 * self.Nb * tau - 0.5 * torch.exp(tau) * bgap)
+                - (0.5 * self.Nc * v - 0.5 * torch.exp(v) * eq))
+        gtau = -self.llk_weight * (0.5 * self.Nb - 0.5 * torch.exp(tau) * bgap)
+        gv = -(0.5 * self.Nc - 0.5 * torch.exp(v) * eq)
+        self.terms.copy_(torch.stack((loss, ld[0], ld[1], quad, bgap, eq, gtau, gv)))
+        # backward
+        G_ct, Btt = self.r2ct([G_r, Bt_r])
+        T0 = o.toeplitz_rows_add(0, True, G_ct, c1, 0.5, Btt, o.new("T0", G_ct.shape), False)   # (c1 D1^T G + Bt/2)^T
+        V1t = o.kinv_rows(0, T0, "V1t")
+        (V1_r,) = self.ct2r([V1t])
+        P2 = o.toeplitz_rows_add(1, True, G_r, 1.0, 0.5, A_r, o.new("P2", G_r.shape), False)    # G D2 + A/2
+        V2_r = o.kinv_rows(1, P2, "V2_r")
+        gU_r = o.grad_u_sum(U_r, G_r, V1_r, V2_r, self.bidx, eb, self.nseg0, small)
+        gs = self.gsmall
+        gs.zero_()
+        lead = self.rank == 0                        # the K^-1 (log-det) term is added once
+        o.theta_grad_pairs(0, V1t, G_ct, lead, 0.5 * self.logdet * N2, c1, small, gs[0:3 * Q])
+        o.theta_grad_pairs(1, V2_r, G_r, lead, 0.5 * self.logdet * N1, 1.0, small, gs[3 * Q:6 * Q])
+        self._allreduce(gs)
+        gs[6 * Q] = gtau
+        gs[6 * Q + 1] = gv
+        return self.terms, gU_r, gs
+
     def value_and_grad(self):
         """Collective.  Returns (terms[8], gU_r (h,N2), gsmall (6Q+2)) - same layout as gphm_logjoint_grad."""
+        gs_fn = getattr(self.ops, "uses_gs", None)
+        if gs_fn is not None and gs_fn(0) and gs_fn(1):
+            return self.value_and_grad_fft()
         o, Q, c1 = self.ops, self.Q, self.c1
         N1, N2, h, w = self.N1, self.N2, self.h, self.w
         small, U_r = self.small, self.U

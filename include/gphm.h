@@ -235,6 +235,17 @@ GPHM_API int gphm_mg_toeplitz_apply(gphm_plan* plan, int axis, int transposed, c
 GPHM_API int gphm_mg_theta_grad_fft(gphm_plan* plan, int axis, const double* d_X, const double* d_Y, const double* d_G, int rows,
                            int linv_row0, int linv_row1, double beta, double cD, const double* d_small,
                            double* d_gtheta, void* stream);
+/* Rank-local pieces of the all-FFT step (every axis on the Toeplitz inverse generator, gphm_plan_uses_gs):
+ * gphm_mg_toeplitz_rows: d_out[r] = alpha * D x_r (D^T x_r when transposed) + beta * d_add[r] (d_add NULL: beta *
+ *   d_out[r]) for the `rows` rows of d_X, with the derivative-Gram spectrum built by gphm_plan_factor;
+ *   keep_spectrum != 0 stores the transform of every packed row pair of d_X in the plan (one store per axis).
+ * gphm_mg_theta_grad_pairs: theta-gradient of  lead*beta*K^-1 - V^T Y  and  cD * G^T Y, where Y are the rows whose
+ *   transforms the last keep_spectrum call stored (same row count and order), V and G `rows` x n_axis blocks;
+ *   lead != 0 on exactly one rank.  gphm_mg_grad_u: d_S2 and d_V2 may be NULL (dU = W + S1).            */
+GPHM_API int gphm_mg_toeplitz_rows(gphm_plan* plan, int axis, int transposed, const double* d_X, int rows, double alpha,
+                          double beta, const double* d_add, double* d_out, int keep_spectrum, void* stream);
+GPHM_API int gphm_mg_theta_grad_pairs(gphm_plan* plan, int axis, const double* d_V, const double* d_G, int rows, int lead,
+                             double beta, double cD, const double* d_small, double* d_gtheta, void* stream);
 /* d_out = a*d_x + b*d_y (d_y may be NULL).                                                      */
 GPHM_API int gphm_lincomb(double* d_out, double a, const double* d_x, double b, const double* d_y, size_t n, void* stream);
 

@@ -11,13 +11,15 @@ DT = torch.float64
 
 
 class CpuOps(object):
-    def __init__(self, kernel, eq_name, x, y, llk_weight, Q, beta=1.0, jitter=1e-6):
+    def __init__(self, kernel, eq_name, x, y, llk_weight, Q, beta=1.0, jitter=1e-6, gs=True):
         self.kernel, self.eq_name, self.Q, self.jitter = kernel, eq_name, Q, jitter
         self.x, self.y = torch.as_tensor(x, dtype=DT), torch.as_tensor(y, dtype=DT)
         self.order = 1 if eq_name == "advection" else 2
         self.llk_weight = llk_weight
         self.m = {}
         self.ld = torch.zeros(2, dtype=DT)
+        self.gs = gs                 # stand in for the all-FFT step (uniform grids) or the general one
+        self.kept = {}
 
     def zeros(self, shape, dtype=DT):
         return torch.zeros(shape, dtype=dtype)
@@ -63,6 +65,37 @@ class CpuOps(object):
 
     def uses_fft(self, axis):
         return O.is_uniform(self.x if axis == 0 else self.y)
+
+    # ---- the all-FFT step's primitives (uniform grids) ----
+    def uses_gs(self, axis):
+        return self.gs and O.is_uniform(self.x if axis == 0 else self.y)
+
+    def kinv_rows(self, axis, X, tag):
+        Li = self.m[(axis, 2)]
+        return (X @ Li.T) @ Li
+
+    def toeplitz_rows_add(self, axis, transposed, X, alpha, beta, add, out, keep):
+        D = self.m[(axis, 1)]
+        res = alpha * (X @ (D if transposed else D.T))
+        if beta != 0.0:
+            res = res + beta * (add if add is not None else out)
+        if keep:
+            self.kept[axis] = X.clone()
+        out.copy_(res)
+        return out
+
+    def theta_grad_pairs(self, axis, V, G, lead, beta, cD, small, out):
+        Y = self.kept[axis]
+        Li = self.m[(axis, 2)]
+        self.theta_grad(axis, (beta if lead else 0.0) * (Li.T @ Li) - V.T @ Y, cD * (G.T @ Y), small, out)
+
+    def grad_u_sum(self, U, G, V1, V2, bidx, eb, nseg0, small):
+        g = V1 + V2
+        if self.eq_name == "allencahn":
+            g = g + G * (3.0 * U * U - 1.0)
+        s = self.llk_weight * torch.exp(small[6 * self.Q])
+        g.reshape(-1).index_add_(0, bidx.long(), s * eb)
+        return g
 
     def transpose(self, X, tag):
         return X.T.contiguous()

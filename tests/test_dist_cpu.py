@@ -25,7 +25,7 @@ def _small_from(params, Q):
     return s
 
 
-def _run_case(equation, eq_name, kernel, beta, N1, N2, Q, steps):
+def _run_case(equation, eq_name, kernel, beta, N1, N2, Q, steps, gs=True):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -34,7 +34,7 @@ def _run_case(equation, eq_name, kernel, beta, N1, N2, Q, steps):
     D = importlib.import_module("gaussian-process-slover-for-high-freq-pde_b200.dist")
     p, _, _ = O.make_problem_2d(equation, kernel, N1, 2 * math.pi, beta=beta, M=8, N2=N2)
     params = O.state_S1(p, Q=Q, freq_scale=4.0)
-    ops = CpuOps(kernel, eq_name, p.x, p.y, p.llk_weight, Q, beta)
+    ops = CpuOps(kernel, eq_name, p.x, p.y, p.llk_weight, Q, beta, gs=gs)
     solver = D.ShardedSolver2D(kernel, eq_name, p.x.numpy(), p.y.numpy(), p.src.numpy(), p.bvals.numpy(), p.llk_weight,
                                1.0, beta, 1e-6, Q, 0.01, ops=ops)
     solver.set_state(params["U"], _small_from(params, Q))
@@ -77,18 +77,22 @@ def _free_port():
     return port
 
 
+# gs = True: the all-FFT step's host logic (4 exchanges, transposed column blocks); False: the general one (7 exchanges)
+@pytest.mark.parametrize("gs", [True, False])
 @pytest.mark.parametrize("equation,eq_name,kernel,beta", CASES)
-def test_sharded_step_world1(equation, eq_name, kernel, beta):
-    assert _run_case(equation, eq_name, kernel, beta, 24, 20, 4, 2)
+def test_sharded_step_world1(equation, eq_name, kernel, beta, gs):
+    assert _run_case(equation, eq_name, kernel, beta, 24, 20, 4, 2, gs)
 
 
+@pytest.mark.parametrize("gs", [True, False])
 @pytest.mark.parametrize("equation,eq_name,kernel,beta", CASES)
-def test_sharded_step_world2_gloo(equation, eq_name, kernel, beta):
-    mp.spawn(_worker, args=(2, _free_port(), (equation, eq_name, kernel, beta, 24, 20, 4, 2)), nprocs=2, join=True)
+def test_sharded_step_world2_gloo(equation, eq_name, kernel, beta, gs):
+    mp.spawn(_worker, args=(2, _free_port(), (equation, eq_name, kernel, beta, 24, 20, 4, 2, gs)), nprocs=2, join=True)
 
 
-def test_sharded_step_world4_gloo():
-    mp.spawn(_worker, args=(4, _free_port(), ("poisson_2d-sin_add_cos", "poisson", "Matern52_Cos_1d", 1.0, 24, 20, 4, 1)),
+@pytest.mark.parametrize("gs", [True, False])
+def test_sharded_step_world4_gloo(gs):
+    mp.spawn(_worker, args=(4, _free_port(), ("poisson_2d-sin_add_cos", "poisson", "Matern52_Cos_1d", 1.0, 24, 20, 4, 1, gs)),
              nprocs=4, join=True)
 
 

@@ -23,7 +23,7 @@ def _small_from(params, Q):
     return s
 
 
-def _compare(equation, eq_name, kernel, beta, N, Q, steps=2):
+def _compare(equation, eq_name, kernel, beta, N, Q, steps=2, mode=0):
     import gphm_b200 as G
     from oracle import gphm_oracle as O
     D = importlib.import_module("gaussian-process-slover-for-high-freq-pde_b200.dist")
@@ -31,18 +31,19 @@ def _compare(equation, eq_name, kernel, beta, N, Q, steps=2):
     params = O.state_S1(p, Q=Q, freq_scale=6.0)
     small = _small_from(params, Q)
     solver = D.ShardedSolver2D(kernel, eq_name, p.x.numpy(), p.y.numpy(), p.src.numpy(), p.bvals.numpy(), p.llk_weight,
-                               1.0, beta, 1e-6, Q, 0.01)
+                               1.0, beta, 1e-6, Q, 0.01, force_general=mode)
+    assert solver.ops.uses_gs(0) == (mode == 0)          # default: the all-FFT sharded step; 16: Cholesky + GEMM pieces
     solver.set_state(params["U"], small)
     core = G.solver_core.SolverCore(2, kernel, eq_name, p.x.numpy(), p.y.numpy(), p.src.numpy(), p.bvals.numpy(), None,
-                                    p.llk_weight, 1.0, beta, 1e-6, Q)
+                                    p.llk_weight, 1.0, beta, 1e-6, Q, force_general=mode)   # same algorithm family
     st = core.new_state()
     st.U.copy_(params["U"].reshape(-1).cuda()); st.small.copy_(small.cuda())
     terms, gU, gs = core.value_and_grad(st)
     t2, gU_r, gs2 = solver.value_and_grad()
     r0, h = solver.rank * solver.h, solver.h
     ref_rows = gU.reshape(N, N)[r0:r0 + h]
-    # the fused path uses FFT (Toeplitz products, diagonal sums), the sharded path GEMMs for the products:
-    # two correct algorithms, so agreement is at the conditioning level (both are within 1e-6 of the oracle)
+    # the sharded and the fused step order their products differently (mode 16 also: GEMMs vs FFT products):
+    # agreement at the conditioning level (both are within 1e-6 of the oracle)
     assert float((t2 - terms).abs().max() / terms.abs().max()) <= 1e-8
     assert float((gU_r - ref_rows).norm() / ref_rows.norm()) <= 1e-6
     assert float((gs2 - gs).norm() / gs.norm()) <= 1e-6
@@ -59,11 +60,12 @@ def _compare(equation, eq_name, kernel, beta, N, Q, steps=2):
 @pytest.mark.parametrize("equation,eq_name,kernel,beta", [("poisson_2d-sin_add_cos", "poisson", "Matern52_Cos_1d", 1.0),
                                                           ("allencahn_2d-mix-sincos", "allencahn", "SE_Cos_1d", 1.0),
                                                           ("advection-sin", "advection", "Matern52_Cos_1d", 5.0)])
-def test_sharded_world1_matches_fused_path(equation, eq_name, kernel, beta):
-    _compare(equation, eq_name, kernel, beta, 256, 8)
+@pytest.mark.parametrize("mode", [0, 16])
+def test_sharded_world1_matches_fused_path(equation, eq_name, kernel, beta, mode):
+    _compare(equation, eq_name, kernel, beta, 256, 8, mode=mode)
 
 
-def _worker(rank, world, port):
+def _worker(rank, world, port, mode):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -72,12 +74,13 @@ def _worker(rank, world, port):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        _compare("poisson_2d-sin_add_cos", "poisson", "Matern52_Cos_1d", 1.0, 512, 8)
+        _compare("poisson_2d-sin_add_cos", "poisson", "Matern52_Cos_1d", 1.0, 512, 8, mode=mode)
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_sharded_world2_nccl():
+@pytest.mark.parametrize("mode", [0, 16])
+def test_sharded_world2_nccl(mode):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_worker, args=(2, port), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, mode), nprocs=2, join=True)
