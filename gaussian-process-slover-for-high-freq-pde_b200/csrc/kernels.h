@@ -76,8 +76,10 @@ int launch_transpose(const double* in, int R, int C, double* out, cudaStream_t s
 int toeplitz_inv_max_n();
 // nsys SPD Toeplitz systems (first columns tabK + s*sTab, jitter added to entry 0):  g = K^-1 e_0,
 // half_logdet[0] = log|K| / 2, status[0] = 1 + first step with a non-positive prediction error.
+// gkap[n] doubles + prog[1] int per system: hand-over buffer between the generator and the lattice CTA.
 int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitter, double* g, long long sG,
-                          double* half_logdet, long long sLd, int* status, long long sStatus, int nsys, cudaStream_t st);
+                          double* half_logdet, long long sLd, int* status, long long sStatus, double* gkap, long long sKap,
+                          int* prog, long long sProg, int nsys, cudaStream_t st);
 // spec[4][L] complex (strides in doubles): Gohberg-Semencul circulant spectra; sKinv[n]: diagonal sums of K^-1
 int launch_gs_prepare(const double* g, long long sG, int n, int L, const double* W, double* spec, long long sSpec,
                       double* sKinv, long long sS, int nsys, cudaStream_t st);

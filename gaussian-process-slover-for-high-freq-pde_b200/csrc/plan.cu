@@ -70,7 +70,9 @@ struct Axis {
            *T = nullptr, *invdiag = nullptr, *ldpart = nullptr, *tabK = nullptr, *tabD = nullptr, *dspart = nullptr,
            *sK = nullptr, *sD = nullptr, *sKinv = nullptr, *tgpart = nullptr, *twid = nullptr, *specK = nullptr, *specD = nullptr, *specT = nullptr,   // specT: spectrum of the Toeplitz D
            *gsg = nullptr, *gspec = nullptr,   // gsg = K^-1 e_0; gspec: four Gohberg-Semencul circulant spectra
-           *specY = nullptr;                   // transforms of the packed row pairs of A^T (axis 1) / Bt (axis 2)
+           *specY = nullptr,                   // transforms of the packed row pairs of A^T (axis 1) / Bt (axis 2)
+           *gskap = nullptr;                   // reflection coefficients handed from the generator CTA to the lattice CTA
+    int* gsprog = nullptr;
 };
 
 }  // namespace gphm
@@ -153,6 +155,7 @@ size_t carve(gphm_plan& p, void* base) {
         if (p.size_query || X.gs) {
             const size_t other = (d.dim == 2) ? (a == 0 ? (size_t)d.n2 : (size_t)d.n1) : 1;      // rows this axis' operators act on
             c.take(X.gsg, n); c.take(X.gspec, 8 * Lq); c.take(X.specY, 2 * Lq * ((other + 1) / 2));
+            c.take(X.gskap, n); c.take(X.gsprog, 1);
         }
     }
     if (p.size_query || p.ax[0].gs || p.ax[1].gs) c.take(p.gsS, nf);
@@ -253,7 +256,8 @@ int factor_gs(gphm_plan& p, int a0, int count, const double* small, cudaStream_t
         const int nsys = batched ? 2 : 1;
         const Axis& Y = p.ax[batched ? a + 1 : a];
         GPHM_TRY(launch_schur_levinson(X.tabK, Y.tabK - X.tabK, X.n, p.d.jitter, X.gsg, Y.gsg - X.gsg, X.ldpart,
-                                       Y.ldpart - X.ldpart, p.status + a, 1, nsys, st));
+                                       Y.ldpart - X.ldpart, p.status + a, 1, X.gskap, Y.gskap - X.gskap, X.gsprog,
+                                       Y.gsprog - X.gsprog, nsys, st));
         GPHM_TRY(launch_gs_prepare(X.gsg, Y.gsg - X.gsg, X.n, X.fftL, X.twid, X.gspec, Y.gspec - X.gspec, X.sKinv,
                                    Y.sKinv - X.sKinv, nsys, st));
     }
@@ -640,6 +644,7 @@ size_t gphm_toeplitz_work_bytes(int n, int rows) {
     Carver c(nullptr);
     double* p;
     c.take(p, 2 * (size_t)L); c.take(p, 8 * (size_t)L); c.take(p, 1); c.take(p, (size_t)std::max(rows, 1) * n);
+    c.take(p, (size_t)n); c.take(p, 1);
     return c.off;
 }
 
@@ -651,11 +656,12 @@ int gphm_toeplitz_solve(const double* d_t, int n, const double* d_B, int rows, d
     if (rows > 0 && d_B == d_X) { set_last_error("gphm_toeplitz_solve: d_X may not alias d_B"); return GPHM_EINVAL; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Carver c(d_work);
-    double *twid, *spec, *hld, *tmp;
+    double *twid, *spec, *hld, *tmp, *gkap, *progd;
     c.take(twid, 2 * (size_t)L); c.take(spec, 8 * (size_t)L); c.take(hld, 1); c.take(tmp, (size_t)std::max(rows, 1) * n);
+    c.take(gkap, (size_t)n); c.take(progd, 1);
     GPHM_CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(int), st));
     GPHM_TRY(launch_twiddle_init(twid, L, st));
-    GPHM_TRY(launch_schur_levinson(d_t, 0, n, 0.0, d_g, 0, hld, 0, d_status, 0, 1, st));
+    GPHM_TRY(launch_schur_levinson(d_t, 0, n, 0.0, d_g, 0, hld, 0, d_status, 0, gkap, 0, reinterpret_cast<int*>(progd), 0, 1, st));
     GPHM_TRY(launch_gs_prepare(d_g, 0, n, L, twid, spec, 0, d_sKinv, 0, 1, st));
     GPHM_TRY(launch_sum_scaled(hld, 1, 2.0, d_logdet, st));
     if (rows > 0) {

@@ -36,36 +36,41 @@ constexpr int SCHUR_MAX_N = SCHUR_EPT * SCHUR_MAX_THREADS;
 
 int toeplitz_inv_max_n() { return SCHUR_MAX_N; }
 
-// Register layout: thread t owns positions j = 8t .. 8t+7 of
-//   be[j]  = beta_{k-1}[j]       second generator row            (live for j >= k)
-//   alS[j] = alpha_{k-1}[j-1]    first generator row, pre-shifted (the recursion shifts it by one
-//                                position per step; keeping it shifted puts the pair that defines
-//                                kappa_k = -beta[k] / alpha[k-1] into one thread)
-//   a[j]   = A_{k-1}[j],  bS[j] = B_{k-1}[j-1]                   (non-zero for j <= k)
-// Step k:  alpha_k = alS + kappa be,  beta_k = be + kappa alS,  A_k = a + kappa bS,  B_k = bS + kappa a,
-// then the two shifted sequences move up by one position.  The shift costs no register moves: the
-// loop is unrolled by 8 and at unrolled slot I the logical entry i of a shifted array lives in the
-// physical register (i - I) mod 8, updates are in place, and only the entry that leaves the thread
-// travels (warp shuffle; one value per warp through shared memory, patched after the barrier).
-// kappa_{k+1} is produced by its owner (its operands are always physical register 0 / slot I+1)
-// before the step's only barrier, except when the operand crosses a warp boundary (every 256th
-// step: one more barrier).  Warps whose generator entries are all dead / lattice entries all
-// zero skip that half of the update (warp-uniform branches).
+// Two CTAs per system: the GENERATOR CTA runs the Schur recursion (it alone carries the serial
+// dependency kappa_k -> kappa_{k+1}) and hands the reflection coefficients over through global memory
+// in chunks; the LATTICE CTA consumes them (no feedback) and builds A_{n-1}.  Splitting halves the
+// FP64 work on the critical path.
+//
+// Register layout (both roles): thread t owns positions j = 8t .. 8t+7 of
+//   generator:  be[j]  = beta_{k-1}[j]      second generator row             (live for j >= k)
+//               A[j]   = alpha_{k-1}[j-1]   first generator row, pre-shifted (the recursion shifts it by one
+//                                           position per step; keeping it shifted puts the pair that defines
+//                                           kappa_k = -beta[k] / alpha[k-1] into one thread)
+//   lattice:    a[j]   = A_{k-1}[j],  B[j] = B_{k-1}[j-1]                    (non-zero for j <= k)
+// Step k:  alpha_k = A + kappa be,  beta_k = be + kappa A;   A_k = a + kappa B,  B_k = B + kappa a,
+// then the shifted sequence moves up by one position.  The shift costs no register moves: the loop is
+// unrolled by 8 and at unrolled slot I the logical entry i of a shifted array lives in the physical
+// register (i - I) mod 8, updates are in place, and only the entry that leaves the thread travels
+// (warp shuffle; one value per warp through shared memory, patched after the barrier).
+// kappa_{k+1} is produced by its owner (operands: physical register 0 / slot I+1) before the step's only
+// barrier, except when the operand crosses a warp boundary (every 256th step: one more barrier).
+// Warps whose generator entries are all dead / lattice entries all zero skip the update.
+constexpr int SCHUR_CHUNK = 64;                 // reflection coefficients per hand-over
+
 template <int I>
-__device__ __forceinline__ void schur_step(int k, int n, int tid, int lane, int warp, double (&A)[SCHUR_EPT],
-                                           double (&be)[SCHUR_EPT], double (&a)[SCHUR_EPT], double (&B)[SCHUR_EPT],
-                                           double* kap, double (*bndA)[32], double (*bndB)[32]) {
+__device__ __forceinline__ void gen_step(int k, int n, int tid, int lane, int warp, double (&A)[SCHUR_EPT],
+                                         double (&be)[SCHUR_EPT], double* kap, double (*bnd)[32]) {
     constexpr int E = SCHUR_EPT;
     constexpr int I1 = (I + 1) % E;
     constexpr int OUT = (E - 1 - I) % E;       // physical slot of logical entry E-1 (leaves the thread)
     const double kp = kap[k];
-    const int wlo = warp * 32 * E, whi = wlo + 32 * E - 1;
+    const int whi = warp * 32 * E + 32 * E - 1;
     const int owner = (k + 1) / E;
     const bool cross = (I1 == 0) && ((owner & 31) == 0);      // kappa_{k+1}'s alpha comes from the previous warp
     if (whi >= k) {                            // warp still holds live generator entries
 #pragma unroll
         for (int ii = 0; ii < E; ++ii) {
-            const int i = (I + ii) % E;        // start with the entry that defines kappa_{k+1}
+            const int i = (I + ii) % E;        // start with the entries that define kappa_{k+1}
             const int ph = (i - I + E) % E;
             const double al = A[ph], b = be[i];
             A[ph] = fma(kp, b, al);
@@ -73,7 +78,26 @@ __device__ __forceinline__ void schur_step(int k, int n, int tid, int lane, int 
             if (ii == 1 && I1 != 0) { if (tid == owner && k + 1 < n) kap[k + 1] = -be[I1] * __drcp_rn(A[0]); }
         }
     }
-    if (wlo <= k + 1) {                        // warp holds non-zero lattice entries
+    const double out = A[OUT];
+    const double up = __shfl_up_sync(0xffffffffu, out, 1);
+    if (lane == 31) bnd[k & 1][warp] = out;
+    A[OUT] = up;                               // becomes logical entry 0 of the next step; lane 0 is patched below
+    if (I1 == 0 && !cross) { if (tid == owner && k + 1 < n) kap[k + 1] = -be[0] * __drcp_rn(A[OUT]); }
+    __syncthreads();
+    if (lane == 0) A[OUT] = warp > 0 ? bnd[k & 1][warp - 1] : 0.0;
+    if (cross) {                                               // uniform in k
+        if (tid == owner && k + 1 < n) kap[k + 1] = -be[0] * __drcp_rn(A[OUT]);
+        __syncthreads();
+    }
+}
+
+template <int I>
+__device__ __forceinline__ void lat_step(int k, int lane, int warp, double (&a)[SCHUR_EPT], double (&B)[SCHUR_EPT],
+                                         const double* kap, double (*bnd)[32]) {
+    constexpr int E = SCHUR_EPT;
+    constexpr int OUT = (E - 1 - I) % E;
+    const double kp = kap[k];
+    if (warp * 32 * E <= k + 1) {              // warp holds non-zero lattice entries
 #pragma unroll
         for (int i = 0; i < E; ++i) {
             const int ph = (i - I + E) % E;
@@ -82,77 +106,123 @@ __device__ __forceinline__ void schur_step(int k, int n, int tid, int lane, int 
             a[i] = fma(kp, bs, av);
         }
     }
-    const double outA = A[OUT], outB = B[OUT];
-    const double upA = __shfl_up_sync(0xffffffffu, outA, 1);
-    const double upB = __shfl_up_sync(0xffffffffu, outB, 1);
-    if (lane == 31) { bndA[k & 1][warp] = outA; bndB[k & 1][warp] = outB; }
-    A[OUT] = upA; B[OUT] = upB;                // becomes logical entry 0 of the next step; lane 0 is patched below
-    if (I1 == 0 && !cross) { if (tid == owner && k + 1 < n) kap[k + 1] = -be[0] * __drcp_rn(A[OUT]); }
+    const double out = B[OUT];
+    const double up = __shfl_up_sync(0xffffffffu, out, 1);
+    if (lane == 31) bnd[k & 1][warp] = out;
+    B[OUT] = up;
     __syncthreads();
-    if (lane == 0) {
-        if (warp > 0) { A[OUT] = bndA[k & 1][warp - 1]; B[OUT] = bndB[k & 1][warp - 1]; }
-        else { A[OUT] = 0.0; B[OUT] = 0.0; }
-    }
-    if (cross) {                                               // uniform in k
-        if (tid == owner && k + 1 < n) kap[k + 1] = -be[0] * __drcp_rn(A[OUT]);
-        __syncthreads();
-    }
+    if (lane == 0) B[OUT] = warp > 0 ? bnd[k & 1][warp - 1] : 0.0;
 }
 
 template <int I>
-__device__ __forceinline__ void schur_steps(int kb, int n, int tid, int lane, int warp, double (&A)[SCHUR_EPT],
-                                            double (&be)[SCHUR_EPT], double (&a)[SCHUR_EPT], double (&B)[SCHUR_EPT],
-                                            double* kap, double (*bndA)[32], double (*bndB)[32]) {
+__device__ __forceinline__ void gen_steps(int kb, int n, int tid, int lane, int warp, double (&A)[SCHUR_EPT],
+                                          double (&be)[SCHUR_EPT], double* kap, double (*bnd)[32]) {
     if constexpr (I < SCHUR_EPT) {
-        if (kb + I < n) schur_step<I>(kb + I, n, tid, lane, warp, A, be, a, B, kap, bndA, bndB);
-        schur_steps<I + 1>(kb, n, tid, lane, warp, A, be, a, B, kap, bndA, bndB);
+        if (kb + I < n) gen_step<I>(kb + I, n, tid, lane, warp, A, be, kap, bnd);
+        gen_steps<I + 1>(kb, n, tid, lane, warp, A, be, kap, bnd);
+    }
+}
+template <int I>
+__device__ __forceinline__ void lat_steps(int kb, int n, int lane, int warp, double (&a)[SCHUR_EPT], double (&B)[SCHUR_EPT],
+                                          const double* kap, double (*bnd)[32]) {
+    if constexpr (I < SCHUR_EPT) {
+        if (kb + I < n) lat_step<I>(kb + I, lane, warp, a, B, kap, bnd);
+        lat_steps<I + 1>(kb, n, lane, warp, a, B, kap, bnd);
     }
 }
 
+// blockIdx.x = 2 * system + role (0: generator, 1: lattice).  gkap[n] / prog[1] per system: hand-over buffer and
+// the number of valid coefficients in it (zeroed by the launcher).
 __global__ void __launch_bounds__(SCHUR_MAX_THREADS, 1)
 schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, double jitter, double* __restrict__ g,
                       long long sG, double* __restrict__ half_logdet, long long sLd, int* __restrict__ status,
-                      long long sStatus) {
-    tab += blockIdx.x * sTab; g += blockIdx.x * sG; half_logdet += blockIdx.x * sLd; status += blockIdx.x * sStatus;
+                      long long sStatus, double* gkap, long long sKap, int* prog, long long sProg) {
+    const int sys = blockIdx.x >> 1, role = blockIdx.x & 1;
+    tab += sys * sTab; g += sys * sG; half_logdet += sys * sLd; status += sys * sStatus; gkap += sys * sKap; prog += sys * sProg;
     __shared__ double kap[SCHUR_MAX_N];
-    __shared__ double bndA[2][32], bndB[2][32];
+    __shared__ double bnd[2][32];
     __shared__ double red[34];
-    __shared__ int bad;
+    __shared__ int bad, s_have;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int j0 = tid * SCHUR_EPT;
-    double A[SCHUR_EPT], be[SCHUR_EPT], a[SCHUR_EPT], B[SCHUR_EPT];
     const double r0 = tab[0] + jitter;
-    // State "before step 0": unshifted alpha_0 = r, beta_0 = (0, r_1, ...), A_0 = B_0 = 1.  Step 0 runs with
-    // kappa_0 = 0: it changes no value and performs the first shift, so that every step is identical.
+    if (role == 0) {
+        // ---- generator: Schur recursion ----
+        double A[SCHUR_EPT], be[SCHUR_EPT];
+        // State "before step 0": unshifted alpha_0 = r, beta_0 = (0, r_1, ...).  Step 0 runs with kappa_0 = 0:
+        // it changes no value and performs the first shift, so that every step is identical.
 #pragma unroll
-    for (int i = 0; i < SCHUR_EPT; ++i) {
-        const int j = j0 + i;
-        const double rj = (j < n) ? (j == 0 ? r0 : tab[j]) : 0.0;
-        A[i] = rj;
-        be[i] = (j == 0) ? 0.0 : rj;
-        a[i] = (j == 0) ? 1.0 : 0.0;
-        B[i] = (j == 0) ? 1.0 : 0.0;
+        for (int i = 0; i < SCHUR_EPT; ++i) {
+            const int j = j0 + i;
+            const double rj = (j < n) ? (j == 0 ? r0 : tab[j]) : 0.0;
+            A[i] = rj;
+            be[i] = (j == 0) ? 0.0 : rj;
+        }
+        if (tid == 0) { bad = 0x7fffffff; kap[0] = 0.0; }
+        __syncthreads();
+        int published = 0;
+        for (int kb = 0; kb < n; kb += SCHUR_EPT) {           // the position inside a thread is static per unrolled slot
+            gen_steps<0>(kb, n, tid, lane, warp, A, be, kap, bnd);
+            const int valid = min(kb + SCHUR_EPT + 1, n);     // kappa_0 .. kappa_{valid-1} are final
+            if (valid - published >= SCHUR_CHUNK || valid == n) {
+                if (warp == 0) {
+                    for (int i = published + lane; i < valid; i += 32) gkap[i] = kap[i];
+                    __syncwarp();
+                    if (lane == 0) { __threadfence(); *reinterpret_cast<volatile int*>(prog) = valid; }
+                }
+                published = valid;
+            }
+        }
+        // log|K| = n log r0 + sum_k (n - k) log(1 - kappa_k^2); first |kappa| >= 1 <=> first non-positive prediction error
+        double lsum = 0.0;
+#pragma unroll
+        for (int i = 0; i < SCHUR_EPT; ++i) {
+            const int k = j0 + i;
+            if (k >= 1 && k < n) {
+                const double kp = kap[k];
+                if (!(fabs(kp) < 1.0)) atomicMin(&bad, k);     // also catches NaN
+                lsum += (double)(n - k) * log1p(-kp * kp);
+            }
+        }
+        if (!(r0 > 0.0) && tid == 0) atomicMin(&bad, 0);
+        const double ltot = block_sum(lsum, red);
+        if (tid == 0) {
+            half_logdet[0] = 0.5 * ((double)n * log(r0) + ltot);
+            if (bad != 0x7fffffff) status[0] = bad + 1;        // like a Cholesky pivot index
+        }
+        return;
     }
-    if (tid == 0) { bad = 0x7fffffff; kap[0] = 0.0; }
-    __syncthreads();
-    for (int kb = 0; kb < n; kb += SCHUR_EPT)             // the position inside a thread is static per unrolled slot
-        schur_steps<0>(kb, n, tid, lane, warp, A, be, a, B, kap, bndA, bndB);
-    // After the last step (k = n-1, slot I = (n-1) % 8) logical entry i of A_{n-1} is a[i] (a does not shift).
-    // E_{n-1} = r0 * prod (1 - kappa_k^2);  log|K| = n log r0 + sum_k (n - k) log(1 - kappa_k^2)
-    double prod = 1.0, lsum = 0.0;
+    // ---- lattice: A_k = A_{k-1} + kappa_k z B_{k-1},  B_k = z B_{k-1} + kappa_k A_{k-1} ----
+    double a[SCHUR_EPT], B[SCHUR_EPT];
+#pragma unroll
+    for (int i = 0; i < SCHUR_EPT; ++i) { a[i] = (j0 + i == 0) ? 1.0 : 0.0; B[i] = a[i]; }
+    int have = 0;
+    bool dead = false;
+    for (int kb = 0; kb < n; kb += SCHUR_EPT) {
+        const int need = min(kb + SCHUR_EPT, n);
+        if (need > have) {                                     // uniform
+            if (tid == 0) {
+                int v = 0;
+                long long spins = 0;
+                while ((v = *reinterpret_cast<volatile int*>(prog)) < need && spins < (1ll << 24)) { __nanosleep(100); ++spins; }
+                s_have = v;
+            }
+            __syncthreads();
+            const int now = s_have;
+            if (now < need) { dead = true; break; }            // the producer never arrived (cannot happen when both CTAs run)
+            for (int i = have + tid; i < now; i += blockDim.x) kap[i] = __ldcg(gkap + i);
+            __syncthreads();
+            have = now;
+        }
+        lat_steps<0>(kb, n, lane, warp, a, B, kap, bnd);
+    }
+    // g = A_{n-1} / E_{n-1},  E_{n-1} = r0 * prod_k (1 - kappa_k^2)   (a does not shift: entry i is a[i])
+    double prod = 1.0;
 #pragma unroll
     for (int i = 0; i < SCHUR_EPT; ++i) {
         const int k = j0 + i;
-        if (k >= 1 && k < n) {
-            const double kp = kap[k];
-            if (!(fabs(kp) < 1.0)) atomicMin(&bad, k);         // also catches NaN
-            const double om = (1.0 - kp) * (1.0 + kp);
-            prod *= om;
-            lsum += (double)(n - k) * log1p(-kp * kp);
-        }
+        if (k >= 1 && k < n) { const double kp = kap[k]; prod *= (1.0 - kp) * (1.0 + kp); }
     }
-    if (!(r0 > 0.0) && tid == 0) atomicMin(&bad, 0);
-    const double ltot = block_sum(lsum, red);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) prod *= __shfl_xor_sync(0xffffffffu, prod, o);
     __syncthreads();
@@ -160,13 +230,9 @@ schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, dou
     __syncthreads();
     double E = r0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) E *= red[w];
-    const double invE = 1.0 / E;
+    const double invE = dead ? __longlong_as_double(0x7ff8000000000000ll) : 1.0 / E;
 #pragma unroll
     for (int i = 0; i < SCHUR_EPT; ++i) { const int j = j0 + i; if (j < n) g[j] = a[i] * invE; }
-    if (tid == 0) {
-        half_logdet[0] = 0.5 * ((double)n * log(r0) + ltot);
-        if (bad != 0x7fffffff) status[0] = bad + 1;            // first non-positive prediction error (like a Cholesky pivot)
-    }
 }
 
 // One CTA per axis.  spec[0..3][L] (bit-reversed order, scaled like launch_toeplitz_spectrum):
@@ -242,12 +308,16 @@ int toeplitz_inv_init() {
 }
 
 int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitter, double* g, long long sG,
-                          double* half_logdet, long long sLd, int* status, long long sStatus, int nsys, cudaStream_t st) {
+                          double* half_logdet, long long sLd, int* status, long long sStatus, double* gkap, long long sKap,
+                          int* prog, long long sProg, int nsys, cudaStream_t st) {
     if (n < 1 || n > SCHUR_MAX_N) { set_last_error("schur: n=%d outside [1,%d]", n, SCHUR_MAX_N); return GPHM_EINVAL; }
+    if (nsys < 1 || nsys > 2) { set_last_error("schur: nsys=%d", nsys); return GPHM_EINVAL; }
     const int threads = std::min(SCHUR_MAX_THREADS, ((n + SCHUR_EPT - 1) / SCHUR_EPT + 31) / 32 * 32);
+    for (int s = 0; s < nsys; ++s) GPHM_CUDA_OK(cudaMemsetAsync(prog + s * sProg, 0, sizeof(int), st));
     {
-        LaunchScope scope(CAT_CHOL_DIAG, st, 6.0 * (double)n * n * nsys);
-        schur_levinson_kernel<<<nsys, threads, 0, st>>>(tabK, sTab, n, jitter, g, sG, half_logdet, sLd, status, sStatus);
+        LaunchScope scope(CAT_CHOL_DIAG, st, 8.0 * (double)n * n * nsys);
+        schur_levinson_kernel<<<2 * nsys, threads, 0, st>>>(tabK, sTab, n, jitter, g, sG, half_logdet, sLd, status, sStatus,
+                                                              gkap, sKap, prog, sProg);
     }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
