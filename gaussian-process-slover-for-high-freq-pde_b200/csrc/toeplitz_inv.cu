@@ -57,6 +57,18 @@ int toeplitz_inv_max_n() { return SCHUR_MAX_N; }
 // Warps whose generator entries are all dead / lattice entries all zero skip the update.
 constexpr int SCHUR_CHUNK = 64;                 // reflection coefficients per hand-over
 
+// 1/x to ~1 ulp without a slow path: MUFU.RCP64H seed (2^-23) + two Newton steps.  Straight-line, so that
+// the scheduler can interleave the step's independent FMAs with this dependent chain; every lane of a live
+// warp evaluates it (only the owner's value is stored; other lanes may produce Inf/NaN harmlessly).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
 template <int I>
 __device__ __forceinline__ void gen_step(int k, int n, int tid, int lane, int warp, double (&A)[SCHUR_EPT],
                                          double (&be)[SCHUR_EPT], double* kap, double (*bnd)[32]) {
@@ -67,6 +79,7 @@ __device__ __forceinline__ void gen_step(int k, int n, int tid, int lane, int wa
     const int whi = warp * 32 * E + 32 * E - 1;
     const int owner = (k + 1) / E;
     const bool cross = (I1 == 0) && ((owner & 31) == 0);      // kappa_{k+1}'s alpha comes from the previous warp
+    double cand = 0.0;                         // kappa_{k+1} in the owner thread
     if (whi >= k) {                            // warp still holds live generator entries
 #pragma unroll
         for (int ii = 0; ii < E; ++ii) {
@@ -75,18 +88,19 @@ __device__ __forceinline__ void gen_step(int k, int n, int tid, int lane, int wa
             const double al = A[ph], b = be[i];
             A[ph] = fma(kp, b, al);
             be[i] = fma(kp, al, b);
-            if (ii == 1 && I1 != 0) { if (tid == owner && k + 1 < n) kap[k + 1] = -be[I1] * __drcp_rn(A[0]); }
+            if (ii == 1 && I1 != 0) cand = -be[I1] * fast_rcp(A[0]);
         }
     }
     const double out = A[OUT];
     const double up = __shfl_up_sync(0xffffffffu, out, 1);
     if (lane == 31) bnd[k & 1][warp] = out;
     A[OUT] = up;                               // becomes logical entry 0 of the next step; lane 0 is patched below
-    if (I1 == 0 && !cross) { if (tid == owner && k + 1 < n) kap[k + 1] = -be[0] * __drcp_rn(A[OUT]); }
+    if (I1 == 0 && !cross) cand = -be[0] * fast_rcp(up);
+    if (!cross && tid == owner && k + 1 < n) kap[k + 1] = cand;
     __syncthreads();
     if (lane == 0) A[OUT] = warp > 0 ? bnd[k & 1][warp - 1] : 0.0;
     if (cross) {                                               // uniform in k
-        if (tid == owner && k + 1 < n) kap[k + 1] = -be[0] * __drcp_rn(A[OUT]);
+        if (tid == owner && k + 1 < n) kap[k + 1] = -be[0] * fast_rcp(A[OUT]);
         __syncthreads();
     }
 }
