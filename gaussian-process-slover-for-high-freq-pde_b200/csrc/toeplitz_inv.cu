@@ -30,8 +30,8 @@
 
 namespace gphm {
 
-constexpr int SCHUR_EPT = 8;                    // consecutive elements per thread
-constexpr int SCHUR_MAX_THREADS = 512;
+constexpr int SCHUR_EPT = 16;                   // consecutive elements per thread
+constexpr int SCHUR_MAX_THREADS = 256;
 constexpr int SCHUR_MAX_N = SCHUR_EPT * SCHUR_MAX_THREADS;
 
 int toeplitz_inv_max_n() { return SCHUR_MAX_N; }

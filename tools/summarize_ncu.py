@@ -79,7 +79,42 @@ def kernel(src, dst):
     print(open(dst).read())
 
 
+KEYS2 = KEYS + ["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+                "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+                "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+                "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
+
+
+def kernels(src, dst, command, traffic_kernel=None, traffic_json=None, note=""):
+    """Any capture: one column per launch; optionally the mean DRAM traffic of `traffic_kernel` launches -> json."""
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    short = lambda r: re.sub(r"<.*|\(.*|gphm::|void ", "", r[idx["Kernel Name"]])
+    with open(dst, "w") as f:
+        f.write("# ncu --set full: %s\n\nCommand: `%s`\n\n%s\n\n" % (os.path.basename(src), command, note))
+        f.write("| metric | unit | " + " | ".join("launch %d" % i for i in range(len(data))) + " |\n")
+        f.write("|---|---|" + "---:|" * len(data) + "\n")
+        f.write("| kernel | | " + " | ".join("`%s`" % short(r) for r in data) + " |\n")
+        for k in KEYS2:
+            if k in idx and "dmma" not in k and "fp64.avg.pct_of_peak_sustained_elapsed" not in k:
+                f.write("| %s | %s | " % (k, units[idx[k]]) + " | ".join(r[idx[k]] for r in data) + " |\n")
+    if traffic_kernel:
+        scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+        sel = [r for r in data if traffic_kernel in r[idx["Kernel Name"]]]
+        tr = [float(r[idx["dram__bytes_read.sum"]].replace(",", "")) * scale[units[idx["dram__bytes_read.sum"]]] +
+              float(r[idx["dram__bytes_write.sum"]].replace(",", "")) * scale[units[idx["dram__bytes_write.sum"]]] for r in sel]
+        json.dump({"dram_bytes_per_launch": sum(tr) / len(tr), "launches": len(tr), "kernel": traffic_kernel,
+                   "launch": "one K^-1 application to 4096 rows of length 4096 (algorithmic 2*N^2*8 = 268.4 MB)",
+                   "source": os.path.basename(dst)}, open(traffic_json, "w"), indent=1)
+    print(open(dst).read()[:3000])
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "kernels":
+        kernels(*sys.argv[2:])
+        sys.exit(0)
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 1)
     else:
