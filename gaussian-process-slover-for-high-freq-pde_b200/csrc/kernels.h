@@ -79,7 +79,7 @@ int toeplitz_inv_max_n();
 // gkap[n] doubles + prog[1] int per system: hand-over buffer between the generator and the lattice CTA.
 int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitter, double* g, long long sG,
                           double* half_logdet, long long sLd, int* status, long long sStatus, double* gkap, long long sKap,
-                          int* prog, long long sProg, int nsys, cudaStream_t st);
+                          int* prog, long long sProg, int nsys, cudaStream_t st, long long* dbg_cycles = nullptr);
 // spec[4][L] complex (strides in doubles): Gohberg-Semencul circulant spectra; sKinv[n]: diagonal sums of K^-1
 int launch_gs_prepare(const double* g, long long sG, int n, int L, const double* W, double* spec, long long sSpec,
                       double* sKinv, long long sS, int nsys, cudaStream_t st);

@@ -17,6 +17,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "../../include/gphm.h"
@@ -661,7 +662,8 @@ int gphm_toeplitz_solve(const double* d_t, int n, const double* d_B, int rows, d
     c.take(gkap, (size_t)n); c.take(progd, 1);
     GPHM_CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(int), st));
     GPHM_TRY(launch_twiddle_init(twid, L, st));
-    GPHM_TRY(launch_schur_levinson(d_t, 0, n, 0.0, d_g, 0, hld, 0, d_status, 0, gkap, 0, reinterpret_cast<int*>(progd), 0, 1, st));
+    GPHM_TRY(launch_schur_levinson(d_t, 0, n, 0.0, d_g, 0, hld, 0, d_status, 0, gkap, 0, reinterpret_cast<int*>(progd), 0, 1, st,
+                                   getenv("GPHM_SCHUR_CYCLES") ? reinterpret_cast<long long*>(tmp) : nullptr));
     GPHM_TRY(launch_gs_prepare(d_g, 0, n, L, twid, spec, 0, d_sKinv, 0, 1, st));
     GPHM_TRY(launch_sum_scaled(hld, 1, 2.0, d_logdet, st));
     if (rows > 0) {

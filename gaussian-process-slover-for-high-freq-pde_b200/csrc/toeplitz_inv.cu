@@ -30,7 +30,7 @@
 
 namespace gphm {
 
-constexpr int SCHUR_EPT = 16;                   // consecutive elements per thread
+constexpr int SCHUR_EPT = 16;                   // consecutive elements per thread (8 and 4 measured: same or slower)
 constexpr int SCHUR_MAX_THREADS = 256;
 constexpr int SCHUR_MAX_N = SCHUR_EPT * SCHUR_MAX_THREADS;
 
@@ -57,21 +57,25 @@ int toeplitz_inv_max_n() { return SCHUR_MAX_N; }
 // Warps whose generator entries are all dead / lattice entries all zero skip the update.
 constexpr int SCHUR_CHUNK = 64;                 // reflection coefficients per hand-over
 
-// 1/x to ~1 ulp without a slow path: MUFU.RCP64H seed (2^-23) + two Newton steps.  Straight-line, so that
-// the scheduler can interleave the step's independent FMAs with this dependent chain; every lane of a live
-// warp evaluates it (only the owner's value is stored; other lanes may produce Inf/NaN harmlessly).
-__device__ __forceinline__ double fast_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
+// -num/den to ~1 ulp in FIVE dependent FP64 operations after den is known (a division is seven):
+//   r0 = MUFU.RCP64H(den) (2^-23), e = 1 - den r0, w = e + e^2, q0 = -num r0 (parallel to e),
+//   result = q0 + q0 w = -num r0 (1 + e + e^2) = -num/den (1 - e^3).
+// Straight-line (no slow path), so that the scheduler interleaves the step's independent FMAs with this
+// chain - the one dependent chain of the whole recursion; every lane of a live warp evaluates it (only
+// the owner's value is stored; other lanes may produce Inf/NaN harmlessly).
+__device__ __forceinline__ double neg_div(double num, double den) {
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(den));
+    const double e = fma(-den, r0, 1.0);
+    const double q0 = -num * r0;
+    const double w = fma(e, e, e);
+    return fma(q0, w, q0);
 }
+struct SchurTiming { long long t_kappa = 0, t_rest = 0, t_barrier = 0, t_last = 0; bool on = false; };
 
 template <int I>
 __device__ __forceinline__ void gen_step(int k, int n, int tid, int lane, int warp, double (&A)[SCHUR_EPT],
-                                         double (&be)[SCHUR_EPT], double* kap, double (*bnd)[32]) {
+                                         double (&be)[SCHUR_EPT], double* kap, double (*bnd)[32], SchurTiming& tm) {
     constexpr int E = SCHUR_EPT;
     constexpr int I1 = (I + 1) % E;
     constexpr int OUT = (E - 1 - I) % E;       // physical slot of logical entry E-1 (leaves the thread)
@@ -88,19 +92,29 @@ __device__ __forceinline__ void gen_step(int k, int n, int tid, int lane, int wa
             const double al = A[ph], b = be[i];
             A[ph] = fma(kp, b, al);
             be[i] = fma(kp, al, b);
-            if (ii == 1 && I1 != 0) cand = -be[I1] * fast_rcp(A[0]);
+            if (ii == 1 && I1 != 0) cand = neg_div(be[I1], A[0]);
         }
     }
     const double out = A[OUT];
     const double up = __shfl_up_sync(0xffffffffu, out, 1);
     if (lane == 31) bnd[k & 1][warp] = out;
     A[OUT] = up;                               // becomes logical entry 0 of the next step; lane 0 is patched below
-    if (I1 == 0 && !cross) cand = -be[0] * fast_rcp(up);
+    if (I1 == 0 && !cross) cand = neg_div(be[0], up);
     if (!cross && tid == owner && k + 1 < n) kap[k + 1] = cand;
+    long long t1 = 0;
+    if (tm.on && tid == owner) {               // owner thread: barrier release -> kappa stored
+        t1 = clock64();
+        tm.t_kappa += t1 - tm.t_last;
+    }
     __syncthreads();
+    if (tm.on) {
+        const long long t2 = clock64();
+        if (tid == owner) tm.t_barrier += t2 - t1;
+        tm.t_last = t2;
+    }
     if (lane == 0) A[OUT] = warp > 0 ? bnd[k & 1][warp - 1] : 0.0;
     if (cross) {                                               // uniform in k
-        if (tid == owner && k + 1 < n) kap[k + 1] = -be[0] * fast_rcp(A[OUT]);
+        if (tid == owner && k + 1 < n) kap[k + 1] = neg_div(be[0], A[OUT]);
         __syncthreads();
     }
 }
@@ -130,10 +144,10 @@ __device__ __forceinline__ void lat_step(int k, int lane, int warp, double (&a)[
 
 template <int I>
 __device__ __forceinline__ void gen_steps(int kb, int n, int tid, int lane, int warp, double (&A)[SCHUR_EPT],
-                                          double (&be)[SCHUR_EPT], double* kap, double (*bnd)[32]) {
+                                          double (&be)[SCHUR_EPT], double* kap, double (*bnd)[32], SchurTiming& tm) {
     if constexpr (I < SCHUR_EPT) {
-        if (kb + I < n) gen_step<I>(kb + I, n, tid, lane, warp, A, be, kap, bnd);
-        gen_steps<I + 1>(kb, n, tid, lane, warp, A, be, kap, bnd);
+        if (kb + I < n) gen_step<I>(kb + I, n, tid, lane, warp, A, be, kap, bnd, tm);
+        gen_steps<I + 1>(kb, n, tid, lane, warp, A, be, kap, bnd, tm);
     }
 }
 template <int I>
@@ -150,8 +164,9 @@ __device__ __forceinline__ void lat_steps(int kb, int n, int lane, int warp, dou
 __global__ void __launch_bounds__(SCHUR_MAX_THREADS, 1)
 schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, double jitter, double* __restrict__ g,
                       long long sG, double* __restrict__ half_logdet, long long sLd, int* __restrict__ status,
-                      long long sStatus, double* gkap, long long sKap, int* prog, long long sProg) {
+                      long long sStatus, double* gkap, long long sKap, int* prog, long long sProg, long long* dbg) {
     const int sys = blockIdx.x >> 1, role = blockIdx.x & 1;
+    const long long t_start = clock64();
     tab += sys * sTab; g += sys * sG; half_logdet += sys * sLd; status += sys * sStatus; gkap += sys * sKap; prog += sys * sProg;
     __shared__ double kap[SCHUR_MAX_N];
     __shared__ double bnd[2][32];
@@ -175,8 +190,11 @@ schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, dou
         if (tid == 0) { bad = 0x7fffffff; kap[0] = 0.0; }
         __syncthreads();
         int published = 0;
+        SchurTiming tm;
+        tm.on = dbg != nullptr;
+        tm.t_last = clock64();
         for (int kb = 0; kb < n; kb += SCHUR_EPT) {           // the position inside a thread is static per unrolled slot
-            gen_steps<0>(kb, n, tid, lane, warp, A, be, kap, bnd);
+            gen_steps<0>(kb, n, tid, lane, warp, A, be, kap, bnd, tm);
             const int valid = min(kb + SCHUR_EPT + 1, n);     // kappa_0 .. kappa_{valid-1} are final
             if (valid - published >= SCHUR_CHUNK || valid == n) {
                 if (warp == 0) {
@@ -200,9 +218,14 @@ schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, dou
         }
         if (!(r0 > 0.0) && tid == 0) atomicMin(&bad, 0);
         const double ltot = block_sum(lsum, red);
+        if (tm.on) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(dbg) + 8, (unsigned long long)tm.t_kappa);
+            atomicAdd(reinterpret_cast<unsigned long long*>(dbg) + 9, (unsigned long long)tm.t_barrier);
+        }
         if (tid == 0) {
             half_logdet[0] = 0.5 * ((double)n * log(r0) + ltot);
             if (bad != 0x7fffffff) status[0] = bad + 1;        // like a Cholesky pivot index
+            if (dbg) dbg[blockIdx.x] = clock64() - t_start;
         }
         return;
     }
@@ -247,6 +270,7 @@ schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, dou
     const double invE = dead ? __longlong_as_double(0x7ff8000000000000ll) : 1.0 / E;
 #pragma unroll
     for (int i = 0; i < SCHUR_EPT; ++i) { const int j = j0 + i; if (j < n) g[j] = a[i] * invE; }
+    if (dbg && tid == 0) dbg[blockIdx.x] = clock64() - t_start;
 }
 
 // One CTA per axis.  spec[0..3][L] (bit-reversed order, scaled like launch_toeplitz_spectrum):
@@ -323,7 +347,7 @@ int toeplitz_inv_init() {
 
 int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitter, double* g, long long sG,
                           double* half_logdet, long long sLd, int* status, long long sStatus, double* gkap, long long sKap,
-                          int* prog, long long sProg, int nsys, cudaStream_t st) {
+                          int* prog, long long sProg, int nsys, cudaStream_t st, long long* dbg) {
     if (n < 1 || n > SCHUR_MAX_N) { set_last_error("schur: n=%d outside [1,%d]", n, SCHUR_MAX_N); return GPHM_EINVAL; }
     if (nsys < 1 || nsys > 2) { set_last_error("schur: nsys=%d", nsys); return GPHM_EINVAL; }
     const int threads = std::min(SCHUR_MAX_THREADS, ((n + SCHUR_EPT - 1) / SCHUR_EPT + 31) / 32 * 32);
@@ -331,7 +355,7 @@ int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitt
     {
         LaunchScope scope(CAT_CHOL_DIAG, st, 8.0 * (double)n * n * nsys);
         schur_levinson_kernel<<<2 * nsys, threads, 0, st>>>(tabK, sTab, n, jitter, g, sG, half_logdet, sLd, status, sStatus,
-                                                              gkap, sKap, prog, sProg);
+                                                              gkap, sKap, prog, sProg, dbg);
     }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
