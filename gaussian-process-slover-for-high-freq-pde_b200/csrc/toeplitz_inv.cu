@@ -30,39 +30,49 @@
 
 namespace gphm {
 
-constexpr int SCHUR_EPT = 16;                   // consecutive elements per thread (8 and 4 measured: same or slower)
-constexpr int SCHUR_MAX_THREADS = 256;
+constexpr int SCHUR_EPT = 8;                    // consecutive positions per thread = steps per batch
+constexpr int SCHUR_MAX_THREADS = 512;
 constexpr int SCHUR_MAX_N = SCHUR_EPT * SCHUR_MAX_THREADS;
+constexpr int SCHUR_WCHUNK = 32 * SCHUR_EPT;    // positions per warp
+constexpr int SCHUR_BPW = 32;                   // batches led by one warp (= its lanes)
+constexpr int SCHUR_RING = 32;                  // boundary values kept per warp (4 batches)
+constexpr int SCHUR_PUBLISH = 8;                // led batches per hand-over to the lattice CTA (64 coefficients)
 
 int toeplitz_inv_max_n() { return SCHUR_MAX_N; }
 
 // Two CTAs per system: the GENERATOR CTA runs the Schur recursion (it alone carries the serial
-// dependency kappa_k -> kappa_{k+1}) and hands the reflection coefficients over through global memory
-// in chunks; the LATTICE CTA consumes them (no feedback) and builds A_{n-1}.  Splitting halves the
-// FP64 work on the critical path.
+// dependency kappa_j -> kappa_{j+1}) and hands the reflection coefficients over through global memory;
+// the LATTICE CTA consumes them (no feedback) and builds A_{n-1}.
 //
-// Register layout (both roles): thread t owns positions j = 8t .. 8t+7 of
-//   generator:  be[j]  = beta_{k-1}[j]      second generator row             (live for j >= k)
-//               A[j]   = alpha_{k-1}[j-1]   first generator row, pre-shifted (the recursion shifts it by one
+// Register layout (both roles): thread t owns positions 8t .. 8t+7 of
+//   generator:  be[p]  = beta_{j-1}[p]      second generator row             (live for p >= j)
+//               A[p]   = alpha_{j-1}[p-1]   first generator row, pre-shifted (the recursion shifts it by one
 //                                           position per step; keeping it shifted puts the pair that defines
-//                                           kappa_k = -beta[k] / alpha[k-1] into one thread)
-//   lattice:    a[j]   = A_{k-1}[j],  B[j] = B_{k-1}[j-1]                    (non-zero for j <= k)
-// Step k:  alpha_k = A + kappa be,  beta_k = be + kappa A;   A_k = a + kappa B,  B_k = B + kappa a,
-// then the shifted sequence moves up by one position.  The shift costs no register moves: the loop is
+//                                           kappa_j = -beta_{j-1}[j] / alpha_{j-1}[j-1] into one thread)
+//   lattice:    a[p]   = A_{j-1}[p],  B[p] = B_{j-1}[p-1]                    (non-zero for p <= j)
+// Step j:  alpha_j = A + kappa_j be,  beta_j = be + kappa_j A;   A_j = a + kappa_j B,  B_j = B + kappa_j a,
+// then the shifted sequence moves up by one position.  The shift costs no register moves: steps are
 // unrolled by 8 and at unrolled slot I the logical entry i of a shifted array lives in the physical
 // register (i - I) mod 8, updates are in place, and only the entry that leaves the thread travels
-// (warp shuffle; one value per warp through shared memory, patched after the barrier).
-// kappa_{k+1} is produced by its owner (operands: physical register 0 / slot I+1) before the step's only
-// barrier, except when the operand crosses a warp boundary (every 256th step: one more barrier).
-// Warps whose generator entries are all dead / lattice entries all zero skip the update.
-constexpr int SCHUR_CHUNK = 64;                 // reflection coefficients per hand-over
+// (warp shuffle; across warps through a ring in shared memory).
+//
+// Schedule.  All information flows upward (to higher positions): a warp needs the coefficients and the
+// boundary values of the warp below it, nothing else.  Steps are grouped in batches of 8 (batch m =
+// steps 8m .. 8m+7, whose coefficients all come from thread m's own eight positions) and time in
+// periods separated by ONE block barrier: warp w processes batch m in period m + w.  The warp that
+// owns thread m LEADS batch m: it needs nothing from the other warps, so inside the batch the
+// coefficient chain (five dependent FP64 operations per step, see neg_div) runs back to back in the
+// owner lane's registers, with no barrier, shared-memory round trip or shuffle on it; the coefficient
+// reaches the warp's other lanes by shuffle and the other warps through shared memory, which they read
+// one or more periods later.  (The earlier one-barrier-per-step kernel spent 405 cycles per step:
+// 114 in store -> barrier -> load, ~200 in the owner warp's in-order issue, tools/ubench/lat.cu.)
+// The schedule is a closed form - no flags, no spinning inside the CTA.
 
 // -num/den to ~1 ulp in FIVE dependent FP64 operations after den is known (a division is seven):
 //   r0 = MUFU.RCP64H(den) (2^-23), e = 1 - den r0, w = e + e^2, q0 = -num r0 (parallel to e),
 //   result = q0 + q0 w = -num r0 (1 + e + e^2) = -num/den (1 - e^3).
-// Straight-line (no slow path), so that the scheduler interleaves the step's independent FMAs with this
-// chain - the one dependent chain of the whole recursion; every lane of a live warp evaluates it (only
-// the owner's value is stored; other lanes may produce Inf/NaN harmlessly).
+// Straight-line (no slow path); every lane evaluates it, only the owner's value is used (other lanes may
+// produce Inf/NaN harmlessly).
 __device__ __forceinline__ double neg_div(double num, double den) {
     double r0;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(den));
@@ -71,91 +81,99 @@ __device__ __forceinline__ double neg_div(double num, double den) {
     const double w = fma(e, e, e);
     return fma(q0, w, q0);
 }
-struct SchurTiming { long long t_kappa = 0, t_rest = 0, t_barrier = 0, t_last = 0; bool on = false; };
+
+// One step of a warp on a pair of (shifted, static) arrays: S <- S + kp * T,  T <- T + kp * S_old, then S moves up.
+// Generator: S = A (alpha), T = be.   Lattice: S = B, T = a.   ring: boundary values of every warp.
+// Guarded form (branches): only the last, partial batch of an n that is not a multiple of 8 runs it.
+template <int I>
+__device__ __forceinline__ void pair_step(int j, double kp, int lane, int warp, double (&S)[SCHUR_EPT], double (&T)[SCHUR_EPT],
+                                          double (*ring)[SCHUR_RING]) {
+    constexpr int E = SCHUR_EPT;
+    constexpr int OUT = (E - 1 - I) % E;       // physical slot of logical entry E-1 (leaves the thread)
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const int ph = (i - I + E) % E;
+        const double sv = S[ph], tv = T[i];
+        S[ph] = fma(kp, tv, sv);
+        T[i] = fma(kp, sv, tv);
+    }
+    const double out = S[OUT];
+    double up = __shfl_up_sync(0xffffffffu, out, 1);
+    if (lane == 31) ring[warp][j & (SCHUR_RING - 1)] = out;
+    if (lane == 0) up = warp > 0 ? ring[warp - 1][j & (SCHUR_RING - 1)] : 0.0;     // written at least one period ago
+    S[OUT] = up;                               // logical entry 0 of the next step
+}
 
 template <int I>
-__device__ __forceinline__ void gen_step(int k, int n, int tid, int lane, int warp, double (&A)[SCHUR_EPT],
-                                         double (&be)[SCHUR_EPT], double* kap, double (*bnd)[32], SchurTiming& tm) {
-    constexpr int E = SCHUR_EPT;
-    constexpr int I1 = (I + 1) % E;
-    constexpr int OUT = (E - 1 - I) % E;       // physical slot of logical entry E-1 (leaves the thread)
-    const double kp = kap[k];
-    const int whi = warp * 32 * E + 32 * E - 1;
-    const int owner = (k + 1) / E;
-    const bool cross = (I1 == 0) && ((owner & 31) == 0);      // kappa_{k+1}'s alpha comes from the previous warp
-    double cand = 0.0;                         // kappa_{k+1} in the owner thread
-    if (whi >= k) {                            // warp still holds live generator entries
-#pragma unroll
-        for (int ii = 0; ii < E; ++ii) {
-            const int i = (I + ii) % E;        // start with the entries that define kappa_{k+1}
-            const int ph = (i - I + E) % E;
-            const double al = A[ph], b = be[i];
-            A[ph] = fma(kp, b, al);
-            be[i] = fma(kp, al, b);
-            if (ii == 1 && I1 != 0) cand = neg_div(be[I1], A[0]);
-        }
-    }
-    const double out = A[OUT];
-    const double up = __shfl_up_sync(0xffffffffu, out, 1);
-    if (lane == 31) bnd[k & 1][warp] = out;
-    A[OUT] = up;                               // becomes logical entry 0 of the next step; lane 0 is patched below
-    if (I1 == 0 && !cross) cand = neg_div(be[0], up);
-    if (!cross && tid == owner && k + 1 < n) kap[k + 1] = cand;
-    long long t1 = 0;
-    if (tm.on && tid == owner) {               // owner thread: barrier release -> kappa stored
-        t1 = clock64();
-        tm.t_kappa += t1 - tm.t_last;
-    }
-    __syncthreads();
-    if (tm.on) {
-        const long long t2 = clock64();
-        if (tid == owner) tm.t_barrier += t2 - t1;
-        tm.t_last = t2;
-    }
-    if (lane == 0) A[OUT] = warp > 0 ? bnd[k & 1][warp - 1] : 0.0;
-    if (cross) {                                               // uniform in k
-        if (tid == owner && k + 1 < n) kap[k + 1] = neg_div(be[0], A[OUT]);
-        __syncthreads();
+__device__ __forceinline__ void bulk_tail(int j0, int n, int lane, int warp, double (&S)[SCHUR_EPT], double (&T)[SCHUR_EPT],
+                                          const double* kap, double (*ring)[SCHUR_RING]) {
+    if constexpr (I < SCHUR_EPT) {
+        if (j0 + I < n) pair_step<I>(j0 + I, kap[j0 + I], lane, warp, S, T, ring);
+        bulk_tail<I + 1>(j0, n, lane, warp, S, T, kap, ring);
     }
 }
 
 template <int I>
-__device__ __forceinline__ void lat_step(int k, int lane, int warp, double (&a)[SCHUR_EPT], double (&B)[SCHUR_EPT],
-                                         const double* kap, double (*bnd)[32]) {
+__device__ __forceinline__ void lead_tail(int j0, int n, int lane, int warp, int ol, double cand, double (&A)[SCHUR_EPT],
+                                          double (&be)[SCHUR_EPT], double* kap, double* gkap, double (*ring)[SCHUR_RING]) {
+    if constexpr (I < SCHUR_EPT) {
+        const int j = j0 + I;
+        if (j < n) {
+            if (lane == ol) { kap[j] = cand; gkap[j] = cand; }
+            double next = 0.0;
+            if constexpr (I + 1 < SCHUR_EPT) next = neg_div(fma(cand, A[1], be[I + 1]), fma(cand, be[I], A[0]));
+            const double kp = __shfl_sync(0xffffffffu, cand, ol);
+            pair_step<I>(j, kp, lane, warp, A, be, ring);
+            lead_tail<I + 1>(j0, n, lane, warp, ol, next, A, be, kap, gkap, ring);
+        }
+    }
+}
+
+// A FULL batch (eight steps j0 .. j0+7) of one warp as straight-line code - no branch, so that the eight
+// steps form one basic block and the scheduler overlaps the shuffles, the shared-memory accesses and, in
+// the leading warp, the coefficient chain of step j+1 with the sixteen FMAs of step j (as separate
+// blocks they ran back to back in the in-order issue: ~430 cycles per step, 3.4x the FP64-pipe time).
+//   rin[8]   the eight values that enter lane 0 during the batch (the warp below wrote them a period ago;
+//            don't-care in a leading warp - they only reach dead positions)
+//   rout     this warp's eight ring slots for the values that leave lane 31
+//   LEAD     lane ol owns positions j0 .. j0+7: it produces kappa_{j+1} = -beta_j[j+1] / alpha_j[j] from its
+//            own registers one step ahead (logical entries I, I+1 = physical 0, 1) and the coefficient
+//            reaches the other lanes by shuffle - off the chain;   else kp[8] holds the coefficients.
+template <int I, bool LEAD>
+__device__ __forceinline__ void batch_full(double cand, int ol, bool own, bool lane0, bool lane31, const double (&kp8)[SCHUR_EPT],
+                                           const double (&rin)[SCHUR_EPT], double* __restrict__ rout, double* __restrict__ kout,
+                                           double* __restrict__ gkout, double (&S)[SCHUR_EPT], double (&T)[SCHUR_EPT]) {
     constexpr int E = SCHUR_EPT;
-    constexpr int OUT = (E - 1 - I) % E;
-    const double kp = kap[k];
-    if (warp * 32 * E <= k + 1) {              // warp holds non-zero lattice entries
+    if constexpr (I < E) {
+        constexpr int OUT = (E - 1 - I) % E;
+        double kp, next = 0.0;
+        if constexpr (LEAD) {
+            if (own) { kout[I] = cand; gkout[I] = cand; }
+            if constexpr (I + 1 < E) next = neg_div(fma(cand, S[1], T[I + 1]), fma(cand, T[I], S[0]));
+            kp = __shfl_sync(0xffffffffu, cand, ol);
+        } else {
+            kp = kp8[I];
+        }
 #pragma unroll
         for (int i = 0; i < E; ++i) {
             const int ph = (i - I + E) % E;
-            const double bs = B[ph], av = a[i];
-            B[ph] = fma(kp, av, bs);
-            a[i] = fma(kp, bs, av);
+            const double sv = S[ph], tv = T[i];
+            S[ph] = fma(kp, tv, sv);
+            T[i] = fma(kp, sv, tv);
         }
+        const double out = S[OUT];
+        const double up = __shfl_up_sync(0xffffffffu, out, 1);
+        if (lane31) rout[I] = out;
+        S[OUT] = lane0 ? rin[I] : up;
+        batch_full<I + 1, LEAD>(next, ol, own, lane0, lane31, kp8, rin, rout, kout, gkout, S, T);
     }
-    const double out = B[OUT];
-    const double up = __shfl_up_sync(0xffffffffu, out, 1);
-    if (lane == 31) bnd[k & 1][warp] = out;
-    B[OUT] = up;
-    __syncthreads();
-    if (lane == 0) B[OUT] = warp > 0 ? bnd[k & 1][warp - 1] : 0.0;
 }
 
-template <int I>
-__device__ __forceinline__ void gen_steps(int kb, int n, int tid, int lane, int warp, double (&A)[SCHUR_EPT],
-                                          double (&be)[SCHUR_EPT], double* kap, double (*bnd)[32], SchurTiming& tm) {
-    if constexpr (I < SCHUR_EPT) {
-        if (kb + I < n) gen_step<I>(kb + I, n, tid, lane, warp, A, be, kap, bnd, tm);
-        gen_steps<I + 1>(kb, n, tid, lane, warp, A, be, kap, bnd, tm);
-    }
-}
-template <int I>
-__device__ __forceinline__ void lat_steps(int kb, int n, int lane, int warp, double (&a)[SCHUR_EPT], double (&B)[SCHUR_EPT],
-                                          const double* kap, double (*bnd)[32]) {
-    if constexpr (I < SCHUR_EPT) {
-        if (kb + I < n) lat_step<I>(kb + I, lane, warp, a, B, kap, bnd);
-        lat_steps<I + 1>(kb, n, lane, warp, a, B, kap, bnd);
+__device__ __forceinline__ void load8(double (&v)[SCHUR_EPT], const double* p) {       // 64-byte aligned
+#pragma unroll
+    for (int i = 0; i < SCHUR_EPT; i += 2) {
+        const double2 t = *reinterpret_cast<const double2*>(p + i);
+        v[i] = t.x; v[i + 1] = t.y;
     }
 }
 
@@ -168,12 +186,14 @@ schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, dou
     const int sys = blockIdx.x >> 1, role = blockIdx.x & 1;
     const long long t_start = clock64();
     tab += sys * sTab; g += sys * sG; half_logdet += sys * sLd; status += sys * sStatus; gkap += sys * sKap; prog += sys * sProg;
-    __shared__ double kap[SCHUR_MAX_N];
-    __shared__ double bnd[2][32];
+    __shared__ __align__(16) double kap[SCHUR_MAX_N];
+    __shared__ __align__(16) double ring[SCHUR_MAX_THREADS / 32][SCHUR_RING];
     __shared__ double red[34];
     __shared__ int bad, s_have;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int j0 = tid * SCHUR_EPT;
+    const int nwarps = blockDim.x >> 5;
+    const int j0t = tid * SCHUR_EPT;
+    const int nb = (n + SCHUR_EPT - 1) / SCHUR_EPT;            // batches
     const double r0 = tab[0] + jitter;
     if (role == 0) {
         // ---- generator: Schur recursion ----
@@ -182,62 +202,89 @@ schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, dou
         // it changes no value and performs the first shift, so that every step is identical.
 #pragma unroll
         for (int i = 0; i < SCHUR_EPT; ++i) {
-            const int j = j0 + i;
-            const double rj = (j < n) ? (j == 0 ? r0 : tab[j]) : 0.0;
-            A[i] = rj;
-            be[i] = (j == 0) ? 0.0 : rj;
+            const int p = j0t + i;
+            const double rp = (p < n) ? (p == 0 ? r0 : tab[p]) : 0.0;
+            A[i] = rp;
+            be[i] = (p == 0) ? 0.0 : rp;
         }
-        if (tid == 0) { bad = 0x7fffffff; kap[0] = 0.0; }
+        if (tid == 0) bad = 0x7fffffff;
         __syncthreads();
-        int published = 0;
-        SchurTiming tm;
-        tm.on = dbg != nullptr;
-        tm.t_last = clock64();
-        for (int kb = 0; kb < n; kb += SCHUR_EPT) {           // the position inside a thread is static per unrolled slot
-            gen_steps<0>(kb, n, tid, lane, warp, A, be, kap, bnd, tm);
-            const int valid = min(kb + SCHUR_EPT + 1, n);     // kappa_0 .. kappa_{valid-1} are final
-            if (valid - published >= SCHUR_CHUNK || valid == n) {
-                if (warp == 0) {
-                    for (int i = published + lane; i < valid; i += 32) gkap[i] = kap[i];
-                    __syncwarp();
-                    if (lane == 0) { __threadfence(); *reinterpret_cast<volatile int*>(prog) = valid; }
+        int led = 0;                                               // batches led so far (all threads agree)
+        long long c_lead = 0, c_bulk = 0, c_wait = 0, n_lead = 0, n_bulk = 0;   // cycle counters (dbg only)
+        for (int T = 0; T < nb + nwarps - 1; ++T) {
+            const int m = T - warp, j0 = m * SCHUR_EPT;
+            const bool live = m >= 0 && m < nb && m < SCHUR_BPW * (warp + 1);   // else: not started yet / every position of the warp is dead
+            const bool lead = live && m / SCHUR_BPW == warp;
+            const long long t0 = dbg ? clock64() : 0;
+            long long t1 = t0;
+            // votes: the branch conditions are warp-uniform, and the compiler has to know it (no divergence handling around the shuffles)
+            if (__all_sync(0xffffffffu, live)) {
+                const double cand = j0 == 0 ? 0.0 : neg_div(be[0], A[0]);          // kappa_{8m} (leading warp): slot 0, logical 0 = physical 0
+                if (__all_sync(0xffffffffu, j0 + SCHUR_EPT <= n)) {
+                    const int rs = j0 & (SCHUR_RING - 1);
+                    double rin[SCHUR_EPT], kp8[SCHUR_EPT];
+                    load8(rin, &ring[warp > 0 ? warp - 1 : 0][rs]);
+                    if (__all_sync(0xffffffffu, lead)) {
+                        batch_full<0, true>(cand, m % SCHUR_BPW, lane == m % SCHUR_BPW, lane == 0, lane == 31, kp8, rin, &ring[warp][rs],
+                                            kap + j0, gkap + j0, A, be);
+                        if (dbg) { t1 = clock64(); c_lead += t1 - t0; ++n_lead; }
+                    } else {
+                        load8(kp8, kap + j0);
+                        batch_full<0, false>(0.0, 0, false, lane == 0, lane == 31, kp8, rin, &ring[warp][rs], nullptr, nullptr, A, be);
+                        if (dbg) { t1 = clock64(); c_bulk += t1 - t0; ++n_bulk; }
+                    }
+                } else if (__all_sync(0xffffffffu, lead)) {
+                    lead_tail<0>(j0, n, lane, warp, m % SCHUR_BPW, cand, A, be, kap, gkap, ring);
+                } else {
+                    bulk_tail<0>(j0, n, lane, warp, A, be, kap, ring);
                 }
-                published = valid;
+            }
+            __syncthreads();
+            if (dbg) c_wait += clock64() - t1;
+            // batch `led` is led in period led + led / 32; hand over every SCHUR_PUBLISH led batches and at the end
+            if (led < nb && led + led / SCHUR_BPW == T) {
+                ++led;
+                if ((led % SCHUR_PUBLISH == 0 || led == nb) && tid == blockDim.x - 1) {
+                    __threadfence();                               // cumulative: the owners' gkap stores were ordered by the barrier
+                    *reinterpret_cast<volatile int*>(prog) = min(led * SCHUR_EPT, n);
+                }
             }
         }
         // log|K| = n log r0 + sum_k (n - k) log(1 - kappa_k^2); first |kappa| >= 1 <=> first non-positive prediction error
         double lsum = 0.0;
 #pragma unroll
         for (int i = 0; i < SCHUR_EPT; ++i) {
-            const int k = j0 + i;
+            const int k = j0t + i;
             if (k >= 1 && k < n) {
                 const double kp = kap[k];
-                if (!(fabs(kp) < 1.0)) atomicMin(&bad, k);     // also catches NaN
+                if (!(fabs(kp) < 1.0)) atomicMin(&bad, k);         // also catches NaN
                 lsum += (double)(n - k) * log1p(-kp * kp);
             }
         }
         if (!(r0 > 0.0) && tid == 0) atomicMin(&bad, 0);
         const double ltot = block_sum(lsum, red);
-        if (tm.on) {
-            atomicAdd(reinterpret_cast<unsigned long long*>(dbg) + 8, (unsigned long long)tm.t_kappa);
-            atomicAdd(reinterpret_cast<unsigned long long*>(dbg) + 9, (unsigned long long)tm.t_barrier);
+        if (dbg && lane == 0) {
+            unsigned long long* d = reinterpret_cast<unsigned long long*>(dbg);
+            atomicAdd(d + 8, (unsigned long long)c_lead); atomicAdd(d + 9, (unsigned long long)n_lead);
+            atomicAdd(d + 10, (unsigned long long)c_bulk); atomicAdd(d + 11, (unsigned long long)n_bulk);
+            atomicAdd(d + 12, (unsigned long long)c_wait);
         }
         if (tid == 0) {
             half_logdet[0] = 0.5 * ((double)n * log(r0) + ltot);
-            if (bad != 0x7fffffff) status[0] = bad + 1;        // like a Cholesky pivot index
+            if (bad != 0x7fffffff) status[0] = bad + 1;            // like a Cholesky pivot index
             if (dbg) dbg[blockIdx.x] = clock64() - t_start;
         }
         return;
     }
-    // ---- lattice: A_k = A_{k-1} + kappa_k z B_{k-1},  B_k = z B_{k-1} + kappa_k A_{k-1} ----
+    // ---- lattice: A_j = A_{j-1} + kappa_j z B_{j-1},  B_j = z B_{j-1} + kappa_j A_{j-1};  warp 0 always leads ----
     double a[SCHUR_EPT], B[SCHUR_EPT];
 #pragma unroll
-    for (int i = 0; i < SCHUR_EPT; ++i) { a[i] = (j0 + i == 0) ? 1.0 : 0.0; B[i] = a[i]; }
+    for (int i = 0; i < SCHUR_EPT; ++i) { a[i] = (j0t + i == 0) ? 1.0 : 0.0; B[i] = a[i]; }
     int have = 0;
     bool dead = false;
-    for (int kb = 0; kb < n; kb += SCHUR_EPT) {
-        const int need = min(kb + SCHUR_EPT, n);
-        if (need > have) {                                     // uniform
+    for (int T = 0; T < nb + nwarps - 1; ++T) {
+        const int need = min((T + 1) * SCHUR_EPT, n);              // warp 0 processes batch T now; the others older ones
+        if (need > have) {                                         // uniform
             if (tid == 0) {
                 int v = 0;
                 long long spins = 0;
@@ -246,18 +293,36 @@ schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, dou
             }
             __syncthreads();
             const int now = s_have;
-            if (now < need) { dead = true; break; }            // the producer never arrived (cannot happen when both CTAs run)
+            if (now < need) { dead = true; break; }                // the producer never arrived (cannot happen when both CTAs run)
             for (int i = have + tid; i < now; i += blockDim.x) kap[i] = __ldcg(gkap + i);
             __syncthreads();
             have = now;
         }
-        lat_steps<0>(kb, n, lane, warp, a, B, kap, bnd);
+        const int m = T - warp, j0 = m * SCHUR_EPT;
+        // positions of this warp become non-zero at step 256 w - 1: earlier batches would only move zeros
+        const bool live = m >= 0 && m < nb && (m + 1) * SCHUR_EPT >= warp * SCHUR_WCHUNK;
+        if (__all_sync(0xffffffffu, live)) {
+            if (__all_sync(0xffffffffu, j0 + SCHUR_EPT <= n)) {
+                const int rs = j0 & (SCHUR_RING - 1);
+                double rin[SCHUR_EPT], kp8[SCHUR_EPT];
+                load8(rin, &ring[warp > 0 ? warp - 1 : 0][rs]);
+                load8(kp8, kap + j0);
+                if (warp == 0) {
+#pragma unroll
+                    for (int i = 0; i < SCHUR_EPT; ++i) rin[i] = 0.0;                  // B[-1] = 0
+                }
+                batch_full<0, false>(0.0, 0, false, lane == 0, lane == 31, kp8, rin, &ring[warp][rs], nullptr, nullptr, B, a);
+            } else {
+                bulk_tail<0>(j0, n, lane, warp, B, a, kap, ring);
+            }
+        }
+        __syncthreads();
     }
     // g = A_{n-1} / E_{n-1},  E_{n-1} = r0 * prod_k (1 - kappa_k^2)   (a does not shift: entry i is a[i])
     double prod = 1.0;
 #pragma unroll
     for (int i = 0; i < SCHUR_EPT; ++i) {
-        const int k = j0 + i;
+        const int k = j0t + i;
         if (k >= 1 && k < n) { const double kp = kap[k]; prod *= (1.0 - kp) * (1.0 + kp); }
     }
 #pragma unroll
@@ -266,10 +331,10 @@ schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, dou
     if (lane == 0) red[warp] = prod;
     __syncthreads();
     double E = r0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) E *= red[w];
+    for (int w = 0; w < nwarps; ++w) E *= red[w];
     const double invE = dead ? __longlong_as_double(0x7ff8000000000000ll) : 1.0 / E;
 #pragma unroll
-    for (int i = 0; i < SCHUR_EPT; ++i) { const int j = j0 + i; if (j < n) g[j] = a[i] * invE; }
+    for (int i = 0; i < SCHUR_EPT; ++i) { const int p = j0t + i; if (p < n) g[p] = a[i] * invE; }
     if (dbg && tid == 0) dbg[blockIdx.x] = clock64() - t_start;
 }
 

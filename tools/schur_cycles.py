@@ -26,7 +26,8 @@ for it in range(3):
     while L < 2 * n: L <<= 1
     off = ((2 * L * 8 + 255) // 256 * 256) + ((8 * L * 8 + 255) // 256 * 256) + 256
     cyc = work[off:off + 16].view(torch.int64).tolist()
-    tk = work[off + 64:off + 80].view(torch.int64).tolist()
-    print("   owner thread: barrier release -> kappa stored %.0f cycles/step, kappa stored -> next barrier release %.0f cycles/step" % (tk[0] / n, tk[1] / n))
+    tk = work[off + 64:off + 104].view(torch.int64).tolist()
+    print("   generator warps: led batch %.0f cycles (%d), bulk batch %.0f cycles (%d), barrier wait per warp-period %.0f" %
+          (tk[0] / max(tk[1], 1), tk[1], tk[2] / max(tk[3], 1), tk[3], tk[4] / max((n // 8 + max(n // 256, 1)) * max(n // 256, 1), 1)))
     work[off:off + 128].zero_()
     print("n=%d generator %d cycles (%.0f/step), lattice %d cycles (%.0f/step), status %d" % (n, cyc[0], cyc[0] / n, cyc[1], cyc[1] / n, int(stt)))
