@@ -46,6 +46,13 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
     ap.add_argument("--no-peak", action="store_true", help="profiling runs only: skip the cuBLAS DGEMM denominator")
     ap.add_argument("--no-general", action="store_true", help="skip the short dense-path (Cholesky + DGEMM) measurement")
+    ap.add_argument("--workload", default="grid", choices=["grid", "ensemble"],
+                    help="grid: the 4096^2 step (BASELINE metric, the default); ensemble: BASELINE configs[4], independent "
+                         "solves partitioned over the ranks (64 members per GPU, weak scaling)")
+    ap.add_argument("--ensemble-equation", default="poisson_2d-sin_sin", help="any equation of the config table (1-D or 2-D)")
+    ap.add_argument("--members-per-gpu", type=int, default=64)
+    ap.add_argument("--streams", type=int, default=8)
+    ap.add_argument("--no-graph", action="store_true", help="ensemble: plain launches instead of CUDA-graph replay")
     return ap.parse_args()
 
 
@@ -396,6 +403,79 @@ def run_ours(args, rank, world, local):
     print(json.dumps(line), flush=True)
 
 
+def run_ensemble(args, rank, world, local):
+    """BASELINE configs[4]: 64 x 8 = 512 independent solves (seeds x frequency inits) over 8 GPUs = 64 members per
+    GPU; every rank steps its own members (CUDA-graph replay over several streams), no data-path collective."""
+    import gphm_b200 as G
+    from importlib import import_module
+    E = import_module("gaussian-process-slover-for-high-freq-pde_b200.ensemble")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    eq = args.ensemble_equation
+    tp = G.configs.load_config(eq, "/nonexistent")
+    tp.update(equation=eq, kernel=KERNEL, scale=2 * math.pi if tp["scale"] == "2pi" else 1.0)
+    n_total = args.members_per_gpu * world
+    seeds = (n_total + len(E.DEFAULT_FREQ_SCALES) - 1) // len(E.DEFAULT_FREQ_SCALES)
+    members = E.ensemble_members(seeds)[:n_total]
+    ens, mine = E.build_ensemble(tp, members, rank=rank, world=world, streams=args.streams, graph=not args.no_graph)
+    lib = G._lib.load()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ens.step(max(args.warmup, 3))
+    barrier()
+    launches0 = lib.gphm_launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    ens.step(args.steps)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.gphm_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    res = torch.stack((ens.losses(), ens.errors()), dim=1)
+    ens.raise_on_bad_status()
+    full = E.gather_results(res, n_total, rank, world)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t)
+    if rank != 0:
+        return
+    if not bool(torch.isfinite(full).all()):
+        raise SystemExit("bench.py: non-finite member loss")
+    ms_step = ms_total / args.steps
+    per_member = ens.models[0].core
+    line = {"metric": "ensemble member-iterations/sec (log-joint+grad+Adam), %d independent solves" % n_total,
+            "value": n_total * 1e3 / ms_step, "unit": "member-it/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "ensemble %s N_col=%d %s Q=%d, %d members (%d per GPU): seeds x freq_scale %s"
+                                   % (eq, tp["N_col"], KERNEL, tp["Q"], n_total, args.members_per_gpu, list(E.DEFAULT_FREQ_SCALES)),
+                       "parallelism": "members partitioned over %d GPU(s), no collective on the data path" % world,
+                       "issue": ("CUDA-graph replay, %d streams" if not args.no_graph else "plain launches, %d streams") % ens.n_streams,
+                       "l2": "per-member working set %.1f MB x %d members resident" % (per_member.workspace.numel() / 1e6, len(ens)),
+                       "loss_min_max": [float(full[:, 0].min()), float(full[:, 0].max())],
+                       "rel_l2_min_max": [float(full[:, 1].min()), float(full[:, 1].max())]},
+            "clocks": clocks, "e2e": None,
+            # graph replay launches no kernel from the host: count the kernel nodes one replay executes
+            "gpu_launches": int(launches) * world if args.no_graph else int(ens.kernels_per_step) * args.steps * world,
+            "kernels_per_ensemble_step_per_gpu": ens.kernels_per_step}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
     rank, world, local = dist_env()
@@ -404,7 +484,10 @@ def main():
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit("bench.py: --gpus %d needs torchrun (one rank per GPU)" % args.gpus)
-    run_ours(args, rank, world, local)
+    if args.workload == "ensemble":
+        run_ensemble(args, rank, world, local)
+    else:
+        run_ours(args, rank, world, local)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
