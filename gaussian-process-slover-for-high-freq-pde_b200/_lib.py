@@ -56,6 +56,9 @@ _SIGS = {
     "gphm_plan_logdet": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gphm_mg_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
                                  c_void_p]),
+    "gphm_mg_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gphm_mg_pack_transposed": (c_int, [c_void_p, c_int, c_int, c_int, c_size_t, c_void_p, c_void_p]),
+    "gphm_mg_unpack_segments": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gphm_mg_boundary": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "gphm_mg_grad_u": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
                                c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -106,6 +106,34 @@ int launch_finalize(const LossConsts& c, const double* U, const double* bvals, c
     return GPHM_OK;
 }
 
+// Sharded step: loss terms and the two scalar gradients from the ALL-REDUCED partial sums
+// sums = [eq_gap, quad, boundary_gap], ld = [log|K1|, log|K2|] (model_GP_solver_2d.py:158-174).
+__global__ void mg_finalize_kernel(LossConsts c, const double* __restrict__ sums, const double* __restrict__ ld,
+                                   const double* __restrict__ small, double* __restrict__ terms, double* __restrict__ gsmall,
+                                   int* __restrict__ status) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double e = sums[0], q = sums[1], b = sums[2], l1 = ld[0], l2 = ld[1];
+    const double tau = small[6 * c.Q], v = small[6 * c.Q + 1];
+    const double Nc = (double)c.n1 * (double)c.n2, Nb = (double)c.nb;
+    const double prior = 0.5 * c.logdet * ((double)c.n2 * l1 + (double)c.n1 * l2) + 0.5 * q;
+    const double loss = prior - c.llk_weight * (0.5 * Nb * tau - 0.5 * exp(tau) * b) - (0.5 * Nc * v - 0.5 * exp(v) * e);
+    const double gtau = -c.llk_weight * (0.5 * Nb - 0.5 * exp(tau) * b);
+    const double gv = -(0.5 * Nc - 0.5 * exp(v) * e);
+    terms[0] = loss; terms[1] = l1; terms[2] = l2; terms[3] = q; terms[4] = b; terms[5] = e; terms[6] = gtau; terms[7] = gv;
+    if (gsmall) { gsmall[6 * c.Q] = gtau; gsmall[6 * c.Q + 1] = gv; }
+    if (status && !isfinite(loss)) status[2] = 1;
+}
+
+int launch_mg_finalize(const LossConsts& c, const double* sums, const double* ld, const double* small, double* terms,
+                       double* gsmall, int* status, cudaStream_t st) {
+    {
+        LaunchScope scope(CAT_ELEMWISE, st);
+        mg_finalize_kernel<<<1, 32, 0, st>>>(c, sums, ld, small, terms, gsmall, status);
+    }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // dL/dU = W + S1 + S2 [+ G*(3U^2-1)] + lambda*e^{tau}*E_b ;  V1 = S1 + W/2, V2 = S2 + W/2
 // ---------------------------------------------------------------------------------------------

@@ -238,6 +238,52 @@ transpose_kernel(const double* __restrict__ in, int R, int C, double* __restrict
     }
 }
 
+// Exchange packing of the sharded step (dist.py r2ct / ct2r): the transpose of in (R x C), split into
+// parts of wc consecutive output rows; part d goes to out + d * pstride (+ the caller's array offset):
+//   out[(c / wc) * pstride + (c % wc) * R + r] = in[r][c]
+__global__ void __launch_bounds__(256)
+transpose_parts_kernel(const double* __restrict__ in, int R, int C, int wc, size_t pstride, double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        if (r < R && c < C) tile[i][tx] = in[(size_t)r * C + c];
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;
+        if (r < R && c < C) out[(size_t)(c / wc) * pstride + (size_t)(c % wc) * R + r] = tile[tx][i];
+    }
+}
+
+// Exchange unpacking: recv[s][a][r][c] (P x k x rows x seg) -> out[a][r][s * seg + c]  (k x rows x P*seg).
+// One CTA row per (s, a, r): contiguous runs of seg doubles on both sides.
+__global__ void __launch_bounds__(256)
+unpack_segments_kernel(const double* __restrict__ recv, int P, int k, int rows, int seg, double* __restrict__ out) {
+    const int nrun = P * k * rows;
+    for (int run = blockIdx.x; run < nrun; run += gridDim.x) {
+        const int r = run % rows, t = run / rows;
+        const int a = t % k, sidx = t / k;
+        const double* src = recv + (size_t)run * seg;
+        double* dst = out + ((size_t)a * rows + r) * ((size_t)P * seg) + (size_t)sidx * seg;
+        if ((seg & 1) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+            const double2* s2 = reinterpret_cast<const double2*>(src);
+            double2* d2 = reinterpret_cast<double2*>(dst);
+            const int n2 = seg >> 1;
+            for (int c0 = threadIdx.x; c0 < n2; c0 += 4 * blockDim.x) {          // four loads in flight per thread
+                double2 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int c = c0 + u * blockDim.x; if (c < n2) v[u] = __ldcs(s2 + c); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int c = c0 + u * blockDim.x; if (c < n2) d2[c] = v[u]; }
+            }
+        } else {
+            for (int c = threadIdx.x; c < seg; c += blockDim.x) dst[c] = src[c];
+        }
+    }
+}
+
 static int ilog2(int L) { int l = 0; while ((1 << l) < L) ++l; return l; }
 
 int fft_init() {
@@ -325,6 +371,23 @@ int launch_transpose(const double* in, int R, int C, double* out, cudaStream_t s
     if (R <= 0 || C <= 0) return GPHM_OK;
     dim3 grid((C + 31) / 32, (R + 31) / 32);
     { LaunchScope scope(CAT_ELEMWISE, st); transpose_kernel<<<grid, 256, 0, st>>>(in, R, C, out); }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+int launch_transpose_parts(const double* in, int R, int C, int wc, size_t pstride, double* out, cudaStream_t st) {
+    if (R <= 0 || C <= 0) return GPHM_OK;
+    dim3 grid((C + 31) / 32, (R + 31) / 32);
+    { LaunchScope scope(CAT_ELEMWISE, st); transpose_parts_kernel<<<grid, 256, 0, st>>>(in, R, C, wc, pstride, out); }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+int launch_unpack_segments(const double* recv, int P, int k, int rows, int seg, double* out, cudaStream_t st) {
+    const size_t total = (size_t)P * k * rows * seg;
+    if (total == 0) return GPHM_OK;
+    const int grid = (int)std::min<size_t>((size_t)P * k * rows, (size_t)148 * 32);
+    { LaunchScope scope(CAT_ELEMWISE, st); unpack_segments_kernel<<<grid, 256, 0, st>>>(recv, P, k, rows, seg, out); }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }

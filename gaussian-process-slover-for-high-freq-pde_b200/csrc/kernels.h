@@ -71,6 +71,8 @@ int launch_toeplitz_spectrum(const double* tab, int n, int L, const double* W, b
 int launch_toeplitz_apply(const double* X, int rows, int n, int ldx, const double* spec, int L, const double* W, double alpha,
                           double beta, double* Out, int ldo, cudaStream_t st);
 int launch_transpose(const double* in, int R, int C, double* out, cudaStream_t st);
+int launch_transpose_parts(const double* in, int R, int C, int wc, size_t pstride, double* out, cudaStream_t st);
+int launch_unpack_segments(const double* recv, int P, int k, int rows, int seg, double* out, cudaStream_t st);
 
 // ---- toeplitz_inv.cu -----------------------------------------------------------------------
 int toeplitz_inv_max_n();
@@ -104,6 +106,8 @@ int launch_residual(double* R, const double* U, const double* F, const double* A
 int launch_finalize(const LossConsts& c, const double* U, const double* bvals, const int* xind,
                     const double* part, const double* ldp1, int nblk1, const double* ldp2, int nblk2,
                     const double* small, double* eb, double* terms, double* gsmall, int* status, cudaStream_t st);
+int launch_mg_finalize(const LossConsts& c, const double* sums, const double* ld, const double* small, double* terms,
+                       double* gsmall, int* status, cudaStream_t st);
 int launch_grad_u(const LossConsts& c, const double* base, const double* U, const double* G, const double* W, const double* S1,
                   const double* S2, const double* eb, const int* xind, const double* small, double* gU,
                   double* V1, double* V2, cudaStream_t st);

@@ -965,6 +965,18 @@ int gphm_transpose(const double* d_in, int rows, int cols, double* d_out, void* 
     return launch_transpose(d_in, rows, cols, d_out, static_cast<cudaStream_t>(stream));
 }
 
+int gphm_mg_pack_transposed(const double* d_in, int rows, int cols, int part_cols, size_t part_stride, double* d_out, void* stream) {
+    if (rows <= 0 || cols <= 0) return GPHM_OK;
+    if (!d_in || !d_out || part_cols <= 0 || cols % part_cols) { set_last_error("gphm_mg_pack_transposed: bad argument"); return GPHM_EINVAL; }
+    return launch_transpose_parts(d_in, rows, cols, part_cols, part_stride, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int gphm_mg_unpack_segments(const double* d_recv, int parts, int arrays, int rows, int seg, double* d_out, void* stream) {
+    if (parts <= 0 || arrays <= 0 || rows <= 0 || seg <= 0) return GPHM_OK;
+    if (!d_recv || !d_out) { set_last_error("gphm_mg_unpack_segments: null pointer"); return GPHM_EINVAL; }
+    return launch_unpack_segments(d_recv, parts, arrays, rows, seg, d_out, static_cast<cudaStream_t>(stream));
+}
+
 int gphm_mg_theta_grad_fft(gphm_plan* plan, int axis, const double* d_X, const double* d_Y, const double* d_G, int rows,
                            int linv_row0, int linv_row1, double beta, double cD, const double* d_small,
                            double* d_gtheta, void* stream) {
@@ -1017,6 +1029,13 @@ int gphm_mg_boundary(const double* d_U, const int* d_bidx, const double* d_bvals
                      double* d_out1, void* stream) {
     if (!d_U || !d_out1 || (nb_local > 0 && (!d_bidx || !d_bvals || !d_eb))) { set_last_error("gphm_mg_boundary: null pointer"); return GPHM_EINVAL; }
     return launch_boundary_indexed(d_U, d_bidx, d_bvals, nb_local, d_eb, d_out1, static_cast<cudaStream_t>(stream));
+}
+
+int gphm_mg_finalize(gphm_plan* plan, const double* d_sums3, const double* d_ld2, const double* d_small, double* d_terms,
+                     double* d_gsmall, void* stream) {
+    if (!plan || !d_sums3 || !d_ld2 || !d_small || !d_terms) { set_last_error("gphm_mg_finalize: null pointer"); return GPHM_EINVAL; }
+    return launch_mg_finalize(loss_consts(*plan), d_sums3, d_ld2, d_small, d_terms, d_gsmall, plan->status,
+                              static_cast<cudaStream_t>(stream));
 }
 
 int gphm_mg_grad_u(gphm_plan* plan, const double* d_U, const double* d_G, const double* d_W, const double* d_S1,

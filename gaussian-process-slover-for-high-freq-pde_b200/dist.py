@@ -168,6 +168,53 @@ class CudaOps(object):
                                            _lib.ptr(gU), None, self._s()), "gphm_mg_grad_u")
         return gU
 
+    def pack_transposed(self, Xs, part_cols):
+        """send[d][a] = (X_a^T)[d * part_cols : (d+1) * part_cols]  for the arrays X_a (rows x cols): one tiled transpose
+        per array, written straight into the all-to-all send buffer."""
+        k, (rows, cols) = len(Xs), Xs[0].shape
+        parts = cols // part_cols
+        send = torch.empty((parts, k, part_cols, rows), dtype=DT, device=self.device)
+        blk = part_cols * rows
+        for a, X in enumerate(Xs):
+            dst = send.view(-1)[a * blk:]
+            _lib.check(self.lib.gphm_mg_pack_transposed(_lib.ptr(X), rows, cols, part_cols, k * blk, _lib.ptr(dst), self._s()),
+                       "gphm_mg_pack_transposed")
+        return send
+
+    def unpack_segments(self, recv):
+        """recv[s][a][r][c] -> out[a][r][s * seg + c]."""
+        parts, k, rows, seg = recv.shape
+        out = torch.empty((k, rows, parts * seg), dtype=DT, device=self.device)
+        _lib.check(self.lib.gphm_mg_unpack_segments(_lib.ptr(recv), parts, k, rows, seg, _lib.ptr(out), self._s()),
+                   "gphm_mg_unpack_segments")
+        return out
+
+    def finalize(self, sums3, ld2, small, terms, gsmall):
+        """terms[8] and gsmall[6Q:6Q+2] from the all-reduced [eq_gap, quad, boundary_gap] and the log-dets (one kernel)."""
+        _lib.check(self.lib.gphm_mg_finalize(self.plan, _lib.ptr(sums3), _lib.ptr(ld2), _lib.ptr(small), _lib.ptr(terms),
+                                             _lib.ptr(gsmall), self._s()), "gphm_mg_finalize")
+
+    # ---- communication stream: an exchange (packing copies + all-to-all) issued with fork() runs beside the
+    # kernels the main stream launches until join() ----
+    def fork(self, fn):
+        if getattr(self, "_comm", None) is None:
+            self._comm = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        self._comm.wait_stream(cur)                       # everything issued so far is visible to the exchange
+        with torch.cuda.stream(self._comm):
+            res = fn()
+            ev = torch.cuda.Event()
+            ev.record(self._comm)
+        return res, ev
+
+    def join(self, handle):
+        res, ev = handle
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for t in res:
+            t.record_stream(cur)                          # allocated on the communication stream, consumed on this one
+        return res
+
     def adam(self, p, g, m, v, count, lr):
         _lib.check(self.lib.gphm_adam_update(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), p.numel(), _lib.ptr(count),
                                              float(lr), self._s()), "gphm_adam_update")
@@ -197,7 +244,7 @@ class ShardedSolver2D(object):
     construct it with identical arguments; `step()` is collective."""
 
     def __init__(self, kernel_name, eq_name, x, y, src, bvals, llk_weight, logdet, beta, jitter, Q, lr, ops=None,
-                 group=None, force_general=0):
+                 group=None, force_general=0, overlap=False):
         import numpy as np
         self.group = group
         self.P = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -231,6 +278,8 @@ class ShardedSolver2D(object):
         self.gsmall = ops.zeros((ns,))
         self.count = ops.zeros((1,), dtype=torch.int64)
         self.terms = ops.zeros((8,))
+        self.acc = ops.zeros((3 + ns,))
+        self.overlap = bool(overlap)
         self.bytes_exchanged = 0
 
     # ---- state ---------------------------------------------------------------------------------
@@ -284,22 +333,32 @@ class ShardedSolver2D(object):
         recv = self._a2a(X.contiguous().reshape(P, h, w))               # chunk s = my rows, columns of rank s
         return recv.transpose(0, 1).reshape(h, self.N2).contiguous()
 
+    def _pack_t(self, Xs, part_cols):
+        """[dest][array][c][r] = X_array[r][dest * part_cols + c]  (backend kernel, else torch)."""
+        f = getattr(self.ops, "pack_transposed", None)
+        if f is not None:
+            return f([X.contiguous() for X in Xs], part_cols)
+        k, (rows, cols) = len(Xs), Xs[0].shape
+        return torch.stack(Xs).reshape(k, rows, cols // part_cols, part_cols).permute(2, 0, 3, 1).contiguous()
+
+    def _unpack(self, recv):
+        """[src][array][r][c] -> [array][r][src * seg + c]."""
+        f = getattr(self.ops, "unpack_segments", None)
+        if f is not None:
+            return f(recv)
+        parts, k, rows, seg = recv.shape
+        return recv.permute(1, 2, 0, 3).reshape(k, rows, parts * seg).contiguous()
+
     def r2ct(self, Xs):
         """Row blocks (h, N2) -> TRANSPOSED column blocks (w, N1): row j holds column rank*w + j of the field.
         Several arrays travel in one all-to-all."""
-        P, h, w, k = self.P, self.h, self.w, len(Xs)
-        send = torch.stack(Xs).reshape(k, h, P, w).permute(2, 0, 3, 1).contiguous()       # [dest][array][j][i]
-        recv = self._a2a(send)                                                            # [src][array][j][i]
-        out = recv.permute(1, 2, 0, 3).reshape(k, w, self.N1).contiguous()
-        return [out[a] for a in range(k)]
+        out = self._unpack(self._a2a(self._pack_t(Xs, self.w)))          # send [dest][array][j][i] -> recv [src][array][j][i]
+        return [out[a] for a in range(len(Xs))]
 
     def ct2r(self, Ys):
         """Transposed column blocks (w, N1) -> row blocks (h, N2)."""
-        P, h, w, k = self.P, self.h, self.w, len(Ys)
-        send = torch.stack(Ys).reshape(k, w, P, h).permute(2, 0, 3, 1).contiguous()       # [dest][array][i][j]
-        recv = self._a2a(send)                                                            # [src][array][i][j]
-        out = recv.permute(1, 2, 0, 3).reshape(k, h, self.N2).contiguous()
-        return [out[a] for a in range(k)]
+        out = self._unpack(self._a2a(self._pack_t(Ys, self.h)))          # send [dest][array][i][j] -> recv [src][array][i][j]
+        return [out[a] for a in range(len(Ys))]
 
     def _allreduce(self, t):
         if self.P > 1:
@@ -336,49 +395,60 @@ class ShardedSolver2D(object):
     def value_and_grad_fft(self):
         """All-FFT step (both axes on the Toeplitz inverse generator): four K^-1 applications
         (V1 = K1^-1 (c1 D1^T G + Bt/2), V2 = (G D2 + A/2) K2^-1, dU = V1 + V2 + ...), axis-1 operands
-        kept as transposed column blocks, four all-to-alls:  [U] R->Ct, [c1 D1 A, A] Ct->R, [G, Bt] R->Ct, [V1] Ct->R."""
+        kept as transposed column blocks, four all-to-alls:  [U] R->Ct, [c1 D1 A, A] Ct->R, [G, Bt] R->Ct, [V1] Ct->R.
+        The first exchange runs on the communication stream beside the (serial, 4-CTA) Schur recursion; with
+        `overlap` every exchange is issued there as early as its operands exist and joined as late as its results
+        are needed, with axis-2 work in between.  The loss sums do not feed the reverse pass, so they share ONE
+        all-reduce with the theta-gradients at the end."""
         o, Q, c1 = self.ops, self.Q, self.c1
         N1, N2 = self.N1, self.N2
         small, U_r = self.small, self.U
+        fork = getattr(o, "fork", None) or (lambda fn: (fn(), None))
+        join = getattr(o, "join", None) or (lambda h: h[0])
+        lazy = self.overlap
+        hU = fork(lambda: self.r2ct([U_r]))
         o.factor(small, 3)                          # O(n^2) generators + spectra, local to every rank
         ld = o.logdets()
-        (U_ct,) = self.r2ct([U_r])
+        (U_ct,) = join(hU)
         At = o.kinv_rows(0, U_ct, "At")                                           # (K1^-1 U)^T      (Ct)
-        Bt_r = o.kinv_rows(1, U_r, "Bt_r")                                        # U K2^-1          (R)
         Rt = o.toeplitz_rows_add(0, False, At, c1, 0.0, None, o.new("Rt", At.shape), True)      # (c1 D1 A)^T
-        R_r, A_r = self.ct2r([Rt, At])
-        o.toeplitz_rows_add(1, False, Bt_r, 1.0, 1.0, R_r, R_r, True)             # + Bt D2^T
-        red = torch.empty(3, dtype=DT, device=R_r.device)
-        red[0:2] = o.residual(R_r, U_r, self.F, A_r, Bt_r, small)                 # R_r <- G_r ; [eqgap, quad]
-        G_r = R_r
+        hRA = fork(lambda: self.ct2r([Rt, At]))
+        if not lazy:
+            R_r, A_r = join(hRA)
+        Bt_r = o.kinv_rows(1, U_r, "Bt_r")                                        # U K2^-1          (R)
         eb, bg = o.boundary(U_r, self.bidx, self.bvals)
-        red[2:3] = bg
-        self._allreduce(red)
-        eq, quad, bgap = red[0], red[1], red[2]
-        tau, v = small[6 * Q], small[6 * Q + 1]
-        loss = (0.5 * self.logdet * (N2 * ld[0] + N1 * ld[1]) + 0.5 * quad
-                - self.llk_weight * (0.5 * self.Nb * tau - 0.5 * torch.exp(tau) * bgap)
-                - (0.5 * self.Nc * v - 0.5 * torch.exp(v) * eq))
-        gtau = -self.llk_weight * (0.5 * self.Nb - 0.5 * torch.exp(tau) * bgap)
-        gv = -(0.5 * self.Nc - 0.5 * torch.exp(v) * eq)
-        self.terms.copy_(torch.stack((loss, ld[0], ld[1], quad, bgap, eq, gtau, gv)))
+        if lazy:
+            R_r, A_r = join(hRA)
+        o.toeplitz_rows_add(1, False, Bt_r, 1.0, 1.0, R_r, R_r, True)             # + Bt D2^T
+        acc = self.acc                               # [eqgap, quad, bgap | 6Q theta-gradients | 2 unused]: one all-reduce
+        acc.zero_()
+        acc[0:2] = o.residual(R_r, U_r, self.F, A_r, Bt_r, small)                 # R_r <- G_r ; [eqgap, quad]
+        acc[2:3] = bg
+        G_r = R_r
+        gs = acc[3:]
+        lead = self.rank == 0                        # the K^-1 (log-det) term is added once
         # backward
-        G_ct, Btt = self.r2ct([G_r, Bt_r])
-        T0 = o.toeplitz_rows_add(0, True, G_ct, c1, 0.5, Btt, o.new("T0", G_ct.shape), False)   # (c1 D1^T G + Bt/2)^T
-        V1t = o.kinv_rows(0, T0, "V1t")
-        (V1_r,) = self.ct2r([V1t])
+        hGB = fork(lambda: self.r2ct([G_r, Bt_r]))
+        if not lazy:
+            G_ct, Btt = join(hGB)
         P2 = o.toeplitz_rows_add(1, True, G_r, 1.0, 0.5, A_r, o.new("P2", G_r.shape), False)    # G D2 + A/2
         V2_r = o.kinv_rows(1, P2, "V2_r")
-        gU_r = o.grad_u_sum(U_r, G_r, V1_r, V2_r, self.bidx, eb, self.nseg0, small)
-        gs = self.gsmall
-        gs.zero_()
-        lead = self.rank == 0                        # the K^-1 (log-det) term is added once
-        o.theta_grad_pairs(0, V1t, G_ct, lead, 0.5 * self.logdet * N2, c1, small, gs[0:3 * Q])
         o.theta_grad_pairs(1, V2_r, G_r, lead, 0.5 * self.logdet * N1, 1.0, small, gs[3 * Q:6 * Q])
-        self._allreduce(gs)
-        gs[6 * Q] = gtau
-        gs[6 * Q + 1] = gv
-        return self.terms, gU_r, gs
+        if lazy:
+            G_ct, Btt = join(hGB)
+        T0 = o.toeplitz_rows_add(0, True, G_ct, c1, 0.5, Btt, o.new("T0", G_ct.shape), False)   # (c1 D1^T G + Bt/2)^T
+        V1t = o.kinv_rows(0, T0, "V1t")
+        hV1 = fork(lambda: self.ct2r([V1t]))
+        if not lazy:
+            (V1_r,) = join(hV1)
+        o.theta_grad_pairs(0, V1t, G_ct, lead, 0.5 * self.logdet * N2, c1, small, gs[0:3 * Q])
+        if lazy:
+            (V1_r,) = join(hV1)
+        gU_r = o.grad_u_sum(U_r, G_r, V1_r, V2_r, self.bidx, eb, self.nseg0, small)
+        self._allreduce(acc)
+        o.finalize(acc[0:3], ld, small, self.terms, gs)                           # terms[8]; gs[6Q], gs[6Q+1]
+        self.gsmall.copy_(gs)
+        return self.terms, gU_r, self.gsmall
 
     def value_and_grad(self):
         """Collective.  Returns (terms[8], gU_r (h,N2), gsmall (6Q+2)) - same layout as gphm_logjoint_grad."""

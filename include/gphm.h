@@ -207,6 +207,19 @@ GPHM_API int gphm_mg_residual(gphm_plan* plan, double* d_R, const double* d_U, c
                      const double* d_Bt, size_t n_local, const double* d_small, double* d_out2, void* stream);
 GPHM_API int gphm_mg_boundary(const double* d_U, const int* d_bidx, const double* d_bvals, int nb_local, double* d_eb,
                      double* d_out1, void* stream);
+/* Layout exchange of the sharded step (the block transposes around the NCCL all-to-all; the reference has
+ * no counterpart - its jnp.matmul / solve calls at model_GP_solver_2d.py:104-119 see whole matrices):
+ *  pack_transposed : d_out[(c / part_cols) * part_stride + (c % part_cols) * rows + r] = d_in[r * cols + c]
+ *                    (the transpose of a rows x cols block, cut into parts of part_cols rows, one per destination rank)
+ *  unpack_segments : d_out[a][r][s * seg + c] = d_recv[s][a][r][c]   (parts x arrays x rows x seg -> arrays x rows x parts*seg) */
+GPHM_API int gphm_mg_pack_transposed(const double* d_in, int rows, int cols, int part_cols, size_t part_stride, double* d_out,
+                            void* stream);
+GPHM_API int gphm_mg_unpack_segments(const double* d_recv, int parts, int arrays, int rows, int seg, double* d_out, void* stream);
+/*  finalize : the eight loss terms [loss, logdet1, logdet2, quad, boundary_gap, eq_gap, dL/dlog_tau, dL/dlog_v]
+ *             (model_GP_solver_2d.py:158-174) from the all-reduced sums [eq_gap, quad, boundary_gap] and the two
+ *             log-dets; d_gsmall (may be NULL) receives the two scalar gradients at [6Q], [6Q+1].        */
+GPHM_API int gphm_mg_finalize(gphm_plan* plan, const double* d_sums3, const double* d_ld2, const double* d_small,
+                     double* d_terms, double* d_gsmall, void* stream);
 GPHM_API int gphm_mg_grad_u(gphm_plan* plan, const double* d_U, const double* d_G, const double* d_W, const double* d_S1,
                    const double* d_S2, size_t n_local, const int* d_bidx, const double* d_eb, int nseg0, int nb_local,
                    const double* d_small, double* d_gU, double* d_V2, void* stream);

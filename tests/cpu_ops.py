@@ -144,6 +144,19 @@ class CpuOps(object):
         g = O._theta_grad_axis(self.kernel, xs, self._theta(small, axis), self.order, Kbar, Dbar)
         out.copy_(torch.cat((g["log-w"], g["log-ls"], g["freq"])))
 
+    def finalize(self, sums3, ld2, small, terms, gsmall):
+        Q = self.Q
+        e, q, b = sums3[0], sums3[1], sums3[2]
+        tau, v = small[6 * Q], small[6 * Q + 1]
+        N1, N2 = self.x.numel(), self.y.numel()
+        Nb, Nc = 2 * N1 + 2 * N2, N1 * N2
+        loss = (0.5 * (N2 * ld2[0] + N1 * ld2[1]) + 0.5 * q - self.llk_weight * (0.5 * Nb * tau - 0.5 * torch.exp(tau) * b)
+                - (0.5 * Nc * v - 0.5 * torch.exp(v) * e))
+        gtau = -self.llk_weight * (0.5 * Nb - 0.5 * torch.exp(tau) * b)
+        gv = -(0.5 * Nc - 0.5 * torch.exp(v) * e)
+        terms.copy_(torch.stack((loss, ld2[0], ld2[1], q, b, e, gtau, gv)))
+        gsmall[6 * Q], gsmall[6 * Q + 1] = gtau, gv
+
     def adam(self, p, g, m, v, count, lr):
         t = int(count) + 1
         m.mul_(0.9).add_(0.1 * g)

@@ -150,3 +150,22 @@ def test_adam_matches_oracle(gphm, oracle):
                                          gphm._lib.ptr(zero.clone()), 4, gphm._lib.ptr(count), 0.01,
                                          gphm._lib.stream_ptr()), "adam")
     assert bool((pz == 1.0).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols,part_cols,k", [(6, 8, 4, 1), (33, 70, 35, 2), (64, 96, 32, 3), (5, 7, 7, 1)])
+def test_exchange_pack_unpack_match_permute(gphm, rows, cols, part_cols, k):
+    """The sharded step's packing kernels against the torch permutes they replace (bit-exact copies)."""
+    import importlib
+    D = importlib.import_module("gaussian-process-slover-for-high-freq-pde_b200.dist")
+
+    class _Core(object):
+        lib, plan, device, Q = gphm._lib.load(), None, torch.device("cuda"), 1
+    ops = D.CudaOps(_Core())
+    Xs = [torch.randn(rows, cols, dtype=torch.float64, device="cuda") for _ in range(k)]
+    send = ops.pack_transposed(Xs, part_cols)
+    want = torch.stack(Xs).reshape(k, rows, cols // part_cols, part_cols).permute(2, 0, 3, 1).contiguous()
+    assert send.shape == want.shape and torch.equal(send, want)
+    out = ops.unpack_segments(send)
+    parts = cols // part_cols
+    assert torch.equal(out, send.permute(1, 2, 0, 3).reshape(k, part_cols, parts * rows).contiguous())
