@@ -23,6 +23,14 @@ namespace gphm {
 
 namespace {
 
+// L2 prefetch of a contiguous range (one 128-byte line per thread and iteration): issued a whole row pair ahead,
+// so that the first pass of the next pair (and the stored spectra of xcorr_pairs) find their operands in L2.
+__device__ __forceinline__ void prefetch_l2(const void* p, size_t bytes, int tid) {
+    const char* c = static_cast<const char*>(p);
+    for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)FFT_THREADS * 128)
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(c + off));
+}
+
 struct RowPairIO {
     const double* x0; const double* x1; double* o0; double* o1; const double* a0; const double* a1;
     int n; bool two; double alpha, beta;
@@ -33,6 +41,11 @@ struct RowPairIO {
     __device__ __forceinline__ double2 addend(int idx) const {
         if (beta == 0.0 || idx >= n) return make_double2(0.0, 0.0);
         return make_double2(a0[idx], two ? a1[idx] : 0.0);
+    }
+    __device__ __forceinline__ void prefetch(int tid) const {
+        prefetch_l2(x0, sizeof(double) * n, tid);
+        if (two) prefetch_l2(x1, sizeof(double) * n, tid);
+        if (beta != 0.0) { prefetch_l2(a0, sizeof(double) * n, tid); if (two) prefetch_l2(a1, sizeof(double) * n, tid); }
     }
     __device__ __forceinline__ void store(int idx, double2 v, double2 add) const {
         if (idx >= n) return;
@@ -68,6 +81,7 @@ toeplitz_apply_fused_kernel(const double* X, int rows, int n, int ldx, const dou
     const int npairs = (rows + 1) / 2;
     for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
         const RowPairIO io = row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr, alpha, beta);
+        if (pr + (int)gridDim.x < npairs) row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr + gridDim.x, alpha, beta).prefetch(tid);
         dif_first(xs, L, tw0, tid, [&](int idx) { return io.load(idx); });
         dif_middle(xs, L, logL, np8, tid);
         double2* so = SpecOut ? SpecOut + (size_t)pr * L : nullptr;      // spectrum of the packed row pair, kept for the diagonal sums
@@ -96,6 +110,7 @@ gs_apply_fused_kernel(const double* X, int rows, int n, int ldx, const double2* 
     double2 stash[FFT_ACC];
     for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
         const RowPairIO io = row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr, alpha, beta);
+        if (pr + (int)gridDim.x < npairs) row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr + gridDim.x, alpha, beta).prefetch(tid);
         dif_first(xs, L, tw0, tid, [&](int idx) { return io.load(idx); });
         dif_middle(xs, L, logL, np8, tid);
         mid_fused<KT>(xs, L, tid, [&](int slot, int p, double2 v) { stash[slot] = v; return cmul(v, sGt[p]); });   // Z kept
@@ -146,6 +161,11 @@ xcorr_pairs_kernel(const double* __restrict__ X, int rows, int n, int ldx, const
         const double* x0 = X + (size_t)r0 * ldx;
         const double* x1 = X + (size_t)(two ? r0 + 1 : r0) * ldx;
         const double2* __restrict__ sy = SpecY + (size_t)pr * L;
+        prefetch_l2(sy, sizeof(double2) * L, tid);                  // needed after the transform below
+        if (pr + (int)gridDim.x < npairs) {
+            prefetch_l2(X + (size_t)(r0 + 2 * gridDim.x) * ldx, sizeof(double) * n, tid);
+            if (r0 + 2 * (int)gridDim.x + 1 < rows) prefetch_l2(X + (size_t)(r0 + 2 * gridDim.x + 1) * ldx, sizeof(double) * n, tid);
+        }
         dif_first(xs, L, tw0, tid, [&](int idx) { return idx < n ? make_double2(x0[idx], two ? x1[idx] : 0.0) : make_double2(0.0, 0.0); });
         dif_middle(xs, L, logL, np8, tid);
 #pragma unroll
