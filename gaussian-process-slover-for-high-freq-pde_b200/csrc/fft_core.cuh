@@ -11,6 +11,7 @@
 // inverse = DIT (bit-reversed in, natural out), passes (head,8,...,8); the inverse pass at stage s
 // uses the table of the forward pass at stage logL-3-s.  The tail/head pass has q = 1: constants only.
 #pragma once
+#include <algorithm>
 #include <cuda_runtime.h>
 
 namespace gphm {
@@ -18,6 +19,13 @@ namespace gphm {
 constexpr int FFT_THREADS = 512;
 constexpr int FFT_MAX_L = 8192;                       // 144 KB of (padded) complex doubles in shared memory
 constexpr int FFT_ACC = FFT_MAX_L / FFT_THREADS;      // spectrum bins per thread
+// Threads per CTA are a LAUNCH parameter (blockDim.x <= FFT_THREADS): the fused row kernels run short transforms
+// with L/8 threads (one radix-8 butterfly per thread and pass; several CTAs per SM) instead of idling 3/4 of a
+// 512-thread CTA at L = 1024.  Every loop below strides by fft_nt<NT>(); the per-thread register arrays (FFT_ACC
+// slots) need blockDim.x >= L / 16.
+// NT > 0: compile-time stride (the 512-thread launches of long transforms); NT = 0: blockDim.x.
+template <int NT> __device__ __forceinline__ int fft_nt() { return NT > 0 ? NT : (int)blockDim.x; }
+__host__ inline int fft_threads_for(int L) { return std::max(64, std::min(FFT_THREADS, L >> 3)); }
 
 // shared-memory layout: one pad slot per 8 complex values, so that the 8 lanes of a quarter-warp
 // always hit 8 different 16-byte bank groups for every stride the passes use
@@ -45,11 +53,12 @@ __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_doub
 // Shared-memory twiddle table behind the data buffer; W is the global per-stage table built by
 // twiddle_init_kernel:  W[(L - (L >> s)) + j] = T_s[j],  j < L >> (s+1).   Ends with a barrier.
 __device__ __forceinline__ double2* fft_twiddles(double2* xs, int L) { return xs + fft_data_slots(L); }
+template <int NT = FFT_THREADS>
 __device__ __forceinline__ void fft_load_twiddles(double2* xs, int L, int logL, const double2* __restrict__ W, int tid) {
     double2* tw = fft_twiddles(xs, L);
     for (int s = 0; logL - s >= 3; s += 3) {
         const int q = L >> (s + 3);
-        for (int i = tid; i < 3 * q; i += FFT_THREADS) {
+        for (int i = tid; i < 3 * q; i += fft_nt<NT>()) {
             const int t = i / q, j = i - t * q;
             tw[i] = W[(L - (L >> (s + t))) + j];
         }
@@ -121,9 +130,10 @@ __device__ __forceinline__ void bfly8_dit_inv(double2 (&e)[8], double2 u1, doubl
 }
 
 // Radix-8 DIF pass over stages s..s+2; tw = this pass' compact table [w1 | w2 | w4], q entries each.
+template <int NT = FFT_THREADS>
 __device__ __forceinline__ void dif_pass8(double2* xs, int L, int logL, int s, const double2* tw, int tid) {
     const int lq = logL - s - 3, q = 1 << lq;
-    for (int b = tid; b < (L >> 3); b += FFT_THREADS) {
+    for (int b = tid; b < (L >> 3); b += fft_nt<NT>()) {
         const int j = b & (q - 1);
         const int base = ((b >> lq) << (lq + 3)) + j;
         double2 e[8];
@@ -136,9 +146,10 @@ __device__ __forceinline__ void dif_pass8(double2* xs, int L, int logL, int s, c
     __syncthreads();
 }
 
+template <int NT = FFT_THREADS>
 __device__ __forceinline__ void dit_pass8(double2* xs, int L, int logL, int s, const double2* tw, int tid) {
     const int q = 1 << s;
-    for (int b = tid; b < (L >> 3); b += FFT_THREADS) {
+    for (int b = tid; b < (L >> 3); b += fft_nt<NT>()) {
         const int j = b & (q - 1);
         const int base = ((b >> s) << (s + 3)) + j;
         double2 e[8];
@@ -152,10 +163,10 @@ __device__ __forceinline__ void dit_pass8(double2* xs, int L, int logL, int s, c
 }
 
 // Tail (forward) / head (inverse) pass of 2^K points with unit stride: every twiddle is a constant.
-template <int K>
+template <int K, int NT = FFT_THREADS>
 __device__ __forceinline__ void unit_pass(double2* xs, int L, bool inverse, int tid) {
     constexpr int R = 1 << K;
-    for (int b = tid; b < (L >> K); b += FFT_THREADS) {
+    for (int b = tid; b < (L >> K); b += fft_nt<NT>()) {
         const int base = b << K;
         double2 e[R];
 #pragma unroll
@@ -181,23 +192,25 @@ __device__ __forceinline__ void unit_pass(double2* xs, int L, bool inverse, int 
 }
 
 // natural order in -> bit-reversed order out.  Needs fft_load_twiddles(xs, L, ...) once per CTA.
+template <int NT = FFT_THREADS>
 __device__ __forceinline__ void fft_dif_inplace(double2* xs, int L, int logL, const double2* __restrict__, int tid) {
     const double2* tw = fft_twiddles(xs, L);
     int s = 0;
-    for (; logL - s >= 3; s += 3) { dif_pass8(xs, L, logL, s, tw, tid); tw += 3 * (L >> (s + 3)); }
-    if (logL - s == 2) unit_pass<2>(xs, L, false, tid);
-    else if (logL - s == 1) unit_pass<1>(xs, L, false, tid);
+    for (; logL - s >= 3; s += 3) { dif_pass8<NT>(xs, L, logL, s, tw, tid); tw += 3 * (L >> (s + 3)); }
+    if (logL - s == 2) unit_pass<2, NT>(xs, L, false, tid);
+    else if (logL - s == 1) unit_pass<1, NT>(xs, L, false, tid);
 }
 // bit-reversed order in -> natural order out (unscaled inverse)
+template <int NT = FFT_THREADS>
 __device__ __forceinline__ void fft_dit_inverse_inplace(double2* xs, int L, int logL, const double2* __restrict__, int tid) {
     const int r = logL % 3;
-    if (r == 2) unit_pass<2>(xs, L, true, tid);
-    else if (r == 1) unit_pass<1>(xs, L, true, tid);
+    if (r == 2) unit_pass<2, NT>(xs, L, true, tid);
+    else if (r == 1) unit_pass<1, NT>(xs, L, true, tid);
     // inverse pass at stage s pairs with the forward pass at stage logL-3-s: walk the table backwards
     const double2* tw = fft_twiddles(xs, L) + fft_twiddle_slots(L);
     for (int s = r; s + 3 <= logL; s += 3) {
         tw -= 3 * (1 << s);
-        dit_pass8(xs, L, logL, s, tw, tid);
+        dit_pass8<NT>(xs, L, logL, s, tw, tid);
     }
 }
 
@@ -296,10 +309,10 @@ __device__ __forceinline__ void unit_inv(double2 (&e)[1 << KT]) {
 }
 
 // First forward pass (stage 0, q = L/8) with the input taken from ld(index); indices >= L/2 are zero padding.
-template <class Load>
+template <int NT = FFT_THREADS, class Load>
 __device__ __forceinline__ void dif_first(double2* xs, int L, const double2* tw, int tid, Load ld) {
     const int q = L >> 3;
-    for (int j = tid; j < q; j += FFT_THREADS) {
+    for (int j = tid; j < q; j += fft_nt<NT>()) {
         double2 e[8];
 #pragma unroll
         for (int m = 0; m < 4; ++m) e[m] = ld(j + m * q);
@@ -313,29 +326,31 @@ __device__ __forceinline__ void dif_first(double2* xs, int L, const double2* tw,
 }
 
 // Forward passes 1 .. np8-1 (after dif_first).
+template <int NT = FFT_THREADS>
 __device__ __forceinline__ void dif_middle(double2* xs, int L, int logL, int np8, int tid) {
     const double2* tw = fft_twiddles(xs, L) + 3 * (L >> 3);
-    for (int p = 1; p < np8; ++p) { dif_pass8(xs, L, logL, 3 * p, tw, tid); tw += 3 * (L >> (3 * p + 3)); }
+    for (int p = 1; p < np8; ++p) { dif_pass8<NT>(xs, L, logL, 3 * p, tw, tid); tw += 3 * (L >> (3 * p + 3)); }
 }
 // Inverse passes at stages KT, KT+3, ..., logL-6 (all but the last one).
+template <int NT = FFT_THREADS>
 __device__ __forceinline__ void dit_middle(double2* xs, int L, int logL, int np8, int KT, int tid) {
     const double2* tw = fft_twiddles(xs, L);
     for (int p = 0; p < np8; ++p) tw += 3 * (L >> (3 * p + 3));
     for (int p = np8 - 1; p >= 1; --p) {          // inverse stage s = logL - 3 - 3p pairs with forward pass p
         tw -= 3 * (L >> (3 * p + 3));
-        dit_pass8(xs, L, logL, logL - 3 - 3 * p, tw, tid);
+        dit_pass8<NT>(xs, L, logL, logL - 3 - 3 * p, tw, tid);
     }
 }
 
 // Forward tail + functor + inverse head on groups of 2^KT contiguous (bit-reversed-order) bins.
 // f(slot, p, v): slot = static register slot (0 .. 15) of this thread, p = bin position, v = spectrum value.
-template <int KT, class F>
+template <int KT, int NT = FFT_THREADS, class F>
 __device__ __forceinline__ void mid_fused(double2* xs, int L, int tid, F f) {
     constexpr int R = 1 << KT;
     constexpr int MAXG = FFT_MAX_L / (R * FFT_THREADS);
 #pragma unroll
     for (int i = 0; i < MAXG; ++i) {
-        const int g = tid + i * FFT_THREADS;
+        const int g = tid + i * fft_nt<NT>();
         if (g < (L >> KT)) {
             const int base = g << KT;
             double2 e[R];
@@ -355,10 +370,10 @@ __device__ __forceinline__ void mid_fused(double2* xs, int L, int tid, F f) {
 // Last inverse pass (stage logL-3, q = L/8); st(index, value, addend) for the live half (index < L/2).
 // The addends pre(index) are fetched before the butterfly so that their global-memory latency
 // hides behind it (the stores may alias the addend, so the compiler cannot hoist the loads itself).
-template <class Pre, class Store>
+template <int NT = FFT_THREADS, class Pre, class Store>
 __device__ __forceinline__ void dit_last(double2* xs, int L, const double2* tw, int tid, Pre pre, Store st) {
     const int q = L >> 3;
-    for (int j = tid; j < q; j += FFT_THREADS) {
+    for (int j = tid; j < q; j += fft_nt<NT>()) {
         double2 add[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m) add[m] = pre(j + m * q);
@@ -373,9 +388,10 @@ __device__ __forceinline__ void dit_last(double2* xs, int L, const double2* tw, 
 }
 
 // Last inverse pass, truncation to the first n entries, first forward pass of the next convolution.
+template <int NT = FFT_THREADS>
 __device__ __forceinline__ void dit_last_dif_first(double2* xs, int L, const double2* tw, int tid, int n) {
     const int q = L >> 3;
-    for (int j = tid; j < q; j += FFT_THREADS) {
+    for (int j = tid; j < q; j += fft_nt<NT>()) {
         double2 e[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m) e[m] = xs[PADI(j + m * q)];

@@ -25,9 +25,10 @@ namespace {
 
 // L2 prefetch of a contiguous range (one 128-byte line per thread and iteration): issued a whole row pair ahead,
 // so that the first pass of the next pair (and the stored spectra of xcorr_pairs) find their operands in L2.
+template <int NT>
 __device__ __forceinline__ void prefetch_l2(const void* p, size_t bytes, int tid) {
     const char* c = static_cast<const char*>(p);
-    for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)FFT_THREADS * 128)
+    for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)fft_nt<NT>() * 128)
         asm volatile("prefetch.global.L2 [%0];" :: "l"(c + off));
 }
 
@@ -42,10 +43,11 @@ struct RowPairIO {
         if (beta == 0.0 || idx >= n) return make_double2(0.0, 0.0);
         return make_double2(a0[idx], two ? a1[idx] : 0.0);
     }
+    template <int NT>
     __device__ __forceinline__ void prefetch(int tid) const {
-        prefetch_l2(x0, sizeof(double) * n, tid);
-        if (two) prefetch_l2(x1, sizeof(double) * n, tid);
-        if (beta != 0.0) { prefetch_l2(a0, sizeof(double) * n, tid); if (two) prefetch_l2(a1, sizeof(double) * n, tid); }
+        prefetch_l2<NT>(x0, sizeof(double) * n, tid);
+        if (two) prefetch_l2<NT>(x1, sizeof(double) * n, tid);
+        if (beta != 0.0) { prefetch_l2<NT>(a0, sizeof(double) * n, tid); if (two) prefetch_l2<NT>(a1, sizeof(double) * n, tid); }
     }
     __device__ __forceinline__ void store(int idx, double2 v, double2 add) const {
         if (idx >= n) return;
@@ -68,38 +70,38 @@ __device__ __forceinline__ RowPairIO row_pair(const double* X, int ldx, double* 
 
 }  // namespace
 
-template <int KT>
+template <int KT, int NT>
 __global__ void __launch_bounds__(FFT_THREADS, 1)
 toeplitz_apply_fused_kernel(const double* X, int rows, int n, int ldx, const double2* __restrict__ spec, int L,
                             int logL, const double2* __restrict__ W, double alpha, double beta, const double* Add, int lda,
                             double* Out, int ldo, double2* __restrict__ SpecOut) {
     extern __shared__ double2 xs[];
     const int tid = threadIdx.x;
-    fft_load_twiddles(xs, L, logL, W, tid);
+    fft_load_twiddles<NT>(xs, L, logL, W, tid);
     const int np8 = (logL - KT) / 3;
     const double2* tw0 = fft_twiddles(xs, L);
     const int npairs = (rows + 1) / 2;
     for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
         const RowPairIO io = row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr, alpha, beta);
-        if (pr + (int)gridDim.x < npairs) row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr + gridDim.x, alpha, beta).prefetch(tid);
-        dif_first(xs, L, tw0, tid, [&](int idx) { return io.load(idx); });
-        dif_middle(xs, L, logL, np8, tid);
+        if (pr + (int)gridDim.x < npairs) row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr + gridDim.x, alpha, beta).template prefetch<NT>(tid);
+        dif_first<NT>(xs, L, tw0, tid, [&](int idx) { return io.load(idx); });
+        dif_middle<NT>(xs, L, logL, np8, tid);
         double2* so = SpecOut ? SpecOut + (size_t)pr * L : nullptr;      // spectrum of the packed row pair, kept for the diagonal sums
-        mid_fused<KT>(xs, L, tid, [&](int, int p, double2 v) { if (so) so[p] = v; return cmul(v, spec[p]); });
-        dit_middle(xs, L, logL, np8, KT, tid);
-        dit_last(xs, L, tw0, tid, [&](int idx) { return io.addend(idx); }, [&](int idx, double2 v, double2 add) { io.store(idx, v, add); });
+        mid_fused<KT, NT>(xs, L, tid, [&](int, int p, double2 v) { if (so) so[p] = v; return cmul(v, spec[p]); });
+        dit_middle<NT>(xs, L, logL, np8, KT, tid);
+        dit_last<NT>(xs, L, tw0, tid, [&](int idx) { return io.addend(idx); }, [&](int idx, double2 v, double2 add) { io.store(idx, v, add); });
     }
 }
 
 // spec: the four Gohberg-Semencul spectra of gs_prepare_kernel, L complex values each.
-template <int KT>
+template <int KT, int NT>
 __global__ void __launch_bounds__(FFT_THREADS, 1)
 gs_apply_fused_kernel(const double* X, int rows, int n, int ldx, const double2* __restrict__ spec, int L,
                       int logL, const double2* __restrict__ W, double alpha, double beta, const double* Add, int lda,
                       double* Out, int ldo) {
     extern __shared__ double2 xs[];
     const int tid = threadIdx.x;
-    fft_load_twiddles(xs, L, logL, W, tid);
+    fft_load_twiddles<NT>(xs, L, logL, W, tid);
     const int np8 = (logL - KT) / 3;
     const double2* tw0 = fft_twiddles(xs, L);
     const double2* __restrict__ sGt = spec;             // conj(G)/L
@@ -110,27 +112,27 @@ gs_apply_fused_kernel(const double* X, int rows, int n, int ldx, const double2* 
     double2 stash[FFT_ACC];
     for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
         const RowPairIO io = row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr, alpha, beta);
-        if (pr + (int)gridDim.x < npairs) row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr + gridDim.x, alpha, beta).prefetch(tid);
-        dif_first(xs, L, tw0, tid, [&](int idx) { return io.load(idx); });
-        dif_middle(xs, L, logL, np8, tid);
-        mid_fused<KT>(xs, L, tid, [&](int slot, int p, double2 v) { stash[slot] = v; return cmul(v, sGt[p]); });   // Z kept
-        dit_middle(xs, L, logL, np8, KT, tid);
-        dit_last_dif_first(xs, L, tw0, tid, n);                                   // [L(g)^T v]_n
-        dif_middle(xs, L, logL, np8, tid);
-        mid_fused<KT>(xs, L, tid, [&](int slot, int p, double2 v) {
+        if (pr + (int)gridDim.x < npairs) row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr + gridDim.x, alpha, beta).template prefetch<NT>(tid);
+        dif_first<NT>(xs, L, tw0, tid, [&](int idx) { return io.load(idx); });
+        dif_middle<NT>(xs, L, logL, np8, tid);
+        mid_fused<KT, NT>(xs, L, tid, [&](int slot, int p, double2 v) { stash[slot] = v; return cmul(v, sGt[p]); });   // Z kept
+        dit_middle<NT>(xs, L, logL, np8, KT, tid);
+        dit_last_dif_first<NT>(xs, L, tw0, tid, n);                                   // [L(g)^T v]_n
+        dif_middle<NT>(xs, L, logL, np8, tid);
+        mid_fused<KT, NT>(xs, L, tid, [&](int slot, int p, double2 v) {
             const double2 z = stash[slot];
             stash[slot] = cmul(v, sG[p]);                                         // G'.Q1 kept
             return cmul(z, sHt[p]);
         });
-        dit_middle(xs, L, logL, np8, KT, tid);
-        dit_last_dif_first(xs, L, tw0, tid, n);                                   // [L(h)^T v]_n
-        dif_middle(xs, L, logL, np8, tid);
-        mid_fused<KT>(xs, L, tid, [&](int slot, int p, double2 v) {
+        dit_middle<NT>(xs, L, logL, np8, KT, tid);
+        dit_last_dif_first<NT>(xs, L, tw0, tid, n);                                   // [L(h)^T v]_n
+        dif_middle<NT>(xs, L, logL, np8, tid);
+        mid_fused<KT, NT>(xs, L, tid, [&](int slot, int p, double2 v) {
             const double2 a = stash[slot], b = cmul(v, sH[p]);
             return make_double2(a.x + b.x, a.y + b.y);
         });
-        dit_middle(xs, L, logL, np8, KT, tid);
-        dit_last(xs, L, tw0, tid, [&](int idx) { return io.addend(idx); }, [&](int idx, double2 v, double2 add) { io.store(idx, v, add); });
+        dit_middle<NT>(xs, L, logL, np8, KT, tid);
+        dit_last<NT>(xs, L, tw0, tid, [&](int idx) { return io.addend(idx); }, [&](int idx, double2 v, double2 add) { io.store(idx, v, add); });
     }
 }
 
@@ -140,13 +142,13 @@ gs_apply_fused_kernel(const double* X, int rows, int n, int ldx, const double2* 
 // conj(X1) Y1 + i (conj(X0) Y1 - conj(X1) Y0): the cross term transforms back to a purely imaginary
 // sequence, so the real part of the inverse transform of the sum is exactly the sum over ROWS of the
 // cross-correlations - one transform per row pair and no spectrum separation.
-template <int KT>
+template <int KT, int NT>
 __global__ void __launch_bounds__(FFT_THREADS, 1)
 xcorr_pairs_kernel(const double* __restrict__ X, int rows, int n, int ldx, const double2* __restrict__ SpecY, int L, int logL,
                    const double2* __restrict__ W, double weight, double2* __restrict__ partial) {
     extern __shared__ double2 xs[];
     const int tid = threadIdx.x;
-    fft_load_twiddles(xs, L, logL, W, tid);
+    fft_load_twiddles<NT>(xs, L, logL, W, tid);
     const int np8 = (logL - KT) / 3;
     const double2* tw0 = fft_twiddles(xs, L);
     const int npairs = (rows + 1) / 2;
@@ -161,16 +163,16 @@ xcorr_pairs_kernel(const double* __restrict__ X, int rows, int n, int ldx, const
         const double* x0 = X + (size_t)r0 * ldx;
         const double* x1 = X + (size_t)(two ? r0 + 1 : r0) * ldx;
         const double2* __restrict__ sy = SpecY + (size_t)pr * L;
-        prefetch_l2(sy, sizeof(double2) * L, tid);                  // needed after the transform below
+        prefetch_l2<NT>(sy, sizeof(double2) * L, tid);                  // needed after the transform below
         if (pr + (int)gridDim.x < npairs) {
-            prefetch_l2(X + (size_t)(r0 + 2 * gridDim.x) * ldx, sizeof(double) * n, tid);
-            if (r0 + 2 * (int)gridDim.x + 1 < rows) prefetch_l2(X + (size_t)(r0 + 2 * gridDim.x + 1) * ldx, sizeof(double) * n, tid);
+            prefetch_l2<NT>(X + (size_t)(r0 + 2 * gridDim.x) * ldx, sizeof(double) * n, tid);
+            if (r0 + 2 * (int)gridDim.x + 1 < rows) prefetch_l2<NT>(X + (size_t)(r0 + 2 * gridDim.x + 1) * ldx, sizeof(double) * n, tid);
         }
-        dif_first(xs, L, tw0, tid, [&](int idx) { return idx < n ? make_double2(x0[idx], two ? x1[idx] : 0.0) : make_double2(0.0, 0.0); });
-        dif_middle(xs, L, logL, np8, tid);
+        dif_first<NT>(xs, L, tw0, tid, [&](int idx) { return idx < n ? make_double2(x0[idx], two ? x1[idx] : 0.0) : make_double2(0.0, 0.0); });
+        dif_middle<NT>(xs, L, logL, np8, tid);
 #pragma unroll
         for (int i = 0; i < MAXG; ++i) {                       // forward tail in registers + accumulation
-            const int g = tid + i * FFT_THREADS;
+            const int g = tid + i * fft_nt<NT>();
             if (g < (L >> KT)) {
                 const int base = g << KT;
                 double2 y[R], e[R];
@@ -191,7 +193,7 @@ xcorr_pairs_kernel(const double* __restrict__ X, int rows, int n, int ldx, const
     double2* out = partial + (size_t)blockIdx.x * L;
 #pragma unroll
     for (int i = 0; i < MAXG; ++i) {
-        const int g = tid + i * FFT_THREADS;
+        const int g = tid + i * fft_nt<NT>();
         if (g < (L >> KT)) {
 #pragma unroll
             for (int m = 0; m < R; ++m) out[(g << KT) + m] = make_double2(weight * acc[i * R + m].x, weight * acc[i * R + m].y);
@@ -199,21 +201,34 @@ xcorr_pairs_kernel(const double* __restrict__ X, int rows, int n, int ldx, const
     }
 }
 
+// (KT, NT) dispatch: NT = FFT_THREADS (compile-time strides) for the full-size CTA, 0 (blockDim.x) for shorter transforms
+#define GPHM_FUSED_LAUNCH(K, GRID, ...)                                                                      \
+    do {                                                                                                     \
+        if (nt == FFT_THREADS) {                                                                             \
+            if (KT == 1) K<1, FFT_THREADS><<<GRID, nt, smem, st>>>(__VA_ARGS__);                             \
+            else if (KT == 2) K<2, FFT_THREADS><<<GRID, nt, smem, st>>>(__VA_ARGS__);                        \
+            else K<3, FFT_THREADS><<<GRID, nt, smem, st>>>(__VA_ARGS__);                                     \
+        } else {                                                                                             \
+            if (KT == 1) K<1, 0><<<GRID, nt, smem, st>>>(__VA_ARGS__);                                       \
+            else if (KT == 2) K<2, 0><<<GRID, nt, smem, st>>>(__VA_ARGS__);                                  \
+            else K<3, 0><<<GRID, nt, smem, st>>>(__VA_ARGS__);                                               \
+        }                                                                                                    \
+    } while (0)
+
 static int ilog2f(int L) { int l = 0; while ((1 << l) < L) ++l; return l; }
 
 int toeplitz_fused_init() {
     static int done = -1;
     if (done >= 0) return done;
     const int bytes = (int)fft_smem_bytes(FFT_MAX_L);
-    GPHM_CUDA_OK(cudaFuncSetAttribute(toeplitz_apply_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    GPHM_CUDA_OK(cudaFuncSetAttribute(toeplitz_apply_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    GPHM_CUDA_OK(cudaFuncSetAttribute(toeplitz_apply_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    GPHM_CUDA_OK(cudaFuncSetAttribute(xcorr_pairs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    GPHM_CUDA_OK(cudaFuncSetAttribute(xcorr_pairs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    GPHM_CUDA_OK(cudaFuncSetAttribute(xcorr_pairs_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    GPHM_CUDA_OK(cudaFuncSetAttribute(gs_apply_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    GPHM_CUDA_OK(cudaFuncSetAttribute(gs_apply_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    GPHM_CUDA_OK(cudaFuncSetAttribute(gs_apply_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+#define GPHM_FUSED_ATTR(K, KT, NT) GPHM_CUDA_OK(cudaFuncSetAttribute(K<KT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
+#define GPHM_FUSED_ATTR6(K) GPHM_FUSED_ATTR(K, 1, FFT_THREADS); GPHM_FUSED_ATTR(K, 2, FFT_THREADS); GPHM_FUSED_ATTR(K, 3, FFT_THREADS); \
+                            GPHM_FUSED_ATTR(K, 1, 0); GPHM_FUSED_ATTR(K, 2, 0); GPHM_FUSED_ATTR(K, 3, 0)
+    GPHM_FUSED_ATTR6(toeplitz_apply_fused_kernel);
+    GPHM_FUSED_ATTR6(xcorr_pairs_kernel);
+    GPHM_FUSED_ATTR6(gs_apply_fused_kernel);
+#undef GPHM_FUSED_ATTR6
+#undef GPHM_FUSED_ATTR
     done = GPHM_OK;
     return done;
 }
@@ -229,7 +244,8 @@ int launch_toeplitz_apply_fused(const double* X, int rows, int n, int ldx, const
     if (rows <= 0) return GPHM_OK;
     if (!toeplitz_fused_supported(L) || L < 2 * n) { set_last_error("toeplitz_apply_fused: L=%d does not fit n=%d", L, n); return GPHM_EINVAL; }
     const int logL = ilog2f(L), KT = fft_tail_stages(logL);
-    const int grid = std::min(fft_grid(), (rows + 1) / 2);
+    const int nt = fft_threads_for(L);
+    const int grid = std::min(fft_grid() * (FFT_THREADS / nt), (rows + 1) / 2);
     const size_t smem = fft_smem_bytes(L);
     auto sp = reinterpret_cast<const double2*>(spec);
     auto w = reinterpret_cast<const double2*>(W);
@@ -238,9 +254,7 @@ int launch_toeplitz_apply_fused(const double* X, int rows, int n, int ldx, const
         const double pairs = (rows + 1) / 2;
         LaunchScope scope(CAT_TOEPLITZ_APPLY, st, pairs * (2.0 * fft_flops(L) + 6.0 * L),
                           (beta != 0.0 ? 24.0 : 16.0) * rows * (double)n + (SpecOut ? 16.0 * pairs * L : 0.0));
-        if (KT == 1) toeplitz_apply_fused_kernel<1><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo, so);
-        else if (KT == 2) toeplitz_apply_fused_kernel<2><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo, so);
-        else toeplitz_apply_fused_kernel<3><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo, so);
+        GPHM_FUSED_LAUNCH(toeplitz_apply_fused_kernel, grid, X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo, so);
     }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
@@ -254,16 +268,15 @@ int launch_gs_apply_fused(const double* X, int rows, int n, int ldx, const doubl
     if (!toeplitz_fused_supported(L) || L < 2 * n) { set_last_error("gs_apply_fused: L=%d does not fit n=%d", L, n); return GPHM_EINVAL; }
     if (beta != 0.0 && !Add) { set_last_error("gs_apply_fused: beta without Add"); return GPHM_EINVAL; }
     const int logL = ilog2f(L), KT = fft_tail_stages(logL);
-    const int grid = std::min(fft_grid(), (rows + 1) / 2);
+    const int nt = fft_threads_for(L);
+    const int grid = std::min(fft_grid() * (FFT_THREADS / nt), (rows + 1) / 2);
     const size_t smem = fft_smem_bytes(L);
     auto sp = reinterpret_cast<const double2*>(gspec);
     auto w = reinterpret_cast<const double2*>(W);
     {
         const double pairs = (rows + 1) / 2;
         LaunchScope scope(CAT_GS_APPLY, st, pairs * (6.0 * fft_flops(L) + 18.0 * L), (beta != 0.0 ? 24.0 : 16.0) * rows * (double)n);
-        if (KT == 1) gs_apply_fused_kernel<1><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
-        else if (KT == 2) gs_apply_fused_kernel<2><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
-        else gs_apply_fused_kernel<3><<<grid, FFT_THREADS, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
+        GPHM_FUSED_LAUNCH(gs_apply_fused_kernel, grid, X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
     }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
@@ -276,15 +289,14 @@ int launch_xcorr_pairs(const double* X, int rows, int n, int ldx, const double* 
     if (!toeplitz_fused_supported(L) || L < 2 * n) { set_last_error("xcorr_pairs: L=%d does not fit n=%d", L, n); return GPHM_EINVAL; }
     const int logL = ilog2f(L), KT = fft_tail_stages(logL);
     const size_t smem = fft_smem_bytes(L);
+    const int nt = fft_threads_for(L);
     auto sy = reinterpret_cast<const double2*>(SpecY);
     auto w = reinterpret_cast<const double2*>(W);
     auto pt = reinterpret_cast<double2*>(partial);
     {
         const double pairs = (rows + 1) / 2;
         LaunchScope scope(CAT_FFT, st, pairs * (fft_flops(L) + 8.0 * L), 8.0 * rows * (double)n + 16.0 * pairs * L);
-        if (KT == 1) xcorr_pairs_kernel<1><<<fft_grid(), FFT_THREADS, smem, st>>>(X, rows, n, ldx, sy, L, logL, w, weight, pt);
-        else if (KT == 2) xcorr_pairs_kernel<2><<<fft_grid(), FFT_THREADS, smem, st>>>(X, rows, n, ldx, sy, L, logL, w, weight, pt);
-        else xcorr_pairs_kernel<3><<<fft_grid(), FFT_THREADS, smem, st>>>(X, rows, n, ldx, sy, L, logL, w, weight, pt);
+        GPHM_FUSED_LAUNCH(xcorr_pairs_kernel, fft_grid(), X, rows, n, ldx, sy, L, logL, w, weight, pt);
     }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
