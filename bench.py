@@ -54,7 +54,7 @@ def parse_args():
                          "solves partitioned over the ranks (64 members per GPU, weak scaling)")
     ap.add_argument("--ensemble-equation", default="poisson_2d-sin_sin", help="any equation of the config table (1-D or 2-D)")
     ap.add_argument("--members-per-gpu", type=int, default=64)
-    ap.add_argument("--streams", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=16)
     ap.add_argument("--no-graph", action="store_true", help="ensemble: plain launches instead of CUDA-graph replay")
     return ap.parse_args()
 

@@ -73,7 +73,7 @@ class Ensemble(object):
     GP_solver_2d_single_advection: anything with `.core`, `.lr`, `.init_params()`), one per member,
     with their initial params.  `step()` advances every member by one Adam iteration."""
 
-    def __init__(self, models, params_list, streams=8, graph=True):
+    def __init__(self, models, params_list, streams=16, graph=True):
         if len(models) != len(params_list) or not models:
             raise ValueError("need one params pytree per member")
         self.models = list(models)
@@ -149,7 +149,7 @@ class Ensemble(object):
             m.core.raise_on_bad_status()
 
 
-def build_ensemble(trick_paras, members, rank=0, world=1, streams=8, graph=True, quiet=True):
+def build_ensemble(trick_paras, members, rank=0, world=1, streams=16, graph=True, quiet=True):
     """Ensemble of this rank's share of `members` [(seed, freq_scale)] for one equation config
     (`trick_paras` as evals() builds it; its `equation` prefix selects the solver class).
     Returns (Ensemble, indices of the members it holds)."""
