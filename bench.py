@@ -247,11 +247,17 @@ def run_ours(args, rank, world, local):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    marks = []
     for _ in range(args.steps):
         step()
+        m = torch.cuda.Event(enable_timing=True)
+        m.record()
+        marks.append(m)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    per_step = sorted(a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks))      # this rank's steps
+    step_spread = {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]}
     NF = 8
     cat_ms = (ctypes.c_double * NF)(); cat_fl = (ctypes.c_double * NF)(); cat_by = (ctypes.c_double * NF)()
     cat_n = (ctypes.c_longlong * NF)()
@@ -402,7 +408,7 @@ def run_ours(args, rank, world, local):
             "data": "synthetic",
             "config": {"workload": "%s %dx%d %s Q=%d S0" % (EQUATION, n, n, KERNEL, Q), "parallelism": parallelism,
                        "l2": "working set per step ~%.1f GB >> 126 MB L2 (no flush needed)" % (28 * n * n * 8 / 1e9),
-                       "loss_after": loss},
+                       "loss_after": loss, "step_ms_rank0": step_spread},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
 

@@ -37,6 +37,8 @@ class CudaOps(object):
         self.device = core.device
         self.Q = core.Q
         self._cache = {}
+        import os
+        self.use_comm_stream = os.environ.get("GPHM_MG_COMM_STREAM", "1") != "0"
 
     def _buf(self, tag, shape):
         key = (tag,) + tuple(shape)
@@ -168,12 +170,12 @@ class CudaOps(object):
                                            _lib.ptr(gU), None, self._s()), "gphm_mg_grad_u")
         return gU
 
-    def pack_transposed(self, Xs, part_cols):
+    def pack_transposed(self, Xs, part_cols, tag="pack"):
         """send[d][a] = (X_a^T)[d * part_cols : (d+1) * part_cols]  for the arrays X_a (rows x cols): one tiled transpose
-        per array, written straight into the all-to-all send buffer."""
+        per array, written straight into the (persistent) all-to-all send buffer."""
         k, (rows, cols) = len(Xs), Xs[0].shape
         parts = cols // part_cols
-        send = torch.empty((parts, k, part_cols, rows), dtype=DT, device=self.device)
+        send = self._buf(tag + ".send", (parts, k, part_cols, rows))
         blk = part_cols * rows
         for a, X in enumerate(Xs):
             dst = send.view(-1)[a * blk:]
@@ -181,10 +183,10 @@ class CudaOps(object):
                        "gphm_mg_pack_transposed")
         return send
 
-    def unpack_segments(self, recv):
-        """recv[s][a][r][c] -> out[a][r][s * seg + c]."""
+    def unpack_segments(self, recv, tag="pack"):
+        """recv[s][a][r][c] -> out[a][r][s * seg + c]  (persistent output buffer)."""
         parts, k, rows, seg = recv.shape
-        out = torch.empty((k, rows, parts * seg), dtype=DT, device=self.device)
+        out = self._buf(tag + ".out", (k, rows, parts * seg))
         _lib.check(self.lib.gphm_mg_unpack_segments(_lib.ptr(recv), parts, k, rows, seg, _lib.ptr(out), self._s()),
                    "gphm_mg_unpack_segments")
         return out
@@ -197,6 +199,8 @@ class CudaOps(object):
     # ---- communication stream: an exchange (packing copies + all-to-all) issued with fork() runs beside the
     # kernels the main stream launches until join() ----
     def fork(self, fn):
+        if not self.use_comm_stream:
+            return fn(), None
         if getattr(self, "_comm", None) is None:
             self._comm = torch.cuda.Stream(device=self.device)
         cur = torch.cuda.current_stream(self.device)
@@ -209,10 +213,10 @@ class CudaOps(object):
 
     def join(self, handle):
         res, ev = handle
-        cur = torch.cuda.current_stream(self.device)
-        cur.wait_event(ev)
-        for t in res:
-            t.record_stream(cur)                          # allocated on the communication stream, consumed on this one
+        if ev is not None:
+            # the exchange buffers are persistent (one set per exchange of the step), so stream order is all that is
+            # needed: no allocator hand-over (record_stream) and no allocation inside the step
+            torch.cuda.current_stream(self.device).wait_event(ev)
         return res
 
     def adam(self, p, g, m, v, count, lr):
@@ -312,8 +316,8 @@ class ShardedSolver2D(object):
         return self.terms[0]
 
     # ---- layout exchanges ------------------------------------------------------------------------
-    def _a2a(self, send):
-        recv = torch.empty_like(send)
+    def _a2a(self, send, tag=None):
+        recv = torch.empty_like(send) if tag is None else self.ops.new(tag + ".recv", tuple(send.shape))
         if self.P == 1:
             recv.copy_(send)
         else:
@@ -333,31 +337,35 @@ class ShardedSolver2D(object):
         recv = self._a2a(X.contiguous().reshape(P, h, w))               # chunk s = my rows, columns of rank s
         return recv.transpose(0, 1).reshape(h, self.N2).contiguous()
 
-    def _pack_t(self, Xs, part_cols):
+    def _pack_t(self, Xs, part_cols, tag):
         """[dest][array][c][r] = X_array[r][dest * part_cols + c]  (backend kernel, else torch)."""
         f = getattr(self.ops, "pack_transposed", None)
         if f is not None:
-            return f([X.contiguous() for X in Xs], part_cols)
+            return f([X.contiguous() for X in Xs], part_cols, tag)
         k, (rows, cols) = len(Xs), Xs[0].shape
         return torch.stack(Xs).reshape(k, rows, cols // part_cols, part_cols).permute(2, 0, 3, 1).contiguous()
 
-    def _unpack(self, recv):
+    def _unpack(self, recv, tag):
         """[src][array][r][c] -> [array][r][src * seg + c]."""
         f = getattr(self.ops, "unpack_segments", None)
         if f is not None:
-            return f(recv)
+            return f(recv, tag)
         parts, k, rows, seg = recv.shape
         return recv.permute(1, 2, 0, 3).reshape(k, rows, parts * seg).contiguous()
 
-    def r2ct(self, Xs):
+    def r2ct(self, Xs, tag="r2ct"):
         """Row blocks (h, N2) -> TRANSPOSED column blocks (w, N1): row j holds column rank*w + j of the field.
-        Several arrays travel in one all-to-all."""
-        out = self._unpack(self._a2a(self._pack_t(Xs, self.w)))          # send [dest][array][j][i] -> recv [src][array][j][i]
+        Several arrays travel in one all-to-all.  `tag` names the persistent buffer set of this exchange."""
+        tag = "%s%d" % (tag, len(Xs))
+        send = self._pack_t(Xs, self.w, tag)                              # [dest][array][j][i]
+        out = self._unpack(self._a2a(send, tag), tag)                     # recv [src][array][j][i]
         return [out[a] for a in range(len(Xs))]
 
-    def ct2r(self, Ys):
+    def ct2r(self, Ys, tag="ct2r"):
         """Transposed column blocks (w, N1) -> row blocks (h, N2)."""
-        out = self._unpack(self._a2a(self._pack_t(Ys, self.h)))          # send [dest][array][i][j] -> recv [src][array][i][j]
+        tag = "%s%d" % (tag, len(Ys))
+        send = self._pack_t(Ys, self.h, tag)                              # [dest][array][i][j]
+        out = self._unpack(self._a2a(send, tag), tag)                     # recv [src][array][i][j]
         return [out[a] for a in range(len(Ys))]
 
     def _allreduce(self, t):
