@@ -23,7 +23,6 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-import numpy as np
 import torch
 
 METRIC = "log-joint+grad iters/sec, 2D Poisson 4096^2 grid"

@@ -47,7 +47,28 @@ def build(force=False, verbose=True):
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+    build_ffi_shim(verbose)
     return OUT
+
+
+def build_ffi_shim(verbose=True):
+    """csrc/ffi_shim.cc -> libgphm_ffi.so, ONLY where JAX ships the XLA FFI headers (not in this image)."""
+    try:
+        import jax
+        inc = jax.ffi.include_dir()
+    except Exception:
+        if verbose:
+            print("ffi_shim.cc skipped: no jax / XLA FFI headers in this environment", flush=True)
+        return None
+    out = os.path.join(HERE, "libgphm_ffi.so")
+    src = os.path.join(CSRC, "ffi_shim.cc")
+    if _stale(out, [src, OUT]):
+        cmd = ["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-I" + inc, "-I" + os.path.join(HERE, "..", "include"),
+               "-I/usr/local/cuda/include", src, "-L" + HERE, "-lgphm", "-Wl,-rpath," + HERE, "-o", out]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return out
 
 
 if __name__ == "__main__":

@@ -15,7 +15,6 @@ times per step.  Scalars (loss terms, 6Q theta-gradients) use one small all-redu
 The numerical pieces are calls into libgphm through the `ops` object (CudaOps below).  The step
 logic itself is backend-agnostic so that tests can drive it with a CPU stand-in over gloo.
 """
-import ctypes
 import math
 
 import torch

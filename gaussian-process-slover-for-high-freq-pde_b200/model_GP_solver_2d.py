@@ -9,7 +9,6 @@ numerical core (value_and_grad of the log-joint + Adam) runs in libgphm on the G
   train                                       :235-352
   get_source_val / get_mesh_data / get_boundary_vals / test / evals   :355-514
 """
-import math
 import time
 
 import numpy as np
