@@ -48,15 +48,16 @@ def test_member_init_is_deterministic_and_scaled():
             assert not np.array_equal(a[keys[0]]["freq"], a[keys[1]]["freq"])
 
 
-def _worker(rank, world, port, n):
+def _worker(rank, world, port, sizes):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        mine = E.shard_members(n, rank, world)
-        local = torch.tensor([[float(i), 10.0 * i] for i in mine], dtype=torch.float64).reshape(len(mine), 2)
-        full = E.gather_results(local, n, rank, world)
-        assert full.shape == (n, 2)
-        assert torch.equal(full[:, 0], torch.arange(n, dtype=torch.float64)) and torch.equal(full[:, 1], 10 * full[:, 0])
+        for n in sizes:                                       # 1: rank 1 holds no member at all
+            mine = E.shard_members(n, rank, world)
+            local = torch.tensor([[float(i), 10.0 * i] for i in mine], dtype=torch.float64).reshape(len(mine), 2)
+            full = E.gather_results(local, n, rank, world)
+            assert full.shape == (n, 2)
+            assert torch.equal(full[:, 0], torch.arange(n, dtype=torch.float64)) and torch.equal(full[:, 1], 10 * full[:, 0])
     finally:
         dist.destroy_process_group()
 
@@ -70,8 +71,7 @@ def _free_port():
 
 
 def test_gather_results_world2_gloo():
-    for n in (7, 8, 1):
-        mp.spawn(_worker, args=(2, _free_port(), n), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), (7, 8, 1)), nprocs=2, join=True)
 
 
 def test_gather_results_world1():

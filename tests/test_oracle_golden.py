@@ -60,8 +60,9 @@ def test_golden_2d_trajectory(oracle):
             j = i // 5
             tol = 1e-12 if i == 0 else (1e-7 if i <= 5 else 1e-4)       # trajectories are chaotic
             assert abs(_loglike(terms["loss"]) - g["log_loss_list"][j]) <= tol * abs(g["log_loss_list"][j]), (i,)
-            err = O.rel_l2(O.preds_2d(p, params, xt[0], xt[1]), ut)
-            assert abs(err - g["log_err_list"][j]) <= (1e-7 if i <= 5 else 1e-3) * g["log_err_list"][j], (i, err)
+            if j in (0, 1, 2, 5, 10, 15, 19):           # the prediction is 5x a step's cost: a spread of checkpoints
+                err = O.rel_l2(O.preds_2d(p, params, xt[0], xt[1]), ut)
+                assert abs(err - g["log_err_list"][j]) <= (1e-7 if i <= 5 else 1e-3) * g["log_err_list"][j], (i, err)
     final = O.rel_l2(O.preds_2d(p, params, xt[0], xt[1]), ut)
     assert abs(final - 0.46758844) <= 0.05 * 0.46758844                   # log.txt:2-3
 
