@@ -98,7 +98,11 @@ struct gphm_plan {
     double* hs = nullptr;
     long long* hs_count = nullptr;
     cudaStream_t hs_stream = nullptr;     // second copy stream: the Adam moments travel while the gradient is computed
-    cudaEvent_t hs_ev_u = nullptr, hs_ev_mv = nullptr;
+    cudaEvent_t hs_ev_u = nullptr, hs_ev_mv = nullptr, hs_ev_gu = nullptr, hs_ev_adam = nullptr;
+    // hooks of gphm_step_host into the all-FFT step (null otherwise):
+    cudaEvent_t u_ready = nullptr;        // waited for on the step's stream after the factor stage (U still uploading)
+    int (*on_gu)(gphm_plan&, cudaStream_t) = nullptr;   // called once dL/dU is complete (before the theta-gradient)
+    bool gu_hook_ran = false;
 };
 
 namespace {
@@ -350,7 +354,8 @@ int logjoint_grad_gs(gphm_plan& p, const double* U, const double* small, double*
     const bool anti = order == 1;
     Axis& X1 = p.ax[0];
     Axis& X2 = p.ax[1];
-    GPHM_TRY(factor_gs(p, 0, two ? 2 : 1, small, st));       // includes the spectra of D1, D2
+    GPHM_TRY(factor_gs(p, 0, two ? 2 : 1, small, st));       // includes the spectra of D1, D2; needs only theta
+    if (p.u_ready) GPHM_CUDA_OK(cudaStreamWaitEvent(st, p.u_ready, 0));     // gphm_step_host: U arrives meanwhile
     auto gs1 = [&](const double* Xr, double* out) {       // rows of length n1 (columns of the field)
         return launch_gs_apply_fused(Xr, n2, n1, n1, X1.gspec, X1.fftL, X1.twid, 1.0, 0.0, nullptr, 0, out, n1, st);
     };
@@ -405,6 +410,7 @@ int logjoint_grad_gs(gphm_plan& p, const double* U, const double* small, double*
         GPHM_TRY(launch_grad_u(lc, p.has_base ? p.base : nullptr, U, G, p.V1, p.S1, nullptr, p.eb, p.xind, small, gU, nullptr,
                                nullptr, st));
     }
+    if (p.on_gu) { GPHM_TRY(p.on_gu(p, st)); p.gu_hook_ran = true; }        // nothing below reads U or gU
     // diagonal sums of Kbar_a = ld/2 N_b K_a^-1 - V_a (.)^T and Dbar_a by row cross-correlations
     // (one transform per row PAIR against the stored transforms of A^T / Bt)
     GPHM_TRY(launch_xcorr_pairs(V1t, n2, n1, n1, X1.specY, X1.fftL, X1.twid, -1.0, X1.specK, st));
@@ -438,6 +444,7 @@ int logjoint_grad(gphm_plan& p, const double* U, const double* small, double* gU
     const double c1 = coef_c1(p);
     Axis& X1 = p.ax[0];
     Axis& X2 = p.ax[1];
+    if (p.u_ready) GPHM_CUDA_OK(cudaStreamWaitEvent(st, p.u_ready, 0));
 
     const bool fft_kinv = (d.force_general & 4) == 0;   // then K^-1 itself is never formed on FFT axes
     const bool kinv0 = !fwd_only && !(fft_kinv && X1.fftL > 0), kinv1 = !fwd_only && !(fft_kinv && X2.fftL > 0);
@@ -740,6 +747,8 @@ void gphm_plan_destroy(gphm_plan* plan) {
     if (plan->hs_stream) cudaStreamDestroy(plan->hs_stream);
     if (plan->hs_ev_u) cudaEventDestroy(plan->hs_ev_u);
     if (plan->hs_ev_mv) cudaEventDestroy(plan->hs_ev_mv);
+    if (plan->hs_ev_gu) cudaEventDestroy(plan->hs_ev_gu);
+    if (plan->hs_ev_adam) cudaEventDestroy(plan->hs_ev_adam);
     delete plan;
 }
 
@@ -813,35 +822,60 @@ int gphm_step_host(gphm_plan* plan, double* h_U, double* h_small, double* h_mU, 
         GPHM_CUDA_OK(cudaStreamCreateWithFlags(&plan->hs_stream, cudaStreamNonBlocking));
         GPHM_CUDA_OK(cudaEventCreateWithFlags(&plan->hs_ev_u, cudaEventDisableTiming));
         GPHM_CUDA_OK(cudaEventCreateWithFlags(&plan->hs_ev_mv, cudaEventDisableTiming));
+        GPHM_CUDA_OK(cudaEventCreateWithFlags(&plan->hs_ev_gu, cudaEventDisableTiming));
+        GPHM_CUDA_OK(cudaEventCreateWithFlags(&plan->hs_ev_adam, cudaEventDisableTiming));
     }
     double *U = plan->hs, *mU = U + nfp, *vU = mU + nfp, *sm = vU + nfp, *msm = sm + nsp, *vsm = msm + nsp,
            *terms = vsm + nsp;
-    // params first (the gradient needs only them); the Adam moments follow on a second stream and
-    // overlap the log-joint + gradient kernels - they are first touched by the Adam update.
+    // Schedule (PCIe carries 134 MB up before and 403 MB down after the 6 ms of kernels at 4096^2):
+    //   st        : small params up -> factor stage (needs only theta) -> [wait U] gradient ... theta-gradient -> Adam(small) -> down
+    //   hs_stream : U up -> mU, vU up (hidden behind the gradient) -> [wait dL/dU] Adam(U) -> U, mU, vU down while st
+    //               still computes the theta-gradient
     GPHM_CUDA_OK(cudaMemcpyAsync(sm, h_small, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
     GPHM_CUDA_OK(cudaMemcpyAsync(msm, h_msmall, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
     GPHM_CUDA_OK(cudaMemcpyAsync(vsm, h_vsmall, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
     GPHM_CUDA_OK(cudaMemcpyAsync(plan->hs_count, h_count, sizeof(long long), cudaMemcpyHostToDevice, st));
-    GPHM_CUDA_OK(cudaMemcpyAsync(U, h_U, sizeof(double) * nf, cudaMemcpyHostToDevice, st));
-    GPHM_CUDA_OK(cudaEventRecord(plan->hs_ev_u, st));
-    GPHM_CUDA_OK(cudaStreamWaitEvent(plan->hs_stream, plan->hs_ev_u, 0));
+    GPHM_CUDA_OK(cudaMemcpyAsync(U, h_U, sizeof(double) * nf, cudaMemcpyHostToDevice, plan->hs_stream));
+    GPHM_CUDA_OK(cudaEventRecord(plan->hs_ev_u, plan->hs_stream));
     GPHM_CUDA_OK(cudaMemcpyAsync(mU, h_mU, sizeof(double) * nf, cudaMemcpyHostToDevice, plan->hs_stream));
     GPHM_CUDA_OK(cudaMemcpyAsync(vU, h_vU, sizeof(double) * nf, cudaMemcpyHostToDevice, plan->hs_stream));
-    GPHM_CUDA_OK(cudaEventRecord(plan->hs_ev_mv, plan->hs_stream));
-    GPHM_TRY(logjoint_grad(*plan, U, sm, plan->gU, plan->gsmall, terms, 0, st));
-    GPHM_CUDA_OK(cudaStreamWaitEvent(st, plan->hs_ev_mv, 0));
-    GPHM_TRY(launch_adam(U, plan->gU, mU, vU, nf, plan->hs_count, lr, st));
+    struct Ctx { double *U, *mU, *vU, *hU, *hmU, *hvU; size_t nf; double lr; };
+    static thread_local Ctx ctx;
+    ctx = Ctx{U, mU, vU, h_U, h_mU, h_vU, nf, lr};
+    plan->u_ready = plan->hs_ev_u;
+    plan->gu_hook_ran = false;
+    plan->on_gu = [](gphm_plan& p, cudaStream_t s) -> int {                  // dL/dU complete on s
+        GPHM_CUDA_OK(cudaEventRecord(p.hs_ev_gu, s));
+        GPHM_CUDA_OK(cudaStreamWaitEvent(p.hs_stream, p.hs_ev_gu, 0));
+        GPHM_TRY(launch_adam(ctx.U, p.gU, ctx.mU, ctx.vU, ctx.nf, p.hs_count, ctx.lr, p.hs_stream));
+        GPHM_CUDA_OK(cudaEventRecord(p.hs_ev_adam, p.hs_stream));
+        GPHM_CUDA_OK(cudaMemcpyAsync(ctx.hU, ctx.U, sizeof(double) * ctx.nf, cudaMemcpyDeviceToHost, p.hs_stream));
+        GPHM_CUDA_OK(cudaMemcpyAsync(ctx.hmU, ctx.mU, sizeof(double) * ctx.nf, cudaMemcpyDeviceToHost, p.hs_stream));
+        GPHM_CUDA_OK(cudaMemcpyAsync(ctx.hvU, ctx.vU, sizeof(double) * ctx.nf, cudaMemcpyDeviceToHost, p.hs_stream));
+        return GPHM_OK;
+    };
+    const int rc = logjoint_grad(*plan, U, sm, plan->gU, plan->gsmall, terms, 0, st);
+    plan->u_ready = nullptr;
+    plan->on_gu = nullptr;
+    if (rc != GPHM_OK) { cudaStreamSynchronize(plan->hs_stream); cudaStreamSynchronize(st); return rc; }
+    if (!plan->gu_hook_ran) {            // dense path: no early hand-over, Adam(U) after the whole gradient
+        GPHM_CUDA_OK(cudaEventRecord(plan->hs_ev_mv, plan->hs_stream));
+        GPHM_CUDA_OK(cudaStreamWaitEvent(st, plan->hs_ev_mv, 0));
+        GPHM_TRY(launch_adam(U, plan->gU, mU, vU, nf, plan->hs_count, lr, st));
+        GPHM_CUDA_OK(cudaMemcpyAsync(h_U, U, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+        GPHM_CUDA_OK(cudaMemcpyAsync(h_mU, mU, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+        GPHM_CUDA_OK(cudaMemcpyAsync(h_vU, vU, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+    }
     GPHM_TRY(launch_adam(sm, plan->gsmall, msm, vsm, ns, plan->hs_count, lr, st));
+    if (plan->gu_hook_ran) GPHM_CUDA_OK(cudaStreamWaitEvent(st, plan->hs_ev_adam, 0));      // Adam(U) has read the count
     GPHM_TRY(launch_count_inc(plan->hs_count, st));
-    GPHM_CUDA_OK(cudaMemcpyAsync(h_U, U, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
-    GPHM_CUDA_OK(cudaMemcpyAsync(h_mU, mU, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
-    GPHM_CUDA_OK(cudaMemcpyAsync(h_vU, vU, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
     GPHM_CUDA_OK(cudaMemcpyAsync(h_small, sm, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
     GPHM_CUDA_OK(cudaMemcpyAsync(h_msmall, msm, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
     GPHM_CUDA_OK(cudaMemcpyAsync(h_vsmall, vsm, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
     GPHM_CUDA_OK(cudaMemcpyAsync(h_count, plan->hs_count, sizeof(long long), cudaMemcpyDeviceToHost, st));
     GPHM_CUDA_OK(cudaMemcpyAsync(h_terms, terms, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
     GPHM_CUDA_OK(cudaStreamSynchronize(st));
+    GPHM_CUDA_OK(cudaStreamSynchronize(plan->hs_stream));
     return GPHM_OK;
 }
 

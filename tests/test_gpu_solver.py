@@ -320,3 +320,35 @@ def test_extra_gp_second_stage_parity(gphm, oracle, equation):
     assert log["epoch_list"] == full[:len(log["epoch_list"])] and np.isfinite(log["loss_list"]).all() and min_err < 2.0
     # the reference's rule (model_GP_solver_1d_extra.py:316-321): stop once the error rose more than 7 times
     assert early["flag"] == (len(log["epoch_list"]) < len(full))
+
+
+@pytest.mark.parametrize("mode", [0, 16])
+@pytest.mark.parametrize("dim", [2, 1])
+def test_step_host_matches_step_inplace(gphm, oracle, mode, dim):
+    """gphm_step_host (pinned host buffers in / out, transfers overlapped with the factor stage and the
+    theta-gradient) returns exactly what the device-resident gphm_step computes, three steps in a row."""
+    O = oracle
+    Q = 6
+    if dim == 2:
+        p, _, _ = O.make_problem_2d("allencahn_2d-mix-sincos", "SE_Cos_1d", 72, 1.0, M=8, N2=56)
+        core = gphm.solver_core.SolverCore(2, "SE_Cos_1d", "allencahn", p.x.numpy(), p.y.numpy(), p.src.numpy(), p.bvals.numpy(),
+                                           None, p.llk_weight, 1.0, 1.0, 1e-6, Q, force_general=mode)
+        params = O.state_S1(p, Q=Q, freq_scale=5.0)
+    else:
+        p, _, _ = O.make_problem_1d("poisson_1d-sin_cos", "Matern52_Cos_1d", 90, 2 * math.pi)
+        core = gphm.solver_core.SolverCore(1, "Matern52_Cos_1d", "poisson", p.x.numpy(), None, p.src.numpy(), p.yb.numpy(),
+                                           p.xind.numpy(), p.llk_weight, 1.0, 1.0, 1e-6, Q, force_general=mode)
+        params = O.init_params_1d(90, Q, 5.0)
+        params["u"] = (0.3 * torch.sin(2 * p.x)).reshape(-1, 1)
+    st = core.new_state(params)
+    pin = lambda t: t.detach().cpu().clone().pin_memory()
+    h = [pin(st.U), pin(st.small), pin(st.mU), pin(st.vU), pin(st.msmall), pin(st.vsmall), pin(st.count)]
+    hterms = torch.zeros(8, dtype=torch.float64).pin_memory()
+    for k in range(3):
+        core.step_inplace(st, 0.01)
+        core.step_host(h[0], h[1], h[2], h[3], h[4], h[5], h[6], hterms, 0.01)
+        torch.cuda.synchronize()
+        assert torch.equal(hterms, st.terms.cpu()), k
+        for a, b in zip(h, (st.U, st.small, st.mU, st.vU, st.msmall, st.vsmall, st.count)):
+            assert torch.equal(a, b.cpu()), k
+    assert int(h[6]) == 3
