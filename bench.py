@@ -45,9 +45,6 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
     ap.add_argument("--no-peak", action="store_true", help="profiling runs only: skip the cuBLAS DGEMM denominator")
     ap.add_argument("--no-general", action="store_true", help="skip the short dense-path (Cholesky + DGEMM) measurement")
-    ap.add_argument("--overlap", action="store_true",
-                    help="N > 1: keep every exchange on the communication stream until its result is needed (measured slower: "
-                         "the NCCL kernels and the one-CTA-per-SM FFT kernels evict each other)")
     ap.add_argument("--workload", default="grid", choices=["grid", "ensemble"],
                     help="grid: the 4096^2 step (BASELINE metric, the default); ensemble: BASELINE configs[4], independent "
                          "solves partitioned over the ranks (64 members per GPU, weak scaling)")
@@ -224,8 +221,7 @@ def run_ours(args, rank, world, local):
     else:
         from importlib import import_module
         distmod = import_module("gaussian-process-slover-for-high-freq-pde_b200.dist")
-        solver = distmod.ShardedSolver2D(KERNEL, "poisson", X_col[0], X_col[1], src, bvals, LLK, 1.0, 1.0, 1e-6, Q, LR,
-                                         overlap=args.overlap)
+        solver = distmod.ShardedSolver2D(KERNEL, "poisson", X_col[0], X_col[1], src, bvals, LLK, 1.0, 1.0, 1e-6, Q, LR)
         solver.init_state(FREQ_SCALE)
         step = solver.step
         st = None

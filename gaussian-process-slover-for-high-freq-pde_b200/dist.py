@@ -247,7 +247,7 @@ class ShardedSolver2D(object):
     construct it with identical arguments; `step()` is collective."""
 
     def __init__(self, kernel_name, eq_name, x, y, src, bvals, llk_weight, logdet, beta, jitter, Q, lr, ops=None,
-                 group=None, force_general=0, overlap=False):
+                 group=None, force_general=0):
         import numpy as np
         self.group = group
         self.P = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -282,7 +282,6 @@ class ShardedSolver2D(object):
         self.count = ops.zeros((1,), dtype=torch.int64)
         self.terms = ops.zeros((8,))
         self.acc = ops.zeros((3 + ns,))
-        self.overlap = bool(overlap)
         self.bytes_exchanged = 0
 
     # ---- state ---------------------------------------------------------------------------------
@@ -403,29 +402,24 @@ class ShardedSolver2D(object):
         """All-FFT step (both axes on the Toeplitz inverse generator): four K^-1 applications
         (V1 = K1^-1 (c1 D1^T G + Bt/2), V2 = (G D2 + A/2) K2^-1, dU = V1 + V2 + ...), axis-1 operands
         kept as transposed column blocks, four all-to-alls:  [U] R->Ct, [c1 D1 A, A] Ct->R, [G, Bt] R->Ct, [V1] Ct->R.
-        The first exchange runs on the communication stream beside the (serial, 4-CTA) Schur recursion; with
-        `overlap` every exchange is issued there as early as its operands exist and joined as late as its results
-        are needed, with axis-2 work in between.  The loss sums do not feed the reverse pass, so they share ONE
-        all-reduce with the theta-gradients at the end."""
+        The first exchange runs on the communication stream beside the (serial, 4-CTA) Schur recursion, which
+        needs only theta.  (Keeping the later exchanges in flight behind axis-2 work was measured and rejected:
+        an NCCL kernel and a one-CTA-per-SM FFT kernel evict each other, 10.7 vs 4.8 ms per step at P = 2.)
+        The loss sums do not feed the reverse pass, so they share ONE all-reduce with the theta-gradients."""
         o, Q, c1 = self.ops, self.Q, self.c1
         N1, N2 = self.N1, self.N2
         small, U_r = self.small, self.U
         fork = getattr(o, "fork", None) or (lambda fn: (fn(), None))
         join = getattr(o, "join", None) or (lambda h: h[0])
-        lazy = self.overlap
         hU = fork(lambda: self.r2ct([U_r]))
         o.factor(small, 3)                          # O(n^2) generators + spectra, local to every rank
         ld = o.logdets()
         (U_ct,) = join(hU)
         At = o.kinv_rows(0, U_ct, "At")                                           # (K1^-1 U)^T      (Ct)
         Rt = o.toeplitz_rows_add(0, False, At, c1, 0.0, None, o.new("Rt", At.shape), True)      # (c1 D1 A)^T
-        hRA = fork(lambda: self.ct2r([Rt, At]))
-        if not lazy:
-            R_r, A_r = join(hRA)
+        R_r, A_r = self.ct2r([Rt, At])
         Bt_r = o.kinv_rows(1, U_r, "Bt_r")                                        # U K2^-1          (R)
         eb, bg = o.boundary(U_r, self.bidx, self.bvals)
-        if lazy:
-            R_r, A_r = join(hRA)
         o.toeplitz_rows_add(1, False, Bt_r, 1.0, 1.0, R_r, R_r, True)             # + Bt D2^T
         acc = self.acc                               # [eqgap, quad, bgap | 6Q theta-gradients | 2 unused]: one all-reduce
         acc.zero_()
@@ -435,23 +429,15 @@ class ShardedSolver2D(object):
         gs = acc[3:]
         lead = self.rank == 0                        # the K^-1 (log-det) term is added once
         # backward
-        hGB = fork(lambda: self.r2ct([G_r, Bt_r]))
-        if not lazy:
-            G_ct, Btt = join(hGB)
-        P2 = o.toeplitz_rows_add(1, True, G_r, 1.0, 0.5, A_r, o.new("P2", G_r.shape), False)    # G D2 + A/2
-        V2_r = o.kinv_rows(1, P2, "V2_r")
-        o.theta_grad_pairs(1, V2_r, G_r, lead, 0.5 * self.logdet * N1, 1.0, small, gs[3 * Q:6 * Q])
-        if lazy:
-            G_ct, Btt = join(hGB)
+        G_ct, Btt = self.r2ct([G_r, Bt_r])
         T0 = o.toeplitz_rows_add(0, True, G_ct, c1, 0.5, Btt, o.new("T0", G_ct.shape), False)   # (c1 D1^T G + Bt/2)^T
         V1t = o.kinv_rows(0, T0, "V1t")
-        hV1 = fork(lambda: self.ct2r([V1t]))
-        if not lazy:
-            (V1_r,) = join(hV1)
-        o.theta_grad_pairs(0, V1t, G_ct, lead, 0.5 * self.logdet * N2, c1, small, gs[0:3 * Q])
-        if lazy:
-            (V1_r,) = join(hV1)
+        (V1_r,) = self.ct2r([V1t])
+        P2 = o.toeplitz_rows_add(1, True, G_r, 1.0, 0.5, A_r, o.new("P2", G_r.shape), False)    # G D2 + A/2
+        V2_r = o.kinv_rows(1, P2, "V2_r")
         gU_r = o.grad_u_sum(U_r, G_r, V1_r, V2_r, self.bidx, eb, self.nseg0, small)
+        o.theta_grad_pairs(0, V1t, G_ct, lead, 0.5 * self.logdet * N2, c1, small, gs[0:3 * Q])
+        o.theta_grad_pairs(1, V2_r, G_r, lead, 0.5 * self.logdet * N1, 1.0, small, gs[3 * Q:6 * Q])
         self._allreduce(acc)
         o.finalize(acc[0:3], ld, small, self.terms, gs)                           # terms[8]; gs[6Q], gs[6Q+1]
         self.gsmall.copy_(gs)
