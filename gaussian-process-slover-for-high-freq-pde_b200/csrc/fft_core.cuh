@@ -25,6 +25,17 @@ constexpr int FFT_ACC = FFT_MAX_L / FFT_THREADS;      // spectrum bins per threa
 // slots) need blockDim.x >= L / 16.
 // NT > 0: compile-time stride (the 512-thread launches of long transforms); NT = 0: blockDim.x.
 template <int NT> __device__ __forceinline__ int fft_nt() { return NT > 0 ? NT : (int)blockDim.x; }
+// Octant groups (L = 8192 on 512 threads).  After the first forward pass the eight octants of the data are
+// independent sub-transforms until the last inverse pass, and the butterfly -> thread map of every pass in
+// between (b = tid + k*512, octant = b >> 7) keeps octants g and g+4 in thread group g = tid >> 7 (4 warps, one per
+// scheduler).  With GR those passes synchronise per group (named barriers 1..4, 128 threads) instead of per CTA:
+// 2 CTA-wide barriers per convolution instead of 9, and the groups no longer move through their
+// load / compute / store phases in step.
+__device__ __forceinline__ void fft_group_sync(int tid) { asm volatile("bar.sync %0, 128;" :: "r"(1 + (tid >> 7)) : "memory"); }
+template <bool GR> __device__ __forceinline__ void fft_pass_sync(int tid) {
+    if (GR) fft_group_sync(tid);
+    else __syncthreads();
+}
 __host__ inline int fft_threads_for(int L) { return std::max(64, std::min(FFT_THREADS, L >> 3)); }
 
 // shared-memory layout: one pad slot per 8 complex values, so that the 8 lanes of a quarter-warp
@@ -130,7 +141,7 @@ __device__ __forceinline__ void bfly8_dit_inv(double2 (&e)[8], double2 u1, doubl
 }
 
 // Radix-8 DIF pass over stages s..s+2; tw = this pass' compact table [w1 | w2 | w4], q entries each.
-template <int NT = FFT_THREADS>
+template <int NT = FFT_THREADS, bool GR = false>
 __device__ __forceinline__ void dif_pass8(double2* xs, int L, int logL, int s, const double2* tw, int tid) {
     const int lq = logL - s - 3, q = 1 << lq;
     for (int b = tid; b < (L >> 3); b += fft_nt<NT>()) {
@@ -143,10 +154,10 @@ __device__ __forceinline__ void dif_pass8(double2* xs, int L, int logL, int s, c
 #pragma unroll
         for (int m = 0; m < 8; ++m) xs[PADI(base + m * q)] = e[m];
     }
-    __syncthreads();
+    fft_pass_sync<GR>(tid);
 }
 
-template <int NT = FFT_THREADS>
+template <int NT = FFT_THREADS, bool GR = false>
 __device__ __forceinline__ void dit_pass8(double2* xs, int L, int logL, int s, const double2* tw, int tid) {
     const int q = 1 << s;
     for (int b = tid; b < (L >> 3); b += fft_nt<NT>()) {
@@ -159,7 +170,7 @@ __device__ __forceinline__ void dit_pass8(double2* xs, int L, int logL, int s, c
 #pragma unroll
         for (int m = 0; m < 8; ++m) xs[PADI(base + m * q)] = e[m];
     }
-    __syncthreads();
+    fft_pass_sync<GR>(tid);
 }
 
 // Tail (forward) / head (inverse) pass of 2^K points with unit stride: every twiddle is a constant.
@@ -326,31 +337,34 @@ __device__ __forceinline__ void dif_first(double2* xs, int L, const double2* tw,
 }
 
 // Forward passes 1 .. np8-1 (after dif_first).
-template <int NT = FFT_THREADS>
+template <int NT = FFT_THREADS, bool GR = false>
 __device__ __forceinline__ void dif_middle(double2* xs, int L, int logL, int np8, int tid) {
     const double2* tw = fft_twiddles(xs, L) + 3 * (L >> 3);
-    for (int p = 1; p < np8; ++p) { dif_pass8<NT>(xs, L, logL, 3 * p, tw, tid); tw += 3 * (L >> (3 * p + 3)); }
+    for (int p = 1; p < np8; ++p) { dif_pass8<NT, GR>(xs, L, logL, 3 * p, tw, tid); tw += 3 * (L >> (3 * p + 3)); }
 }
 // Inverse passes at stages KT, KT+3, ..., logL-6 (all but the last one).
-template <int NT = FFT_THREADS>
+// With GR the caller needs a CTA-wide barrier before the last inverse pass (it mixes the octants): added here.
+template <int NT = FFT_THREADS, bool GR = false>
 __device__ __forceinline__ void dit_middle(double2* xs, int L, int logL, int np8, int KT, int tid) {
     const double2* tw = fft_twiddles(xs, L);
     for (int p = 0; p < np8; ++p) tw += 3 * (L >> (3 * p + 3));
     for (int p = np8 - 1; p >= 1; --p) {          // inverse stage s = logL - 3 - 3p pairs with forward pass p
         tw -= 3 * (L >> (3 * p + 3));
-        dit_pass8<NT>(xs, L, logL, logL - 3 - 3 * p, tw, tid);
+        dit_pass8<NT, GR>(xs, L, logL, logL - 3 - 3 * p, tw, tid);
     }
+    if (GR) __syncthreads();
 }
 
 // Forward tail + functor + inverse head on groups of 2^KT contiguous (bit-reversed-order) bins.
 // f(slot, p, v): slot = static register slot (0 .. 15) of this thread, p = bin position, v = spectrum value.
-template <int KT, int NT = FFT_THREADS, class F>
+template <int KT, int NT = FFT_THREADS, bool GR = false, class F>
 __device__ __forceinline__ void mid_fused(double2* xs, int L, int tid, F f) {
     constexpr int R = 1 << KT;
     constexpr int MAXG = FFT_MAX_L / (R * FFT_THREADS);
 #pragma unroll
     for (int i = 0; i < MAXG; ++i) {
-        const int g = tid + i * fft_nt<NT>();
+        // GR (L = 8192, KT = 1): iteration i of group g = tid >> 7 works on octant g + 4 (i >> 2), 128 bin pairs per quarter
+        const int g = GR ? ((((tid >> 7) + 4 * (i >> 2)) << 9) + (tid & 127) + 128 * (i & 3)) : tid + i * fft_nt<NT>();
         if (g < (L >> KT)) {
             const int base = g << KT;
             double2 e[R];
@@ -364,7 +378,7 @@ __device__ __forceinline__ void mid_fused(double2* xs, int L, int tid, F f) {
             for (int m = 0; m < R; ++m) xs[PADI(base + m)] = e[m];
         }
     }
-    __syncthreads();
+    fft_pass_sync<GR>(tid);
 }
 
 // Last inverse pass (stage logL-3, q = L/8); st(index, value, addend) for the live half (index < L/2).

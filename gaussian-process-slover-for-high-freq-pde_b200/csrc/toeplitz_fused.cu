@@ -15,6 +15,7 @@
 // convolutions into one register butterfly, the global store into the last pass - 2 np8 + 1
 // sweeps per convolution (9 for L = 8192) instead of 12, and 24 instead of 48 for K^-1.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 #include "fft_core.cuh"
@@ -70,7 +71,7 @@ __device__ __forceinline__ RowPairIO row_pair(const double* X, int ldx, double* 
 
 }  // namespace
 
-template <int KT, int NT>
+template <int KT, int NT, bool GR>
 __global__ void __launch_bounds__(FFT_THREADS, 1)
 toeplitz_apply_fused_kernel(const double* X, int rows, int n, int ldx, const double2* __restrict__ spec, int L,
                             int logL, const double2* __restrict__ W, double alpha, double beta, const double* Add, int lda,
@@ -85,16 +86,16 @@ toeplitz_apply_fused_kernel(const double* X, int rows, int n, int ldx, const dou
         const RowPairIO io = row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr, alpha, beta);
         if (pr + (int)gridDim.x < npairs) row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr + gridDim.x, alpha, beta).template prefetch<NT>(tid);
         dif_first<NT>(xs, L, tw0, tid, [&](int idx) { return io.load(idx); });
-        dif_middle<NT>(xs, L, logL, np8, tid);
+        dif_middle<NT, GR>(xs, L, logL, np8, tid);
         double2* so = SpecOut ? SpecOut + (size_t)pr * L : nullptr;      // spectrum of the packed row pair, kept for the diagonal sums
-        mid_fused<KT, NT>(xs, L, tid, [&](int, int p, double2 v) { if (so) so[p] = v; return cmul(v, spec[p]); });
-        dit_middle<NT>(xs, L, logL, np8, KT, tid);
+        mid_fused<KT, NT, GR>(xs, L, tid, [&](int, int p, double2 v) { if (so) so[p] = v; return cmul(v, spec[p]); });
+        dit_middle<NT, GR>(xs, L, logL, np8, KT, tid);
         dit_last<NT>(xs, L, tw0, tid, [&](int idx) { return io.addend(idx); }, [&](int idx, double2 v, double2 add) { io.store(idx, v, add); });
     }
 }
 
 // spec: the four Gohberg-Semencul spectra of gs_prepare_kernel, L complex values each.
-template <int KT, int NT>
+template <int KT, int NT, bool GR>
 __global__ void __launch_bounds__(FFT_THREADS, 1)
 gs_apply_fused_kernel(const double* X, int rows, int n, int ldx, const double2* __restrict__ spec, int L,
                       int logL, const double2* __restrict__ W, double alpha, double beta, const double* Add, int lda,
@@ -114,24 +115,24 @@ gs_apply_fused_kernel(const double* X, int rows, int n, int ldx, const double2* 
         const RowPairIO io = row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr, alpha, beta);
         if (pr + (int)gridDim.x < npairs) row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr + gridDim.x, alpha, beta).template prefetch<NT>(tid);
         dif_first<NT>(xs, L, tw0, tid, [&](int idx) { return io.load(idx); });
-        dif_middle<NT>(xs, L, logL, np8, tid);
-        mid_fused<KT, NT>(xs, L, tid, [&](int slot, int p, double2 v) { stash[slot] = v; return cmul(v, sGt[p]); });   // Z kept
-        dit_middle<NT>(xs, L, logL, np8, KT, tid);
+        dif_middle<NT, GR>(xs, L, logL, np8, tid);
+        mid_fused<KT, NT, GR>(xs, L, tid, [&](int slot, int p, double2 v) { stash[slot] = v; return cmul(v, sGt[p]); });   // Z kept
+        dit_middle<NT, GR>(xs, L, logL, np8, KT, tid);
         dit_last_dif_first<NT>(xs, L, tw0, tid, n);                                   // [L(g)^T v]_n
-        dif_middle<NT>(xs, L, logL, np8, tid);
-        mid_fused<KT, NT>(xs, L, tid, [&](int slot, int p, double2 v) {
+        dif_middle<NT, GR>(xs, L, logL, np8, tid);
+        mid_fused<KT, NT, GR>(xs, L, tid, [&](int slot, int p, double2 v) {
             const double2 z = stash[slot];
             stash[slot] = cmul(v, sG[p]);                                         // G'.Q1 kept
             return cmul(z, sHt[p]);
         });
-        dit_middle<NT>(xs, L, logL, np8, KT, tid);
+        dit_middle<NT, GR>(xs, L, logL, np8, KT, tid);
         dit_last_dif_first<NT>(xs, L, tw0, tid, n);                                   // [L(h)^T v]_n
-        dif_middle<NT>(xs, L, logL, np8, tid);
-        mid_fused<KT, NT>(xs, L, tid, [&](int slot, int p, double2 v) {
+        dif_middle<NT, GR>(xs, L, logL, np8, tid);
+        mid_fused<KT, NT, GR>(xs, L, tid, [&](int slot, int p, double2 v) {
             const double2 a = stash[slot], b = cmul(v, sH[p]);
             return make_double2(a.x + b.x, a.y + b.y);
         });
-        dit_middle<NT>(xs, L, logL, np8, KT, tid);
+        dit_middle<NT, GR>(xs, L, logL, np8, KT, tid);
         dit_last<NT>(xs, L, tw0, tid, [&](int idx) { return io.addend(idx); }, [&](int idx, double2 v, double2 add) { io.store(idx, v, add); });
     }
 }
@@ -142,7 +143,7 @@ gs_apply_fused_kernel(const double* X, int rows, int n, int ldx, const double2* 
 // conj(X1) Y1 + i (conj(X0) Y1 - conj(X1) Y0): the cross term transforms back to a purely imaginary
 // sequence, so the real part of the inverse transform of the sum is exactly the sum over ROWS of the
 // cross-correlations - one transform per row pair and no spectrum separation.
-template <int KT, int NT>
+template <int KT, int NT, bool GR>
 __global__ void __launch_bounds__(FFT_THREADS, 1)
 xcorr_pairs_kernel(const double* __restrict__ X, int rows, int n, int ldx, const double2* __restrict__ SpecY, int L, int logL,
                    const double2* __restrict__ W, double weight, double2* __restrict__ partial) {
@@ -169,7 +170,7 @@ xcorr_pairs_kernel(const double* __restrict__ X, int rows, int n, int ldx, const
             if (r0 + 2 * (int)gridDim.x + 1 < rows) prefetch_l2<NT>(X + (size_t)(r0 + 2 * gridDim.x + 1) * ldx, sizeof(double) * n, tid);
         }
         dif_first<NT>(xs, L, tw0, tid, [&](int idx) { return idx < n ? make_double2(x0[idx], two ? x1[idx] : 0.0) : make_double2(0.0, 0.0); });
-        dif_middle<NT>(xs, L, logL, np8, tid);
+        dif_middle<NT, false>(xs, L, logL, np8, tid);      // ungrouped: the accumulation below uses the plain bin map
 #pragma unroll
         for (int i = 0; i < MAXG; ++i) {                       // forward tail in registers + accumulation
             const int g = tid + i * fft_nt<NT>();
@@ -201,19 +202,27 @@ xcorr_pairs_kernel(const double* __restrict__ X, int rows, int n, int ldx, const
     }
 }
 
-// (KT, NT) dispatch: NT = FFT_THREADS (compile-time strides) for the full-size CTA, 0 (blockDim.x) for shorter transforms
+// (KT, NT, GR) dispatch: NT = FFT_THREADS (compile-time strides) for the full-size CTA, 0 (blockDim.x) for shorter
+// transforms; GR (octant-group barriers, fft_core.cuh) for L = FFT_MAX_L, whose tail is one stage (KT = 1)
 #define GPHM_FUSED_LAUNCH(K, GRID, ...)                                                                      \
     do {                                                                                                     \
-        if (nt == FFT_THREADS) {                                                                             \
-            if (KT == 1) K<1, FFT_THREADS><<<GRID, nt, smem, st>>>(__VA_ARGS__);                             \
-            else if (KT == 2) K<2, FFT_THREADS><<<GRID, nt, smem, st>>>(__VA_ARGS__);                        \
-            else K<3, FFT_THREADS><<<GRID, nt, smem, st>>>(__VA_ARGS__);                                     \
+        if (nt == FFT_THREADS && L == FFT_MAX_L && KT == 1 && !getenv_flag("GPHM_FFT_NO_GROUPS")) {          \
+            K<1, FFT_THREADS, true><<<GRID, nt, smem, st>>>(__VA_ARGS__);                                    \
+        } else if (nt == FFT_THREADS) {                                                                      \
+            if (KT == 1) K<1, FFT_THREADS, false><<<GRID, nt, smem, st>>>(__VA_ARGS__);                      \
+            else if (KT == 2) K<2, FFT_THREADS, false><<<GRID, nt, smem, st>>>(__VA_ARGS__);                 \
+            else K<3, FFT_THREADS, false><<<GRID, nt, smem, st>>>(__VA_ARGS__);                              \
         } else {                                                                                             \
-            if (KT == 1) K<1, 0><<<GRID, nt, smem, st>>>(__VA_ARGS__);                                       \
-            else if (KT == 2) K<2, 0><<<GRID, nt, smem, st>>>(__VA_ARGS__);                                  \
-            else K<3, 0><<<GRID, nt, smem, st>>>(__VA_ARGS__);                                               \
+            if (KT == 1) K<1, 0, false><<<GRID, nt, smem, st>>>(__VA_ARGS__);                                \
+            else if (KT == 2) K<2, 0, false><<<GRID, nt, smem, st>>>(__VA_ARGS__);                           \
+            else K<3, 0, false><<<GRID, nt, smem, st>>>(__VA_ARGS__);                                        \
         }                                                                                                    \
     } while (0)
+
+static bool getenv_flag(const char* name) {       // read once per name would need a map: two callers, cheap enough
+    const char* v = getenv(name);
+    return v && v[0] && v[0] != '0';
+}
 
 static int ilog2f(int L) { int l = 0; while ((1 << l) < L) ++l; return l; }
 
@@ -221,9 +230,10 @@ int toeplitz_fused_init() {
     static int done = -1;
     if (done >= 0) return done;
     const int bytes = (int)fft_smem_bytes(FFT_MAX_L);
-#define GPHM_FUSED_ATTR(K, KT, NT) GPHM_CUDA_OK(cudaFuncSetAttribute(K<KT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
-#define GPHM_FUSED_ATTR6(K) GPHM_FUSED_ATTR(K, 1, FFT_THREADS); GPHM_FUSED_ATTR(K, 2, FFT_THREADS); GPHM_FUSED_ATTR(K, 3, FFT_THREADS); \
-                            GPHM_FUSED_ATTR(K, 1, 0); GPHM_FUSED_ATTR(K, 2, 0); GPHM_FUSED_ATTR(K, 3, 0)
+#define GPHM_FUSED_ATTR(K, KT, NT, GR) GPHM_CUDA_OK(cudaFuncSetAttribute(K<KT, NT, GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
+#define GPHM_FUSED_ATTR6(K) GPHM_FUSED_ATTR(K, 1, FFT_THREADS, false); GPHM_FUSED_ATTR(K, 2, FFT_THREADS, false); GPHM_FUSED_ATTR(K, 3, FFT_THREADS, false); \
+                            GPHM_FUSED_ATTR(K, 1, 0, false); GPHM_FUSED_ATTR(K, 2, 0, false); GPHM_FUSED_ATTR(K, 3, 0, false); \
+                            GPHM_FUSED_ATTR(K, 1, FFT_THREADS, true)
     GPHM_FUSED_ATTR6(toeplitz_apply_fused_kernel);
     GPHM_FUSED_ATTR6(xcorr_pairs_kernel);
     GPHM_FUSED_ATTR6(gs_apply_fused_kernel);
