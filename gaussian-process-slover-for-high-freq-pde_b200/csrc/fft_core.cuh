@@ -355,6 +355,13 @@ __device__ __forceinline__ void dit_middle(double2* xs, int L, int logL, int np8
     if (GR) __syncthreads();
 }
 
+// Bin group (2^KT contiguous bins) of iteration i of a thread in the tail / head pass.  GR (L = 8192, KT = 1):
+// thread group tid >> 7 works on its own octants, tid >> 7 + 4 (i >> 2), 128 bin pairs per quarter of an octant.
+template <int NT, bool GR>
+__device__ __forceinline__ int fft_mid_group(int tid, int i) {
+    return GR ? ((((tid >> 7) + 4 * (i >> 2)) << 9) + (tid & 127) + 128 * (i & 3)) : tid + i * fft_nt<NT>();
+}
+
 // Forward tail + functor + inverse head on groups of 2^KT contiguous (bit-reversed-order) bins.
 // f(slot, p, v): slot = static register slot (0 .. 15) of this thread, p = bin position, v = spectrum value.
 template <int KT, int NT = FFT_THREADS, bool GR = false, class F>
@@ -363,8 +370,7 @@ __device__ __forceinline__ void mid_fused(double2* xs, int L, int tid, F f) {
     constexpr int MAXG = FFT_MAX_L / (R * FFT_THREADS);
 #pragma unroll
     for (int i = 0; i < MAXG; ++i) {
-        // GR (L = 8192, KT = 1): iteration i of group g = tid >> 7 works on octant g + 4 (i >> 2), 128 bin pairs per quarter
-        const int g = GR ? ((((tid >> 7) + 4 * (i >> 2)) << 9) + (tid & 127) + 128 * (i & 3)) : tid + i * fft_nt<NT>();
+        const int g = fft_mid_group<NT, GR>(tid, i);
         if (g < (L >> KT)) {
             const int base = g << KT;
             double2 e[R];

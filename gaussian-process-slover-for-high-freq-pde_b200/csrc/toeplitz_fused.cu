@@ -170,10 +170,10 @@ xcorr_pairs_kernel(const double* __restrict__ X, int rows, int n, int ldx, const
             if (r0 + 2 * (int)gridDim.x + 1 < rows) prefetch_l2<NT>(X + (size_t)(r0 + 2 * gridDim.x + 1) * ldx, sizeof(double) * n, tid);
         }
         dif_first<NT>(xs, L, tw0, tid, [&](int idx) { return idx < n ? make_double2(x0[idx], two ? x1[idx] : 0.0) : make_double2(0.0, 0.0); });
-        dif_middle<NT, false>(xs, L, logL, np8, tid);      // ungrouped: the accumulation below uses the plain bin map
+        dif_middle<NT, GR>(xs, L, logL, np8, tid);
 #pragma unroll
         for (int i = 0; i < MAXG; ++i) {                       // forward tail in registers + accumulation
-            const int g = tid + i * fft_nt<NT>();
+            const int g = fft_mid_group<NT, GR>(tid, i);
             if (g < (L >> KT)) {
                 const int base = g << KT;
                 double2 y[R], e[R];
@@ -194,7 +194,7 @@ xcorr_pairs_kernel(const double* __restrict__ X, int rows, int n, int ldx, const
     double2* out = partial + (size_t)blockIdx.x * L;
 #pragma unroll
     for (int i = 0; i < MAXG; ++i) {
-        const int g = tid + i * fft_nt<NT>();
+        const int g = fft_mid_group<NT, GR>(tid, i);
         if (g < (L >> KT)) {
 #pragma unroll
             for (int m = 0; m < R; ++m) out[(g << KT) + m] = make_double2(weight * acc[i * R + m].x, weight * acc[i * R + m].y);
