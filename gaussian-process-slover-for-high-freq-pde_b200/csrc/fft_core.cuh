@@ -25,17 +25,18 @@ constexpr int FFT_ACC = FFT_MAX_L / FFT_THREADS;      // spectrum bins per threa
 // slots) need blockDim.x >= L / 16.
 // NT > 0: compile-time stride (the 512-thread launches of long transforms); NT = 0: blockDim.x.
 template <int NT> __device__ __forceinline__ int fft_nt() { return NT > 0 ? NT : (int)blockDim.x; }
-// Octant groups (L = 8192 on 512 threads).  After the first forward pass the eight octants of the data are
-// independent sub-transforms until the last inverse pass, and the butterfly -> thread map of every pass in
-// between (b = tid + k*512, octant = b >> 7) keeps octants g and g+4 in thread group g = tid >> 7 (4 warps, one per
-// scheduler).  With GR those passes synchronise per group (named barriers 1..4, 128 threads) instead of per CTA:
-// 2 CTA-wide barriers per convolution instead of 9, and the groups no longer move through their
-// load / compute / store phases in step.
-__device__ __forceinline__ void fft_group_sync(int tid) { asm volatile("bar.sync %0, 128;" :: "r"(1 + (tid >> 7)) : "memory"); }
-template <bool GR> __device__ __forceinline__ void fft_pass_sync(int tid) {
-    if (GR) fft_group_sync(tid);
-    else __syncthreads();
+// Octant groups (L >= 512, L/8 threads; 512 threads at L = 8192).  After the first forward pass the eight
+// octants of the data are independent sub-transforms until the last inverse pass, and the butterfly -> thread map
+// of every pass in between (b = tid + k * threads, octant = b / (L/64)) keeps an octant inside one group of
+// G = L/64 consecutive threads (L = 8192: octants g and g+4 in group g of 128 threads, one warp per scheduler).
+// With GR those passes synchronise per group - a named barrier (ids 1..8) for G >= 64, __syncwarp below -
+// instead of per CTA: 2 CTA-wide barriers per convolution instead of 9.  lG = log2(G) = logL - 6.
+template <bool GR> __device__ __forceinline__ void fft_pass_sync(int tid, int lG) {
+    if (!GR) __syncthreads();
+    else if (lG >= 6) asm volatile("bar.sync %0, %1;" :: "r"(1 + (tid >> lG)), "r"(1 << lG) : "memory");
+    else __syncwarp();
 }
+__host__ inline bool fft_groups_supported(int L) { return L >= 512; }
 __host__ inline int fft_threads_for(int L) { return std::max(64, std::min(FFT_THREADS, L >> 3)); }
 
 // shared-memory layout: one pad slot per 8 complex values, so that the 8 lanes of a quarter-warp
@@ -154,7 +155,7 @@ __device__ __forceinline__ void dif_pass8(double2* xs, int L, int logL, int s, c
 #pragma unroll
         for (int m = 0; m < 8; ++m) xs[PADI(base + m * q)] = e[m];
     }
-    fft_pass_sync<GR>(tid);
+    fft_pass_sync<GR>(tid, logL - 6);
 }
 
 template <int NT = FFT_THREADS, bool GR = false>
@@ -170,7 +171,7 @@ __device__ __forceinline__ void dit_pass8(double2* xs, int L, int logL, int s, c
 #pragma unroll
         for (int m = 0; m < 8; ++m) xs[PADI(base + m * q)] = e[m];
     }
-    fft_pass_sync<GR>(tid);
+    fft_pass_sync<GR>(tid, logL - 6);
 }
 
 // Tail (forward) / head (inverse) pass of 2^K points with unit stride: every twiddle is a constant.
@@ -355,22 +356,25 @@ __device__ __forceinline__ void dit_middle(double2* xs, int L, int logL, int np8
     if (GR) __syncthreads();
 }
 
-// Bin group (2^KT contiguous bins) of iteration i of a thread in the tail / head pass.  GR (L = 8192, KT = 1):
-// thread group tid >> 7 works on its own octants, tid >> 7 + 4 (i >> 2), 128 bin pairs per quarter of an octant.
-template <int NT, bool GR>
-__device__ __forceinline__ int fft_mid_group(int tid, int i) {
-    return GR ? ((((tid >> 7) + 4 * (i >> 2)) << 9) + (tid & 127) + 128 * (i & 3)) : tid + i * fft_nt<NT>();
+// Bin group (2^KT contiguous bins) of iteration i of a thread in the tail / head pass.  GR: the thread group
+// tid >> lG works on its own octant(s): 8 >> KT iterations per octant, G bin groups of the octant per iteration.
+template <int KT, int NT, bool GR>
+__device__ __forceinline__ int fft_mid_group(int tid, int i, int L, int lG) {
+    if (!GR) return tid + i * fft_nt<NT>();
+    constexpr int IPO = 8 >> KT;                                  // iterations per octant
+    const int octant = (tid >> lG) + (fft_nt<NT>() >> lG) * (i / IPO);
+    return octant * ((L >> 3) >> KT) + (tid & ((1 << lG) - 1)) + ((i % IPO) << lG);
 }
 
 // Forward tail + functor + inverse head on groups of 2^KT contiguous (bit-reversed-order) bins.
 // f(slot, p, v): slot = static register slot (0 .. 15) of this thread, p = bin position, v = spectrum value.
 template <int KT, int NT = FFT_THREADS, bool GR = false, class F>
-__device__ __forceinline__ void mid_fused(double2* xs, int L, int tid, F f) {
+__device__ __forceinline__ void mid_fused(double2* xs, int L, int logL, int tid, F f) {
     constexpr int R = 1 << KT;
     constexpr int MAXG = FFT_MAX_L / (R * FFT_THREADS);
 #pragma unroll
     for (int i = 0; i < MAXG; ++i) {
-        const int g = fft_mid_group<NT, GR>(tid, i);
+        const int g = fft_mid_group<KT, NT, GR>(tid, i, L, logL - 6);
         if (g < (L >> KT)) {
             const int base = g << KT;
             double2 e[R];
@@ -384,7 +388,7 @@ __device__ __forceinline__ void mid_fused(double2* xs, int L, int tid, F f) {
             for (int m = 0; m < R; ++m) xs[PADI(base + m)] = e[m];
         }
     }
-    fft_pass_sync<GR>(tid);
+    fft_pass_sync<GR>(tid, logL - 6);
 }
 
 // Last inverse pass (stage logL-3, q = L/8); st(index, value, addend) for the live half (index < L/2).

@@ -88,7 +88,7 @@ toeplitz_apply_fused_kernel(const double* X, int rows, int n, int ldx, const dou
         dif_first<NT>(xs, L, tw0, tid, [&](int idx) { return io.load(idx); });
         dif_middle<NT, GR>(xs, L, logL, np8, tid);
         double2* so = SpecOut ? SpecOut + (size_t)pr * L : nullptr;      // spectrum of the packed row pair, kept for the diagonal sums
-        mid_fused<KT, NT, GR>(xs, L, tid, [&](int, int p, double2 v) { if (so) so[p] = v; return cmul(v, spec[p]); });
+        mid_fused<KT, NT, GR>(xs, L, logL, tid, [&](int, int p, double2 v) { if (so) so[p] = v; return cmul(v, spec[p]); });
         dit_middle<NT, GR>(xs, L, logL, np8, KT, tid);
         dit_last<NT>(xs, L, tw0, tid, [&](int idx) { return io.addend(idx); }, [&](int idx, double2 v, double2 add) { io.store(idx, v, add); });
     }
@@ -116,11 +116,11 @@ gs_apply_fused_kernel(const double* X, int rows, int n, int ldx, const double2* 
         if (pr + (int)gridDim.x < npairs) row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr + gridDim.x, alpha, beta).template prefetch<NT>(tid);
         dif_first<NT>(xs, L, tw0, tid, [&](int idx) { return io.load(idx); });
         dif_middle<NT, GR>(xs, L, logL, np8, tid);
-        mid_fused<KT, NT, GR>(xs, L, tid, [&](int slot, int p, double2 v) { stash[slot] = v; return cmul(v, sGt[p]); });   // Z kept
+        mid_fused<KT, NT, GR>(xs, L, logL, tid, [&](int slot, int p, double2 v) { stash[slot] = v; return cmul(v, sGt[p]); });   // Z kept
         dit_middle<NT, GR>(xs, L, logL, np8, KT, tid);
         dit_last_dif_first<NT>(xs, L, tw0, tid, n);                                   // [L(g)^T v]_n
         dif_middle<NT, GR>(xs, L, logL, np8, tid);
-        mid_fused<KT, NT, GR>(xs, L, tid, [&](int slot, int p, double2 v) {
+        mid_fused<KT, NT, GR>(xs, L, logL, tid, [&](int slot, int p, double2 v) {
             const double2 z = stash[slot];
             stash[slot] = cmul(v, sG[p]);                                         // G'.Q1 kept
             return cmul(z, sHt[p]);
@@ -128,7 +128,7 @@ gs_apply_fused_kernel(const double* X, int rows, int n, int ldx, const double2* 
         dit_middle<NT, GR>(xs, L, logL, np8, KT, tid);
         dit_last_dif_first<NT>(xs, L, tw0, tid, n);                                   // [L(h)^T v]_n
         dif_middle<NT, GR>(xs, L, logL, np8, tid);
-        mid_fused<KT, NT, GR>(xs, L, tid, [&](int slot, int p, double2 v) {
+        mid_fused<KT, NT, GR>(xs, L, logL, tid, [&](int slot, int p, double2 v) {
             const double2 a = stash[slot], b = cmul(v, sH[p]);
             return make_double2(a.x + b.x, a.y + b.y);
         });
@@ -173,7 +173,7 @@ xcorr_pairs_kernel(const double* __restrict__ X, int rows, int n, int ldx, const
         dif_middle<NT, GR>(xs, L, logL, np8, tid);
 #pragma unroll
         for (int i = 0; i < MAXG; ++i) {                       // forward tail in registers + accumulation
-            const int g = fft_mid_group<NT, GR>(tid, i);
+            const int g = fft_mid_group<KT, NT, GR>(tid, i, L, logL - 6);
             if (g < (L >> KT)) {
                 const int base = g << KT;
                 double2 y[R], e[R];
@@ -194,7 +194,7 @@ xcorr_pairs_kernel(const double* __restrict__ X, int rows, int n, int ldx, const
     double2* out = partial + (size_t)blockIdx.x * L;
 #pragma unroll
     for (int i = 0; i < MAXG; ++i) {
-        const int g = fft_mid_group<NT, GR>(tid, i);
+        const int g = fft_mid_group<KT, NT, GR>(tid, i, L, logL - 6);
         if (g < (L >> KT)) {
 #pragma unroll
             for (int m = 0; m < R; ++m) out[(g << KT) + m] = make_double2(weight * acc[i * R + m].x, weight * acc[i * R + m].y);
@@ -203,19 +203,22 @@ xcorr_pairs_kernel(const double* __restrict__ X, int rows, int n, int ldx, const
 }
 
 // (KT, NT, GR) dispatch: NT = FFT_THREADS (compile-time strides) for the full-size CTA, 0 (blockDim.x) for shorter
-// transforms; GR (octant-group barriers, fft_core.cuh) for L = FFT_MAX_L, whose tail is one stage (KT = 1)
+// transforms; GR = octant-group barriers (fft_core.cuh) for L >= 512
+#define GPHM_FUSED_KT(K, NT, GR, GRID, ...)                                                                  \
+    do {                                                                                                     \
+        if (KT == 1) K<1, NT, GR><<<GRID, nt, smem, st>>>(__VA_ARGS__);                                      \
+        else if (KT == 2) K<2, NT, GR><<<GRID, nt, smem, st>>>(__VA_ARGS__);                                 \
+        else K<3, NT, GR><<<GRID, nt, smem, st>>>(__VA_ARGS__);                                              \
+    } while (0)
 #define GPHM_FUSED_LAUNCH(K, GRID, ...)                                                                      \
     do {                                                                                                     \
-        if (nt == FFT_THREADS && L == FFT_MAX_L && KT == 1 && !getenv_flag("GPHM_FFT_NO_GROUPS")) {          \
-            K<1, FFT_THREADS, true><<<GRID, nt, smem, st>>>(__VA_ARGS__);                                    \
-        } else if (nt == FFT_THREADS) {                                                                      \
-            if (KT == 1) K<1, FFT_THREADS, false><<<GRID, nt, smem, st>>>(__VA_ARGS__);                      \
-            else if (KT == 2) K<2, FFT_THREADS, false><<<GRID, nt, smem, st>>>(__VA_ARGS__);                 \
-            else K<3, FFT_THREADS, false><<<GRID, nt, smem, st>>>(__VA_ARGS__);                              \
+        const bool gr = fft_groups_supported(L) && !getenv_flag("GPHM_FFT_NO_GROUPS");                      \
+        if (nt == FFT_THREADS) {                                                                             \
+            if (gr) GPHM_FUSED_KT(K, FFT_THREADS, true, GRID, __VA_ARGS__);                                  \
+            else GPHM_FUSED_KT(K, FFT_THREADS, false, GRID, __VA_ARGS__);                                    \
         } else {                                                                                             \
-            if (KT == 1) K<1, 0, false><<<GRID, nt, smem, st>>>(__VA_ARGS__);                                \
-            else if (KT == 2) K<2, 0, false><<<GRID, nt, smem, st>>>(__VA_ARGS__);                           \
-            else K<3, 0, false><<<GRID, nt, smem, st>>>(__VA_ARGS__);                                        \
+            if (gr) GPHM_FUSED_KT(K, 0, true, GRID, __VA_ARGS__);                                            \
+            else GPHM_FUSED_KT(K, 0, false, GRID, __VA_ARGS__);                                              \
         }                                                                                                    \
     } while (0)
 
@@ -231,12 +234,13 @@ int toeplitz_fused_init() {
     if (done >= 0) return done;
     const int bytes = (int)fft_smem_bytes(FFT_MAX_L);
 #define GPHM_FUSED_ATTR(K, KT, NT, GR) GPHM_CUDA_OK(cudaFuncSetAttribute(K<KT, NT, GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
-#define GPHM_FUSED_ATTR6(K) GPHM_FUSED_ATTR(K, 1, FFT_THREADS, false); GPHM_FUSED_ATTR(K, 2, FFT_THREADS, false); GPHM_FUSED_ATTR(K, 3, FFT_THREADS, false); \
-                            GPHM_FUSED_ATTR(K, 1, 0, false); GPHM_FUSED_ATTR(K, 2, 0, false); GPHM_FUSED_ATTR(K, 3, 0, false); \
-                            GPHM_FUSED_ATTR(K, 1, FFT_THREADS, true)
+#define GPHM_FUSED_ATTR3(K, NT, GR) GPHM_FUSED_ATTR(K, 1, NT, GR); GPHM_FUSED_ATTR(K, 2, NT, GR); GPHM_FUSED_ATTR(K, 3, NT, GR)
+#define GPHM_FUSED_ATTR6(K) GPHM_FUSED_ATTR3(K, FFT_THREADS, false); GPHM_FUSED_ATTR3(K, 0, false); \
+                            GPHM_FUSED_ATTR3(K, FFT_THREADS, true); GPHM_FUSED_ATTR3(K, 0, true)
     GPHM_FUSED_ATTR6(toeplitz_apply_fused_kernel);
     GPHM_FUSED_ATTR6(xcorr_pairs_kernel);
     GPHM_FUSED_ATTR6(gs_apply_fused_kernel);
+#undef GPHM_FUSED_ATTR3
 #undef GPHM_FUSED_ATTR6
 #undef GPHM_FUSED_ATTR
     done = GPHM_OK;
