@@ -173,7 +173,10 @@ GPHM_API int gphm_step(gphm_plan* plan, double* d_U, double* d_small, double* d_
               double* d_vsmall, long long* d_count, double lr, double* d_terms, void* stream);
 
 /* The same step with HOST buffers (functional JAX calling convention: params and opt_state come
- * from and return to host memory).  Copies in, steps, copies out, synchronises.               */
+ * from and return to host memory).  Copies in, steps, copies out, synchronises.  Pinned buffers let
+ * the transfers overlap the kernels: U uploads beside the factor stage (which needs only theta), the
+ * Adam moments behind the gradient kernels, and Adam(U) + the download of U and its moments start on a
+ * second stream as soon as dL/dU exists, while the theta-gradient is still being computed.        */
 GPHM_API int gphm_step_host(gphm_plan* plan, double* h_U, double* h_small, double* h_mU, double* h_vU, double* h_msmall,
                    double* h_vsmall, long long* h_count, double lr, double* h_terms, void* stream);
 
