@@ -4,13 +4,15 @@ This file is a torch-FP64 **CPU restatement** of the reference algorithm.  It is
 never the product: only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline /
 `--impl reference` legs may import it.  The shipped package never imports anything in `oracle/`.
 
-Parity status: PINNED for 1-D Poisson and 2-D Poisson with Matern52_Cos_1d by the reference's
-own two golden runs (tests/golden/*.npz, converted by tests/golden/make_golden.py from
-code/result_log/**.pkl; replayed by tests/test_oracle_golden.py).  SE_Cos_1d, Matern52_1d,
-SE_1d, Allen-Cahn and advection are *parity unpinned* by any reference artefact (the reference
-ships no tests and JAX is not installable here): for those the oracle is this restatement
-itself, which shares every line with the pinned cases and is cross-checked analytically
-(closed forms vs autograd, literal vs efficient formulation).
+Parity status: PINNED.  (1) 1-D Poisson and 2-D Poisson with Matern52_Cos_1d by the reference's own two
+golden runs (tests/golden/*.npz, converted by tests/golden/make_golden.py from code/result_log/**.pkl;
+replayed by tests/test_oracle_golden.py).  (2) Every kernel class (SE_Cos_1d, Matern52_Cos_1d,
+Matern52_1d, SE_1d) x {Poisson, Allen-Cahn} in 1-D and 2-D and advection by vectors obtained from
+EXECUTING the reference's unmodified sources with a torch-backed stand-in for the jax / optax API
+(tests/golden/make_ref_exec_golden.py -> tests/golden/ref_exec.npz; checked by
+tests/test_oracle_ref_exec.py): loss, every gradient leaf, two Adam steps, predictions.  Not pinned:
+XLA's own evaluation order, and optax beyond what the two result logs exercise (restated from its
+published algorithm).
 
 Reference lines followed (all under /root/reference/code):
   kernel_matrix.py:21-30     Kernel_matrix.get_kernel_matrix  (vmap(kappa) + jitter*I)
