@@ -54,6 +54,7 @@ def main():
     import model_GP_solver_2d as M2               # first: utils.py imports the solver modules circularly
     import model_GP_solver_1d as M1
     import model_GP_solver_advection as MA
+    import model_GP_solver_1d_extra as ME
     from oracle import gphm_oracle as O               # problem data and states only (inputs), not results
     out = {}
     quiet = contextlib.redirect_stdout(io.StringIO())
@@ -106,6 +107,37 @@ def main():
             tag = "%s1d|%s|%s" % (sz, eq, kname)
             out[tag + "|src"], out[tag + "|yb"] = p.src.numpy(), p.yb.numpy()
             run(tag, model, state_1d(O, p, N1D, Q), one_d=True)
+
+    # two-stage extra-GP solver (model_GP_solver_1d_extra.py:107-152): loss_extra with the first GP frozen
+    for eq in ("poisson_1d-sin_cos", "allencahn_1d-single_sin"):
+        N1D, Q = SIZES["g"][2], SIZES["g"][3]
+        p, xte, yte = O.make_problem_1d(eq, "SE_Cos_1d", N1D, 2 * math.pi, M=M_TEST)
+        tp = {"lr": LR, "llk_weight": p.llk_weight, "kernel": KM.SE_Cos_1d, "kernel_extra": KM.Matern52_1d, "equation": eq,
+              "logdet": True, "Q": Q, "freq_scale": FS, "nepoch": 2}
+        with quiet:
+            model = ME.GP_solver_1d_extra(p.xind.numpy(), p.yb.numpy(), p.x.numpy().reshape(-1, 1), p.src.numpy().reshape(-1, 1),
+                                          1e-6, xte.numpy().reshape(-1, 1), yte.numpy().reshape(-1, 1), tp)
+        model.y, model.src_col = torch.as_tensor(model.y), torch.as_tensor(model.src_col)
+        model.params = state_1d(O, p, N1D, Q)                                     # the frozen first stage
+        pe = {"u": (0.2 * torch.cos(2 * p.x) - 0.1 * torch.sin(p.x)).reshape(-1, 1),
+              "kernel_paras": {"log-w": torch.tensor([0.1], dtype=torch.float64), "log-ls": torch.tensor([-0.3], dtype=torch.float64)},
+              "log_tau": torch.tensor(0.2, dtype=torch.float64), "log_v": torch.tensor(-0.1, dtype=torch.float64)}
+        tag = "x1d|%s|SE_Cos_1d+Matern52_1d" % eq
+        val, grads = jax.value_and_grad(model.loss_extra)(pe, 0)
+        rec = {"loss": np.float64(val), "src": p.src.numpy(), "yb": p.yb.numpy()}
+        _flat("grad/", _np(grads), rec)
+        _flat("params0/", _np(pe), rec)
+        _flat("first/", _np(model.params), rec)
+        opt, pr, losses = model.optimizer_extra.init(pe), pe, []
+        for _ in range(2):
+            pr, opt, l = model.step_extra(pr, opt, 0)
+            losses.append(float(l))
+        rec["step_losses"] = np.asarray(losses)
+        _flat("params2/", _np(pr), rec)
+        rec["pred2"] = np.asarray(torch.as_tensor(model.preds_extra(pr, model.Xte)[0]).detach().numpy(), dtype=np.float64)
+        for k, v in rec.items():
+            out[tag + "|" + k] = v
+        print(tag, "loss %.12e" % float(val), flush=True)
 
     np.savez_compressed(os.path.join(HERE, "ref_exec.npz"), **out)
     print("wrote", os.path.join(HERE, "ref_exec.npz"), len(out), "arrays")

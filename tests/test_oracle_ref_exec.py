@@ -74,3 +74,42 @@ def test_oracle_matches_executed_reference(oracle, tag):
         assert float((a.reshape(-1) - b.reshape(-1)).abs().max()) <= tol_par, ka           # Adam steps are ~lr: absolute
     pred = O.preds_2d(p, pr, xte[0], xte[1]) if two else O.preds_1d(p, pr, xte)
     assert float((pred.reshape(-1) - torch.as_tensor(GOLD[tag + "|pred2"]).reshape(-1)).abs().max()) <= tol_pred
+
+
+XTAGS = sorted({"|".join(k.split("|")[:3]) for k in GOLD.files if k.startswith("x1d")})
+
+
+@pytest.mark.parametrize("tag", XTAGS)
+def test_oracle_extra_gp_matches_executed_reference(oracle, tag):
+    """Second stage of GP_solver_1d_extra (model_GP_solver_1d_extra.py:107-152) executed by the reference itself:
+    loss_extra, its gradient, two step_extra updates (oracle side: autograd of loss_extra_literal + the oracle's Adam)."""
+    O = oracle
+    _, eq, _ = tag.split("|")
+    N, Qg = SIZES["g"][2], SIZES["g"][3]
+    p, xte, _ = O.make_problem_1d(eq, "SE_Cos_1d", N, 2 * math.pi, M=M_TEST)
+    assert np.array_equal(p.src.numpy(), GOLD[tag + "|src"])
+    first = _tree(tag, "first/", O.init_params_1d(N, Qg, FS))
+    like = {"u": 0, "kernel_paras": {"log-w": 0, "log-ls": 0}, "log_tau": 0, "log_v": 0}
+    pe = _tree(tag, "params0/", like)
+
+    def value_and_grad(params_extra):
+        leaves = O._clone_leaves(params_extra, True)
+        val = O.loss_extra_literal(p, "Matern52_1d", first, leaves)
+        flat = O.flatten(leaves)
+        grads = torch.autograd.grad(val, [t for _, t in flat])
+        return float(val.detach()), dict(zip([k for k, _ in flat], grads))
+
+    val, grads = value_and_grad(pe)
+    want = float(GOLD[tag + "|loss"])
+    assert abs(val - want) <= 1e-10 * abs(want)
+    for path, w in O.flatten(_tree(tag, "grad/", like)):
+        assert _rel(grads[path], w) <= 1e-6, (path, _rel(grads[path], w))
+    st, cur = O.adam_init(pe), pe
+    for k in range(2):
+        v, g = value_and_grad(cur)
+        assert abs(v - float(GOLD[tag + "|step_losses"][k])) <= 1e-9 * abs(v)
+        gtree = {"u": g["u"], "kernel_paras": {"log-w": g["kernel_paras/log-w"], "log-ls": g["kernel_paras/log-ls"]},
+                 "log_tau": g["log_tau"], "log_v": g["log_v"]}
+        cur, st = O.adam_update(cur, gtree, st, LR)
+    for (ka, a), (kb, b) in zip(O.flatten(cur), O.flatten(_tree(tag, "params2/", like))):
+        assert float((a.reshape(-1) - b.reshape(-1)).abs().max()) <= 1e-6, ka
