@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libgphm.so")
 KERNEL_IDS = {"SE_Cos_1d": 0, "Matern52_Cos_1d": 1, "Matern52_1d": 2, "SE_1d": 3}
 EQ_IDS = {"poisson": 0, "allencahn": 1, "advection": 2}
 FORWARD_ONLY = 1
-NOT_SPD, NONFINITE = 1, 2
+NOT_SPD, NONFINITE, ILL_CONDITIONED = 1, 2, 3
 
 
 class ProblemDesc(ctypes.Structure):
@@ -41,11 +41,13 @@ _SIGS = {
     "gphm_plan_destroy": (None, [c_void_p]),
     "gphm_plan_status": (c_int, [c_void_p, POINTER(c_int), c_void_p]),
     "gphm_plan_uses_toeplitz": (c_int, [c_void_p, c_int]),
+    "gphm_plan_use_cholesky": (c_int, [c_void_p]),
     "gphm_plan_set_base_field": (c_int, [c_void_p, c_void_p]),
     "gphm_logjoint_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "gphm_adam_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_double, c_void_p]),
     "gphm_step": (c_int, [c_void_p] * 8 + [c_double, c_void_p, c_void_p]),
     "gphm_step_host": (c_int, [c_void_p] * 8 + [c_double, c_void_p, c_void_p]),
+    "gphm_step_host_params": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_double, c_void_p, c_void_p]),
     "gphm_predict_work_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "gphm_predict": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "gphm_rel_l2_work_bytes": (c_size_t, []),

@@ -506,4 +506,14 @@ int launch_sum_scaled(const double* v, int n, double scale, double* out, cudaStr
     return GPHM_OK;
 }
 
+// gphm_toeplitz_solve: status 0 (SPD) becomes -1 when the conditioning guard fired
+__global__ void status_merge_guard_kernel(int* __restrict__ status, const int* __restrict__ guard) {
+    if (*status == 0 && *guard != 0) *status = -1;
+}
+int launch_status_merge_guard(int* status, const int* guard, cudaStream_t st) {
+    { LaunchScope scope(CAT_ELEMWISE, st); status_merge_guard_kernel<<<1, 1, 0, st>>>(status, guard); }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
 }  // namespace gphm

@@ -81,7 +81,10 @@ int toeplitz_inv_max_n();
 // gkap[n] doubles + prog[1] int per system: hand-over buffer between the generator and the lattice CTA.
 int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitter, double* g, long long sG,
                           double* half_logdet, long long sLd, int* status, long long sStatus, double* gkap, long long sKap,
-                          int* prog, long long sProg, int nsys, cudaStream_t st, long long* dbg_cycles = nullptr);
+                          int* prog, long long sProg, int nsys, cudaStream_t st, long long* dbg_cycles = nullptr,
+                          int* guard = nullptr, int guard_bit0 = 0);
+// guard: bit (guard_bit0 + s) is OR-ed in when system s has min_k (1 - kappa_k^2) < toeplitz_guard_min()
+double toeplitz_guard_min();
 // spec[4][L] complex (strides in doubles): Gohberg-Semencul circulant spectra; sKinv[n]: diagonal sums of K^-1
 int launch_gs_prepare(const double* g, long long sG, int n, int L, const double* W, double* spec, long long sSpec,
                       double* sKinv, long long sS, int nsys, cudaStream_t st);
@@ -135,5 +138,6 @@ int launch_lincomb(double* out, double a, const double* x, double b, const doubl
 int launch_grad_u_local(size_t n, int allencahn, const double* U, const double* G, const double* W, const double* S1,
                         const double* S2, double* gU, double* V1, double* V2, cudaStream_t st);
 int launch_sum_scaled(const double* v, int n, double scale, double* out, cudaStream_t st);
+int launch_status_merge_guard(int* status, const int* guard, cudaStream_t st);
 
 }  // namespace gphm

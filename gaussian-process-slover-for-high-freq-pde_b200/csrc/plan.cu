@@ -262,7 +262,7 @@ int factor_gs(gphm_plan& p, int a0, int count, const double* small, cudaStream_t
         const Axis& Y = p.ax[batched ? a + 1 : a];
         GPHM_TRY(launch_schur_levinson(X.tabK, Y.tabK - X.tabK, X.n, p.d.jitter, X.gsg, Y.gsg - X.gsg, X.ldpart,
                                        Y.ldpart - X.ldpart, p.status + a, 1, X.gskap, Y.gskap - X.gskap, X.gsprog,
-                                       Y.gsprog - X.gsprog, nsys, st));
+                                       Y.gsprog - X.gsprog, nsys, st, nullptr, p.status + 3, a));
         GPHM_TRY(launch_gs_prepare(X.gsg, Y.gsg - X.gsg, X.n, X.fftL, X.twid, X.gspec, Y.gspec - X.gspec, X.sKinv,
                                    Y.sKinv - X.sKinv, nsys, st));
     }
@@ -669,8 +669,11 @@ int gphm_toeplitz_solve(const double* d_t, int n, const double* d_B, int rows, d
     c.take(gkap, (size_t)n); c.take(progd, 1);
     GPHM_CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(int), st));
     GPHM_TRY(launch_twiddle_init(twid, L, st));
+    GPHM_CUDA_OK(cudaMemsetAsync(reinterpret_cast<int*>(progd) + 1, 0, sizeof(int), st));
     GPHM_TRY(launch_schur_levinson(d_t, 0, n, 0.0, d_g, 0, hld, 0, d_status, 0, gkap, 0, reinterpret_cast<int*>(progd), 0, 1, st,
-                                   getenv("GPHM_SCHUR_CYCLES") ? reinterpret_cast<long long*>(tmp) : nullptr));
+                                   getenv("GPHM_SCHUR_CYCLES") ? reinterpret_cast<long long*>(tmp) : nullptr,
+                                   reinterpret_cast<int*>(progd) + 1, 0));
+    GPHM_TRY(launch_status_merge_guard(d_status, reinterpret_cast<int*>(progd) + 1, st));
     GPHM_TRY(launch_gs_prepare(d_g, 0, n, L, twid, spec, 0, d_sKinv, 0, 1, st));
     GPHM_TRY(launch_sum_scaled(hld, 1, 2.0, d_logdet, st));
     if (rows > 0) {
@@ -762,6 +765,14 @@ int gphm_plan_status(gphm_plan* plan, int* pivot, void* stream) {
     if (pivot) *pivot = h[0] ? h[0] : (h[1] ? plan->d.n1 + h[1] : 0);
     if (h[0] || h[1]) return GPHM_NOT_SPD;
     if (h[2]) return GPHM_NONFINITE;
+    if (h[3]) { if (pivot) *pivot = h[3]; return GPHM_ILL_CONDITIONED; }
+    return GPHM_OK;
+}
+
+int gphm_plan_use_cholesky(gphm_plan* plan) {
+    if (!plan) { set_last_error("null plan"); return GPHM_EINVAL; }
+    plan->d.force_general |= 16;
+    for (int a = 0; a < 2; ++a) plan->ax[a].gs = false;
     return GPHM_OK;
 }
 
@@ -807,15 +818,15 @@ int gphm_step(gphm_plan* plan, double* d_U, double* d_small, double* d_mU, doubl
     return GPHM_OK;
 }
 
-int gphm_step_host(gphm_plan* plan, double* h_U, double* h_small, double* h_mU, double* h_vU, double* h_msmall,
-                   double* h_vsmall, long long* h_count, double lr, double* h_terms, void* stream) {
-    if (!plan || !h_U || !h_small || !h_mU || !h_vU || !h_msmall || !h_vsmall || !h_count || !h_terms) {
-        set_last_error("gphm_step_host: null pointer");
-        return GPHM_EINVAL;
-    }
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+// Shared body of gphm_step_host / gphm_step_host_params.  resident: the Adam moments and the step count live in the
+// plan's staging area (the caller's opt_state never leaves the device, as in the reference where optax's state is a
+// pytree of device arrays); only params travel.
+static int step_host_impl(gphm_plan* plan, double* h_U, double* h_small, double* h_mU, double* h_vU, double* h_msmall,
+                          double* h_vsmall, long long* h_count, double lr, double* h_terms, bool resident, bool reset_opt,
+                          cudaStream_t st) {
     const size_t nf = (size_t)plan->d.n1 * plan->d.n2, ns = 6 * (size_t)plan->d.Q + 2;
     const size_t nfp = (nf + 31) / 32 * 32, nsp = (ns + 31) / 32 * 32;
+    bool fresh = false;
     if (!plan->hs) {
         GPHM_CUDA_OK(cudaMalloc(&plan->hs, sizeof(double) * (3 * nfp + 3 * nsp + 32)));
         GPHM_CUDA_OK(cudaMalloc(&plan->hs_count, sizeof(long long)));
@@ -824,24 +835,35 @@ int gphm_step_host(gphm_plan* plan, double* h_U, double* h_small, double* h_mU, 
         GPHM_CUDA_OK(cudaEventCreateWithFlags(&plan->hs_ev_mv, cudaEventDisableTiming));
         GPHM_CUDA_OK(cudaEventCreateWithFlags(&plan->hs_ev_gu, cudaEventDisableTiming));
         GPHM_CUDA_OK(cudaEventCreateWithFlags(&plan->hs_ev_adam, cudaEventDisableTiming));
+        fresh = true;
     }
     double *U = plan->hs, *mU = U + nfp, *vU = mU + nfp, *sm = vU + nfp, *msm = sm + nsp, *vsm = msm + nsp,
            *terms = vsm + nsp;
-    // Schedule (PCIe carries 134 MB up before and 403 MB down after the 6 ms of kernels at 4096^2):
+    // Schedule (PCIe carries 134 MB up before and 134 (403 with the moments) MB down after the kernels at 4096^2):
     //   st        : small params up -> factor stage (needs only theta) -> [wait U] gradient ... theta-gradient -> Adam(small) -> down
-    //   hs_stream : U up -> mU, vU up (hidden behind the gradient) -> [wait dL/dU] Adam(U) -> U, mU, vU down while st
+    //   hs_stream : U up -> [mU, vU up, hidden behind the gradient] -> [wait dL/dU] Adam(U) -> U [, mU, vU] down while st
     //               still computes the theta-gradient
     GPHM_CUDA_OK(cudaMemcpyAsync(sm, h_small, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
-    GPHM_CUDA_OK(cudaMemcpyAsync(msm, h_msmall, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
-    GPHM_CUDA_OK(cudaMemcpyAsync(vsm, h_vsmall, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
-    GPHM_CUDA_OK(cudaMemcpyAsync(plan->hs_count, h_count, sizeof(long long), cudaMemcpyHostToDevice, st));
+    if (!resident) {
+        GPHM_CUDA_OK(cudaMemcpyAsync(msm, h_msmall, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
+        GPHM_CUDA_OK(cudaMemcpyAsync(vsm, h_vsmall, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
+        GPHM_CUDA_OK(cudaMemcpyAsync(plan->hs_count, h_count, sizeof(long long), cudaMemcpyHostToDevice, st));
+    } else if (reset_opt || fresh) {                 // optimizer.init(params): zero moments, count 0
+        GPHM_CUDA_OK(cudaMemsetAsync(mU, 0, sizeof(double) * 2 * nfp, st));
+        GPHM_CUDA_OK(cudaMemsetAsync(msm, 0, sizeof(double) * 2 * nsp, st));
+        GPHM_CUDA_OK(cudaMemsetAsync(plan->hs_count, 0, sizeof(long long), st));
+        GPHM_CUDA_OK(cudaEventRecord(plan->hs_ev_mv, st));
+        GPHM_CUDA_OK(cudaStreamWaitEvent(plan->hs_stream, plan->hs_ev_mv, 0));
+    }
     GPHM_CUDA_OK(cudaMemcpyAsync(U, h_U, sizeof(double) * nf, cudaMemcpyHostToDevice, plan->hs_stream));
     GPHM_CUDA_OK(cudaEventRecord(plan->hs_ev_u, plan->hs_stream));
-    GPHM_CUDA_OK(cudaMemcpyAsync(mU, h_mU, sizeof(double) * nf, cudaMemcpyHostToDevice, plan->hs_stream));
-    GPHM_CUDA_OK(cudaMemcpyAsync(vU, h_vU, sizeof(double) * nf, cudaMemcpyHostToDevice, plan->hs_stream));
-    struct Ctx { double *U, *mU, *vU, *hU, *hmU, *hvU; size_t nf; double lr; };
+    if (!resident) {
+        GPHM_CUDA_OK(cudaMemcpyAsync(mU, h_mU, sizeof(double) * nf, cudaMemcpyHostToDevice, plan->hs_stream));
+        GPHM_CUDA_OK(cudaMemcpyAsync(vU, h_vU, sizeof(double) * nf, cudaMemcpyHostToDevice, plan->hs_stream));
+    }
+    struct Ctx { double *U, *mU, *vU, *hU, *hmU, *hvU; size_t nf; double lr; bool resident; };
     static thread_local Ctx ctx;
-    ctx = Ctx{U, mU, vU, h_U, h_mU, h_vU, nf, lr};
+    ctx = Ctx{U, mU, vU, h_U, h_mU, h_vU, nf, lr, resident};
     plan->u_ready = plan->hs_ev_u;
     plan->gu_hook_ran = false;
     plan->on_gu = [](gphm_plan& p, cudaStream_t s) -> int {                  // dL/dU complete on s
@@ -850,8 +872,10 @@ int gphm_step_host(gphm_plan* plan, double* h_U, double* h_small, double* h_mU, 
         GPHM_TRY(launch_adam(ctx.U, p.gU, ctx.mU, ctx.vU, ctx.nf, p.hs_count, ctx.lr, p.hs_stream));
         GPHM_CUDA_OK(cudaEventRecord(p.hs_ev_adam, p.hs_stream));
         GPHM_CUDA_OK(cudaMemcpyAsync(ctx.hU, ctx.U, sizeof(double) * ctx.nf, cudaMemcpyDeviceToHost, p.hs_stream));
-        GPHM_CUDA_OK(cudaMemcpyAsync(ctx.hmU, ctx.mU, sizeof(double) * ctx.nf, cudaMemcpyDeviceToHost, p.hs_stream));
-        GPHM_CUDA_OK(cudaMemcpyAsync(ctx.hvU, ctx.vU, sizeof(double) * ctx.nf, cudaMemcpyDeviceToHost, p.hs_stream));
+        if (!ctx.resident) {
+            GPHM_CUDA_OK(cudaMemcpyAsync(ctx.hmU, ctx.mU, sizeof(double) * ctx.nf, cudaMemcpyDeviceToHost, p.hs_stream));
+            GPHM_CUDA_OK(cudaMemcpyAsync(ctx.hvU, ctx.vU, sizeof(double) * ctx.nf, cudaMemcpyDeviceToHost, p.hs_stream));
+        }
         return GPHM_OK;
     };
     const int rc = logjoint_grad(*plan, U, sm, plan->gU, plan->gsmall, terms, 0, st);
@@ -863,20 +887,41 @@ int gphm_step_host(gphm_plan* plan, double* h_U, double* h_small, double* h_mU, 
         GPHM_CUDA_OK(cudaStreamWaitEvent(st, plan->hs_ev_mv, 0));
         GPHM_TRY(launch_adam(U, plan->gU, mU, vU, nf, plan->hs_count, lr, st));
         GPHM_CUDA_OK(cudaMemcpyAsync(h_U, U, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
-        GPHM_CUDA_OK(cudaMemcpyAsync(h_mU, mU, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
-        GPHM_CUDA_OK(cudaMemcpyAsync(h_vU, vU, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+        if (!resident) {
+            GPHM_CUDA_OK(cudaMemcpyAsync(h_mU, mU, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+            GPHM_CUDA_OK(cudaMemcpyAsync(h_vU, vU, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+        }
     }
     GPHM_TRY(launch_adam(sm, plan->gsmall, msm, vsm, ns, plan->hs_count, lr, st));
     if (plan->gu_hook_ran) GPHM_CUDA_OK(cudaStreamWaitEvent(st, plan->hs_ev_adam, 0));      // Adam(U) has read the count
     GPHM_TRY(launch_count_inc(plan->hs_count, st));
     GPHM_CUDA_OK(cudaMemcpyAsync(h_small, sm, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
-    GPHM_CUDA_OK(cudaMemcpyAsync(h_msmall, msm, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
-    GPHM_CUDA_OK(cudaMemcpyAsync(h_vsmall, vsm, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
-    GPHM_CUDA_OK(cudaMemcpyAsync(h_count, plan->hs_count, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    if (!resident) {
+        GPHM_CUDA_OK(cudaMemcpyAsync(h_msmall, msm, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
+        GPHM_CUDA_OK(cudaMemcpyAsync(h_vsmall, vsm, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
+    }
+    if (h_count) GPHM_CUDA_OK(cudaMemcpyAsync(h_count, plan->hs_count, sizeof(long long), cudaMemcpyDeviceToHost, st));
     GPHM_CUDA_OK(cudaMemcpyAsync(h_terms, terms, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
     GPHM_CUDA_OK(cudaStreamSynchronize(st));
     GPHM_CUDA_OK(cudaStreamSynchronize(plan->hs_stream));
     return GPHM_OK;
+}
+
+int gphm_step_host(gphm_plan* plan, double* h_U, double* h_small, double* h_mU, double* h_vU, double* h_msmall,
+                   double* h_vsmall, long long* h_count, double lr, double* h_terms, void* stream) {
+    if (!plan || !h_U || !h_small || !h_mU || !h_vU || !h_msmall || !h_vsmall || !h_count || !h_terms) {
+        set_last_error("gphm_step_host: null pointer");
+        return GPHM_EINVAL;
+    }
+    return step_host_impl(plan, h_U, h_small, h_mU, h_vU, h_msmall, h_vsmall, h_count, lr, h_terms, false, false,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int gphm_step_host_params(gphm_plan* plan, double* h_U, double* h_small, int reset_opt, long long* h_count, double lr,
+                          double* h_terms, void* stream) {
+    if (!plan || !h_U || !h_small || !h_terms) { set_last_error("gphm_step_host_params: null pointer"); return GPHM_EINVAL; }
+    return step_host_impl(plan, h_U, h_small, nullptr, nullptr, nullptr, nullptr, h_count, lr, h_terms, true, reset_opt != 0,
+                          static_cast<cudaStream_t>(stream));
 }
 
 size_t gphm_predict_work_bytes(const gphm_plan* plan, int m1, int m2) {

@@ -24,6 +24,7 @@
 // relative), g from Schur+lattice 1e-9, log|K| 4e-11 relative.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 #include "fft_core.cuh"
@@ -39,6 +40,14 @@ constexpr int SCHUR_RING = 32;                  // boundary values kept per warp
 constexpr int SCHUR_PUBLISH = 8;                // led batches per hand-over to the lattice CTA (64 coefficients)
 
 int toeplitz_inv_max_n() { return SCHUR_MAX_N; }
+
+// min_k (1 - kappa_k^2) below which the Toeplitz inverse-generator route is declared ill-conditioned.  Measured error of
+// K^-1 v on that route ~ 7e-13 / min(1 - kappa^2) (tools/cond_guard_study.py): 3.5e-5 keeps it below 2e-8, a factor 50
+// under the 1e-6 parity bound.  GPHM_GS_GUARD_MIN overrides (0 disables the guard).
+double toeplitz_guard_min() {
+    static const double v = [] { const char* e = getenv("GPHM_GS_GUARD_MIN"); return e ? atof(e) : 3.5e-5; }();
+    return v;
+}
 
 // Two CTAs per system: the GENERATOR CTA runs the Schur recursion (it alone carries the serial
 // dependency kappa_j -> kappa_{j+1}) and hands the reflection coefficients over through global memory;
@@ -182,7 +191,8 @@ __device__ __forceinline__ void load8(double (&v)[SCHUR_EPT], const double* p) {
 __global__ void __launch_bounds__(SCHUR_MAX_THREADS, 1)
 schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, double jitter, double* __restrict__ g,
                       long long sG, double* __restrict__ half_logdet, long long sLd, int* __restrict__ status,
-                      long long sStatus, double* gkap, long long sKap, int* prog, long long sProg, long long* dbg) {
+                      long long sStatus, double* gkap, long long sKap, int* prog, long long sProg, int* guard, int guard_bit0,
+                      double guard_min, long long* dbg) {
     const int sys = blockIdx.x >> 1, role = blockIdx.x & 1;
     const long long t_start = clock64();
     tab += sys * sTab; g += sys * sG; half_logdet += sys * sLd; status += sys * sStatus; gkap += sys * sKap; prog += sys * sProg;
@@ -251,7 +261,10 @@ schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, dou
             }
         }
         // log|K| = n log r0 + sum_k (n - k) log(1 - kappa_k^2); first |kappa| >= 1 <=> first non-positive prediction error
-        double lsum = 0.0;
+        // Conditioning guard (the Gohberg-Semencul formula divides a difference of two triangular products by g0 and
+        // loses ~7e-13 / min_k(1 - kappa_k^2) of relative accuracy, tools/cond_guard_study.py): flag the system when
+        // that margin falls below guard_min so that the host moves the plan to the Cholesky path.
+        double lsum = 0.0, gmin = 1.0;
 #pragma unroll
         for (int i = 0; i < SCHUR_EPT; ++i) {
             const int k = j0t + i;
@@ -259,10 +272,14 @@ schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, dou
                 const double kp = kap[k];
                 if (!(fabs(kp) < 1.0)) atomicMin(&bad, k);         // also catches NaN
                 lsum += (double)(n - k) * log1p(-kp * kp);
+                gmin = fmin(gmin, (1.0 - kp) * (1.0 + kp));
             }
         }
         if (!(r0 > 0.0) && tid == 0) atomicMin(&bad, 0);
         const double ltot = block_sum(lsum, red);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gmin = fmin(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
+        if (lane == 0 && gmin < guard_min && guard) atomicOr(guard, 1 << (guard_bit0 + sys));
         if (dbg && lane == 0) {
             unsigned long long* d = reinterpret_cast<unsigned long long*>(dbg);
             atomicAdd(d + 8, (unsigned long long)c_lead); atomicAdd(d + 9, (unsigned long long)n_lead);
@@ -412,7 +429,7 @@ int toeplitz_inv_init() {
 
 int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitter, double* g, long long sG,
                           double* half_logdet, long long sLd, int* status, long long sStatus, double* gkap, long long sKap,
-                          int* prog, long long sProg, int nsys, cudaStream_t st, long long* dbg) {
+                          int* prog, long long sProg, int nsys, cudaStream_t st, long long* dbg, int* guard, int guard_bit0) {
     if (n < 1 || n > SCHUR_MAX_N) { set_last_error("schur: n=%d outside [1,%d]", n, SCHUR_MAX_N); return GPHM_EINVAL; }
     if (nsys < 1 || nsys > 2) { set_last_error("schur: nsys=%d", nsys); return GPHM_EINVAL; }
     const int threads = std::min(SCHUR_MAX_THREADS, ((n + SCHUR_EPT - 1) / SCHUR_EPT + 31) / 32 * 32);
@@ -420,7 +437,7 @@ int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitt
     {
         LaunchScope scope(CAT_CHOL_DIAG, st, 8.0 * (double)n * n * nsys);
         schur_levinson_kernel<<<2 * nsys, threads, 0, st>>>(tabK, sTab, n, jitter, g, sG, half_logdet, sLd, status, sStatus,
-                                                              gkap, sKap, prog, sProg, dbg);
+                                                              gkap, sKap, prog, sProg, guard, guard_bit0, toeplitz_guard_min(), dbg);
     }
     GPHM_LAUNCH_OK();
     return GPHM_OK;

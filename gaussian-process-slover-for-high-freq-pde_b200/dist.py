@@ -66,9 +66,6 @@ class CudaOps(object):
         off = p - self.core.workspace.data_ptr()
         return self.core.workspace[off:off + n * n * 8].view(DT).view(n, n)
 
-    def logdet_parts(self, axis):
-        raise NotImplementedError
-
     def logdets(self):
         out = self._buf("logdets", (2,))
         _lib.check(self.lib.gphm_plan_logdet(self.plan, _lib.ptr(out), self._s()), "gphm_plan_logdet")
@@ -312,6 +309,9 @@ class ShardedSolver2D(object):
 
     def last_loss(self):
         return self.terms[0]
+
+    def exchange_name(self):
+        return "NCCL all-to-all"
 
     # ---- layout exchanges ------------------------------------------------------------------------
     def _a2a(self, send, tag=None):

@@ -89,6 +89,9 @@ class Ensemble(object):
     def __len__(self):
         return len(self.models)
 
+    def issue_mode(self):
+        return ("CUDA-graph replay, %d streams" if self.use_graph else "plain launches, %d streams") % self.n_streams
+
     def _issue(self):
         """One gphm_step per member, round-robin over the side streams, joined on the current stream."""
         cur = torch.cuda.current_stream(self.device)
@@ -149,7 +152,7 @@ class Ensemble(object):
             m.core.raise_on_bad_status()
 
 
-def build_ensemble(trick_paras, members, rank=0, world=1, streams=16, graph=True, quiet=True):
+def build_ensemble(trick_paras, members, rank=0, world=1, streams=16, graph=True, quiet=True, batched=False):
     """Ensemble of this rank's share of `members` [(seed, freq_scale)] for one equation config
     (`trick_paras` as evals() builds it; its `equation` prefix selects the solver class).
     Returns (Ensemble, indices of the members it holds)."""

@@ -122,6 +122,7 @@ class GP_solver_1d_single(object):
         """model_GP_solver_1d.py:193-296 (same cadence, log_dict keys and return tuple)."""
         early_stopping = {"flag": False, "epoch": self.trick_paras["nepoch"]}
         st = self.core.new_state(self.init_params())
+        self.core.check_conditioning(st)
         log = {k: [] for k in ("loss_list", "err_list", "w_list", "freq_list", "ls_list", "epoch_list")}
         min_err = 2.0
         self.pred_func = self.preds

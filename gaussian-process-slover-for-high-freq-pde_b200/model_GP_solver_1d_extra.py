@@ -164,6 +164,7 @@ class GP_solver_1d_extra(m1d.GP_solver_1d_single):
         early_stopping = {"flag": False, "epoch": self.trick_paras["nepoch"]}
         error_increase_count, min_err, threshold = 0, 2.0, 1e-3
         st = self.core.new_state(m1d.GP_solver_1d_single.init_params(self))
+        self.core.check_conditioning(st)
         st2 = None
         log = {k: [] for k in ("loss_list", "err_list", "w_list", "freq_list", "ls_list", "epoch_list")}
         change_point = int(nepoch * self.trick_paras["change_point"])
@@ -180,12 +181,14 @@ class GP_solver_1d_extra(m1d.GP_solver_1d_single):
                 params = self.core.unpack_tree(st.U, st.small)
                 self.freeze_first_stage(params)
                 st2 = self._state_extra(self.init_params_extra(params))
+                self.core_extra.check_conditioning(st2)      # Matern52_1d, Q = 1: the plain-kernel case of the guard
             if i % (nepoch / 20) == 0:
                 loss = float(loss_t[0])
                 pred = self.core.predict(st, self.Xte)
                 if i > change_point:
                     pred = pred + self.core_extra.predict(st2, self.Xte)
                 err = float(self.core.rel_l2(pred, self.yte))
+                (self.core_extra if i > change_point else self.core).raise_on_bad_status()
                 if err < min_err:
                     min_err = err
                 elif err - min_err > threshold:

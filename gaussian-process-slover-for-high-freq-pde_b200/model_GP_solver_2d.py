@@ -145,6 +145,7 @@ class GP_solver_2d_single(object):
         persistent device state; the host only synchronises at the 20 evaluation points."""
         early_stopping = {"flag": False, "epoch": self.trick_paras["nepoch"]}
         st = self.core.new_state(self.init_params())
+        self.core.check_conditioning(st)
         log = {k: [] for k in ("loss_list", "err_list", "w_list_k1", "freq_list_k1", "ls_list_k1", "w_list_k2",
                                "freq_list_k2", "ls_list_k2", "epoch_list")}
         min_err = 2.0

@@ -154,6 +154,12 @@ class SolverCore(object):
                                            _lib.ptr(hmsmall), _lib.ptr(hvsmall), _lib.ptr(hcount), float(lr),
                                            _lib.ptr(hterms), _lib.stream_ptr()), "gphm_step_host")
 
+    def step_host_params(self, hU, hsmall, hterms, lr, reset_opt=False, hcount=None):
+        """Step on HOST params with the Adam state resident in the plan (gphm_step_host_params)."""
+        _lib.check(self.lib.gphm_step_host_params(self.plan, _lib.ptr(hU), _lib.ptr(hsmall), int(bool(reset_opt)),
+                                                  _lib.ptr(hcount), float(lr), _lib.ptr(hterms), _lib.stream_ptr()),
+                   "gphm_step_host_params")
+
     def status(self):
         piv = ctypes.c_int(0)
         rc = self.lib.gphm_plan_status(self.plan, ctypes.byref(piv), _lib.stream_ptr())
@@ -162,11 +168,27 @@ class SolverCore(object):
         return rc, piv.value
 
     def raise_on_bad_status(self):
+        """Raises on a non-SPD Gram matrix / non-finite loss.  GPHM_ILL_CONDITIONED (the conditioning guard of the
+        Toeplitz inverse-generator route fired) is not an error: the plan moves to the Cholesky route for every
+        following call, with a warning."""
         rc, piv = self.status()
+        if rc == _lib.ILL_CONDITIONED:
+            import warnings
+            _lib.check(self.lib.gphm_plan_use_cholesky(self.plan), "gphm_plan_use_cholesky")
+            self.fell_back_to_cholesky = True
+            warnings.warn("libgphm: Gram matrix too ill-conditioned for the Toeplitz inverse-generator route (axis mask %d): "
+                          "continuing on the blocked Cholesky route" % piv, RuntimeWarning)
+            return
         if rc == _lib.NOT_SPD:
             raise FloatingPointError("Gram matrix is not positive definite (pivot %d)" % piv)
         if rc == _lib.NONFINITE:
             raise FloatingPointError("loss is not finite")
+
+    def check_conditioning(self, st):
+        """One forward-only evaluation + a status read (the only host sync): lets the conditioning guard of the Toeplitz
+        inverse-generator route move the plan to the Cholesky route BEFORE a training loop starts."""
+        self.value_and_grad(st, forward_only=True)
+        self.raise_on_bad_status()
 
     def predict(self, st, xt, yt=None):
         xt = as_dev(xt).reshape(-1)

@@ -48,6 +48,9 @@ extern "C" {
 #define GPHM_ENOMEM     -3
 #define GPHM_NOT_SPD     1   /* gphm_plan_status: a Gram matrix had a non-positive pivot */
 #define GPHM_NONFINITE   2   /* gphm_plan_status: the loss is not finite */
+#define GPHM_ILL_CONDITIONED 3 /* gphm_plan_status: a uniform-grid axis is too ill-conditioned for the Toeplitz
+                                 inverse-generator route (min_k (1 - kappa_k^2) < 3.5e-5): results are still finite, but
+                                 call gphm_plan_use_cholesky to stay inside the 1e-6 parity bound */
 
 /* flags for gphm_logjoint_grad */
 #define GPHM_FORWARD_ONLY  1   /* loss terms only (compute_early_stopping, loss) */
@@ -125,7 +128,8 @@ GPHM_API int gphm_potrf_inv(double* d_K, int n, double* d_L, double* d_Linv, dou
  * recursion for d_g = K^-1 e_0 (n) and log|K|, then each of the `rows` right-hand sides (rows of
  * d_B, rows x n) is solved by the Gohberg-Semencul formula as four FFT convolutions -> d_X.
  * d_sKinv (n) gets the diagonal sums of K^-1 (d > 0: both triangles) that the theta-gradient of
- * log|K| needs.  n <= 4096; d_status: 0 = SPD, else 1 + first step with a non-positive prediction
+ * log|K| needs.  n <= 4096; d_status: 0 = SPD, -1 = SPD but below the conditioning guard of this route
+ * (min_k (1 - kappa_k^2) < 3.5e-5, see GPHM_ILL_CONDITIONED), else 1 + first step with a non-positive prediction
  * error; d_work holds gphm_toeplitz_work_bytes(n, rows) bytes; d_X may not alias d_B.             */
 GPHM_API size_t gphm_toeplitz_work_bytes(int n, int rows);
 GPHM_API int gphm_toeplitz_solve(const double* d_t, int n, const double* d_B, int rows, double* d_X, double* d_g,
@@ -141,9 +145,15 @@ GPHM_API int gphm_plan_create(const gphm_problem_desc* desc, const double* h_x, 
                      const double* h_bvals, const int* h_xind, void* d_workspace, size_t workspace_bytes,
                      gphm_plan** out);
 GPHM_API void gphm_plan_destroy(gphm_plan* plan);
-/* Synchronises `stream`, returns GPHM_OK / GPHM_NOT_SPD / GPHM_NONFINITE; *pivot = 1 + index of
- * the first bad pivot (axis 1: 1..n1, axis 2: n1+1..) or 0. Clears the flag.                  */
+/* Synchronises `stream`, returns GPHM_OK / GPHM_NOT_SPD / GPHM_NONFINITE / GPHM_ILL_CONDITIONED; *pivot = 1 + index
+ * of the first bad pivot (axis 1: 1..n1, axis 2: n1+1..) or 0 (GPHM_ILL_CONDITIONED: bit mask of the flagged axes).
+ * Clears the flags.                                                                            */
 GPHM_API int gphm_plan_status(gphm_plan* plan, int* pivot, void* stream);
+/* Moves every uniform-grid axis of the plan from the Toeplitz inverse generator (Schur/Levinson + Gohberg-Semencul
+ * FFT products) to the blocked Cholesky + triangular-GEMM route (force_general bit 4) for all following calls: the
+ * answer to GPHM_ILL_CONDITIONED.  Both routes replace the same jnp.linalg.solve / slogdet
+ * (model_GP_solver_2d.py:104-105,158-161); the plan's workspace already holds the dense buffers.   */
+GPHM_API int gphm_plan_use_cholesky(gphm_plan* plan);
 GPHM_API int gphm_plan_uses_toeplitz(const gphm_plan* plan, int axis);
 /* Frozen base field (n1*n2 host doubles, NULL clears it): the nonlinearity becomes nl(U + base).
  * This is what the second stage of GP_solver_1d_extra needs - u of the frozen first GP inside
@@ -179,6 +189,14 @@ GPHM_API int gphm_step(gphm_plan* plan, double* d_U, double* d_small, double* d_
  * second stream as soon as dL/dU exists, while the theta-gradient is still being computed.        */
 GPHM_API int gphm_step_host(gphm_plan* plan, double* h_U, double* h_small, double* h_mU, double* h_vU, double* h_msmall,
                    double* h_vsmall, long long* h_count, double lr, double* h_terms, void* stream);
+
+/* step() with HOST params and a DEVICE-resident opt_state: what `params, opt_state, loss =
+ * self.step(params, opt_state, key)` (model_GP_solver_2d.py:176-183, 289) moves per iteration when only the
+ * params are consumed on the host - optax's ScaleByAdamState (count, mu, nu) stays where the jitted step left
+ * it.  The plan owns the moments and the count; reset_opt != 0 (and the first call) re-initialises them as
+ * optimizer.init(params) does (:263).  h_count (may be NULL) receives the updated count.               */
+GPHM_API int gphm_step_host_params(gphm_plan* plan, double* h_U, double* h_small, int reset_opt, long long* h_count,
+                          double lr, double* h_terms, void* stream);
 
 /* preds(): posterior mean on a test grid (model_GP_solver_2d.py:185-220, _1d.py:160-180).
  * d_xt (m1), d_yt (m2; ignored in 1-D) are device test coordinates; d_out is m1 x m2 (m1 x 1).

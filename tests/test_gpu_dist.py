@@ -42,6 +42,19 @@ def _compare(equation, eq_name, kernel, beta, N, Q, steps=2, mode=0):
     t2, gU_r, gs2 = solver.value_and_grad()
     r0, h = solver.rank * solver.h, solver.h
     ref_rows = gU.reshape(N, N)[r0:r0 + h]
+    # first against the ORACLE (all six loss terms, the two scalar gradients, every gradient leaf): the 1e-6 bound
+    te, ge = O.loss_and_grad_efficient(p, params)
+    want_terms = [te["loss"], te["logdet1"], te["logdet2"], te["quad"], te["bgap"], te["eqgap"],
+                  float(ge["log_tau"]), float(ge["log_v"])]
+    for got, want in zip(t2.tolist(), want_terms):
+        assert abs(got - want) <= 1e-6 * abs(want), (got, want)
+    wantU = ge["U"][r0:r0 + h]
+    assert float((gU_r.cpu() - wantU).norm()) <= 1e-6 * float(wantU.norm())
+    gs_want = _small_from(ge, Q)
+    for j in range(6):
+        a, b = gs2.cpu()[j * Q:(j + 1) * Q], gs_want[j * Q:(j + 1) * Q]
+        assert float((a - b).norm()) <= 1e-6 * float(b.norm()), j
+    # then against the fused single-GPU step of the same algorithm family
     # the sharded and the fused step order their products differently (mode 16 also: GEMMs vs FFT products):
     # agreement at the conditioning level (both are within 1e-6 of the oracle)
     assert float((t2 - terms).abs().max() / terms.abs().max()) <= 1e-8

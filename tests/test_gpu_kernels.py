@@ -117,6 +117,31 @@ def test_toeplitz_solve_matches_cholesky(gphm, oracle, kernel, n):
     assert rel(X.cpu() @ K, B) <= 1e-7
 
 
+@pytest.mark.parametrize("kernel", ["SE_1d", "Matern52_1d"])
+@pytest.mark.parametrize("n,scale", [(400, 2 * math.pi), (400, 1.0), (900, 1.0), (900, 2 * math.pi)])
+def test_toeplitz_solve_plain_kernels_guard(gphm, oracle, kernel, n, scale):
+    """Plain kernels at the reference's shipped N_col and initial length-scale (log-ls = 0): cond(K) 1e8 .. 8e8.
+    Where the guard stays silent (status 0) the Toeplitz route must hold 2e-7 against Cholesky; status -1 marks the
+    systems whose min_k (1 - kappa_k^2) is below 3.5e-5 (their solution is still finite and within 1e-6)."""
+    x = torch.linspace(0, 1, n, dtype=DT) * scale
+    Q = 30
+    th = {"log-w": torch.full((Q,), math.log(1.0 / Q), dtype=DT), "log-ls": torch.zeros(Q, dtype=DT),
+          "freq": torch.linspace(0, 1, Q, dtype=DT) * 20.0}
+    K = oracle.gram(kernel, x, x, th, 0, 1e-6)
+    B = torch.stack([torch.sin(3 * x) + 0.2 * torch.cos(17 * x), torch.ones(n, dtype=DT)])
+    X, g, sK, logdet, status = gphm.solver_core.toeplitz_solve(K[:, 0], B)
+    assert int(status) in (0, -1)
+    L = torch.linalg.cholesky(K)
+    want = torch.cholesky_solve(B.T.contiguous(), L).T
+    assert rel(X, want) <= (2e-7 if int(status) == 0 else 1e-6)
+    if kernel == "SE_1d" and scale == 1.0:
+        assert int(status) == -1           # min(1 - kappa^2) = 1.5e-5 (n = 400), 4.5e-6 (n = 900)
+    if scale > 1.0 and n == 400:
+        assert int(status) == 0            # 5e-4 / 4e-4: comfortably on the fast route
+    want_ld = float(2.0 * torch.log(torch.diagonal(L)).sum())
+    assert abs(float(logdet) - want_ld) <= 1e-8 * max(1.0, abs(want_ld))
+
+
 def test_toeplitz_solve_flags_non_spd(gphm):
     t = torch.zeros(300, dtype=DT)
     t[0], t[1] = 1.0, 0.8                  # tridiagonal Toeplitz with 2*0.8 > 1: indefinite for n = 300

@@ -135,6 +135,44 @@ def test_logjoint_grad_1d_parity(gphm, oracle, equation, kernel, N, Q, fs, scale
     check_terms_and_grads(oracle, p, model, params)
 
 
+@pytest.mark.parametrize("kernel", ["SE_1d", "Matern52_1d"])
+@pytest.mark.parametrize("equation,N,fs,scale", [("poisson_1d-single_sin", 400, 20.0, 2 * math.pi),
+                                                 ("poisson_1d-mix_sin", 900, 30.0, 1.0),
+                                                 ("poisson_1d-x_time_sinx", 900, 50.0, 2 * math.pi),
+                                                 ("poisson_1d-x2_add_sinx", 400, 100.0, 1.0)])
+def test_plain_kernels_at_shipped_sizes_guarded(gphm, oracle, kernel, equation, N, fs, scale):
+    """The reference's shipped 1-D configs (N_col = 400 / 900, Q = 30, log-ls = 0, jitter 1e-6) with the plain kernels:
+    cond(K) reaches 1e8 .. 8e8 and min_k (1 - kappa_k^2) falls to 4e-6, where the Gohberg-Semencul formula cancels.
+    The conditioning guard must keep the result inside the 1e-6 bound - on the Toeplitz inverse-generator route
+    where it is accurate, on the Cholesky route where the guard fires."""
+    import warnings
+    O = oracle
+    p, model, _, _ = make_1d(gphm, oracle, equation, kernel, N, 30, fs, scale)
+    params = O.init_params_1d(N, 30, fs)
+    params["u"] = (0.6 * torch.sin(7 * p.x) + 0.2 * torch.cos(3 * p.x)).reshape(-1, 1)
+    params["log_tau"], params["log_v"] = torch.tensor(0.3, dtype=DT), torch.tensor(-0.2, dtype=DT)
+    st = model.core.new_state(params)
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        model.core.check_conditioning(st)
+    fired = any("ill-conditioned" in str(w.message) for w in caught)
+    assert fired == (not model.core.lib.gphm_plan_uses_gs(model.core.plan, 0))
+    if N == 900 and scale == 1.0 and kernel == "SE_1d":
+        assert fired                       # min(1 - kappa^2) = 4.5e-6 (tools/cond_guard_study.py)
+    te, ge = O.loss_and_grad_efficient(p, params)
+    terms, gU, gs = model.core.value_and_grad(st)
+    model.core.raise_on_bad_status()
+    got = dict(zip(("loss", "logdet1", "logdet2", "quad", "bgap", "eqgap"), terms.tolist()))
+    for k, w in te.items():
+        assert abs(got[k] - w) <= TOL * abs(w), (k, got[k], w, fired)
+    grads = model.core.unpack_tree(gU, gs)
+    want = dict(tree_flatten(ge))
+    for path, g in tree_flatten(grads):
+        den = float(want[path].norm())
+        if den > 0:
+            assert float((g.reshape(-1) - want[path].reshape(-1)).norm()) <= TOL * den, (path, fired)
+
+
 def test_step_matches_oracle_and_is_functional(gphm, oracle):
     p, model, _, _ = make_2d(gphm, oracle, "poisson_2d-sin_add_cos", "Matern52_Cos_1d", 100, 90, 10, 10.0, 2 * math.pi)
     params = oracle.state_S1(p, Q=10, freq_scale=10.0)
@@ -280,6 +318,29 @@ def test_properties_at_scale(gphm, oracle, N):
     assert abs(slope - gg2) <= 1e-5 * gg2
 
 
+def test_headline_size_parity_4096(gphm, oracle):
+    """The bench workload at its own size (poisson_2d-sin_add_cos, 4096 x 4096, Matern52_Cos_1d, Q=30): one
+    value_and_grad at the non-degenerate state S1 and at the reference's initial state S0 against the oracle's
+    efficient formulation - all six loss terms and every gradient leaf within 1e-6 (cond(K) ~ 5e7 here)."""
+    O = oracle
+    N = 4096
+    p, model, _, _ = make_2d(gphm, oracle, "poisson_2d-sin_add_cos", "Matern52_Cos_1d", N, N, 30, 20.0, 2 * math.pi)
+    assert gphm_uses_gs(model)
+    for state in (O.state_S1(p), O.init_params_2d(N, N, 30, 20.0)):
+        te, ge = O.loss_and_grad_efficient(p, state)
+        st = model.core.new_state(state)
+        terms, gU, gs = model.core.value_and_grad(st)
+        model.core.raise_on_bad_status()
+        got = dict(zip(("loss", "logdet1", "logdet2", "quad", "bgap", "eqgap"), terms.tolist()))
+        for k, w in te.items():
+            assert abs(got[k] - w) <= TOL * abs(w) if w != 0.0 else got[k] == 0.0, (k, got[k], w)
+        grads = model.core.unpack_tree(gU, gs)
+        want = dict(tree_flatten(ge))
+        for path, gch in tree_flatten(grads):
+            den = float(want[path].norm())
+            assert float((gch.reshape(-1) - want[path].reshape(-1)).norm()) <= TOL * (den if den > 0 else 1.0), path
+
+
 @pytest.mark.parametrize("equation", ["poisson_1d-x2_add_sinx", "allencahn_1d-sin_cos"])
 def test_extra_gp_second_stage_parity(gphm, oracle, equation):
     """GP_solver_1d_extra: loss_extra and its gradient vs the oracle's literal restatement of
@@ -352,3 +413,13 @@ def test_step_host_matches_step_inplace(gphm, oracle, mode, dim):
         for a, b in zip(h, (st.U, st.small, st.mU, st.vU, st.msmall, st.vsmall, st.count)):
             assert torch.equal(a, b.cpu()), k
     assert int(h[6]) == 3
+    # params-only variant: the Adam state stays in the plan (optax state is device-resident in the reference's loop)
+    st2 = core.new_state(params)
+    hU, hs = pin(st2.U), pin(st2.small)
+    hcount = torch.zeros(1, dtype=torch.int64).pin_memory()
+    for k in range(3):
+        core.step_inplace(st2, 0.01)
+        core.step_host_params(hU, hs, hterms, 0.01, reset_opt=(k == 0), hcount=hcount)
+        assert torch.equal(hterms, st2.terms.cpu()), k
+        assert torch.equal(hU, st2.U.cpu()) and torch.equal(hs, st2.small.cpu()), k
+    assert int(hcount) == 3
