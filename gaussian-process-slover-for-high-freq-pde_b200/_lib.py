@@ -45,6 +45,7 @@ _SIGS = {
     "gphm_plan_set_base_field": (c_int, [c_void_p, c_void_p]),
     "gphm_logjoint_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "gphm_adam_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_double, c_void_p]),
+    "gphm_adam_update_inc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_double, c_void_p]),
     "gphm_step": (c_int, [c_void_p] * 8 + [c_double, c_void_p, c_void_p]),
     "gphm_step_host": (c_int, [c_void_p] * 8 + [c_double, c_void_p, c_void_p]),
     "gphm_step_host_params": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_double, c_void_p, c_void_p]),

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include "../../include/gphm.h"   // status codes GPHM_OK / GPHM_EINVAL / ...
 
 namespace gphm {
@@ -28,6 +29,34 @@ void set_last_error(const char* fmt, ...);
     } while (0)
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+
+// cudaFuncSetAttribute is per DEVICE: one-time kernel set-up keyed by the current device, thread-safe.
+//   static DeviceOnce once;  if (once.needed()) { ...set attributes...; once.done(); }   (needed() holds the lock until done())
+struct DeviceOnce {
+    static constexpr int kMaxDevices = 64;
+    std::mutex mu;
+    bool ready[kMaxDevices] = {};
+    int dev = 0;
+    bool needed() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+        mu.lock();
+        if (ready[d]) { mu.unlock(); return false; }
+        dev = d;
+        return true;
+    }
+    void done(bool ok = true) { ready[dev] = ok; mu.unlock(); }
+};
+#define GPHM_ONCE_CUDA_OK(once, expr)                                                        \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            (once).done(false);                                                              \
+            ::gphm::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,             \
+                                   cudaGetErrorString(_e));                                  \
+            return GPHM_ECUDA;                                                               \
+        }                                                                                    \
+    } while (0)
 
 // Launch accounting / optional CUDA-event profiling per kernel family (gphm_profile_* in gphm.h).
 enum : int { CAT_GRAM = 0, CAT_DGEMM = 1, CAT_CHOL_DIAG = 2, CAT_ELEMWISE = 3, CAT_ADAM = 4, CAT_FFT = 5, CAT_GS_APPLY = 6,

@@ -277,15 +277,15 @@ static int set_attr() {
     F(false, false, 1) F(false, true, 1) F(true, false, 1) F(true, true, 1)
 
 int dgemm_init() {
-    static int done = -1;
-    if (done >= 0) return done;
-#define GPHM_SET(TA, TB, VEC)                                         \
-    GPHM_TRY((set_attr<128, 128, 4, 4, TA, TB, VEC, 1>()));           \
-    GPHM_TRY((set_attr<64, 64, 2, 2, TA, TB, VEC, 3>()));
+    static DeviceOnce once;
+    if (!once.needed()) return GPHM_OK;
+#define GPHM_SET(TA, TB, VEC)                                                                              \
+    if (set_attr<128, 128, 4, 4, TA, TB, VEC, 1>() != GPHM_OK) { once.done(false); return GPHM_ECUDA; }    \
+    if (set_attr<64, 64, 2, 2, TA, TB, VEC, 3>() != GPHM_OK) { once.done(false); return GPHM_ECUDA; }
     GPHM_FOR_ALL_GEMM(GPHM_SET)
 #undef GPHM_SET
-    done = GPHM_OK;
-    return done;
+    once.done();
+    return GPHM_OK;
 }
 
 int launch_dgemm(const GemmArgs& g, cudaStream_t st) {

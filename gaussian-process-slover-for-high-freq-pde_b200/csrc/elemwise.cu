@@ -367,6 +367,29 @@ int launch_adam(double* p, const double* g, double* m, double* v, size_t n, cons
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }
+// Adam on a short vector (the 6Q+2 kernel parameters) and ++count in ONE launch: every thread reads the count before
+// the barrier, thread 0 bumps it after.
+__global__ void __launch_bounds__(1024)
+adam_inc_kernel(double* __restrict__ p, const double* __restrict__ g, double* __restrict__ m, double* __restrict__ v, int n,
+                long long* count, double lr) {
+    constexpr double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+    const double t = (double)(*count + 1);
+    __syncthreads();
+    const double c1 = 1.0 - pow(b1, t), c2 = 1.0 - pow(b2, t);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double gi = g[i];
+        const double mi = b1 * m[i] + (1.0 - b1) * gi;
+        const double vi = b2 * v[i] + (1.0 - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        p[i] -= lr * (mi / c1) / (sqrt(vi / c2) + eps);
+    }
+    if (threadIdx.x == 0) *count += 1;
+}
+int launch_adam_inc(double* p, const double* g, double* m, double* v, size_t n, long long* count, double lr, cudaStream_t st) {
+    { LaunchScope scope(CAT_ADAM, st); adam_inc_kernel<<<1, 1024, 0, st>>>(p, g, m, v, (int)n, count, lr); }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
 int launch_count_inc(long long* count, cudaStream_t st) {
     { LaunchScope scope(CAT_ADAM, st); count_inc_kernel<<<1, 1, 0, st>>>(count); }
     GPHM_LAUNCH_OK();

@@ -185,11 +185,11 @@ __global__ void copy_diag_blocks_kernel(const double* __restrict__ invd, double*
 constexpr size_t kDiagSmem = (size_t)(kNB * SLD + SB * SLD + 2 * kNB + SB) * sizeof(double);
 
 int factor_init() {
-    static int done = -1;
-    if (done >= 0) return done;
-    GPHM_CUDA_OK(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem));
-    done = GPHM_OK;
-    return done;
+    static DeviceOnce once;
+    if (!once.needed()) return GPHM_OK;
+    GPHM_ONCE_CUDA_OK(once, cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem));
+    once.done();
+    return GPHM_OK;
 }
 
 // nsys = 1: one system.  nsys = 2: a second system of the same size at the given element offsets

@@ -287,15 +287,15 @@ unpack_segments_kernel(const double* __restrict__ recv, int P, int k, int rows, 
 static int ilog2(int L) { int l = 0; while ((1 << l) < L) ++l; return l; }
 
 int fft_init() {
-    static int done = -1;
-    if (done >= 0) return done;
+    static DeviceOnce once;
+    if (!once.needed()) return GPHM_OK;
     const int bytes = (int)fft_smem_bytes(FFT_MAX_L);
-    GPHM_CUDA_OK(cudaFuncSetAttribute(xcorr_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    GPHM_CUDA_OK(cudaFuncSetAttribute(spectrum_to_diag_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    GPHM_CUDA_OK(cudaFuncSetAttribute(toeplitz_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    GPHM_CUDA_OK(cudaFuncSetAttribute(toeplitz_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    done = GPHM_OK;
-    return done;
+    GPHM_ONCE_CUDA_OK(once, cudaFuncSetAttribute(xcorr_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    GPHM_ONCE_CUDA_OK(once, cudaFuncSetAttribute(spectrum_to_diag_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    GPHM_ONCE_CUDA_OK(once, cudaFuncSetAttribute(toeplitz_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    GPHM_ONCE_CUDA_OK(once, cudaFuncSetAttribute(toeplitz_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    once.done();
+    return GPHM_OK;
 }
 
 int launch_twiddle_init(double* W, int L, cudaStream_t st) {

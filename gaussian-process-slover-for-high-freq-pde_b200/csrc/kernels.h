@@ -127,6 +127,7 @@ size_t theta_general_part_doubles(int n, int Q);
 int launch_adam(double* p, const double* g, double* m, double* v, size_t n, const long long* count, double lr,
                 cudaStream_t st);
 int launch_count_inc(long long* count, cudaStream_t st);
+int launch_adam_inc(double* p, const double* g, double* m, double* v, size_t n, long long* count, double lr, cudaStream_t st);
 int launch_rel_l2(const double* pred, const double* truth, size_t n, double* part, double* out, cudaStream_t st);
 int launch_copy(double* dst, const double* src, size_t n, cudaStream_t st);
 int launch_pair_reduce(const double* part, double* out2, cudaStream_t st);

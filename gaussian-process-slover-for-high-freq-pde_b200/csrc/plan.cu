@@ -765,6 +765,7 @@ int gphm_plan_status(gphm_plan* plan, int* pivot, void* stream) {
     if (pivot) *pivot = h[0] ? h[0] : (h[1] ? plan->d.n1 + h[1] : 0);
     if (h[0] || h[1]) return GPHM_NOT_SPD;
     if (h[2]) return GPHM_NONFINITE;
+    if (h[3] & 0xff00) { set_last_error("Schur/Levinson lattice CTA never received its coefficients (generator CTA not resident)"); return GPHM_STALLED; }
     if (h[3]) { if (pivot) *pivot = h[3]; return GPHM_ILL_CONDITIONED; }
     return GPHM_OK;
 }
@@ -803,6 +804,13 @@ int gphm_adam_update(double* d_p, const double* d_g, double* d_m, double* d_v, s
     return launch_adam(d_p, d_g, d_m, d_v, n, d_count, lr, static_cast<cudaStream_t>(stream));
 }
 
+int gphm_adam_update_inc(double* d_p, const double* d_g, double* d_m, double* d_v, size_t n, long long* d_count, double lr,
+                         void* stream) {
+    if (!d_p || !d_g || !d_m || !d_v || !d_count) { set_last_error("gphm_adam_update_inc: null pointer"); return GPHM_EINVAL; }
+    if (n > (1u << 20)) { set_last_error("gphm_adam_update_inc: meant for the short parameter vector (n <= 2^20)"); return GPHM_EINVAL; }
+    return launch_adam_inc(d_p, d_g, d_m, d_v, n, d_count, lr, static_cast<cudaStream_t>(stream));
+}
+
 int gphm_step(gphm_plan* plan, double* d_U, double* d_small, double* d_mU, double* d_vU, double* d_msmall,
               double* d_vsmall, long long* d_count, double lr, double* d_terms, void* stream) {
     if (!plan || !d_U || !d_small || !d_mU || !d_vU || !d_msmall || !d_vsmall || !d_count || !d_terms) {
@@ -813,8 +821,7 @@ int gphm_step(gphm_plan* plan, double* d_U, double* d_small, double* d_mU, doubl
     GPHM_TRY(logjoint_grad(*plan, d_U, d_small, plan->gU, plan->gsmall, d_terms, 0, st));
     const size_t nf = (size_t)plan->d.n1 * plan->d.n2, ns = 6 * (size_t)plan->d.Q + 2;
     GPHM_TRY(launch_adam(d_U, plan->gU, d_mU, d_vU, nf, d_count, lr, st));
-    GPHM_TRY(launch_adam(d_small, plan->gsmall, d_msmall, d_vsmall, ns, d_count, lr, st));
-    GPHM_TRY(launch_count_inc(d_count, st));
+    GPHM_TRY(launch_adam_inc(d_small, plan->gsmall, d_msmall, d_vsmall, ns, d_count, lr, st));     // Adam(small) and ++count
     return GPHM_OK;
 }
 

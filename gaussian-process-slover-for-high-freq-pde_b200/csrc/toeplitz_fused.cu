@@ -230,10 +230,10 @@ static bool getenv_flag(const char* name) {       // read once per name would ne
 static int ilog2f(int L) { int l = 0; while ((1 << l) < L) ++l; return l; }
 
 int toeplitz_fused_init() {
-    static int done = -1;
-    if (done >= 0) return done;
+    static DeviceOnce once;
+    if (!once.needed()) return GPHM_OK;
     const int bytes = (int)fft_smem_bytes(FFT_MAX_L);
-#define GPHM_FUSED_ATTR(K, KT, NT, GR) GPHM_CUDA_OK(cudaFuncSetAttribute(K<KT, NT, GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
+#define GPHM_FUSED_ATTR(K, KT, NT, GR) GPHM_ONCE_CUDA_OK(once, cudaFuncSetAttribute(K<KT, NT, GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
 #define GPHM_FUSED_ATTR3(K, NT, GR) GPHM_FUSED_ATTR(K, 1, NT, GR); GPHM_FUSED_ATTR(K, 2, NT, GR); GPHM_FUSED_ATTR(K, 3, NT, GR)
 #define GPHM_FUSED_ATTR6(K) GPHM_FUSED_ATTR3(K, FFT_THREADS, false); GPHM_FUSED_ATTR3(K, 0, false); \
                             GPHM_FUSED_ATTR3(K, FFT_THREADS, true); GPHM_FUSED_ATTR3(K, 0, true)
@@ -243,8 +243,8 @@ int toeplitz_fused_init() {
 #undef GPHM_FUSED_ATTR3
 #undef GPHM_FUSED_ATTR6
 #undef GPHM_FUSED_ATTR
-    done = GPHM_OK;
-    return done;
+    once.done();
+    return GPHM_OK;
 }
 
 bool toeplitz_fused_supported(int L) { return L >= 16 && L <= FFT_MAX_L; }

@@ -350,6 +350,7 @@ schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, dou
     double E = r0;
     for (int w = 0; w < nwarps; ++w) E *= red[w];
     const double invE = dead ? __longlong_as_double(0x7ff8000000000000ll) : 1.0 / E;
+    if (dead && tid == 0 && guard) atomicOr(guard, 1 << (8 + guard_bit0 + sys));      // distinct status: GPHM_STALLED
 #pragma unroll
     for (int i = 0; i < SCHUR_EPT; ++i) { const int p = j0t + i; if (p < n) g[p] = a[i] * invE; }
     if (dbg && tid == 0) dbg[blockIdx.x] = clock64() - t_start;
@@ -419,12 +420,12 @@ gs_prepare_kernel(const double* __restrict__ g, long long sG, int n, int L, int 
 static int ilog2i(int L) { int l = 0; while ((1 << l) < L) ++l; return l; }
 
 int toeplitz_inv_init() {
-    static int done = -1;
-    if (done >= 0) return done;
-    GPHM_CUDA_OK(cudaFuncSetAttribute(gs_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)fft_smem_bytes(FFT_MAX_L)));
-    done = GPHM_OK;
-    return done;
+    static DeviceOnce once;
+    if (!once.needed()) return GPHM_OK;
+    GPHM_ONCE_CUDA_OK(once, cudaFuncSetAttribute(gs_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)fft_smem_bytes(FFT_MAX_L)));
+    once.done();
+    return GPHM_OK;
 }
 
 int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitter, double* g, long long sG,
@@ -435,9 +436,19 @@ int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitt
     const int threads = std::min(SCHUR_MAX_THREADS, ((n + SCHUR_EPT - 1) / SCHUR_EPT + 31) / 32 * 32);
     for (int s = 0; s < nsys; ++s) GPHM_CUDA_OK(cudaMemsetAsync(prog + s * sProg, 0, sizeof(int), st));
     {
+        // The lattice CTA consumes what the generator CTA of the same system produces: launched as a thread-block CLUSTER
+        // of 2, which the hardware co-schedules - a plain <<<>>> launch does not guarantee that both are resident together
+        // (16-stream CUDA-graph ensembles, MPS, a saturated device).
         LaunchScope scope(CAT_CHOL_DIAG, st, 8.0 * (double)n * n * nsys);
-        schur_levinson_kernel<<<2 * nsys, threads, 0, st>>>(tabK, sTab, n, jitter, g, sG, half_logdet, sLd, status, sStatus,
-                                                              gkap, sKap, prog, sProg, guard, guard_bit0, toeplitz_guard_min(), dbg);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * nsys); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const double gmin = toeplitz_guard_min();
+        GPHM_CUDA_OK(cudaLaunchKernelEx(&cfg, schur_levinson_kernel, tabK, sTab, n, jitter, g, sG, half_logdet, sLd, status, sStatus,
+                                        gkap, sKap, prog, sProg, guard, guard_bit0, gmin, dbg));
     }
     GPHM_LAUNCH_OK();
     return GPHM_OK;

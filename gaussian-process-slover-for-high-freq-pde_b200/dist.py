@@ -87,14 +87,14 @@ class CudaOps(object):
     def new(self, tag, shape):
         return self._buf(tag, shape)
 
-    def residual(self, R, U, F, A, Bt, small):
-        out = self._buf("res2", (2,))
+    def residual(self, R, U, F, A, Bt, small, out=None):
+        out = self._buf("res2", (2,)) if out is None else out
         _lib.check(self.lib.gphm_mg_residual(self.plan, _lib.ptr(R), _lib.ptr(U), _lib.ptr(F), _lib.ptr(A), _lib.ptr(Bt),
                                              R.numel(), _lib.ptr(small), _lib.ptr(out), self._s()), "gphm_mg_residual")
         return out
 
-    def boundary(self, U, bidx, bvals):
-        eb, out = self._buf("eb", (max(bidx.numel(), 1),)), self._buf("bg1", (1,))
+    def boundary(self, U, bidx, bvals, out=None):
+        eb, out = self._buf("eb", (max(bidx.numel(), 1),)), (self._buf("bg1", (1,)) if out is None else out)
         _lib.check(self.lib.gphm_mg_boundary(_lib.ptr(U), _lib.ptr(bidx), _lib.ptr(bvals), bidx.numel(), _lib.ptr(eb),
                                              _lib.ptr(out), self._s()), "gphm_mg_boundary")
         return eb, out
@@ -218,6 +218,10 @@ class CudaOps(object):
     def adam(self, p, g, m, v, count, lr):
         _lib.check(self.lib.gphm_adam_update(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), p.numel(), _lib.ptr(count),
                                              float(lr), self._s()), "gphm_adam_update")
+
+    def adam_inc(self, p, g, m, v, count, lr):
+        _lib.check(self.lib.gphm_adam_update_inc(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), p.numel(), _lib.ptr(count),
+                                                 float(lr), self._s()), "gphm_adam_update_inc")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -419,12 +423,10 @@ class ShardedSolver2D(object):
         Rt = o.toeplitz_rows_add(0, False, At, c1, 0.0, None, o.new("Rt", At.shape), True)      # (c1 D1 A)^T
         R_r, A_r = self.ct2r([Rt, At])
         Bt_r = o.kinv_rows(1, U_r, "Bt_r")                                        # U K2^-1          (R)
-        eb, bg = o.boundary(U_r, self.bidx, self.bvals)
+        eb, _ = o.boundary(U_r, self.bidx, self.bvals, out=self.acc[2:3])
         o.toeplitz_rows_add(1, False, Bt_r, 1.0, 1.0, R_r, R_r, True)             # + Bt D2^T
-        acc = self.acc                               # [eqgap, quad, bgap | 6Q theta-gradients | 2 unused]: one all-reduce
-        acc.zero_()
-        acc[0:2] = o.residual(R_r, U_r, self.F, A_r, Bt_r, small)                 # R_r <- G_r ; [eqgap, quad]
-        acc[2:3] = bg
+        acc = self.acc                               # [eqgap, quad, bgap | 6Q theta-gradients | d/dlog_tau, d/dlog_v]
+        o.residual(R_r, U_r, self.F, A_r, Bt_r, small, out=acc[0:2])              # R_r <- G_r ; [eqgap, quad] (no torch op in the step)
         G_r = R_r
         gs = acc[3:]
         lead = self.rank == 0                        # the K^-1 (log-det) term is added once
@@ -438,10 +440,9 @@ class ShardedSolver2D(object):
         gU_r = o.grad_u_sum(U_r, G_r, V1_r, V2_r, self.bidx, eb, self.nseg0, small)
         o.theta_grad_pairs(0, V1t, G_ct, lead, 0.5 * self.logdet * N2, c1, small, gs[0:3 * Q])
         o.theta_grad_pairs(1, V2_r, G_r, lead, 0.5 * self.logdet * N1, 1.0, small, gs[3 * Q:6 * Q])
-        self._allreduce(acc)
+        self._allreduce(acc[0:3 + 6 * Q])            # every entry of the slice was written above (nothing to zero)
         o.finalize(acc[0:3], ld, small, self.terms, gs)                           # terms[8]; gs[6Q], gs[6Q+1]
-        self.gsmall.copy_(gs)
-        return self.terms, gU_r, self.gsmall
+        return self.terms, gU_r, gs
 
     def value_and_grad(self):
         """Collective.  Returns (terms[8], gU_r (h,N2), gsmall (6Q+2)) - same layout as gphm_logjoint_grad."""
@@ -535,5 +536,9 @@ class ShardedSolver2D(object):
         _, gU_r, gs = self.value_and_grad()
         o = self.ops
         o.adam(self.U, gU_r, self.mU, self.vU, self.count, self.lr)
-        o.adam(self.small, gs, self.msmall, self.vsmall, self.count, self.lr)
-        self.count += 1
+        adam_inc = getattr(o, "adam_inc", None)
+        if adam_inc is not None:                     # Adam on the small leaves and ++count in one launch
+            adam_inc(self.small, gs, self.msmall, self.vsmall, self.count, self.lr)
+        else:
+            o.adam(self.small, gs, self.msmall, self.vsmall, self.count, self.lr)
+            self.count += 1

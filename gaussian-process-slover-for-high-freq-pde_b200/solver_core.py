@@ -179,6 +179,8 @@ class SolverCore(object):
             warnings.warn("libgphm: Gram matrix too ill-conditioned for the Toeplitz inverse-generator route (axis mask %d): "
                           "continuing on the blocked Cholesky route" % piv, RuntimeWarning)
             return
+        if rc == 4:
+            raise _lib.GphmError("gphm_plan_status: " + _lib.last_error())
         if rc == _lib.NOT_SPD:
             raise FloatingPointError("Gram matrix is not positive definite (pivot %d)" % piv)
         if rc == _lib.NONFINITE:

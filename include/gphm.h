@@ -52,6 +52,9 @@ extern "C" {
                                  inverse-generator route (min_k (1 - kappa_k^2) < 3.5e-5): results are still finite, but
                                  call gphm_plan_use_cholesky to stay inside the 1e-6 parity bound */
 
+#define GPHM_STALLED     4   /* gphm_plan_status: the two-CTA Schur/Levinson kernel timed out waiting for its producer
+                                 (results are NaN); cannot happen while the cluster launch co-schedules both CTAs */
+
 /* flags for gphm_logjoint_grad */
 #define GPHM_FORWARD_ONLY  1   /* loss terms only (compute_early_stopping, loss) */
 
@@ -176,6 +179,11 @@ GPHM_API int gphm_logjoint_grad(gphm_plan* plan, const double* d_U, const double
  * int64 holding the number of completed steps (read, not modified).                           */
 GPHM_API int gphm_adam_update(double* d_p, const double* d_g, double* d_m, double* d_v, size_t n, const long long* d_count,
                      double lr, void* stream);
+
+/* The same update for the SHORT leaves (kernel parameters, log_tau, log_v) followed by ++count in one launch - the
+ * last kernel of a step (optax: the count advances once per optimizer.update, model_GP_solver_2d.py:180).   */
+GPHM_API int gphm_adam_update_inc(double* d_p, const double* d_g, double* d_m, double* d_v, size_t n, long long* d_count,
+                         double lr, void* stream);
 
 /* step(): value_and_grad + Adam on every leaf, in place, then ++count
  * (model_GP_solver_2d.py:176-183).  d_terms holds the PRE-update loss terms.                   */

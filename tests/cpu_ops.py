@@ -116,17 +116,24 @@ class CpuOps(object):
         C.copy_(alpha * prod + (beta * C if beta != 0.0 else 0.0))
         return C
 
-    def residual(self, R, U, F, A, Bt, small):
+    def residual(self, R, U, F, A, Bt, small, out=None):
         r = R - F
         if self.eq_name == "allencahn":
             r = r + U * (U * U - 1.0)
-        out = torch.stack(((r * r).sum(), (A * Bt).sum()))
+        res = torch.stack(((r * r).sum(), (A * Bt).sum()))
         R.copy_(torch.exp(small[6 * self.Q + 1]) * r)
-        return out
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
 
-    def boundary(self, U, bidx, bvals):
+    def boundary(self, U, bidx, bvals, out=None):
         eb = U.reshape(-1)[bidx.long()] - bvals
-        return eb, (eb * eb).sum().reshape(1)
+        bg = (eb * eb).sum().reshape(1)
+        if out is not None:
+            out.copy_(bg)
+            return eb, out
+        return eb, bg
 
     def grad_u(self, U, G, W, S1, S2, bidx, eb, nseg0, small):
         g = W + S1 + S2

@@ -40,3 +40,22 @@ def test_product_arm_needs_a_gpu():
         return
     r = _run("--steps", "1")
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_parity_block_helpers_on_cpu():
+    """bench.py's parity checker (OracleSide) fed with the oracle's LITERAL formulation as the 'measured' side: the
+    comparison code (term order, packed small layout, per-leaf norms) is exercised without a GPU."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import gphm_oracle as O
+    side = bench.OracleSide(48)
+    for name in ("S1", "S0"):
+        params = side.state(name)
+        tl, gl = O.loss_and_grad_literal(side.p, params)
+        terms8 = torch.tensor([tl[k] for k in bench.TERM_ORDER] + [float(gl["log_tau"]), float(gl["log_v"])], dtype=torch.float64)
+        rec = side.compare(name, params, terms8, gl["U"], bench.small_from_params(gl))
+        assert rec["state"] == name and rec["max_rel_term"] <= 1e-9 and rec["max_rel_leaf"] <= 1e-7, rec
+        bad = terms8.clone(); bad[3] *= 1.0 + 1e-3                     # a wrong quad term must show up
+        assert side.compare(name, params, bad, gl["U"], bench.small_from_params(gl))["max_rel_term"] >= (9e-4 if name == "S1" else 0.0)
+    run = side.steps_and_rel_l2(2)
+    assert 0.0 < run["rel_l2"] < 2.0 and run["timed_iters"] == 1 and run["U"].shape == (48, 48)

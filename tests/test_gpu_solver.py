@@ -423,3 +423,29 @@ def test_step_host_matches_step_inplace(gphm, oracle, mode, dim):
         assert torch.equal(hterms, st2.terms.cpu()), k
         assert torch.equal(hU, st2.U.cpu()) and torch.equal(hs, st2.small.cpu()), k
     assert int(hcount) == 3
+
+
+def test_evals_end_to_end_run_2d_sh_line(gphm, tmp_path, monkeypatch):
+    """The `run_2d.sh` line  python model_GP_solver_2d.py -equation=poisson_2d-sin_sin -kernel=Matern52_Cos_1d -nepoch=100
+    end to end on the GPU through the fire-style _main(): config merge, problem set-up, train(), store_model and
+    wrirte_log from a real GPU model; the pickle and log.txt are re-read and compared with the reference's own shipped
+    result files (code/result_log/poisson_2d-sin_sin/.../Q30: err 0.4676 at the last checkpoint)."""
+    import pickle
+    import sys as _sys
+    monkeypatch.chdir(tmp_path)
+    m2d = gphm.model_GP_solver_2d
+    monkeypatch.setattr(_sys, "argv", ["model_GP_solver_2d.py", "-equation=poisson_2d-sin_sin", "-kernel=Matern52_Cos_1d", "-nepoch=100"])
+    m2d._main(m2d.evals)
+    d = tmp_path / "result_log" / "poisson_2d-sin_sin" / "kernel_Matern52_Cos_1d" / "epoch_100" / "Q30"
+    name = "llk_weight-200.0-nu-1-Q-30-epoch-100-lr-0.0100-freqscale=20-logdet-1-x-2pi-Ncol-400"     # the reference's file name
+    with open(d / (name + ".pkl"), "rb") as f:
+        params, log_dict, tp = pickle.load(f)
+    g = np.load(os.path.join(GOLD, "poisson_2d_sin_sin_matern52cos_e100.npz"))
+    assert params["U"].shape == (400, 400) and set(params) == {"U", "kernel_paras_1", "kernel_paras_2", "log_tau", "log_v"}
+    assert log_dict["epoch_list"] == list(range(0, 100, 5)) and tp["kernel"] == "Matern52_Cos_1d" and tp["N_col"] == 400
+    assert abs(log_dict["loss_list"][0] - float(g["log_loss_list"][0])) <= 1e-9 * 29.7  # step-0 log-loss of the shipped run (29.7054563...)
+    assert abs(log_dict["err_list"][-1] - float(g["log_err_list"][-1])) <= 1e-3         # 0.46758843; chaos bound of SURVEY 0.6
+    assert abs(float(params["log_tau"]) - float(g["log_tau"])) <= 1e-2
+    lines = (d / "log.txt").read_text().splitlines()
+    assert lines[0] == "llk_weight-200.0--nu-1-Q-30-epoch-100-lr-0.0100-freqscale=20-logdet-1-x-2pi-Ncol-400"
+    assert lines[1].startswith("err_mean: 0.46") and "avg_epochs 100" in lines[1] and lines[2].startswith("err_list: [0.46")
