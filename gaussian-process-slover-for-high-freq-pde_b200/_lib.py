@@ -55,6 +55,7 @@ _SIGS = {
     "gphm_rel_l2": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "gphm_plan_factor": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "gphm_apply_kinv": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "gphm_apply_kinv_rows_refined": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "gphm_plan_matrix": (c_void_p, [c_void_p, c_int, c_int]),
     "gphm_plan_logdet": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gphm_mg_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,

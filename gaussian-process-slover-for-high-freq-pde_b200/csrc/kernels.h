@@ -66,7 +66,7 @@ int launch_spectrum_to_diag_sums(const double* partK, const double* partD, int L
                                  cudaStream_t st);
 // spec (L complex, bit-reversed order, scaled by 1/L) of the circulant embedding of the Toeplitz matrix t(i-j) = tab[|i-j|] (* sign)
 int launch_toeplitz_spectrum(const double* tab, int n, int L, const double* W, bool antisym, double dirsign, double* spec,
-                             cudaStream_t st);
+                             cudaStream_t st, double diag_add = 0.0);
 // Out[r][:] = alpha * T X[r][:] + beta * Out[r][:]   for every row r (T n x n Toeplitz with spectrum `spec`)
 int launch_toeplitz_apply(const double* X, int rows, int n, int ldx, const double* spec, int L, const double* W, double alpha,
                           double beta, double* Out, int ldo, cudaStream_t st);

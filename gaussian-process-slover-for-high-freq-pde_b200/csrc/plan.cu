@@ -71,6 +71,7 @@ struct Axis {
            *T = nullptr, *invdiag = nullptr, *ldpart = nullptr, *tabK = nullptr, *tabD = nullptr, *dspart = nullptr,
            *sK = nullptr, *sD = nullptr, *sKinv = nullptr, *tgpart = nullptr, *twid = nullptr, *specK = nullptr, *specD = nullptr, *specT = nullptr,   // specT: spectrum of the Toeplitz D
            *gsg = nullptr, *gspec = nullptr,   // gsg = K^-1 e_0; gspec: four Gohberg-Semencul circulant spectra
+           *specKm = nullptr,                  // spectrum of K itself (circulant embedding): residuals of the refined K^-1 applications
            *specY = nullptr,                   // transforms of the packed row pairs of A^T (axis 1) / Bt (axis 2)
            *gskap = nullptr;                   // reflection coefficients handed from the generator CTA to the lattice CTA
     int* gsprog = nullptr;
@@ -159,7 +160,7 @@ size_t carve(gphm_plan& p, void* base) {
         } else c.take(X.tgpart, tg);
         if (p.size_query || X.gs) {
             const size_t other = (d.dim == 2) ? (a == 0 ? (size_t)d.n2 : (size_t)d.n1) : 1;      // rows this axis' operators act on
-            c.take(X.gsg, n); c.take(X.gspec, 8 * Lq); c.take(X.specY, 2 * Lq * ((other + 1) / 2));
+            c.take(X.gsg, n); c.take(X.gspec, 8 * Lq); c.take(X.specKm, 2 * Lq); c.take(X.specY, 2 * Lq * ((other + 1) / 2));
             c.take(X.gskap, n); c.take(X.gsprog, 1);
         }
     }
@@ -239,6 +240,15 @@ int invert_axis(gphm_plan& p, int a, bool with_kinv, cudaStream_t st) {
     return GPHM_OK;
 }
 
+// The K^-1 applications of the REVERSE pass (V1 = K1^-1 (c1 D1^T G + Bt/2), V2 = (G D2 + A/2) K2^-1) get one step of
+// iterative refinement, y += GS(b - K y).  The Gohberg-Semencul application is forward-accurate (cond(K) eps relative to
+// |y|, like a Cholesky solve) but its residual b - K y is not small relative to |b|, and the theta-gradient contracts
+// V A^T against dK/dtheta with a ~5000-fold cancellation against G A^T : dD/dtheta that only a small RESIDUAL keeps
+// intact: without refinement the theta-leaves are off by 5e-8 at N = 1024 and 1.4e-6 at N = 4096 against an
+// extended-precision reference (tools/extended_reference.py), with it they match the Cholesky route (1e-9 .. 5e-8).
+// The forward applications (A, Bt) do not need it (measured: no change).  force_general bit 5 switches it off.
+inline bool gs_refine(const gphm_plan& p) { return (p.d.force_general & 32) == 0; }
+
 // Uniform-grid axes a0 .. a0+count-1 without a dense factorisation: Toeplitz tables, Schur/Levinson
 // recursion for g = K^-1 e_0 and log|K|, Gohberg-Semencul spectra and the diagonal sums of K^-1.
 // Two axes of equal size share every launch (one CTA per axis).
@@ -270,6 +280,11 @@ int factor_gs(gphm_plan& p, int a0, int count, const double* small, cudaStream_t
         for (int a = a0; a < a0 + count; ++a) {
             Axis& X = p.ax[a];
             GPHM_TRY(launch_toeplitz_spectrum(X.tabD, X.n, X.fftL, X.twid, order == 1, X.dirsign, X.specT, st));
+        }
+    if (gs_refine(p))   // spectrum of K (with the jitter): residual b - K y of the refined applications
+        for (int a = a0; a < a0 + count; ++a) {
+            Axis& X = p.ax[a];
+            GPHM_TRY(launch_toeplitz_spectrum(X.tabK, X.n, X.fftL, X.twid, false, 1.0, X.specKm, st, p.d.jitter));
         }
     return GPHM_OK;
 }
@@ -312,6 +327,14 @@ int apply_kinv_rows_gs(const Axis& X, const double* Xm, int rows, double* out, d
     GPHM_TRY(launch_toeplitz_apply(out, rows, n, n, X.gspec + 2 * sp, L, X.twid, 1.0, 0.0, out, n, st));  // L(g) . / g0
     GPHM_TRY(launch_toeplitz_apply(tmp, rows, n, n, X.gspec + 3 * sp, L, X.twid, 1.0, 1.0, out, n, st));  // - L(h) . / g0
     return GPHM_OK;
+}
+
+// out[r] += K^-1 (Xm[r] - K out[r]) for every row: one refinement step of out ~ K^-1 Xm.  tmp: rows x n scratch (may alias Xm,
+// which is then destroyed).
+int refine_kinv_rows_gs(const Axis& X, const double* Xm, int rows, double* out, double* tmp, cudaStream_t st) {
+    const int n = X.n, L = X.fftL;
+    GPHM_TRY(launch_toeplitz_apply_fused(out, rows, n, n, X.specKm, L, X.twid, -1.0, 1.0, Xm, n, tmp, n, nullptr, st));   // b - K y
+    return launch_gs_apply_fused(tmp, rows, n, n, X.gspec, L, X.twid, 1.0, 1.0, out, n, out, n, st);                      // y += K^-1 r
 }
 
 // out = K_a^-1 X (side 0, X is n x cols) or X K_a^-1 (side 1, X is rows x n); tmp has X's shape.
@@ -398,14 +421,17 @@ int logjoint_grad_gs(gphm_plan& p, const double* U, const double* small, double*
         GPHM_TRY(launch_transpose(Bt, n1, n2, p.Tf, st));                       // Bt^T
         GPHM_TRY(d1(Gt, anti ? -c1 : c1, 0.5, nullptr, p.Tf));                  // (c1 D1^T G + Bt/2)^T
         GPHM_TRY(gs1(p.Tf, p.W)); V1t = p.W;                                    // V1^T
+        if (gs_refine(p)) GPHM_TRY(refine_kinv_rows_gs(X1, p.Tf, n2, p.W, p.Tf, st));
         GPHM_TRY(launch_transpose(p.W, n2, n1, p.V1, st));
         GPHM_TRY(d2(G, anti ? -1.0 : 1.0, 0.5, nullptr, p.A));                  // G D2 + A/2  (A is free after the residual)
         GPHM_TRY(gs2(p.A, p.V2)); V2 = p.V2;
+        if (gs_refine(p)) GPHM_TRY(refine_kinv_rows_gs(X2, p.A, n1, p.V2, p.A, st));
         GPHM_TRY(launch_grad_u(lc, p.has_base ? p.base : nullptr, U, G, p.V1, p.V2, nullptr, p.eb, p.xind, small, gU, nullptr,
                                nullptr, st));
     } else {
         GPHM_TRY(d1(G, anti ? -c1 : c1, 0.5, U, p.Tf));                         // D^T g + u/2
         GPHM_TRY(gs1(p.Tf, p.V1)); V1t = p.V1;                                  // s + a/2
+        if (gs_refine(p)) GPHM_TRY(refine_kinv_rows_gs(X1, p.Tf, n2, p.V1, p.Tf, st));
         GPHM_TRY(launch_lincomb(p.S1, 0.5, At, 0.0, nullptr, nf, st));
         GPHM_TRY(launch_grad_u(lc, p.has_base ? p.base : nullptr, U, G, p.V1, p.S1, nullptr, p.eb, p.xind, small, gU, nullptr,
                                nullptr, st));
@@ -1092,6 +1118,21 @@ int gphm_apply_kinv(gphm_plan* plan, int axis, int side, const double* d_X, int 
     if (axis < 0 || axis > 1 || plan->ax[axis].n == 0 || (side != 0 && side != 1)) { set_last_error("gphm_apply_kinv: bad axis/side"); return GPHM_EINVAL; }
     if (rows <= 0 || cols <= 0) return GPHM_OK;
     return apply_kinv(*plan, axis, side, d_X, rows, cols, d_out, d_tmp, static_cast<cudaStream_t>(stream));
+}
+
+int gphm_apply_kinv_rows_refined(gphm_plan* plan, int axis, const double* d_X, int rows, double* d_out, double* d_tmp,
+                                 void* stream) {
+    if (!plan || !d_X || !d_out || !d_tmp) { set_last_error("gphm_apply_kinv_rows_refined: null pointer"); return GPHM_EINVAL; }
+    if (axis < 0 || axis > 1 || plan->ax[axis].n == 0) { set_last_error("gphm_apply_kinv_rows_refined: bad axis"); return GPHM_EINVAL; }
+    if (rows <= 0) return GPHM_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Axis& X = plan->ax[axis];
+    GPHM_TRY(apply_kinv(*plan, axis, 1, d_X, rows, X.n, d_out, d_tmp, st));
+    if (X.gs && gs_refine(*plan) && toeplitz_fused_supported(X.fftL)) {
+        GPHM_TRY(launch_copy(d_tmp, d_X, (size_t)rows * X.n, st));             // keep the caller's right-hand side intact
+        GPHM_TRY(refine_kinv_rows_gs(X, d_tmp, rows, d_out, d_tmp, st));
+    }
+    return GPHM_OK;
 }
 
 int gphm_plan_logdet(gphm_plan* plan, double* d_out2, void* stream) {

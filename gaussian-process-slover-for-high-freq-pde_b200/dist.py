@@ -140,11 +140,16 @@ class CudaOps(object):
                                                    float(beta), float(cD), _lib.ptr(small), _lib.ptr(out), self._s()),
                    "gphm_mg_theta_grad_fft")
 
-    def kinv_rows(self, axis, X, tag):
-        """Every row of X (rows x n_axis) times K_axis^-1."""
+    def kinv_rows(self, axis, X, tag, refine=False):
+        """Every row of X (rows x n_axis) times K_axis^-1; refine: one step of iterative refinement (the reverse-pass
+        applications V1, V2 - gphm_apply_kinv_rows_refined)."""
         out, tmp = self._buf(tag, X.shape), self._buf("kinv_tmp", X.shape)
-        _lib.check(self.lib.gphm_apply_kinv(self.plan, axis, 1, _lib.ptr(X), X.shape[0], X.shape[1], _lib.ptr(out),
-                                            _lib.ptr(tmp), self._s()), "gphm_apply_kinv")
+        if refine:
+            _lib.check(self.lib.gphm_apply_kinv_rows_refined(self.plan, axis, _lib.ptr(X), X.shape[0], _lib.ptr(out),
+                                                             _lib.ptr(tmp), self._s()), "gphm_apply_kinv_rows_refined")
+        else:
+            _lib.check(self.lib.gphm_apply_kinv(self.plan, axis, 1, _lib.ptr(X), X.shape[0], X.shape[1], _lib.ptr(out),
+                                                _lib.ptr(tmp), self._s()), "gphm_apply_kinv")
         return out
 
     def toeplitz_rows_add(self, axis, transposed, X, alpha, beta, add, out, keep):
@@ -433,10 +438,10 @@ class ShardedSolver2D(object):
         # backward
         G_ct, Btt = self.r2ct([G_r, Bt_r])
         T0 = o.toeplitz_rows_add(0, True, G_ct, c1, 0.5, Btt, o.new("T0", G_ct.shape), False)   # (c1 D1^T G + Bt/2)^T
-        V1t = o.kinv_rows(0, T0, "V1t")
+        V1t = o.kinv_rows(0, T0, "V1t", refine=True)
         (V1_r,) = self.ct2r([V1t])
         P2 = o.toeplitz_rows_add(1, True, G_r, 1.0, 0.5, A_r, o.new("P2", G_r.shape), False)    # G D2 + A/2
-        V2_r = o.kinv_rows(1, P2, "V2_r")
+        V2_r = o.kinv_rows(1, P2, "V2_r", refine=True)
         gU_r = o.grad_u_sum(U_r, G_r, V1_r, V2_r, self.bidx, eb, self.nseg0, small)
         o.theta_grad_pairs(0, V1t, G_ct, lead, 0.5 * self.logdet * N2, c1, small, gs[0:3 * Q])
         o.theta_grad_pairs(1, V2_r, G_r, lead, 0.5 * self.logdet * N1, 1.0, small, gs[3 * Q:6 * Q])

@@ -73,7 +73,10 @@ typedef struct gphm_problem_desc {
                             bit 3: derivative-Gram products D*A, D^T*G by GEMM, not Toeplitz FFT;
                             bit 4: K^-1 by blocked Cholesky + triangular GEMMs even on uniform grids
                                    (default there: Schur/Levinson recursion + Gohberg-Semencul FFT
-                                   products, no dense factorisation) */
+                                   products, no dense factorisation);
+                            bit 5: no iterative-refinement step on the reverse-pass K^-1 applications of the
+                                   Toeplitz inverse-generator route (measurement only: theta-gradients lose
+                                   ~cond(K)/40 * 1e-13 of relative accuracy, 1.4e-6 at N = 4096) */
     double llk_weight;   /* trick_paras['llk_weight'] */
     double logdet;       /* trick_paras['logdet'] (True -> 1.0) */
     double beta;         /* advection speed, trick_paras['beta'] (ignored otherwise) */
@@ -223,6 +226,14 @@ GPHM_API int gphm_plan_factor(gphm_plan* plan, const double* d_small, int axis_m
 GPHM_API int gphm_apply_kinv(gphm_plan* plan, int axis, int side, const double* d_X, int rows, int cols, double* d_out,
                     double* d_tmp, void* stream);
 GPHM_API const double* gphm_plan_matrix(const gphm_plan* plan, int axis, int which);   /* 0 K^-1, 1 D, 2 Linv, 3 L */
+/* X K^-1 for every row of d_X (rows x n_axis) with ONE step of iterative refinement on the Toeplitz inverse-generator
+ * route (out += K^-1 (X - K out)): the solve-VJPs of the reverse pass (V1, V2) need a small RESIDUAL, not only a small
+ * forward error, because the theta-gradient contracts them with a ~5000-fold cancellation.  Same
+ * result as gphm_apply_kinv(side = 1) on the Cholesky route.  d_tmp: rows x n scratch; d_X is left intact.
+ * Replaces the transposed solves of jax's VJP of jnp.linalg.solve (model_GP_solver_2d.py:104-105 under :179).   */
+GPHM_API int gphm_apply_kinv_rows_refined(gphm_plan* plan, int axis, const double* d_X, int rows, double* d_out, double* d_tmp,
+                                 void* stream);
+
 /* [log|K1|, log|K2|] of the last factorisation into two device doubles.                        */
 GPHM_API int gphm_plan_logdet(gphm_plan* plan, double* d_out2, void* stream);
 /* Rank-local pieces of boundary_and_eq_gap / loss / their reverse pass on a block of the grid

@@ -70,7 +70,7 @@ class CpuOps(object):
     def uses_gs(self, axis):
         return self.gs and O.is_uniform(self.x if axis == 0 else self.y)
 
-    def kinv_rows(self, axis, X, tag):
+    def kinv_rows(self, axis, X, tag, refine=False):
         Li = self.m[(axis, 2)]
         return (X @ Li.T) @ Li
 
