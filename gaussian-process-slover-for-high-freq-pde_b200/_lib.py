@@ -33,6 +33,10 @@ _SIGS = {
     "gphm_kappa_pairs": (c_int, [c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_void_p, c_void_p]),
     "gphm_dgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, c_void_p, c_int, c_void_p, c_int, c_double,
                            c_void_p, c_int, c_void_p]),
+    "gphm_ozaki_work_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "gphm_ozaki_error_factor": (c_double, [c_int, c_int]),
+    "gphm_ozaki_dgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, c_void_p, c_int, c_void_p, c_int, c_double,
+                                 c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "gphm_potrf_work_bytes": (c_size_t, [c_int]),
     "gphm_potrf_inv": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gphm_workspace_bytes": (c_size_t, [POINTER(ProblemDesc)]),

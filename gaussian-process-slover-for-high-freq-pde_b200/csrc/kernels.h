@@ -101,6 +101,13 @@ int launch_xcorr_pairs(const double* X, int rows, int n, int ldx, const double* 
 int launch_gs_apply_fused(const double* X, int rows, int n, int ldx, const double* gspec, int L, const double* W, double alpha,
                           double beta, const double* Add, int lda, double* Out, int ldo, cudaStream_t st);
 
+// ---- ozaki.cu: FP64-accurate GEMM on tcgen05 (int8 Ozaki slices, TMA operands, TMEM accumulators) ----
+int ozaki_default_slices();                                  // GPHM_OZAKI_SLICES, default 8
+size_t ozaki_work_bytes(int M, int N, int K, int S);
+double ozaki_error_factor(int K, int S);                     // |dC_ij| <= |alpha| * factor * max_k|A_ik| * max_k|B_kj|
+int launch_ozaki_dgemm(bool transA, bool transB, int M, int N, int K, double alpha, const double* A, int lda, const double* B,
+                       int ldb, double beta, double* C, int ldc, int S, void* work, size_t work_bytes, cudaStream_t st);
+
 // ---- elemwise.cu ---------------------------------------------------------------------------
 struct LossConsts { int dim, eq_type, n1, n2, nb, Q; double llk_weight, logdet, c1; };
 constexpr int kRedBlocks = 592;         // 148 SMs x 4

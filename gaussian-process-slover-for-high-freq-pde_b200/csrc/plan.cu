@@ -104,6 +104,9 @@ struct gphm_plan {
     cudaEvent_t u_ready = nullptr;        // waited for on the step's stream after the factor stage (U still uploading)
     int (*on_gu)(gphm_plan&, cudaStream_t) = nullptr;   // called once dL/dU is complete (before the theta-gradient)
     bool gu_hook_ran = false;
+    // workspace of the tcgen05 Ozaki GEMM (force_general bit 6), allocated on first use
+    void* oz_ws = nullptr;
+    size_t oz_ws_bytes = 0;
 };
 
 namespace {
@@ -216,6 +219,26 @@ LossConsts loss_consts(const gphm_plan& p) {
     c.dim = p.d.dim; c.eq_type = p.d.eq_type; c.n1 = p.d.n1; c.n2 = p.d.n2; c.nb = p.d.nb; c.Q = p.d.Q;
     c.llk_weight = p.d.llk_weight; c.logdet = p.d.logdet; c.c1 = coef_c1(p);
     return c;
+}
+
+// A plain (non-solve) contraction of the dense path: native FP64 DMMA GEMM, or - force_general bit 6 - the Ozaki-sliced
+// int8 GEMM on tcgen05 (ozaki.cu) with its stated bound.  The triangular products of the K^-1 applications never come here.
+int contract(gphm_plan& p, const GemmArgs& g, cudaStream_t st) {
+    if (!(p.d.force_general & 64) || g.kmode != 0 || g.batch != 1 || g.K > 65536) return launch_dgemm(g, st);
+    const int S = ozaki_default_slices();
+    const size_t need = ozaki_work_bytes(g.M, g.N, g.K, S);
+    if (need > p.oz_ws_bytes) {
+        // sized once for the largest contraction of the plan (max(n1, n2)^3): no allocation inside later steps
+        const int n = std::max(std::max(p.d.n1, p.d.n2), std::max(g.M, std::max(g.N, g.K)));
+        const size_t want = std::max(need, ozaki_work_bytes(n, n, n, S));
+        GPHM_CUDA_OK(cudaStreamSynchronize(st));
+        if (p.oz_ws) GPHM_CUDA_OK(cudaFree(p.oz_ws));
+        p.oz_ws = nullptr; p.oz_ws_bytes = 0;
+        if (cudaMalloc(&p.oz_ws, want) != cudaSuccess) { set_last_error("ozaki workspace: cudaMalloc(%zu) failed", want); return GPHM_ENOMEM; }
+        p.oz_ws_bytes = want;
+    }
+    return launch_ozaki_dgemm(g.transA != 0, g.transB != 0, g.M, g.N, g.K, g.alpha, g.A, g.lda, g.B, g.ldb, g.beta, g.C, g.ldc, S,
+                              p.oz_ws, p.oz_ws_bytes, st);
 }
 
 // Gram matrices of one axis.
@@ -489,14 +512,14 @@ int logjoint_grad(gphm_plan& p, const double* U, const double* small, double* gU
         GPHM_TRY(launch_toeplitz_apply(p.Tf, n2, n1, n1, X1.specT, X1.fftL, X1.twid, c1, 0.0, p.P, n1, st));
         GPHM_TRY(launch_transpose(p.P, n2, n1, p.R, st));
     } else {
-        GPHM_TRY(launch_dgemm(gemm_args(X1.D, n1, false, p.A, n2, false, p.R, n2, n1, n2, n1, c1, 0.0), st));   // c1 D1 A
+        GPHM_TRY(contract(p, gemm_args(X1.D, n1, false, p.A, n2, false, p.R, n2, n1, n2, n1, c1, 0.0), st));   // c1 D1 A
     }
     if (two) {
         if (tfft2) {   // (Bt D2^T)[i,:] = D2 Bt[i,:]
             GPHM_TRY(launch_toeplitz_spectrum(X2.tabD, n2, X2.fftL, X2.twid, anti, X2.dirsign, X2.specT, st));
             GPHM_TRY(launch_toeplitz_apply(Bt, n1, n2, n2, X2.specT, X2.fftL, X2.twid, 1.0, 1.0, p.R, n2, st));
         } else {
-            GPHM_TRY(launch_dgemm(gemm_args(Bt, n2, false, X2.D, n2, true, p.R, n2, n1, n2, n2, 1.0, 1.0), st)); // + Bt D2^T
+            GPHM_TRY(contract(p, gemm_args(Bt, n2, false, X2.D, n2, true, p.R, n2, n1, n2, n2, 1.0, 1.0), st)); // + Bt D2^T
         }
     }
     GPHM_TRY(launch_residual(p.R, U, p.src, p.A, Bt, nf, d.eq_type, p.has_base ? p.base : nullptr, small, Q, p.part, st));    // R <- G
@@ -514,14 +537,14 @@ int logjoint_grad(gphm_plan& p, const double* U, const double* small, double* gU
         GPHM_TRY(launch_toeplitz_apply(p.Tf, n2, n1, n1, X1.specT, X1.fftL, X1.twid, anti ? -c1 : c1, 0.0, p.V1, n1, st));
         GPHM_TRY(launch_transpose(p.V1, n2, n1, p.P, st));
     } else {
-        GPHM_TRY(launch_dgemm(gemm_args(X1.D, n1, true, G, n2, false, p.P, n2, n1, n2, n1, c1, 0.0), st));  // c1 D1^T G
+        GPHM_TRY(contract(p, gemm_args(X1.D, n1, true, G, n2, false, p.P, n2, n1, n2, n1, c1, 0.0), st));  // c1 D1^T G
     }
     GPHM_TRY(apply_kinv(p, 0, 0, p.P, n1, n2, p.S1, p.Tf, st));                                 // S1
     if (two) {
         if (tfft2)     // (G D2)[i,:] = D2^T G[i,:]
             GPHM_TRY(launch_toeplitz_apply(G, n1, n2, n2, X2.specT, X2.fftL, X2.twid, anti ? -1.0 : 1.0, 0.0, p.P, n2, st));
         else
-            GPHM_TRY(launch_dgemm(gemm_args(G, n2, false, X2.D, n2, false, p.P, n2, n1, n2, n2, 1.0, 0.0), st)); // G D2
+            GPHM_TRY(contract(p, gemm_args(G, n2, false, X2.D, n2, false, p.P, n2, n1, n2, n2, 1.0, 0.0), st)); // G D2
         GPHM_TRY(apply_kinv(p, 1, 1, p.P, n1, n2, p.S2, p.Tf, st));                             // S2
     }
     GPHM_TRY(launch_grad_u(lc, p.has_base ? p.base : nullptr, U, G, W, p.S1, two ? p.S2 : nullptr, p.eb, p.xind, small, gU, p.V1,
@@ -544,9 +567,9 @@ int logjoint_grad(gphm_plan& p, const double* U, const double* small, double* gU
         GPHM_TRY(launch_spectrum_to_diag_sums(X1.specK, X1.specD, X1.fftL, X1.twid, n1, order == 1, X1.dirsign,
                                               fk ? nullptr : X1.sKinv, 0.5 * d.logdet * n2, X1.sK, X1.sD, st));
     } else {
-        GPHM_TRY(launch_dgemm(gemm_args(p.V1, n2, false, p.A, n2, true, X1.Kinv, n1, n1, n1, n2, -1.0,
+        GPHM_TRY(contract(p, gemm_args(p.V1, n2, false, p.A, n2, true, X1.Kinv, n1, n1, n1, n2, -1.0,
                                         0.5 * d.logdet * n2), st));
-        GPHM_TRY(launch_dgemm(gemm_args(G, n2, false, p.A, n2, true, X1.Dbar, n1, n1, n1, n2, c1, 0.0), st));
+        GPHM_TRY(contract(p, gemm_args(G, n2, false, p.A, n2, true, X1.Dbar, n1, n1, n1, n2, c1, 0.0), st));
         if (X1.toeplitz) GPHM_TRY(launch_diag_sums(X1.Kinv, X1.Dbar, n1, n1, order == 1, X1.dirsign, X1.dspart, X1.sK, X1.sD, st));
     }
     // ---- axis 2: Kbar2 = ld/2*N1*K2^-1 - V2^T Bt,  Dbar2 = G^T Bt ----
@@ -561,9 +584,9 @@ int logjoint_grad(gphm_plan& p, const double* U, const double* small, double* gU
             GPHM_TRY(launch_spectrum_to_diag_sums(X2.specK, X2.specD, X2.fftL, X2.twid, n2, order == 1, X2.dirsign,
                                                   fk ? nullptr : X2.sKinv, 0.5 * d.logdet * n1, X2.sK, X2.sD, st));
         } else {
-            GPHM_TRY(launch_dgemm(gemm_args(p.V2, n2, true, Bt, n2, false, X2.Kinv, n2, n2, n2, n1, -1.0,
+            GPHM_TRY(contract(p, gemm_args(p.V2, n2, true, Bt, n2, false, X2.Kinv, n2, n2, n2, n1, -1.0,
                                             0.5 * d.logdet * n1), st));
-            GPHM_TRY(launch_dgemm(gemm_args(G, n2, true, Bt, n2, false, X2.Dbar, n2, n2, n2, n1, 1.0, 0.0), st));
+            GPHM_TRY(contract(p, gemm_args(G, n2, true, Bt, n2, false, X2.Dbar, n2, n2, n2, n1, 1.0, 0.0), st));
             if (X2.toeplitz) GPHM_TRY(launch_diag_sums(X2.Kinv, X2.Dbar, n2, n2, order == 1, X2.dirsign, X2.dspart, X2.sK, X2.sD, st));
         }
     }
@@ -644,6 +667,21 @@ int gphm_dgemm(int transA, int transB, int M, int N, int K, double alpha, const 
     if (K == 0) { d_A = d_C; d_B = d_C; }          // C = beta*C; operands are never dereferenced
     return launch_dgemm(gemm_args(d_A, lda, transA != 0, d_B, ldb, transB != 0, d_C, ldc, M, N, K, alpha, beta, 0),
                         static_cast<cudaStream_t>(stream));
+}
+
+size_t gphm_ozaki_work_bytes(int M, int N, int K, int slices) {
+    return ozaki_work_bytes(M, N, K, slices > 0 ? slices : ozaki_default_slices());
+}
+
+double gphm_ozaki_error_factor(int K, int slices) { return ozaki_error_factor(K, slices > 0 ? slices : ozaki_default_slices()); }
+
+int gphm_ozaki_dgemm(int transA, int transB, int M, int N, int K, double alpha, const double* d_A, int lda, const double* d_B,
+                     int ldb, double beta, double* d_C, int ldc, int slices, void* d_work, size_t work_bytes, void* stream) {
+    if (M < 0 || N < 0 || K <= 0) { set_last_error("gphm_ozaki_dgemm: bad size"); return GPHM_EINVAL; }
+    if (M == 0 || N == 0) return GPHM_OK;
+    if (!d_A || !d_B || !d_C || !d_work) { set_last_error("gphm_ozaki_dgemm: null pointer"); return GPHM_EINVAL; }
+    return launch_ozaki_dgemm(transA != 0, transB != 0, M, N, K, alpha, d_A, lda, d_B, ldb, beta, d_C, ldc,
+                              slices > 0 ? slices : ozaki_default_slices(), d_work, work_bytes, static_cast<cudaStream_t>(stream));
 }
 
 size_t gphm_potrf_work_bytes(int n) {
@@ -771,6 +809,7 @@ int gphm_plan_create(const gphm_problem_desc* desc, const double* h_x, const dou
 void gphm_plan_destroy(gphm_plan* plan) {
     if (!plan) return;
     if (plan->owns_ws && plan->ws) cudaFree(plan->ws);
+    if (plan->oz_ws) cudaFree(plan->oz_ws);
     if (plan->hs) cudaFree(plan->hs);
     if (plan->hs_count) cudaFree(plan->hs_count);
     if (plan->hs_stream) cudaStreamDestroy(plan->hs_stream);

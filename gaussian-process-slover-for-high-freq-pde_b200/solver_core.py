@@ -233,6 +233,24 @@ def dgemm(A, B, transA=False, transB=False, alpha=1.0, beta=0.0, C=None):
     return C
 
 
+def ozaki_dgemm(A, B, transA=False, transB=False, alpha=1.0, beta=0.0, C=None, slices=0):
+    """alpha * op(A) op(B) + beta * C through the tcgen05 int8 Ozaki GEMM (gphm_ozaki_dgemm); returns (C, error factor):
+    |C - exact|_ij <= |alpha| * factor * max_k|op(A)_ik| * max_k|op(B)_kj|."""
+    lib = _lib.load()
+    A, B = as_dev(A).contiguous(), as_dev(B).contiguous()
+    M, K = (A.shape[1], A.shape[0]) if transA else A.shape
+    K2, N = (B.shape[1], B.shape[0]) if transB else B.shape
+    if K != K2:
+        raise ValueError("ozaki_dgemm: inner dimensions differ")
+    if C is None:
+        C = torch.zeros((M, N), dtype=DT, device=A.device)
+    work = torch.empty(lib.gphm_ozaki_work_bytes(M, N, K, slices), dtype=torch.uint8, device=A.device)
+    _lib.check(lib.gphm_ozaki_dgemm(int(transA), int(transB), M, N, K, float(alpha), _lib.ptr(A), max(A.shape[1], 1), _lib.ptr(B),
+                                    max(B.shape[1], 1), float(beta), _lib.ptr(C), max(C.shape[1], 1), int(slices), _lib.ptr(work),
+                                    work.numel(), _lib.stream_ptr()), "gphm_ozaki_dgemm")
+    return C, float(lib.gphm_ozaki_error_factor(K, slices))
+
+
 def potrf_inv(K):
     """(L, Linv, logdet, status) of an SPD matrix; K is not modified."""
     lib = _lib.load()

@@ -76,7 +76,11 @@ typedef struct gphm_problem_desc {
                                    products, no dense factorisation);
                             bit 5: no iterative-refinement step on the reverse-pass K^-1 applications of the
                                    Toeplitz inverse-generator route (measurement only: theta-gradients lose
-                                   ~cond(K)/40 * 1e-13 of relative accuracy, 1.4e-6 at N = 4096) */
+                                   ~cond(K)/40 * 1e-13 of relative accuracy, 1.4e-6 at N = 4096);
+                            bit 6: the plain contractions of the general path (D A, Bt D^T, D^T G, G D, V A^T, G A^T:
+                                   jnp.matmul at model_GP_solver_2d.py:112,119 and their reverse pass) on the tensor
+                                   cores - Ozaki int8 slices, tcgen05.mma kind::i8, TMA operands, TMEM accumulators
+                                   (gphm_ozaki_dgemm, stated bound there); the solves stay native FP64 */
     double llk_weight;   /* trick_paras['llk_weight'] */
     double logdet;       /* trick_paras['logdet'] (True -> 1.0) */
     double beta;         /* advection speed, trick_paras['beta'] (ignored otherwise) */
@@ -121,6 +125,19 @@ GPHM_API int gphm_kappa_pairs(int kernel_id, int deriv_order, const double* d_x1
  * C[M,N] = alpha*op(A)*op(B) + beta*C, row-major (jnp.matmul, model_GP_solver_2d.py:112,119).  */
 GPHM_API int gphm_dgemm(int transA, int transB, int M, int N, int K, double alpha, const double* d_A, int lda,
                const double* d_B, int ldb, double beta, double* d_C, int ldc, void* stream);
+/* The same contraction on the 5th-generation tensor cores: both operands are cut into `slices` (2..8, 0 = default 8)
+ * signed 7-bit digits per row / column (Ozaki splitting, exact in FP64), the digit products run as
+ * tcgen05.mma kind::i8 with TMA-staged operands and exact int32 accumulators in TMEM, and the partial products are
+ * recombined in FP64.  STATED BOUND (looser than native FP64, north_star "TF32-emulated GEMMs"):
+ *     |C - C_exact|_ij <= |alpha| * gphm_ozaki_error_factor(K, slices) * max_k |op(A)_ik| * max_k |op(B)_kj|,
+ * factor = 4 K (slices + 1.1) 2^(-7 slices): 5.2e-13 at K = 4096, slices = 8.  d_work: gphm_ozaki_work_bytes bytes.
+ * Plans use it for jnp.matmul(K_dxx1, K1inv_U) (model_GP_solver_2d.py:112,119) and the matching reverse-mode products on
+ * the general path when force_general bit 6 is set; the solves stay on native FP64.                            */
+GPHM_API size_t gphm_ozaki_work_bytes(int M, int N, int K, int slices);
+GPHM_API double gphm_ozaki_error_factor(int K, int slices);
+GPHM_API int gphm_ozaki_dgemm(int transA, int transB, int M, int N, int K, double alpha, const double* d_A, int lda,
+                     const double* d_B, int ldb, double beta, double* d_C, int ldc, int slices, void* d_work,
+                     size_t work_bytes, void* stream);
 /* Cholesky K = L L^T plus explicit L^-1 and log|K| (replaces the LU inside jnp.linalg.solve /
  * slogdet, model_GP_solver_2d.py:104-105,158-161).  d_K (n x n) is destroyed; d_L, d_Linv are
  * n x n lower-triangular outputs; d_logdet gets one double; d_status one int (0 = SPD).

@@ -194,3 +194,30 @@ def test_exchange_pack_unpack_match_permute(gphm, rows, cols, part_cols, k):
     out = ops.unpack_segments(send)
     parts = cols // part_cols
     assert torch.equal(out, send.permute(1, 2, 0, 3).reshape(k, part_cols, parts * rows).contiguous())
+
+
+@pytest.mark.parametrize("M,N,K,tA,tB,slices", [(128, 64, 64, False, False, 8), (300, 200, 500, False, True, 8), (257, 129, 1000, True, False, 8),
+                                                (96, 70, 333, True, True, 6), (512, 512, 2048, False, False, 8), (64, 64, 4096, False, True, 4),
+                                                (1, 1, 7, False, False, 8)])
+def test_ozaki_tcgen05_gemm_within_stated_bound(gphm, M, N, K, tA, tB, slices):
+    """gphm_ozaki_dgemm (int8 Ozaki slices on tcgen05.mma kind::i8, TMA operands, TMEM accumulators) against an
+    extended-precision product: every entry inside the STATED bound  |dC_ij| <= factor * max_k|A_ik| * max_k|B_kj|
+    (+ the FP64 rounding of the recombination), ragged shapes, all transposes, badly scaled rows, alpha / beta."""
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g, dtype=DT) * torch.exp(3.0 * torch.randn(M, 1, generator=g, dtype=DT))      # row scales over ~5 decades
+    B = torch.randn(K, N, generator=g, dtype=DT) * torch.exp(3.0 * torch.randn(1, N, generator=g, dtype=DT))
+    A[:, K // 2:] *= 1e-9                                   # entries far below the row maximum lose relative, not absolute, accuracy
+    if M > 2:
+        A[1] = 0.0                                          # an all-zero row
+    C0 = torch.randn(M, N, generator=g, dtype=DT)
+    Ain, Bin = (A.T.contiguous() if tA else A), (B.T.contiguous() if tB else B)
+    C, factor = gphm.solver_core.ozaki_dgemm(Ain, Bin, transA=tA, transB=tB, alpha=-1.5, beta=0.25, C=C0.clone().cuda(), slices=slices)
+    torch.cuda.synchronize()
+    exact = (-1.5 * (A.to(torch.float64).numpy().astype("longdouble") @ B.numpy().astype("longdouble")) + 0.25 * C0.numpy().astype("longdouble"))
+    err = np.abs(C.cpu().numpy().astype("longdouble") - exact).astype("float64")
+    bound = 1.5 * factor * A.abs().amax(1, keepdim=True).numpy() * B.abs().amax(0, keepdim=True).numpy() + 4e-16 * np.abs(exact).astype("float64") + 1e-300
+    assert factor == 4.0 * K * (slices + 1.1) * 2.0 ** (-7 * slices)
+    assert (err <= bound).all(), float((err / bound).max())
+    if slices == 8 and K >= 500:                            # and it is a genuinely FP64-grade product, not just inside a loose bound
+        ref = A @ B
+        assert rel((C.cpu() - 0.25 * C0) / -1.5, ref) <= 1e-13

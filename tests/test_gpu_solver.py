@@ -91,6 +91,29 @@ def test_logjoint_grad_2d_parity_cholesky_path(gphm, oracle, mode, equation, ker
     check_terms_and_grads(oracle, p, model, oracle.state_S1(p, Q=Q, freq_scale=fs))
 
 
+@pytest.mark.parametrize("equation,kernel,N1,N2,Q,fs,scale,beta,uniform,mode", [
+    ("poisson_2d-sin_add_cos", "Matern52_Cos_1d", 90, 70, 6, 5.0, 2 * math.pi, 1.0, False, 64),       # non-uniform grids: the general path
+    ("advection-sin", "SE_Cos_1d", 40, 45, 5, 3.0, 1.0, 20.0, False, 64),
+    ("allencahn_2d-mix-sincos", "SE_Cos_1d", 130, 130, 9, 10.0, 1.0, 1.0, True, 64 | 16 | 8),          # uniform grid forced onto Cholesky + GEMMs
+    ("poisson_2d-sin_add_cos", "Matern52_Cos_1d", 300, 260, 30, 20.0, 2 * math.pi, 1.0, False, 64)])
+def test_logjoint_grad_2d_parity_tcgen05_contractions(gphm, oracle, equation, kernel, N1, N2, Q, fs, scale, beta, uniform, mode):
+    """force_general bit 6: every plain contraction of the general path runs as the Ozaki-sliced int8 GEMM on tcgen05
+    (8 slices: error <= 4 K 9.1 2^-56 rowmax colmax per contraction, ~1e-13 here).  Same 1e-6 parity bound on all six
+    loss terms and every gradient leaf as the native-FP64 path."""
+    p, model, _, _ = make_2d(gphm, oracle, equation, kernel, N1, N2, Q, fs, scale, beta, uniform, mode=mode)
+    assert not model.core.lib.gphm_plan_uses_gs(model.core.plan, 0)
+    launches0 = model.core.lib.gphm_launch_count()
+    check_terms_and_grads(oracle, p, model, oracle.state_S1(p, Q=Q, freq_scale=fs))
+    assert model.core.lib.gphm_launch_count() > launches0
+    # the tensor-core contractions and the native ones agree far inside the bound
+    _, ref, _, _ = make_2d(gphm, oracle, equation, kernel, N1, N2, Q, fs, scale, beta, uniform, mode=mode & ~64)
+    s1 = oracle.state_S1(p, Q=Q, freq_scale=fs)
+    (l1, g1), (l0, g0) = model.value_and_grad(s1), ref.value_and_grad(s1)
+    assert abs(float(l1) - float(l0)) <= 1e-10 * abs(float(l0))
+    for (path, a), (_, b) in zip(tree_flatten(g1), tree_flatten(g0)):
+        assert float((a - b).norm()) <= 1e-8 * float(b.norm()) + 1e-300, path
+
+
 def test_logjoint_grad_2d_golden_final_state(gphm, oracle):
     """State S2: the final params of the reference's shipped 2-D run (N=400, Q=30)."""
     g = np.load(os.path.join(GOLD, "poisson_2d_sin_sin_matern52cos_e100.npz"))
