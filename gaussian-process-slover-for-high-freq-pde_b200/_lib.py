@@ -67,6 +67,12 @@ _SIGS = {
     "gphm_mg_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gphm_mg_pack_transposed": (c_int, [c_void_p, c_int, c_int, c_int, c_size_t, c_void_p, c_void_p]),
     "gphm_mg_unpack_segments": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "gphm_mg_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "gphm_mg_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "gphm_mg_peer_close": (c_int, [c_void_p]),
+    "gphm_mg_peer_free": (c_int, [c_void_p]),
+    "gphm_mg_peer_exchange": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, ctypes.c_ulonglong, c_size_t,
+                                      c_void_p, c_void_p]),
     "gphm_mg_boundary": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "gphm_mg_grad_u": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
                                c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgphm.so")
-SOURCES = ["gram.cu", "dgemm.cu", "factor.cu", "elemwise.cu", "fft.cu", "toeplitz_inv.cu", "toeplitz_fused.cu", "ozaki.cu", "plan.cu"]
+SOURCES = ["gram.cu", "dgemm.cu", "factor.cu", "elemwise.cu", "fft.cu", "toeplitz_inv.cu", "toeplitz_fused.cu", "ozaki.cu", "peer.cu", "plan.cu"]
 HEADERS = ["common.cuh", "kernfun.cuh", "kernels.h", "fft_core.cuh", os.path.join("..", "..", "include", "gphm.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -108,6 +108,12 @@ double ozaki_error_factor(int K, int S);                     // |dC_ij| <= |alph
 int launch_ozaki_dgemm(bool transA, bool transB, int M, int N, int K, double alpha, const double* A, int lda, const double* B,
                        int ldb, double beta, double* C, int ldc, int S, void* work, size_t work_bytes, cudaStream_t st);
 
+// ---- peer.cu: transposing all-to-all through NVLink peer stores ----
+size_t peer_flag_bytes();
+int launch_a2a_transpose_peer(const double* const* in, int k, int rows, int cols, int pc, double* const* peer_bases, int P, int me,
+                              unsigned long long seq, unsigned int* done, cudaStream_t st);
+int launch_mg_wait_flags(const void* local_base, int P, unsigned long long seq, int* status, cudaStream_t st);
+
 // ---- elemwise.cu ---------------------------------------------------------------------------
 struct LossConsts { int dim, eq_type, n1, n2, nb, Q; double llk_weight, logdet, c1; };
 constexpr int kRedBlocks = 592;         // 148 SMs x 4

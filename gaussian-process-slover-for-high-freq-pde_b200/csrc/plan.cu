@@ -1122,6 +1122,53 @@ int gphm_mg_pack_transposed(const double* d_in, int rows, int cols, int part_col
     return launch_transpose_parts(d_in, rows, cols, part_cols, part_stride, d_out, static_cast<cudaStream_t>(stream));
 }
 
+// ---- exchange buffers in peer-mapped device memory (cudaIpc) --------------------------------------------------------
+int gphm_mg_peer_alloc(size_t data_doubles, void** d_base, unsigned char* h_handle64) {
+    if (!d_base || !h_handle64) { set_last_error("gphm_mg_peer_alloc: null pointer"); return GPHM_EINVAL; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    void* p = nullptr;
+    const size_t bytes = peer_flag_bytes() + sizeof(double) * data_doubles + sizeof(unsigned int) * 4;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { set_last_error("gphm_mg_peer_alloc: cudaMalloc(%zu) failed", bytes); return GPHM_ENOMEM; }
+    GPHM_CUDA_OK(cudaMemset(p, 0, bytes));
+    cudaIpcMemHandle_t h;
+    GPHM_CUDA_OK(cudaIpcGetMemHandle(&h, p));
+    memcpy(h_handle64, &h, 64);
+    *d_base = p;
+    return GPHM_OK;
+}
+
+int gphm_mg_peer_open(const unsigned char* h_handle64, void** d_peer_base) {
+    if (!h_handle64 || !d_peer_base) { set_last_error("gphm_mg_peer_open: null pointer"); return GPHM_EINVAL; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h_handle64, 64);
+    GPHM_CUDA_OK(cudaIpcOpenMemHandle(d_peer_base, h, cudaIpcMemLazyEnablePeerAccess));
+    return GPHM_OK;
+}
+
+int gphm_mg_peer_close(void* d_peer_base) {
+    if (d_peer_base) GPHM_CUDA_OK(cudaIpcCloseMemHandle(d_peer_base));
+    return GPHM_OK;
+}
+
+int gphm_mg_peer_free(void* d_base) {
+    if (d_base) GPHM_CUDA_OK(cudaFree(d_base));
+    return GPHM_OK;
+}
+
+int gphm_mg_peer_exchange(const double* const* h_in, int k, int rows, int cols, int part_cols, void* const* h_peer_bases, int P,
+                          int me, unsigned long long seq, size_t data_doubles, int* d_status, void* stream) {
+    if (!h_in || !h_peer_bases) { set_last_error("gphm_mg_peer_exchange: null pointer"); return GPHM_EINVAL; }
+    if ((size_t)k * rows * cols > data_doubles) { set_last_error("gphm_mg_peer_exchange: buffer too small"); return GPHM_EINVAL; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* bases[16];
+    if (P > 16) { set_last_error("gphm_mg_peer_exchange: P=%d > 16", P); return GPHM_EINVAL; }
+    for (int d = 0; d < P; ++d) bases[d] = static_cast<double*>(h_peer_bases[d]);
+    // the completion counter lives behind the data of this rank's own buffer
+    unsigned int* done = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(h_peer_bases[me]) + peer_flag_bytes() + sizeof(double) * data_doubles);
+    GPHM_TRY(launch_a2a_transpose_peer(h_in, k, rows, cols, part_cols, bases, P, me, seq, done, st));
+    return launch_mg_wait_flags(h_peer_bases[me], P, seq, d_status, st);
+}
+
 int gphm_mg_unpack_segments(const double* d_recv, int parts, int arrays, int rows, int seg, double* d_out, void* stream) {
     if (parts <= 0 || arrays <= 0 || rows <= 0 || seg <= 0) return GPHM_OK;
     if (!d_recv || !d_out) { set_last_error("gphm_mg_unpack_segments: null pointer"); return GPHM_EINVAL; }

@@ -192,6 +192,15 @@ class CudaOps(object):
                    "gphm_mg_unpack_segments")
         return out
 
+    def peer_exchange(self, Xs, part_cols, tag, group):
+        """Transposing all-to-all of the arrays Xs (rows x cols each) through peer stores; returns (k, part_cols, P*rows)."""
+        k, (rows, cols) = len(Xs), Xs[0].shape
+        key = ("peer", tag, k, rows, cols)
+        ex = self._cache.get(key)
+        if ex is None:
+            ex = self._cache[key] = PeerExchange(self, k, rows, cols, group)
+        return ex.run([X.contiguous() for X in Xs], part_cols)
+
     def finalize(self, sums3, ld2, small, terms, gsmall):
         """terms[8] and gsmall[6Q:6Q+2] from the all-reduced [eq_gap, quad, boundary_gap] and the log-dets (one kernel)."""
         _lib.check(self.lib.gphm_mg_finalize(self.plan, _lib.ptr(sums3), _lib.ptr(ld2), _lib.ptr(small), _lib.ptr(terms),
@@ -227,6 +236,76 @@ class CudaOps(object):
     def adam_inc(self, p, g, m, v, count, lr):
         _lib.check(self.lib.gphm_adam_update_inc(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), p.numel(), _lib.ptr(count),
                                                  float(lr), self._s()), "gphm_adam_update_inc")
+
+
+# ------------------------------------------------------------------------------------------------
+class PeerExchange(object):
+    """One exchange of the sharded step through NVLink peer memory (csrc/peer.cu): a buffer in cudaIpc-shared device
+    memory on every rank, the peers' mappings of it, and a sequence counter.  `run(Xs, part_cols)` is collective:
+    it stores this rank's tiles straight into every destination's buffer (transposed, final layout) and enqueues the
+    wait for all sources; the returned views alias the local buffer (valid until the next run of THIS exchange)."""
+
+    def __init__(self, ops, k, rows, cols, group):
+        import ctypes
+        self.ops, self.lib, self.group = ops, ops.lib, group
+        self.P, self.me = dist.get_world_size(group), dist.get_rank(group)
+        self.k, self.rows, self.cols = k, rows, cols
+        self.data_doubles = k * rows * cols
+        base = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.check(self.lib.gphm_mg_peer_alloc(self.data_doubles, ctypes.byref(base), handle), "gphm_mg_peer_alloc")
+        self.base = base.value
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=ops.device)
+        allh = [torch.empty_like(mine) for _ in range(self.P)]
+        dist.all_gather(allh, mine, group=group)
+        self.bases = (ctypes.c_void_p * self.P)()
+        self._opened = []
+        for r in range(self.P):
+            if r == self.me:
+                self.bases[r] = self.base
+                continue
+            hb = (ctypes.c_ubyte * 64)(*allh[r].cpu().tolist())
+            pb = ctypes.c_void_p()
+            _lib.check(self.lib.gphm_mg_peer_open(hb, ctypes.byref(pb)), "gphm_mg_peer_open")
+            self.bases[r] = pb.value
+            self._opened.append(pb.value)
+        self.seq = 0
+        self.status = torch.zeros(1, dtype=torch.int32, device=ops.device)
+        self._in = (ctypes.c_void_p * k)()
+        dist.barrier(group=group)                      # every rank has mapped every buffer before the first store
+
+    def view(self, pc):
+        """(k, pc, P * rows) float64 view of the local result."""
+        return _tensor_from_ptr(self.base + 512, (self.k, pc, self.P * self.rows), self.ops.device)
+
+    def run(self, Xs, part_cols):
+        self.seq += 1
+        for a, X in enumerate(Xs):
+            self._in[a] = X.data_ptr()
+        _lib.check(self.lib.gphm_mg_peer_exchange(self._in, self.k, self.rows, self.cols, part_cols, self.bases, self.P, self.me,
+                                                  self.seq, self.data_doubles, _lib.ptr(self.status), _lib.stream_ptr()),
+                   "gphm_mg_peer_exchange")
+        return self.view(part_cols)
+
+    def close(self):
+        for pb in self._opened:
+            self.lib.gphm_mg_peer_close(pb)
+        self._opened = []
+        if self.base:
+            self.lib.gphm_mg_peer_free(self.base)
+            self.base = None
+
+
+def _tensor_from_ptr(ptr, shape, device):
+    """float64 CUDA tensor over raw device memory owned by libgphm (__cuda_array_interface__)."""
+    class _Raw(object):
+        pass
+    raw = _Raw()
+    n = 1
+    for d in shape:
+        n *= d
+    raw.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(raw, device=device).view(*shape)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -289,6 +368,11 @@ class ShardedSolver2D(object):
         self.terms = ops.zeros((8,))
         self.acc = ops.zeros((3 + ns,))
         self.bytes_exchanged = 0
+        import os
+        # exchange: "peer" = one kernel with NVLink peer stores (csrc/peer.cu; default on CUDA with P > 1), "nccl" = pack ->
+        # all_to_all_single -> unpack (round 1; also what the gloo CPU tests drive)
+        mode = os.environ.get("GPHM_MG_EXCHANGE", "peer")
+        self.exchange = "peer" if (mode == "peer" and self.P > 1 and hasattr(self.ops, "peer_exchange")) else "nccl"
 
     # ---- state ---------------------------------------------------------------------------------
     def init_state(self, freq_scale):
@@ -320,7 +404,8 @@ class ShardedSolver2D(object):
         return self.terms[0]
 
     def exchange_name(self):
-        return "NCCL all-to-all"
+        return ("one transposing kernel per exchange with NVLink peer stores (cudaIpc), flags for completion; NCCL only for the "
+                "3+6Q all-reduce") if self.exchange == "peer" else "NCCL all-to-all"
 
     # ---- layout exchanges ------------------------------------------------------------------------
     def _a2a(self, send, tag=None):
@@ -364,6 +449,10 @@ class ShardedSolver2D(object):
         """Row blocks (h, N2) -> TRANSPOSED column blocks (w, N1): row j holds column rank*w + j of the field.
         Several arrays travel in one all-to-all.  `tag` names the persistent buffer set of this exchange."""
         tag = "%s%d" % (tag, len(Xs))
+        if self.exchange == "peer":
+            out = self.ops.peer_exchange(Xs, self.w, tag, self.group)
+            self.bytes_exchanged += len(Xs) * Xs[0].numel() * 8 * (self.P - 1) // self.P
+            return [out[a] for a in range(len(Xs))]
         send = self._pack_t(Xs, self.w, tag)                              # [dest][array][j][i]
         out = self._unpack(self._a2a(send, tag), tag)                     # recv [src][array][j][i]
         return [out[a] for a in range(len(Xs))]
@@ -371,6 +460,10 @@ class ShardedSolver2D(object):
     def ct2r(self, Ys, tag="ct2r"):
         """Transposed column blocks (w, N1) -> row blocks (h, N2)."""
         tag = "%s%d" % (tag, len(Ys))
+        if self.exchange == "peer":
+            out = self.ops.peer_exchange(Ys, self.h, tag, self.group)
+            self.bytes_exchanged += len(Ys) * Ys[0].numel() * 8 * (self.P - 1) // self.P
+            return [out[a] for a in range(len(Ys))]
         send = self._pack_t(Ys, self.h, tag)                              # [dest][array][i][j]
         out = self._unpack(self._a2a(send, tag), tag)                     # recv [src][array][i][j]
         return [out[a] for a in range(len(Ys))]

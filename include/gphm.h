@@ -264,6 +264,20 @@ GPHM_API int gphm_mg_residual(gphm_plan* plan, double* d_R, const double* d_U, c
                      const double* d_Bt, size_t n_local, const double* d_small, double* d_out2, void* stream);
 GPHM_API int gphm_mg_boundary(const double* d_U, const int* d_bidx, const double* d_bvals, int nb_local, double* d_eb,
                      double* d_out1, void* stream);
+/* Layout exchange of the sharded step as ONE kernel over NVLink peer memory (csrc/peer.cu), replacing
+ * gphm_mg_pack_transposed -> ncclAllToAll -> gphm_mg_unpack_segments:  for every array X_a (rows x cols, cols = P * part_cols)
+ * of this rank,  out_d[a][c][me * rows + r] = X_a[r][d * part_cols + c]  is stored straight into rank d's buffer; a sequence
+ * number per source tells the consumer (a polling kernel enqueued behind it on `stream`) when all P sources have arrived.
+ * Buffers: gphm_mg_peer_alloc (cudaMalloc + cudaIpcGetMemHandle; 64-byte handle to be all-gathered by the host layer),
+ * gphm_mg_peer_open on every other rank's handle.  Data of the local result: d_base + 512 bytes, layout [k][part_cols][P*rows].
+ * This is the "NCCL all-gather of the column contraction over NVLink" step of north_star, done with in-kernel peer stores.  */
+GPHM_API int gphm_mg_peer_alloc(size_t data_doubles, void** d_base, unsigned char* h_handle64);
+GPHM_API int gphm_mg_peer_open(const unsigned char* h_handle64, void** d_peer_base);
+GPHM_API int gphm_mg_peer_close(void* d_peer_base);
+GPHM_API int gphm_mg_peer_free(void* d_base);
+GPHM_API int gphm_mg_peer_exchange(const double* const* h_in, int k, int rows, int cols, int part_cols, void* const* h_peer_bases,
+                          int P, int me, unsigned long long seq, size_t data_doubles, int* d_status, void* stream);
+
 /* Layout exchange of the sharded step (the block transposes around the NCCL all-to-all; the reference has
  * no counterpart - its jnp.matmul / solve calls at model_GP_solver_2d.py:104-119 see whole matrices):
  *  pack_transposed : d_out[(c / part_cols) * part_stride + (c % part_cols) * rows + r] = d_in[r * cols + c]

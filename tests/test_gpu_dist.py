@@ -78,12 +78,13 @@ def test_sharded_world1_matches_fused_path(equation, eq_name, kernel, beta, mode
     _compare(equation, eq_name, kernel, beta, 256, 8, mode=mode)
 
 
-def _worker(rank, world, port, mode):
+def _worker(rank, world, port, mode, exchange):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["GPHM_MG_EXCHANGE"] = exchange
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -93,7 +94,9 @@ def _worker(rank, world, port, mode):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("mode", [0, 16])
-def test_sharded_world2_nccl(mode):
+@pytest.mark.parametrize("mode,exchange", [(0, "peer"), (0, "nccl"), (16, "nccl")])
+def test_sharded_world2_nccl(mode, exchange):
+    """World size 2 on two GPUs: the all-FFT sharded step with the NVLink peer-store exchange (csrc/peer.cu) and with the
+    NCCL all-to-all, and the general sharded step; every variant against the oracle and the fused single-GPU step."""
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_worker, args=(2, port, mode), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, mode, exchange), nprocs=2, join=True)
