@@ -23,6 +23,13 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank; MKL then stays single-threaded whatever torch.set_num_threads says.
+# Rank 0 runs the CPU oracle (parity block, cpu_baseline, --impl reference) and needs the host cores: undo it before
+# torch is imported.  The other ranks keep one thread.
+if os.environ.get("LOCAL_RANK", "0") == "0" and os.environ.get("OMP_NUM_THREADS") == "1" and "TORCHELASTIC_RUN_ID" in os.environ:
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import torch
 
 METRIC = "log-joint+grad iters/sec, 2D Poisson 4096^2 grid"
@@ -397,7 +404,8 @@ def run_ours(args, rank, world, local):
             step()
         ours_rel = predict_rel_l2()
         ours_loss = cur_loss()
-        ours_U = full_U().cpu() if rank == 0 else None
+        ours_U = full_U()                              # collective for N > 1: every rank calls it
+        ours_U = ours_U.cpu() if rank == 0 else None
         if rank == 0:
             oracle_run = side.steps_and_rel_l2(REL_L2_STEPS)
             rel_l2_after = {"steps": REL_L2_STEPS, "ours": ours_rel, "oracle": oracle_run["rel_l2"],

@@ -43,12 +43,22 @@ __host__ inline int fft_threads_for(int L) { return std::max(64, std::min(FFT_TH
 // always hit 8 different 16-byte bank groups for every stride the passes use
 __device__ __forceinline__ int PADI(int i) { return i + (i >> 3); }
 __host__ __device__ inline int fft_data_slots(int L) { return L + (L >> 3) + 1; }
-// entries of the compact twiddle table: 3 * sum over radix-8 passes of q_p = L >> (3p+3)
+// Twiddles of a radix-8 pass: w1 = T_s[j], w2 = T_{s+1}[j], w4 = T_{s+2}[j] from the shared-memory table.  -DGPHM_TW_SQUARE
+// computes w2 = w1^2, w4 = w2^2 instead (6 FP64 operations for two 16-byte shared-memory loads, table 56 -> 19 KB at
+// L = 8192): measured in round 2 on the 4096^2 step and REJECTED - gs_apply_fused 3.87 -> 3.98 ms per step (the FP64 pipe and
+// the register allocation of the 128-register kernels matter as much as the shared-memory traffic), toeplitz_apply_fused
+// 1.50 -> 1.46 ms.
+#ifdef GPHM_TW_SQUARE
+constexpr int kTwPerPass = 1;
+#else
+constexpr int kTwPerPass = 3;
+#endif
+// entries of the compact twiddle table: kTwPerPass * sum over radix-8 passes of q_p = L >> (3p+3)
 __host__ __device__ inline int fft_twiddle_slots(int L) {
     int logL = 0;
     while ((1 << logL) < L) ++logL;
     int n = 0;
-    for (int s = 0; logL - s >= 3; s += 3) n += 3 * (L >> (s + 3));
+    for (int s = 0; logL - s >= 3; s += 3) n += kTwPerPass * (L >> (s + 3));
     return n;
 }
 inline size_t fft_smem_bytes(int L) { return (size_t)(fft_data_slots(L) + fft_twiddle_slots(L)) * sizeof(double2); }
@@ -70,16 +80,24 @@ __device__ __forceinline__ void fft_load_twiddles(double2* xs, int L, int logL, 
     double2* tw = fft_twiddles(xs, L);
     for (int s = 0; logL - s >= 3; s += 3) {
         const int q = L >> (s + 3);
-        for (int i = tid; i < 3 * q; i += fft_nt<NT>()) {
+        for (int i = tid; i < kTwPerPass * q; i += fft_nt<NT>()) {
             const int t = i / q, j = i - t * q;
             tw[i] = W[(L - (L >> (s + t))) + j];
         }
-        tw += 3 * q;
+        tw += kTwPerPass * q;
     }
     __syncthreads();
 }
 
 constexpr double kRsqrt2 = 0.70710678118654752440;
+
+__device__ __forceinline__ double2 csqr(double2 a) { return make_double2(fma(a.x, a.x, -a.y * a.y), 2.0 * a.x * a.y); }
+// (w1, w2, w4) of butterfly j of a pass with q butterflies per group; tw = the pass' table
+__device__ __forceinline__ void fft_tw3(const double2* tw, int q, int j, double2& w1, double2& w2, double2& w4) {
+    w1 = tw[j];
+    if (kTwPerPass == 3) { w2 = tw[q + j]; w4 = tw[2 * q + j]; }
+    else { w2 = csqr(w1); w4 = csqr(w2); }
+}
 
 // One radix-8 DIF butterfly: e[0..7] are the points base + m*q; output slot m holds frequency
 // brev3(m) of the 8-point sub-transform, twiddled for the next pass.
@@ -151,7 +169,9 @@ __device__ __forceinline__ void dif_pass8(double2* xs, int L, int logL, int s, c
         double2 e[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m) e[m] = xs[PADI(base + m * q)];
-        bfly8_dif(e, tw[j], tw[q + j], tw[2 * q + j]);
+        double2 w1, w2, w4;
+        fft_tw3(tw, q, j, w1, w2, w4);
+        bfly8_dif(e, w1, w2, w4);
 #pragma unroll
         for (int m = 0; m < 8; ++m) xs[PADI(base + m * q)] = e[m];
     }
@@ -167,7 +187,9 @@ __device__ __forceinline__ void dit_pass8(double2* xs, int L, int logL, int s, c
         double2 e[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m) e[m] = xs[PADI(base + m * q)];
-        bfly8_dit_inv(e, tw[2 * q + j], tw[q + j], tw[j]);          // table of the forward pass at stage logL-3-s
+        double2 w1, w2, w4;
+        fft_tw3(tw, q, j, w1, w2, w4);
+        bfly8_dit_inv(e, w4, w2, w1);                                // table of the forward pass at stage logL-3-s
 #pragma unroll
         for (int m = 0; m < 8; ++m) xs[PADI(base + m * q)] = e[m];
     }
@@ -208,7 +230,7 @@ template <int NT = FFT_THREADS>
 __device__ __forceinline__ void fft_dif_inplace(double2* xs, int L, int logL, const double2* __restrict__, int tid) {
     const double2* tw = fft_twiddles(xs, L);
     int s = 0;
-    for (; logL - s >= 3; s += 3) { dif_pass8<NT>(xs, L, logL, s, tw, tid); tw += 3 * (L >> (s + 3)); }
+    for (; logL - s >= 3; s += 3) { dif_pass8<NT>(xs, L, logL, s, tw, tid); tw += kTwPerPass * (L >> (s + 3)); }
     if (logL - s == 2) unit_pass<2, NT>(xs, L, false, tid);
     else if (logL - s == 1) unit_pass<1, NT>(xs, L, false, tid);
 }
@@ -221,7 +243,7 @@ __device__ __forceinline__ void fft_dit_inverse_inplace(double2* xs, int L, int 
     // inverse pass at stage s pairs with the forward pass at stage logL-3-s: walk the table backwards
     const double2* tw = fft_twiddles(xs, L) + fft_twiddle_slots(L);
     for (int s = r; s + 3 <= logL; s += 3) {
-        tw -= 3 * (1 << s);
+        tw -= kTwPerPass * (1 << s);
         dit_pass8<NT>(xs, L, logL, s, tw, tid);
     }
 }
@@ -239,6 +261,8 @@ __device__ __forceinline__ void fft_dit_inverse_inplace(double2* xs, int L, int 
 // A convolution costs 2 np8 + 1 sweeps instead of 2 (np8 + 1) + 3.
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ inline int fft_tail_stages(int logL) { return logL % 3 == 0 ? 3 : logL % 3; }
+// kernels without a per-bin register stash (toeplitz_apply_fused) merge the last radix-8 pass into a 16-point tail
+__host__ __device__ inline int fft_tail_stages_wide(int logL) { return (logL % 3 == 1 && logL >= 7) ? 4 : fft_tail_stages(logL); }
 
 __device__ __forceinline__ void bfly8_dif_unit(double2 (&e)[8]) {      // bfly8_dif with w1 = w2 = w4 = 1
     {
@@ -291,9 +315,50 @@ __device__ __forceinline__ void bfly8_dit_inv_unit(double2 (&e)[8]) {
     }
 }
 
+// 16 contiguous points, the last four forward stages (spans 8, 4, 2, 1): span 8 with the constants W16^m, then the
+// 8-point unit butterfly on both halves.  Merges the last radix-8 pass with the radix-2 tail of lengths with
+// log2 L = 1 (mod 3) - one shared-memory sweep less per transform.
+constexpr double kC16 = 0.92387953251128675613, kS16 = 0.38268343236508977173;     // cos(pi/8), sin(pi/8)
+__device__ __forceinline__ double2 mul_w16(double2 v, int m) {       // v * exp(-2 pi i m / 16), m = 0 .. 7 (compile-time after unrolling)
+    switch (m) {
+        case 0: return v;
+        case 1: return make_double2(kC16 * v.x + kS16 * v.y, kC16 * v.y - kS16 * v.x);
+        case 2: return make_double2((v.x + v.y) * kRsqrt2, (v.y - v.x) * kRsqrt2);
+        case 3: return make_double2(kS16 * v.x + kC16 * v.y, kS16 * v.y - kC16 * v.x);
+        case 4: return make_double2(v.y, -v.x);
+        case 5: return make_double2(kC16 * v.y - kS16 * v.x, -(kC16 * v.x + kS16 * v.y));
+        case 6: return make_double2((v.y - v.x) * kRsqrt2, -(v.x + v.y) * kRsqrt2);
+        default: return make_double2(kS16 * v.y - kC16 * v.x, -(kS16 * v.x + kC16 * v.y));
+    }
+}
+__device__ __forceinline__ double2 mul_w16c(double2 v, int m) {      // v * exp(+2 pi i m / 16)
+    const double2 t = mul_w16(make_double2(v.x, -v.y), m);
+    return make_double2(t.x, -t.y);
+}
+__device__ __forceinline__ void bfly16_dif_unit(double2 (&e)[16]) {
+    double2 lo[8], hi[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) { lo[m] = cadd(e[m], e[m + 8]); hi[m] = mul_w16(csub(e[m], e[m + 8]), m); }
+    bfly8_dif_unit(lo);
+    bfly8_dif_unit(hi);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) { e[m] = lo[m]; e[m + 8] = hi[m]; }
+}
+__device__ __forceinline__ void bfly16_dit_inv_unit(double2 (&e)[16]) {
+    double2 lo[8], hi[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) { lo[m] = e[m]; hi[m] = e[m + 8]; }
+    bfly8_dit_inv_unit(lo);
+    bfly8_dit_inv_unit(hi);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) { const double2 t = mul_w16c(hi[m], m); e[m] = cadd(lo[m], t); e[m + 8] = csub(lo[m], t); }
+}
+
 template <int KT>
 __device__ __forceinline__ void unit_fwd(double2 (&e)[1 << KT]) {
-    if constexpr (KT == 1) {
+    if constexpr (KT == 4) {
+        bfly16_dif_unit(e);
+    } else if constexpr (KT == 1) {
         const double2 a = e[0], c = e[1];
         e[0] = cadd(a, c); e[1] = csub(a, c);
     } else if constexpr (KT == 2) {
@@ -307,7 +372,9 @@ __device__ __forceinline__ void unit_fwd(double2 (&e)[1 << KT]) {
 }
 template <int KT>
 __device__ __forceinline__ void unit_inv(double2 (&e)[1 << KT]) {
-    if constexpr (KT == 1) {
+    if constexpr (KT == 4) {
+        bfly16_dit_inv_unit(e);
+    } else if constexpr (KT == 1) {
         const double2 a = e[0], c = e[1];
         e[0] = cadd(a, c); e[1] = csub(a, c);
     } else if constexpr (KT == 2) {
@@ -330,7 +397,9 @@ __device__ __forceinline__ void dif_first(double2* xs, int L, const double2* tw,
         for (int m = 0; m < 4; ++m) e[m] = ld(j + m * q);
 #pragma unroll
         for (int m = 4; m < 8; ++m) e[m] = make_double2(0.0, 0.0);
-        bfly8_dif(e, tw[j], tw[q + j], tw[2 * q + j]);
+        double2 w1, w2, w4;
+        fft_tw3(tw, q, j, w1, w2, w4);
+        bfly8_dif(e, w1, w2, w4);
 #pragma unroll
         for (int m = 0; m < 8; ++m) xs[PADI(j + m * q)] = e[m];
     }
@@ -340,17 +409,17 @@ __device__ __forceinline__ void dif_first(double2* xs, int L, const double2* tw,
 // Forward passes 1 .. np8-1 (after dif_first).
 template <int NT = FFT_THREADS, bool GR = false>
 __device__ __forceinline__ void dif_middle(double2* xs, int L, int logL, int np8, int tid) {
-    const double2* tw = fft_twiddles(xs, L) + 3 * (L >> 3);
-    for (int p = 1; p < np8; ++p) { dif_pass8<NT, GR>(xs, L, logL, 3 * p, tw, tid); tw += 3 * (L >> (3 * p + 3)); }
+    const double2* tw = fft_twiddles(xs, L) + kTwPerPass * (L >> 3);
+    for (int p = 1; p < np8; ++p) { dif_pass8<NT, GR>(xs, L, logL, 3 * p, tw, tid); tw += kTwPerPass * (L >> (3 * p + 3)); }
 }
 // Inverse passes at stages KT, KT+3, ..., logL-6 (all but the last one).
 // With GR the caller needs a CTA-wide barrier before the last inverse pass (it mixes the octants): added here.
 template <int NT = FFT_THREADS, bool GR = false>
 __device__ __forceinline__ void dit_middle(double2* xs, int L, int logL, int np8, int KT, int tid) {
     const double2* tw = fft_twiddles(xs, L);
-    for (int p = 0; p < np8; ++p) tw += 3 * (L >> (3 * p + 3));
+    for (int p = 0; p < np8; ++p) tw += kTwPerPass * (L >> (3 * p + 3));
     for (int p = np8 - 1; p >= 1; --p) {          // inverse stage s = logL - 3 - 3p pairs with forward pass p
-        tw -= 3 * (L >> (3 * p + 3));
+        tw -= kTwPerPass * (L >> (3 * p + 3));
         dit_pass8<NT, GR>(xs, L, logL, logL - 3 - 3 * p, tw, tid);
     }
     if (GR) __syncthreads();
@@ -361,7 +430,14 @@ __device__ __forceinline__ void dit_middle(double2* xs, int L, int logL, int np8
 template <int KT, int NT, bool GR>
 __device__ __forceinline__ int fft_mid_group(int tid, int i, int L, int lG) {
     if (!GR) return tid + i * fft_nt<NT>();
-    constexpr int IPO = 8 >> KT;                                  // iterations per octant
+    if constexpr (KT == 4) {
+        // 16-point bin groups: an octant holds L/128 of them = half a thread group; a thread group owns 8 / #groups octants
+        const int ngroups = fft_nt<NT>() >> lG, opg = 8 / ngroups, lbpo = lG - 1;
+        const int l = tid & ((1 << lG) - 1), k = l >> lbpo;
+        if (k >= opg) return L;                                   // idle thread (lengths <= 4096: one octant per group)
+        return (((tid >> lG) + ngroups * k) << lbpo) + (l & ((1 << lbpo) - 1));
+    }
+    constexpr int IPO = KT >= 4 ? 1 : (8 >> KT);                  // iterations per octant
     const int octant = (tid >> lG) + (fft_nt<NT>() >> lG) * (i / IPO);
     return octant * ((L >> 3) >> KT) + (tid & ((1 << lG) - 1)) + ((i % IPO) << lG);
 }
@@ -372,6 +448,7 @@ template <int KT, int NT = FFT_THREADS, bool GR = false, class F>
 __device__ __forceinline__ void mid_fused(double2* xs, int L, int logL, int tid, F f) {
     constexpr int R = 1 << KT;
     constexpr int MAXG = FFT_MAX_L / (R * FFT_THREADS);
+    static_assert(MAXG >= 1, "bin group too wide");
 #pragma unroll
     for (int i = 0; i < MAXG; ++i) {
         const int g = fft_mid_group<KT, NT, GR>(tid, i, L, logL - 6);
@@ -404,7 +481,9 @@ __device__ __forceinline__ void dit_last(double2* xs, int L, const double2* tw, 
         double2 e[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m) e[m] = xs[PADI(j + m * q)];
-        bfly8_dit_inv(e, tw[2 * q + j], tw[q + j], tw[j]);
+        double2 w1, w2, w4;
+        fft_tw3(tw, q, j, w1, w2, w4);
+        bfly8_dit_inv(e, w4, w2, w1);
 #pragma unroll
         for (int m = 0; m < 4; ++m) st(j + m * q, e[m], add[m]);
     }
@@ -419,7 +498,8 @@ __device__ __forceinline__ void dit_last_dif_first(double2* xs, int L, const dou
         double2 e[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m) e[m] = xs[PADI(j + m * q)];
-        const double2 w1 = tw[j], w2 = tw[q + j], w4 = tw[2 * q + j];
+        double2 w1, w2, w4;
+        fft_tw3(tw, q, j, w1, w2, w4);
         bfly8_dit_inv(e, w4, w2, w1);
 #pragma unroll
         for (int m = 0; m < 4; ++m) if (j + m * q >= n) e[m] = make_double2(0.0, 0.0);

@@ -269,8 +269,12 @@ int invert_axis(gphm_plan& p, int a, bool with_kinv, cudaStream_t st) {
 // V A^T against dK/dtheta with a ~5000-fold cancellation against G A^T : dD/dtheta that only a small RESIDUAL keeps
 // intact: without refinement the theta-leaves are off by 5e-8 at N = 1024 and 1.4e-6 at N = 4096 against an
 // extended-precision reference (tools/extended_reference.py), with it they match the Cholesky route (1e-9 .. 5e-8).
-// The forward applications (A, Bt) do not need it (measured: no change).  force_general bit 5 switches it off.
+// The forward applications (A, Bt) do not need it (measured: no change).  The loss grows like cond(K) N: 5e-8 at N = 1024,
+// 3.2e-7 at 2048, 1.4e-6 at 4096 (same kernel and state), so axes of up to kRefineAbove points skip the step (a 20-fold
+// margin under the 1e-6 bound; every reference config has N_col <= 900).  force_general bit 5 switches it off everywhere.
+constexpr int kRefineAbove = 1024;
 inline bool gs_refine(const gphm_plan& p) { return (p.d.force_general & 32) == 0; }
+inline bool gs_refine_axis(const gphm_plan& p, const Axis& X) { return gs_refine(p) && X.n > kRefineAbove; }
 
 // Uniform-grid axes a0 .. a0+count-1 without a dense factorisation: Toeplitz tables, Schur/Levinson
 // recursion for g = K^-1 e_0 and log|K|, Gohberg-Semencul spectra and the diagonal sums of K^-1.
@@ -304,9 +308,9 @@ int factor_gs(gphm_plan& p, int a0, int count, const double* small, cudaStream_t
             Axis& X = p.ax[a];
             GPHM_TRY(launch_toeplitz_spectrum(X.tabD, X.n, X.fftL, X.twid, order == 1, X.dirsign, X.specT, st));
         }
-    if (gs_refine(p))   // spectrum of K (with the jitter): residual b - K y of the refined applications
-        for (int a = a0; a < a0 + count; ++a) {
+    for (int a = a0; a < a0 + count; ++a) {      // spectrum of K (with the jitter): residual b - K y of the refined applications
             Axis& X = p.ax[a];
+            if (gs_refine_axis(p, X))
             GPHM_TRY(launch_toeplitz_spectrum(X.tabK, X.n, X.fftL, X.twid, false, 1.0, X.specKm, st, p.d.jitter));
         }
     return GPHM_OK;
@@ -444,17 +448,17 @@ int logjoint_grad_gs(gphm_plan& p, const double* U, const double* small, double*
         GPHM_TRY(launch_transpose(Bt, n1, n2, p.Tf, st));                       // Bt^T
         GPHM_TRY(d1(Gt, anti ? -c1 : c1, 0.5, nullptr, p.Tf));                  // (c1 D1^T G + Bt/2)^T
         GPHM_TRY(gs1(p.Tf, p.W)); V1t = p.W;                                    // V1^T
-        if (gs_refine(p)) GPHM_TRY(refine_kinv_rows_gs(X1, p.Tf, n2, p.W, p.Tf, st));
+        if (gs_refine_axis(p, X1)) GPHM_TRY(refine_kinv_rows_gs(X1, p.Tf, n2, p.W, p.Tf, st));
         GPHM_TRY(launch_transpose(p.W, n2, n1, p.V1, st));
         GPHM_TRY(d2(G, anti ? -1.0 : 1.0, 0.5, nullptr, p.A));                  // G D2 + A/2  (A is free after the residual)
         GPHM_TRY(gs2(p.A, p.V2)); V2 = p.V2;
-        if (gs_refine(p)) GPHM_TRY(refine_kinv_rows_gs(X2, p.A, n1, p.V2, p.A, st));
+        if (gs_refine_axis(p, X2)) GPHM_TRY(refine_kinv_rows_gs(X2, p.A, n1, p.V2, p.A, st));
         GPHM_TRY(launch_grad_u(lc, p.has_base ? p.base : nullptr, U, G, p.V1, p.V2, nullptr, p.eb, p.xind, small, gU, nullptr,
                                nullptr, st));
     } else {
         GPHM_TRY(d1(G, anti ? -c1 : c1, 0.5, U, p.Tf));                         // D^T g + u/2
         GPHM_TRY(gs1(p.Tf, p.V1)); V1t = p.V1;                                  // s + a/2
-        if (gs_refine(p)) GPHM_TRY(refine_kinv_rows_gs(X1, p.Tf, n2, p.V1, p.Tf, st));
+        if (gs_refine_axis(p, X1)) GPHM_TRY(refine_kinv_rows_gs(X1, p.Tf, n2, p.V1, p.Tf, st));
         GPHM_TRY(launch_lincomb(p.S1, 0.5, At, 0.0, nullptr, nf, st));
         GPHM_TRY(launch_grad_u(lc, p.has_base ? p.base : nullptr, U, G, p.V1, p.S1, nullptr, p.eb, p.xind, small, gU, nullptr,
                                nullptr, st));
@@ -1214,7 +1218,7 @@ int gphm_apply_kinv_rows_refined(gphm_plan* plan, int axis, const double* d_X, i
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Axis& X = plan->ax[axis];
     GPHM_TRY(apply_kinv(*plan, axis, 1, d_X, rows, X.n, d_out, d_tmp, st));
-    if (X.gs && gs_refine(*plan) && toeplitz_fused_supported(X.fftL)) {
+    if (X.gs && gs_refine_axis(*plan, X) && toeplitz_fused_supported(X.fftL)) {
         GPHM_TRY(launch_copy(d_tmp, d_X, (size_t)rows * X.n, st));             // keep the caller's right-hand side intact
         GPHM_TRY(refine_kinv_rows_gs(X, d_tmp, rows, d_out, d_tmp, st));
     }
