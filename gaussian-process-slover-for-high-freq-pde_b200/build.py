@@ -52,7 +52,8 @@ def build(force=False, verbose=True):
 
 
 def build_ffi_shim(verbose=True):
-    """csrc/ffi_shim.cc -> libgphm_ffi.so, ONLY where JAX ships the XLA FFI headers (not in this image)."""
+    """experimental/ffi_shim.cc -> libgphm_ffi.so, ONLY where JAX ships the XLA FFI headers (not in this image; the shim has
+    never been compiled - see experimental/README.md)."""
     try:
         import jax
         inc = jax.ffi.include_dir()
@@ -61,7 +62,7 @@ def build_ffi_shim(verbose=True):
             print("ffi_shim.cc skipped: no jax / XLA FFI headers in this environment", flush=True)
         return None
     out = os.path.join(HERE, "libgphm_ffi.so")
-    src = os.path.join(CSRC, "ffi_shim.cc")
+    src = os.path.join(HERE, "experimental", "ffi_shim.cc")
     if _stale(out, [src, OUT]):
         cmd = ["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-I" + inc, "-I" + os.path.join(HERE, "..", "include"),
                "-I/usr/local/cuda/include", src, "-L" + HERE, "-lgphm", "-Wl,-rpath," + HERE, "-o", out]

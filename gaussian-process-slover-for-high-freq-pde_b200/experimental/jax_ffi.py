@@ -1,4 +1,4 @@
-"""jax.ffi host side of csrc/ffi_shim.cc - the XLA-FFI layer BASELINE's north_star names.
+"""jax.ffi host side of experimental/ffi_shim.cc - the XLA-FFI layer BASELINE's north_star names.
 
 Importing this module needs JAX >= 0.4.31 and the built `libgphm_ffi.so`; neither exists in the
 image this repo is developed in (no jax wheel, no XLA FFI headers), so this path is UNTESTED here and
@@ -16,7 +16,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FFI_LIB_PATH = os.path.join(HERE, "libgphm_ffi.so")
+FFI_LIB_PATH = os.path.join(os.path.dirname(HERE), "libgphm_ffi.so")     # build.py writes it beside libgphm.so
 _registered = False
 
 
@@ -26,7 +26,7 @@ def _register():
         return
     import jax                                                  # ImportError here is the honest failure mode
     if not os.path.exists(FFI_LIB_PATH):
-        raise RuntimeError("libgphm_ffi.so not found - build csrc/ffi_shim.cc (see its header) against jax.ffi.include_dir()")
+        raise RuntimeError("libgphm_ffi.so not found - build experimental/ffi_shim.cc (see its header) against jax.ffi.include_dir()")
     lib = ctypes.CDLL(FFI_LIB_PATH)
     jax.ffi.register_ffi_target("gphm_step", jax.ffi.pycapsule(lib.GphmStep), platform="CUDA")
     jax.ffi.register_ffi_target("gphm_logjoint_grad", jax.ffi.pycapsule(lib.GphmLogjointGrad), platform="CUDA")

@@ -65,3 +65,63 @@ def wrirte_log(model, err_dict, trick_paras):
         f.write("err_list: " + str([float(np.asarray(e)) for e in err_dict["err_list"]]) + "\n\n\n")
     print("write log to ", path)
     return path
+
+
+# ---- model rebuilders for the notebooks (utils.py:622-837): (params[, params_extra], trick_paras) of a stored pickle
+# -> a live solver object + its prediction on the (optionally finer) test grid -------------------------------------------
+def load_model(path):
+    """The tuple store_model wrote: (params, log_dict, trick_paras) or (params, params_extra, log_dict, trick_paras)."""
+    with open(path, "rb") as f:
+        return pickle.load(f)
+
+
+def _with_scale(trick_paras):
+    tp = dict(trick_paras)
+    if "scale" not in tp and "x_scale" in tp:            # the reference's notebooks pass 'x_scale' (utils.py:647)
+        tp["scale"] = tp["x_scale"]
+    return tp
+
+
+def get_model_1d(params, trick_paras, new_test=False):
+    """utils.py:622-677 -> (model, preds (M,1), Xtr)."""
+    from . import model_GP_solver_1d as m1d
+    tp = _with_scale(trick_paras)
+    Xind, y, X_col, src, X_test, Y_test = m1d.build_problem(tp, M=new_test if new_test else 300)
+    model = m1d.GP_solver_1d_single(Xind, y, X_col, src, 1e-6, X_test, Y_test, tp)
+    model.params = params
+    preds, _ = model.preds(params, model.Xte)
+    return model, preds, np.asarray(X_col)[Xind]
+
+
+def get_model_1d_extra(params, params_extra, trick_paras, new_test=False):
+    """utils.py:679-740 -> (model, preds of the two-stage solver, Xtr)."""
+    from . import model_GP_solver_1d as m1d, model_GP_solver_1d_extra as mex
+    tp = _with_scale(trick_paras)
+    Xind, y, X_col, src, X_test, Y_test = m1d.build_problem(tp, M=new_test if new_test else 300)
+    model = mex.GP_solver_1d_extra(Xind, y, X_col, src, 1e-6, X_test, Y_test, tp)
+    model.freeze_first_stage(params)
+    model.params_extra = params_extra
+    preds, _ = model.preds_extra(params_extra, model.Xte)
+    return model, preds, np.asarray(X_col)[Xind]
+
+
+def get_model_2d(params, trick_paras, new_test=False):
+    """utils.py:742-790 -> (model, preds (M,M))."""
+    from . import model_GP_solver_2d as m2d
+    tp = _with_scale(trick_paras)
+    prob = m2d.build_problem(tp, M=new_test if new_test else 300)
+    model = m2d.GP_solver_2d_single(prob[0], prob[1], prob[2], 1e-6, prob[3], prob[4], tp)
+    model.params = params
+    preds, _ = model.preds(params)
+    return model, preds
+
+
+def get_model_2d_advection(params, trick_paras, new_test=False):
+    """utils.py:792-837 -> (model, preds (M,M))."""
+    from . import model_GP_solver_advection as madv
+    tp = _with_scale(trick_paras)
+    prob = madv.build_problem(tp, M=new_test if new_test else 300)
+    model = madv.GP_solver_2d_single_advection(prob[0], prob[1], prob[2], 1e-6, prob[3], prob[4], tp)
+    model.params = params
+    preds, _ = model.preds(params)
+    return model, preds

@@ -469,6 +469,10 @@ def test_evals_end_to_end_run_2d_sh_line(gphm, tmp_path, monkeypatch):
     assert abs(log_dict["loss_list"][0] - float(g["log_loss_list"][0])) <= 1e-9 * 29.7  # step-0 log-loss of the shipped run (29.7054563...)
     assert abs(log_dict["err_list"][-1] - float(g["log_err_list"][-1])) <= 1e-3         # 0.46758843; chaos bound of SURVEY 0.6
     assert abs(float(params["log_tau"]) - float(g["log_tau"])) <= 1e-2
+    # the notebooks' loader (utils.py:742-790): rebuild a live model from the pickle and predict with it
+    model, preds = gphm.utils.get_model_2d(params, tp)
+    want_err = float(np.linalg.norm(preds.cpu().numpy() - model.ute.cpu().numpy()) / np.linalg.norm(model.ute.cpu().numpy()))
+    assert preds.shape == (300, 300) and abs(want_err - log_dict["err_list"][-1]) <= 2e-2      # epoch-99 params vs the epoch-95 checkpoint
     lines = (d / "log.txt").read_text().splitlines()
     assert lines[0] == "llk_weight-200.0--nu-1-Q-30-epoch-100-lr-0.0100-freqscale=20-logdet-1-x-2pi-Ncol-400"
     assert lines[1].startswith("err_mean: 0.46") and "avg_epochs 100" in lines[1] and lines[2].startswith("err_list: [0.46")
