@@ -61,6 +61,57 @@ gram_general_kernel(const double* __restrict__ x1, int n1, const double* __restr
     if (Dout) { if (vec) *reinterpret_cast<double2*>(Dout + o) = make_double2(g0, g1); else { Dout[o] = g0; if (two) Dout[o + 1] = g1; } }
 }
 
+// Square Gram pair on ONE grid (x1 == x2): K is symmetric and the derivative Gram symmetric (ORDER 2) or antisymmetric
+// (ORDER 1), so only the 32 x 32 tiles on and above the diagonal evaluate the Q-term mixture - half the exp / sincos of the
+// full kernel, which is what bounds it (N^2 Q FP64 transcendentals: 2.7 ms per 4096^2 pair against 0.04 ms of HBM writes).
+// The mirrored tile leaves through a shared-memory transpose so that both stores are coalesced.
+// blockIdx.x enumerates the upper-triangular tile pairs (ti <= tj); block (32, 8).
+template <int KID, int ORDER>
+__global__ void __launch_bounds__(256)
+gram_symmetric_kernel(const double* __restrict__ x, int n, const double* __restrict__ theta, int Q, double jitter,
+                      double* __restrict__ Kout, double* __restrict__ Dout, int ld, int ntiles) {
+    __shared__ CompConst sc[kMaxQ];
+    __shared__ double tK[32][33], tD[32][33];
+    load_comps<KID>(sc, theta, Q);
+    // tile pair from the linear index: row ti has (ntiles - ti) tiles
+    int rem = blockIdx.x, ti = 0;
+    while (rem >= ntiles - ti) { rem -= ntiles - ti; ++ti; }
+    const int tj = ti + rem;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int j = tj * 32 + tx;
+    const double xj = j < n ? x[j] : 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int a = ty + 8 * r, i = ti * 32 + a;
+        double k0 = 0.0, g0 = 0.0;
+        if (i < n && j < n) {
+            const double df = x[i] - xj, d = fabs(df);
+            for (int q = 0; q < Q; ++q) {
+                double u, v;
+                comp_value<KID, ORDER>(d, sc[q], u, v);
+                k0 += u; g0 += v;
+            }
+            if (ORDER == 1 && df < 0.0) g0 = -g0;
+            if (i == j) k0 += jitter;
+            const size_t o = (size_t)i * ld + j;
+            Kout[o] = k0; Dout[o] = g0;
+        }
+        tK[a][tx] = k0; tD[a][tx] = g0;
+    }
+    if (ti == tj) return;                                   // diagonal tiles are complete
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {                           // mirrored tile: entry (j', i') = +-entry (i', j')
+        const int a = ty + 8 * r;
+        const int jj = tj * 32 + a, ii = ti * 32 + tx;
+        if (jj < n && ii < n) {
+            const size_t o = (size_t)jj * ld + ii;
+            Kout[o] = tK[tx][a];
+            Dout[o] = ORDER == 1 ? -tD[tx][a] : tD[tx][a];
+        }
+    }
+}
+
 template <int KID, int ORDER>
 __global__ void __launch_bounds__(128)
 toeplitz_table_kernel(const double* __restrict__ x, int n, const double* __restrict__ theta, int Q,
@@ -153,6 +204,15 @@ int launch_gram_general(int kid, int order, const double* x1, int n1, const doub
                         cudaStream_t st) {
     if (Q > kMaxQ || Q < 1) { set_last_error("gram: Q=%d outside [1,%d]", Q, kMaxQ); return GPHM_EINVAL; }
     if (n1 <= 0 || n2 <= 0) return GPHM_OK;
+    if (x1 == x2 && n1 == n2 && Kout && Dout && order > 0) {             // the plan's own (K, D) pair: evaluate one triangle only
+        const int nt = (n1 + 31) / 32;
+        LaunchScope scope(CAT_GRAM, st, 0.0, 16.0 * n1 * (double)n2);
+        int rc = GPHM_DISPATCH_KID_ORDER(kid, order,
+            gram_symmetric_kernel<KID, ORDER><<<nt * (nt + 1) / 2, dim3(32, 8), 0, st>>>(x1, n1, theta, Q, jitter, Kout, Dout, ld, nt));
+        if (rc != 0) { set_last_error("gram: bad kernel id %d / order %d", kid, order); return GPHM_EINVAL; }
+        GPHM_LAUNCH_OK();
+        return GPHM_OK;
+    }
     dim3 block(64, 4), grid((n2 + 127) / 128, (n1 + 3) / 4);
     LaunchScope scope(CAT_GRAM, st, 0.0, 8.0 * n1 * n2 * ((Kout ? 1 : 0) + (Dout ? 1 : 0)));
     int rc = GPHM_DISPATCH_KID_ORDER(kid, order,

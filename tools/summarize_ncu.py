@@ -27,8 +27,9 @@ def launches(src, dst, steps=1):
     tot = sum(v[1] for v in agg.values())
     with open(dst, "w") as f:
         f.write("# ncu launch list: `%s`\n\n" % os.path.basename(src))
-        f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none ... python bench.py --steps 1 --warmup 3 "
-                "--no-cpu-baseline --no-e2e --no-peak` (N=4096, last %d step(s) captured; %d launches).\n" % (steps, len(rows)))
+        f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/prof_step.py 4096 %d` - the "
+                "bench workload (poisson_2d-sin_add_cos 4096x4096 Matern52_Cos_1d Q=30), plan creation + %d full step(s), %d launches; "
+                "run only after the same command exited 0 without ncu.\n" % (steps, steps, len(rows)))
         f.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES with the live CUDA-event "
                 "numbers in the bench line, not absolutes.\n\n")
         f.write("| kernel | launches | total ms | avg ms | share |\n|---|---:|---:|---:|---:|\n")
