@@ -468,6 +468,88 @@ __device__ __forceinline__ void mid_fused(double2* xs, int L, int logL, int tid,
     fft_pass_sync<GR>(tid, logL - 6);
 }
 
+// mid_fused with the pointwise operand taken from ONE global array `spec` (L complex values, bin order) and loaded one
+// iteration AHEAD of its use: the tail pass does almost no arithmetic, so with the load issued where it is consumed each of
+// its 8 iterations exposed a full L2 round trip (ncu: the three radix-2 tail passes of gs_apply_fused cost 21.6 % of the
+// kernel, 2.4 radix-8 sweeps each).  f(slot, p, v, s): s = spec[p].
+template <int KT, int NT = FFT_THREADS, bool GR = false, bool PF = true, class F>
+__device__ __forceinline__ void mid_fused_spec(double2* xs, int L, int logL, int tid, const double2* __restrict__ spec, F f) {
+    if constexpr (!PF) {          // load where it is used
+        mid_fused<KT, NT, GR>(xs, L, logL, tid, [&](int slot, int p, double2 v) { return f(slot, p, v, spec[p]); });
+        return;
+    }
+    constexpr int R = 1 << KT;
+    constexpr int MAXG = FFT_MAX_L / (R * FFT_THREADS);
+    static_assert(MAXG >= 1, "bin group too wide");
+    double2 sn[R];
+    int gn = fft_mid_group<KT, NT, GR>(tid, 0, L, logL - 6);
+    if (gn < (L >> KT)) {
+#pragma unroll
+        for (int m = 0; m < R; ++m) sn[m] = spec[(gn << KT) + m];
+    }
+#pragma unroll
+    for (int i = 0; i < MAXG; ++i) {
+        const int g = gn;
+        double2 sc[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) sc[m] = sn[m];
+        if (i + 1 < MAXG) {
+            gn = fft_mid_group<KT, NT, GR>(tid, i + 1, L, logL - 6);
+            if (gn < (L >> KT)) {
+#pragma unroll
+                for (int m = 0; m < R; ++m) sn[m] = spec[(gn << KT) + m];
+            }
+        }
+        if (g < (L >> KT)) {
+            const int base = g << KT;
+            double2 e[R];
+#pragma unroll
+            for (int m = 0; m < R; ++m) e[m] = xs[PADI(base + m)];
+            unit_fwd<KT>(e);
+#pragma unroll
+            for (int m = 0; m < R; ++m) e[m] = f(i * R + m, base + m, e[m], sc[m]);
+            unit_inv<KT>(e);
+#pragma unroll
+            for (int m = 0; m < R; ++m) xs[PADI(base + m)] = e[m];
+        }
+    }
+    fft_pass_sync<GR>(tid, logL - 6);
+}
+
+// First forward pass with BOTH butterflies' global loads of a thread issued before the first butterfly (512 threads, L = 8192:
+// two butterflies per thread; the kernels that call it have no live register stash at this point).
+template <int NT = FFT_THREADS, class Load>
+__device__ __forceinline__ void dif_first2(double2* xs, int L, const double2* tw, int tid, Load ld) {
+    const int q = L >> 3, nt = fft_nt<NT>();
+    for (int j0 = tid; j0 < q; j0 += 2 * nt) {
+        const int j1 = j0 + nt;
+        double2 a[4], b[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) a[m] = ld(j0 + m * q);
+        if (j1 < q) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) b[m] = ld(j1 + m * q);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = h == 0 ? j0 : j1;
+            if (j < q) {
+                double2 e[8];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) e[m] = h == 0 ? a[m] : b[m];
+#pragma unroll
+                for (int m = 4; m < 8; ++m) e[m] = make_double2(0.0, 0.0);
+                double2 w1, w2, w4;
+                fft_tw3(tw, q, j, w1, w2, w4);
+                bfly8_dif(e, w1, w2, w4);
+#pragma unroll
+                for (int m = 0; m < 8; ++m) xs[PADI(j + m * q)] = e[m];
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // Last inverse pass (stage logL-3, q = L/8); st(index, value, addend) for the live half (index < L/2).
 // The addends pre(index) are fetched before the butterfly so that their global-memory latency
 // hides behind it (the stores may alias the addend, so the compiler cannot hoist the loads itself).

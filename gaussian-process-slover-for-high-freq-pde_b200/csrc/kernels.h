@@ -82,7 +82,9 @@ int toeplitz_inv_max_n();
 int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitter, double* g, long long sG,
                           double* half_logdet, long long sLd, int* status, long long sStatus, double* gkap, long long sKap,
                           int* prog, long long sProg, int nsys, cudaStream_t st, long long* dbg_cycles = nullptr,
-                          int* guard = nullptr, int guard_bit0 = 0);
+                          int* guard = nullptr, int guard_bit0 = 0, double* gbnd = nullptr, long long sBnd = 0);
+// gbnd (optional): 6 n doubles per system - the hand-over buffers of the multi-CTA recursion (prog then needs 8 ints per system)
+int schur_split_factor(int n);
 // guard: bit (guard_bit0 + s) is OR-ed in when system s has min_k (1 - kappa_k^2) < toeplitz_guard_min()
 double toeplitz_guard_min();
 // spec[4][L] complex (strides in doubles): Gohberg-Semencul circulant spectra; sKinv[n]: diagonal sums of K^-1
@@ -98,8 +100,10 @@ int launch_toeplitz_apply_fused(const double* X, int rows, int n, int ldx, const
 int launch_xcorr_pairs(const double* X, int rows, int n, int ldx, const double* SpecY, int L, const double* W, double weight,
                        double* partial, cudaStream_t st);
 // Out[r] = alpha * K^-1 X[r] + beta * Add[r] for every row, K^-1 through the four spectra of launch_gs_prepare
+// g0ptr (optional): device pointer to g[0] = (K^-1)_00; with it and L == 2n only the first spectrum is read (the others derive from it)
 int launch_gs_apply_fused(const double* X, int rows, int n, int ldx, const double* gspec, int L, const double* W, double alpha,
-                          double beta, const double* Add, int lda, double* Out, int ldo, cudaStream_t st);
+                          double beta, const double* Add, int lda, double* Out, int ldo, cudaStream_t st,
+                          const double* g0ptr = nullptr);
 
 // ---- ozaki.cu: FP64-accurate GEMM on tcgen05 (int8 Ozaki slices, TMA operands, TMEM accumulators) ----
 int ozaki_default_slices();                                  // GPHM_OZAKI_SLICES, default 8

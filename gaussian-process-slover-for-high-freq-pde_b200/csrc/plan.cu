@@ -73,7 +73,8 @@ struct Axis {
            *gsg = nullptr, *gspec = nullptr,   // gsg = K^-1 e_0; gspec: four Gohberg-Semencul circulant spectra
            *specKm = nullptr,                  // spectrum of K itself (circulant embedding): residuals of the refined K^-1 applications
            *specY = nullptr,                   // transforms of the packed row pairs of A^T (axis 1) / Bt (axis 2)
-           *gskap = nullptr;                   // reflection coefficients handed from the generator CTA to the lattice CTA
+           *gskap = nullptr,                   // reflection coefficients handed from the generator CTA to the lattice CTA
+           *gsbnd = nullptr;                   // boundary values handed upward between the CTAs of a split role (6 n)
     int* gsprog = nullptr;
 };
 
@@ -164,7 +165,7 @@ size_t carve(gphm_plan& p, void* base) {
         if (p.size_query || X.gs) {
             const size_t other = (d.dim == 2) ? (a == 0 ? (size_t)d.n2 : (size_t)d.n1) : 1;      // rows this axis' operators act on
             c.take(X.gsg, n); c.take(X.gspec, 8 * Lq); c.take(X.specKm, 2 * Lq); c.take(X.specY, 2 * Lq * ((other + 1) / 2));
-            c.take(X.gskap, n); c.take(X.gsprog, 1);
+            c.take(X.gskap, n); c.take(X.gsprog, 8); c.take(X.gsbnd, 6 * n);
         }
     }
     if (p.size_query || p.ax[0].gs || p.ax[1].gs) c.take(p.gsS, nf);
@@ -299,7 +300,7 @@ int factor_gs(gphm_plan& p, int a0, int count, const double* small, cudaStream_t
         const Axis& Y = p.ax[batched ? a + 1 : a];
         GPHM_TRY(launch_schur_levinson(X.tabK, Y.tabK - X.tabK, X.n, p.d.jitter, X.gsg, Y.gsg - X.gsg, X.ldpart,
                                        Y.ldpart - X.ldpart, p.status + a, 1, X.gskap, Y.gskap - X.gskap, X.gsprog,
-                                       Y.gsprog - X.gsprog, nsys, st, nullptr, p.status + 3, a));
+                                       Y.gsprog - X.gsprog, nsys, st, nullptr, p.status + 3, a, X.gsbnd, Y.gsbnd - X.gsbnd));
         GPHM_TRY(launch_gs_prepare(X.gsg, Y.gsg - X.gsg, X.n, X.fftL, X.twid, X.gspec, Y.gspec - X.gspec, X.sKinv,
                                    Y.sKinv - X.sKinv, nsys, st));
     }
@@ -348,7 +349,7 @@ int apply_kinv_rows_gs(const Axis& X, const double* Xm, int rows, double* out, d
     const int n = X.n, L = X.fftL;
     const size_t sp = 2 * (size_t)L;
     if (toeplitz_fused_supported(L))
-        return launch_gs_apply_fused(Xm, rows, n, n, X.gspec, L, X.twid, 1.0, 0.0, nullptr, 0, out, n, st);
+        return launch_gs_apply_fused(Xm, rows, n, n, X.gspec, L, X.twid, 1.0, 0.0, nullptr, 0, out, n, st, X.gsg);
     GPHM_TRY(launch_toeplitz_apply(Xm, rows, n, n, X.gspec, L, X.twid, 1.0, 0.0, out, n, st));            // L(g)^T v
     GPHM_TRY(launch_toeplitz_apply(Xm, rows, n, n, X.gspec + sp, L, X.twid, 1.0, 0.0, tmp, n, st));       // L(h)^T v
     GPHM_TRY(launch_toeplitz_apply(out, rows, n, n, X.gspec + 2 * sp, L, X.twid, 1.0, 0.0, out, n, st));  // L(g) . / g0
@@ -361,7 +362,7 @@ int apply_kinv_rows_gs(const Axis& X, const double* Xm, int rows, double* out, d
 int refine_kinv_rows_gs(const Axis& X, const double* Xm, int rows, double* out, double* tmp, cudaStream_t st) {
     const int n = X.n, L = X.fftL;
     GPHM_TRY(launch_toeplitz_apply_fused(out, rows, n, n, X.specKm, L, X.twid, -1.0, 1.0, Xm, n, tmp, n, nullptr, st));   // b - K y
-    return launch_gs_apply_fused(tmp, rows, n, n, X.gspec, L, X.twid, 1.0, 1.0, out, n, out, n, st);                      // y += K^-1 r
+    return launch_gs_apply_fused(tmp, rows, n, n, X.gspec, L, X.twid, 1.0, 1.0, out, n, out, n, st, X.gsg);               // y += K^-1 r
 }
 
 // out = K_a^-1 X (side 0, X is n x cols) or X K_a^-1 (side 1, X is rows x n); tmp has X's shape.
@@ -407,10 +408,10 @@ int logjoint_grad_gs(gphm_plan& p, const double* U, const double* small, double*
     GPHM_TRY(factor_gs(p, 0, two ? 2 : 1, small, st));       // includes the spectra of D1, D2; needs only theta
     if (p.u_ready) GPHM_CUDA_OK(cudaStreamWaitEvent(st, p.u_ready, 0));     // gphm_step_host: U arrives meanwhile
     auto gs1 = [&](const double* Xr, double* out) {       // rows of length n1 (columns of the field)
-        return launch_gs_apply_fused(Xr, n2, n1, n1, X1.gspec, X1.fftL, X1.twid, 1.0, 0.0, nullptr, 0, out, n1, st);
+        return launch_gs_apply_fused(Xr, n2, n1, n1, X1.gspec, X1.fftL, X1.twid, 1.0, 0.0, nullptr, 0, out, n1, st, X1.gsg);
     };
     auto gs2 = [&](const double* Xr, double* out) {       // rows of length n2
-        return launch_gs_apply_fused(Xr, n1, n2, n2, X2.gspec, X2.fftL, X2.twid, 1.0, 0.0, nullptr, 0, out, n2, st);
+        return launch_gs_apply_fused(Xr, n1, n2, n2, X2.gspec, X2.fftL, X2.twid, 1.0, 0.0, nullptr, 0, out, n2, st, X2.gsg);
     };
     auto d1 = [&](const double* Xr, double alpha, double beta, const double* add, double* out, double* spec_out = nullptr) {
         return launch_toeplitz_apply_fused(Xr, n2, n1, n1, X1.specT, X1.fftL, X1.twid, alpha, beta, add, n1, out, n1, spec_out, st);
@@ -720,7 +721,7 @@ size_t gphm_toeplitz_work_bytes(int n, int rows) {
     Carver c(nullptr);
     double* p;
     c.take(p, 2 * (size_t)L); c.take(p, 8 * (size_t)L); c.take(p, 1); c.take(p, (size_t)std::max(rows, 1) * n);
-    c.take(p, (size_t)n); c.take(p, 1);
+    c.take(p, (size_t)n); c.take(p, 8); c.take(p, 6 * (size_t)n);
     return c.off;
 }
 
@@ -732,21 +733,21 @@ int gphm_toeplitz_solve(const double* d_t, int n, const double* d_B, int rows, d
     if (rows > 0 && d_B == d_X) { set_last_error("gphm_toeplitz_solve: d_X may not alias d_B"); return GPHM_EINVAL; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Carver c(d_work);
-    double *twid, *spec, *hld, *tmp, *gkap, *progd;
+    double *twid, *spec, *hld, *tmp, *gkap, *progd, *gbnd;
     c.take(twid, 2 * (size_t)L); c.take(spec, 8 * (size_t)L); c.take(hld, 1); c.take(tmp, (size_t)std::max(rows, 1) * n);
-    c.take(gkap, (size_t)n); c.take(progd, 1);
+    c.take(gkap, (size_t)n); c.take(progd, 8); c.take(gbnd, 6 * (size_t)n);
     GPHM_CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(int), st));
     GPHM_TRY(launch_twiddle_init(twid, L, st));
-    GPHM_CUDA_OK(cudaMemsetAsync(reinterpret_cast<int*>(progd) + 1, 0, sizeof(int), st));
+    int* guardp = reinterpret_cast<int*>(progd) + 8;           // progd: 8 progress ints, then the guard word
+    GPHM_CUDA_OK(cudaMemsetAsync(guardp, 0, sizeof(int), st));
     GPHM_TRY(launch_schur_levinson(d_t, 0, n, 0.0, d_g, 0, hld, 0, d_status, 0, gkap, 0, reinterpret_cast<int*>(progd), 0, 1, st,
-                                   getenv("GPHM_SCHUR_CYCLES") ? reinterpret_cast<long long*>(tmp) : nullptr,
-                                   reinterpret_cast<int*>(progd) + 1, 0));
-    GPHM_TRY(launch_status_merge_guard(d_status, reinterpret_cast<int*>(progd) + 1, st));
+                                   getenv("GPHM_SCHUR_CYCLES") ? reinterpret_cast<long long*>(tmp) : nullptr, guardp, 0, gbnd, 0));
+    GPHM_TRY(launch_status_merge_guard(d_status, guardp, st));
     GPHM_TRY(launch_gs_prepare(d_g, 0, n, L, twid, spec, 0, d_sKinv, 0, 1, st));
     GPHM_TRY(launch_sum_scaled(hld, 1, 2.0, d_logdet, st));
     if (rows > 0) {
         Axis X;
-        X.n = n; X.fftL = L; X.twid = twid; X.gspec = spec;
+        X.n = n; X.fftL = L; X.twid = twid; X.gspec = spec; X.gsg = d_g;
         GPHM_TRY(apply_kinv_rows_gs(X, d_B, rows, d_X, tmp, st));
     }
     return GPHM_OK;

@@ -95,11 +95,18 @@ toeplitz_apply_fused_kernel(const double* X, int rows, int n, int ldx, const dou
 }
 
 // spec: the four Gohberg-Semencul spectra of gs_prepare_kernel, L complex values each.
-template <int KT, int NT, bool GR>
+// ONE (L == 2n, g0ptr given): only spec[0] = conj(G)/L is read; with H = (-1)^k (conj(G) - g0) (h is g reversed and shifted,
+// exp(-2 pi i n k / L) = (-1)^k when L = 2n) the other three follow from it and g0:
+//     conj(H)/L = sgn (conj(a) - g0/L),   G/(L g0) = conj(a)/g0,   -H/(L g0) = -sgn (a - g0/L)/g0,   a = spec[0][p],
+//     sgn = (-1)^k = +1 for bin positions p < L/2 (bit-reversed order: the lowest bit of k is the highest bit of p)
+// - 384 KB instead of 512 KB of spectra through L2 per row pair, and one array that stays hot.
+// VAR 0: four spectra, loads where they are used (round 1);  1: ONE + spectrum prefetch + dif_first2;  2: ONE + prefetch;
+// 3: ONE only;  4: four spectra + prefetch.   (variants > 0 are instantiated for the 8192-point configuration only)
+template <int KT, int NT, bool GR, int VAR>
 __global__ void __launch_bounds__(FFT_THREADS, 1)
 gs_apply_fused_kernel(const double* X, int rows, int n, int ldx, const double2* __restrict__ spec, int L,
                       int logL, const double2* __restrict__ W, double alpha, double beta, const double* Add, int lda,
-                      double* Out, int ldo) {
+                      double* Out, int ldo, const double* __restrict__ g0ptr) {
     extern __shared__ double2 xs[];
     const int tid = threadIdx.x;
     fft_load_twiddles<NT>(xs, L, logL, W, tid);
@@ -109,29 +116,53 @@ gs_apply_fused_kernel(const double* X, int rows, int n, int ldx, const double2* 
     const double2* __restrict__ sHt = spec + L;         // conj(H)/L
     const double2* __restrict__ sG = spec + 2 * (size_t)L;   //  G/(L g0)
     const double2* __restrict__ sH = spec + 3 * (size_t)L;   // -H/(L g0)
+    constexpr bool ONE = VAR >= 1 && VAR <= 3, PF = VAR == 1 || VAR == 2 || VAR == 4, F2 = VAR == 1;
+    double c0 = 0.0, ig0 = 0.0;
+    if (ONE) { const double g0 = *g0ptr; c0 = g0 / (double)L; ig0 = 1.0 / g0; }
+    const int half = L >> 1;
     const int npairs = (rows + 1) / 2;
     double2 stash[FFT_ACC];
     for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
         const RowPairIO io = row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr, alpha, beta);
         if (pr + (int)gridDim.x < npairs) row_pair(X, ldx, Out, ldo, Add, lda, rows, n, pr + gridDim.x, alpha, beta).template prefetch<NT>(tid);
-        dif_first<NT>(xs, L, tw0, tid, [&](int idx) { return io.load(idx); });
+        if (F2) dif_first2<NT>(xs, L, tw0, tid, [&](int idx) { return io.load(idx); });
+        else dif_first<NT>(xs, L, tw0, tid, [&](int idx) { return io.load(idx); });
         dif_middle<NT, GR>(xs, L, logL, np8, tid);
-        mid_fused<KT, NT, GR>(xs, L, logL, tid, [&](int slot, int p, double2 v) { stash[slot] = v; return cmul(v, sGt[p]); });   // Z kept
+        mid_fused_spec<KT, NT, GR, PF>(xs, L, logL, tid, sGt, [&](int slot, int, double2 v, double2 a) { stash[slot] = v; return cmul(v, a); });   // Z kept
         dit_middle<NT, GR>(xs, L, logL, np8, KT, tid);
         dit_last_dif_first<NT>(xs, L, tw0, tid, n);                                   // [L(g)^T v]_n
         dif_middle<NT, GR>(xs, L, logL, np8, tid);
-        mid_fused<KT, NT, GR>(xs, L, logL, tid, [&](int slot, int p, double2 v) {
-            const double2 z = stash[slot];
-            stash[slot] = cmul(v, sG[p]);                                         // G'.Q1 kept
-            return cmul(z, sHt[p]);
-        });
+        if (ONE) {
+            mid_fused_spec<KT, NT, GR, PF>(xs, L, logL, tid, sGt, [&](int slot, int p, double2 v, double2 a) {
+                const double2 z = stash[slot];
+                const double2 q1 = cmulc(v, a);                                        // v * conj(a) = v G / L
+                stash[slot] = make_double2(q1.x * ig0, q1.y * ig0);                    // G'.Q1 kept
+                const double sg = p < half ? 1.0 : -1.0;
+                return cmul(z, make_double2(sg * (a.x - c0), -sg * a.y));              // Z . conj(H)/L
+            });
+        } else {
+            mid_fused<KT, NT, GR>(xs, L, logL, tid, [&](int slot, int p, double2 v) {
+                const double2 z = stash[slot];
+                stash[slot] = cmul(v, sG[p]);                                         // G'.Q1 kept
+                return cmul(z, sHt[p]);
+            });
+        }
         dit_middle<NT, GR>(xs, L, logL, np8, KT, tid);
         dit_last_dif_first<NT>(xs, L, tw0, tid, n);                                   // [L(h)^T v]_n
         dif_middle<NT, GR>(xs, L, logL, np8, tid);
-        mid_fused<KT, NT, GR>(xs, L, logL, tid, [&](int slot, int p, double2 v) {
-            const double2 a = stash[slot], b = cmul(v, sH[p]);
-            return make_double2(a.x + b.x, a.y + b.y);
-        });
+        if (ONE) {
+            mid_fused_spec<KT, NT, GR, PF>(xs, L, logL, tid, sGt, [&](int slot, int p, double2 v, double2 a) {
+                const double sg = p < half ? -ig0 : ig0;                               // -(-1)^k / g0
+                const double2 b = cmul(v, make_double2(sg * (a.x - c0), sg * a.y));    // Q2 . (-H/(L g0))
+                const double2 s1 = stash[slot];
+                return make_double2(s1.x + b.x, s1.y + b.y);
+            });
+        } else {
+            mid_fused_spec<KT, NT, GR, PF>(xs, L, logL, tid, sH, [&](int slot, int, double2 v, double2 h) {
+                const double2 a = stash[slot], b = cmul(v, h);
+                return make_double2(a.x + b.x, a.y + b.y);
+            });
+        }
         dit_middle<NT, GR>(xs, L, logL, np8, KT, tid);
         dit_last<NT>(xs, L, tw0, tid, [&](int idx) { return io.addend(idx); }, [&](int idx, double2 v, double2 add) { io.store(idx, v, add); });
     }
@@ -222,6 +253,8 @@ xcorr_pairs_kernel(const double* __restrict__ X, int rows, int n, int ldx, const
         }                                                                                                    \
     } while (0)
 
+constexpr int kGsDefaultVariant = 0;          // see gs_apply_fused_kernel; GPHM_GS_VARIANT overrides
+
 static bool getenv_flag(const char* name) {       // read once per name would need a map: two callers, cheap enough
     const char* v = getenv(name);
     return v && v[0] && v[0] != '0';
@@ -241,7 +274,14 @@ int toeplitz_fused_init() {
     GPHM_FUSED_ATTR(toeplitz_apply_fused_kernel, 4, FFT_THREADS, false); GPHM_FUSED_ATTR(toeplitz_apply_fused_kernel, 4, 0, false);
     GPHM_FUSED_ATTR(toeplitz_apply_fused_kernel, 4, FFT_THREADS, true); GPHM_FUSED_ATTR(toeplitz_apply_fused_kernel, 4, 0, true);
     GPHM_FUSED_ATTR6(xcorr_pairs_kernel);
-    GPHM_FUSED_ATTR6(gs_apply_fused_kernel);
+#define GPHM_GS_ATTR(KT, NT, GR) GPHM_ONCE_CUDA_OK(once, cudaFuncSetAttribute(gs_apply_fused_kernel<KT, NT, GR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
+#define GPHM_GS_ATTR3(NT, GR) GPHM_GS_ATTR(1, NT, GR); GPHM_GS_ATTR(2, NT, GR); GPHM_GS_ATTR(3, NT, GR)
+    GPHM_GS_ATTR3(FFT_THREADS, false); GPHM_GS_ATTR3(0, false); GPHM_GS_ATTR3(FFT_THREADS, true); GPHM_GS_ATTR3(0, true);
+#undef GPHM_GS_ATTR3
+#undef GPHM_GS_ATTR
+#define GPHM_GS_ATTRV(V) GPHM_ONCE_CUDA_OK(once, cudaFuncSetAttribute(gs_apply_fused_kernel<1, FFT_THREADS, true, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
+    GPHM_GS_ATTRV(1); GPHM_GS_ATTRV(2); GPHM_GS_ATTRV(3); GPHM_GS_ATTRV(4);
+#undef GPHM_GS_ATTRV
 #undef GPHM_FUSED_ATTR3
 #undef GPHM_FUSED_ATTR6
 #undef GPHM_FUSED_ATTR
@@ -288,8 +328,21 @@ int launch_toeplitz_apply_fused(const double* X, int rows, int n, int ldx, const
 }
 
 // Out[r] = alpha * K^-1 X[r] + beta * Add[r]  (Add may be NULL when beta == 0; Out may alias X or Add).
+template <class... Args>
+static void gs_dispatch(int KT, int nt, bool gr, int grid, size_t smem, cudaStream_t st, Args... args) {
+#define GPHM_GS_KT(NT, GR)                                                                         \
+    do {                                                                                           \
+        if (KT == 1) gs_apply_fused_kernel<1, NT, GR, 0><<<grid, nt, smem, st>>>(args...);         \
+        else if (KT == 2) gs_apply_fused_kernel<2, NT, GR, 0><<<grid, nt, smem, st>>>(args...);    \
+        else gs_apply_fused_kernel<3, NT, GR, 0><<<grid, nt, smem, st>>>(args...);                 \
+    } while (0)
+    if (nt == FFT_THREADS) { if (gr) GPHM_GS_KT(FFT_THREADS, true); else GPHM_GS_KT(FFT_THREADS, false); }
+    else { if (gr) GPHM_GS_KT(0, true); else GPHM_GS_KT(0, false); }
+#undef GPHM_GS_KT
+}
+
 int launch_gs_apply_fused(const double* X, int rows, int n, int ldx, const double* gspec, int L, const double* W, double alpha,
-                          double beta, const double* Add, int lda, double* Out, int ldo, cudaStream_t st) {
+                          double beta, const double* Add, int lda, double* Out, int ldo, cudaStream_t st, const double* g0ptr) {
     GPHM_TRY(toeplitz_fused_init());
     if (rows <= 0) return GPHM_OK;
     if (!toeplitz_fused_supported(L) || L < 2 * n) { set_last_error("gs_apply_fused: L=%d does not fit n=%d", L, n); return GPHM_EINVAL; }
@@ -303,7 +356,16 @@ int launch_gs_apply_fused(const double* X, int rows, int n, int ldx, const doubl
     {
         const double pairs = (rows + 1) / 2;
         LaunchScope scope(CAT_GS_APPLY, st, pairs * (6.0 * fft_flops(L) + 18.0 * L), (beta != 0.0 ? 24.0 : 16.0) * rows * (double)n);
-        GPHM_FUSED_LAUNCH(gs_apply_fused_kernel, grid, X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo);
+        const bool gr = fft_groups_supported(L) && !getenv_flag("GPHM_FFT_NO_GROUPS");
+        static const int variant = [] { const char* e = getenv("GPHM_GS_VARIANT"); return e ? atoi(e) : kGsDefaultVariant; }();
+        const bool hot = KT == 1 && nt == FFT_THREADS && gr;                 // the 8192-point configuration
+        const bool one_ok = g0ptr && L == 2 * n;
+        int v = hot ? variant : 0;
+        if (!one_ok && v >= 1 && v <= 3) v = (v == 3) ? 0 : 4;
+#define GPHM_GS_V(V) gs_apply_fused_kernel<1, FFT_THREADS, true, V><<<grid, nt, smem, st>>>(X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo, g0ptr)
+        if (v == 1) GPHM_GS_V(1); else if (v == 2) GPHM_GS_V(2); else if (v == 3) GPHM_GS_V(3); else if (v == 4) GPHM_GS_V(4);
+        else gs_dispatch(KT, nt, gr, grid, smem, st, X, rows, n, ldx, sp, L, logL, w, alpha, beta, Add, lda, Out, ldo, g0ptr);
+#undef GPHM_GS_V
     }
     GPHM_LAUNCH_OK();
     return GPHM_OK;

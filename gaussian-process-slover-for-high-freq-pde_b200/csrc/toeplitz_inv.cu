@@ -39,6 +39,9 @@ constexpr int SCHUR_BPW = 32;                   // batches led by one warp (= it
 constexpr int SCHUR_RING = 32;                  // boundary values kept per warp (4 batches)
 constexpr int SCHUR_PUBLISH = 8;                // led batches per hand-over to the lattice CTA (64 coefficients)
 
+constexpr int kSchurDefaultSplit = 4;           // CTAs per role of the recursion (schur_levinson_split_kernel); GPHM_SCHUR_SPLIT overrides
+                                                // measured at n = 4096: 1 CTA 0.494 ms, 2 CTAs 0.384 ms, 4 CTAs 0.364 ms (same bits out)
+
 int toeplitz_inv_max_n() { return SCHUR_MAX_N; }
 
 // min_k (1 - kappa_k^2) below which the Toeplitz inverse-generator route is declared ill-conditioned.  Measured error of
@@ -356,6 +359,192 @@ schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, dou
     if (dbg && tid == 0) dbg[blockIdx.x] = clock64() - t_start;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same recursion with every role spread over NS CTAs (round 2).  CTA c of a role owns the positions
+// [c n/NS, (c+1) n/NS) - the warps 32 c n/(256 NS) ... of the single-CTA wavefront - and runs its own period schedule;
+// what crosses a CTA boundary travels through global memory behind a progress counter, exactly like the reflection
+// coefficients always did between the generator and the lattice CTA:
+//     gkap[n]  + prog[0]                      coefficients kappa_j, published by whichever generator CTA currently leads
+//     gbnd[role][c][n] + prog[1 + 3 role + c] the values that leave the top position of CTA c (eight per batch), for CTA c+1
+// All information flows upward, so there is no feedback between CTAs and a consumer only ever lags.  Why: on ONE SM the
+// lattice is bound by the FP64 pipe late in the recursion (all 16 warps live: 236 cycles per step at n = 4096, 2 x 4096 FMAs
+// per step on 64 lanes = 128) and the generator early; split, every CTA stays under the coefficient chain's ~95 cycles per
+// step.  Requires n to be a multiple of 256 NS (full batches, full warps); the launcher falls back to the single-CTA
+// kernel otherwise.  blockIdx.x = system * 2 NS + role * NS + c; the 2 NS CTAs of a system form one thread-block cluster
+// (co-scheduled: the consumers spin on their producers).
+__global__ void __launch_bounds__(SCHUR_MAX_THREADS, 1)
+schur_levinson_split_kernel(const double* __restrict__ tab, long long sTab, int n, double jitter, double* __restrict__ g,
+                            long long sG, double* __restrict__ half_logdet, long long sLd, int* __restrict__ status,
+                            long long sStatus, double* gkap, long long sKap, int* prog, long long sProg, double* gbnd,
+                            long long sBnd, int ns, int* guard, int guard_bit0, double guard_min) {
+    extern __shared__ __align__(128) double sm_split[];
+    double* kap = sm_split;                                   // [SCHUR_MAX_N]
+    double* bin = kap + SCHUR_MAX_N;                          // [SCHUR_MAX_N] values entering this CTA's lowest position
+    double (*ring)[SCHUR_RING] = reinterpret_cast<double (*)[SCHUR_RING]>(bin + SCHUR_MAX_N);      // [16][32]
+    double* red = reinterpret_cast<double*>(ring + SCHUR_MAX_THREADS / 32);                          // [34]
+    int* s_i = reinterpret_cast<int*>(red + 34);                                                    // [4]
+    const int per_sys = 2 * ns, sys = blockIdx.x / per_sys, rr = blockIdx.x % per_sys, role = rr / ns, c = rr % ns;
+    tab += sys * sTab; g += sys * sG; half_logdet += sys * sLd; status += sys * sStatus; gkap += sys * sKap; prog += sys * sProg;
+    gbnd += sys * sBnd;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nw = blockDim.x >> 5, gw0 = c * nw, gw = gw0 + warp;
+    const int j0t = (gw * 32 + lane) * SCHUR_EPT;
+    const int nb = n / SCHUR_EPT;
+    const double r0 = tab[0] + jitter;
+    volatile int* progK = prog;
+    volatile int* progIn = c > 0 ? prog + 1 + role * 3 + (c - 1) : nullptr;
+    int* progOut = c < ns - 1 ? prog + 1 + role * 3 + c : nullptr;
+    const double* bndIn = c > 0 ? gbnd + (size_t)(role * 3 + c - 1) * n : nullptr;
+    double* bndOut = c < ns - 1 ? gbnd + (size_t)(role * 3 + c) * n : nullptr;
+    const bool top = warp == nw - 1;
+    int haveK = 0, haveB = 0;
+    bool dead = false;
+    // waits (uniform) until needK coefficients and needB boundary batches have been published, then copies the new ones
+    auto fetch = [&](int needK, int needB) -> bool {
+        if (needK <= haveK && needB <= haveB) return true;
+        if (tid == 0) {
+            int vK = haveK, vB = haveB;
+            long long spins = 0;
+            while (spins < (1ll << 24)) {
+                vK = *progK; vB = progIn ? *progIn : needB;
+                if (vK >= needK && vB >= needB) break;
+                __nanosleep(64); ++spins;
+            }
+            s_i[0] = vK; s_i[1] = vB;
+        }
+        __syncthreads();
+        const int nowK = min(s_i[0], n), nowB = min(s_i[1], nb);
+        if (nowK < needK || nowB < needB) return false;            // a producer never arrived
+        for (int i = haveK + tid; i < nowK; i += blockDim.x) kap[i] = __ldcg(gkap + i);
+        if (bndIn) for (int i = haveB * SCHUR_EPT + tid; i < nowB * SCHUR_EPT; i += blockDim.x) bin[i] = __ldcg(bndIn + i);
+        __syncthreads();
+        haveK = max(haveK, nowK); haveB = max(haveB, nowB);
+        return true;
+    };
+    auto publish = [&](int* flag, int value) { __threadfence(); *reinterpret_cast<volatile int*>(flag) = value; };
+    double rin[SCHUR_EPT], kp8[SCHUR_EPT];
+
+    if (role == 0) {
+        // ---- generator ----
+        double A[SCHUR_EPT], be[SCHUR_EPT];
+#pragma unroll
+        for (int i = 0; i < SCHUR_EPT; ++i) {
+            const int p = j0t + i;
+            const double rp = p == 0 ? r0 : tab[p];
+            A[i] = rp;
+            be[i] = p == 0 ? 0.0 : rp;
+        }
+        const int lead_lo = SCHUR_BPW * gw0, lead_hi = min(nb, SCHUR_BPW * (gw0 + nw));      // batches led (and the last ones processed) here
+        int led = lead_lo;
+        __syncthreads();
+        for (int T = 0; T < lead_hi + nw - 1; ++T) {
+            if (c > 0) {       // coefficients and boundary values of the batches the CTAs below lead
+                const int nbat = min(T + 1, lead_lo);
+                if (!fetch(nbat * SCHUR_EPT, nbat)) { dead = true; break; }
+            }
+            const int m = T - warp, j0 = m * SCHUR_EPT;
+            const bool live = m >= 0 && m < nb && m < SCHUR_BPW * (gw + 1);
+            const bool lead = live && (m / SCHUR_BPW) == gw;
+            if (__all_sync(0xffffffffu, live)) {
+                const double cand = j0 == 0 ? 0.0 : neg_div(be[0], A[0]);
+                const int rs = j0 & (SCHUR_RING - 1);
+                if (warp > 0) load8(rin, &ring[warp - 1][rs]);
+                else if (c > 0 && m < lead_lo) load8(rin, bin + j0);
+                else {
+#pragma unroll
+                    for (int i = 0; i < SCHUR_EPT; ++i) rin[i] = 0.0;                        // only reaches dead positions
+                }
+                if (__all_sync(0xffffffffu, lead)) {
+                    batch_full<0, true>(cand, m % SCHUR_BPW, lane == m % SCHUR_BPW, lane == 0, lane == 31, kp8, rin, &ring[warp][rs],
+                                        kap + j0, gkap + j0, A, be);
+                } else {
+                    load8(kp8, kap + j0);
+                    batch_full<0, false>(0.0, 0, false, lane == 0, lane == 31, kp8, rin, &ring[warp][rs], nullptr, nullptr, A, be);
+                }
+                if (bndOut && top && lane == 31) {
+#pragma unroll
+                    for (int i = 0; i < SCHUR_EPT; ++i) bndOut[j0 + i] = ring[warp][rs + i];
+                }
+            }
+            __syncthreads();
+            if (led < lead_hi && led + (led / SCHUR_BPW - gw0) == T) {
+                ++led;
+                if (((led - lead_lo) % SCHUR_PUBLISH == 0 || led == lead_hi) && tid == blockDim.x - 1) publish(prog, led * SCHUR_EPT);
+            }
+            const int mt = T - (nw - 1);                       // batch the top warp finished in this period
+            if (progOut && mt >= 0 && mt < lead_hi && ((mt + 1) % SCHUR_PUBLISH == 0 || mt + 1 == lead_hi) && tid == blockDim.x - 1)
+                publish(progOut, mt + 1);
+        }
+        if (c != ns - 1) return;
+        // the last generator CTA holds every coefficient: log|K|, first non-positive prediction error, conditioning guard
+        if (tid == 0) s_i[2] = 0x7fffffff;
+        __syncthreads();
+        double lsum = 0.0, gmin = 1.0;
+        for (int k = 1 + tid; k < n; k += blockDim.x) {
+            const double kp = kap[k];
+            if (!(fabs(kp) < 1.0)) atomicMin(&s_i[2], k);
+            lsum += (double)(n - k) * log1p(-kp * kp);
+            gmin = fmin(gmin, (1.0 - kp) * (1.0 + kp));
+        }
+        if (!(r0 > 0.0) && tid == 0) atomicMin(&s_i[2], 0);
+        const double ltot = block_sum(lsum, red);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gmin = fmin(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
+        if (lane == 0 && gmin < guard_min && guard) atomicOr(guard, 1 << (guard_bit0 + sys));
+        if (tid == 0) {
+            half_logdet[0] = dead ? __longlong_as_double(0x7ff8000000000000ll) : 0.5 * ((double)n * log(r0) + ltot);
+            if (s_i[2] != 0x7fffffff) status[0] = s_i[2] + 1;
+            if (dead && guard) atomicOr(guard, 1 << (8 + guard_bit0 + sys));
+        }
+        return;
+    }
+    // ---- lattice ----
+    double a[SCHUR_EPT], B[SCHUR_EPT];
+#pragma unroll
+    for (int i = 0; i < SCHUR_EPT; ++i) { a[i] = (j0t + i == 0) ? 1.0 : 0.0; B[i] = a[i]; }
+    const int mstart = max(0, SCHUR_BPW * gw0 - 1);            // warp 0 of this CTA becomes non-zero at step 256 gw0 - 1
+    haveB = mstart;                                            // older boundary batches are zeros nobody reads
+    for (int T = mstart; T < nb + nw - 1; ++T) {
+        if (!fetch(min((T + 1) * SCHUR_EPT, n), c > 0 ? min(T + 1, nb) : 0)) { dead = true; break; }
+        const int m = T - warp, j0 = m * SCHUR_EPT;
+        const bool live = m >= 0 && m < nb && (m + 1) * SCHUR_EPT >= gw * SCHUR_WCHUNK;
+        if (__all_sync(0xffffffffu, live)) {
+            const int rs = j0 & (SCHUR_RING - 1);
+            if (warp > 0) load8(rin, &ring[warp - 1][rs]);
+            else if (c > 0) load8(rin, bin + j0);
+            else {
+#pragma unroll
+                for (int i = 0; i < SCHUR_EPT; ++i) rin[i] = 0.0;                            // B[-1] = 0
+            }
+            load8(kp8, kap + j0);
+            batch_full<0, false>(0.0, 0, false, lane == 0, lane == 31, kp8, rin, &ring[warp][rs], nullptr, nullptr, B, a);
+            if (bndOut && top && lane == 31) {
+#pragma unroll
+                for (int i = 0; i < SCHUR_EPT; ++i) bndOut[j0 + i] = ring[warp][rs + i];
+            }
+        }
+        __syncthreads();
+        const int mt = T - (nw - 1);
+        if (progOut && mt >= 0 && mt < nb && (mt + 1) * SCHUR_EPT >= (gw0 + nw - 1) * SCHUR_WCHUNK &&
+            ((mt + 1) % SCHUR_PUBLISH == 0 || mt + 1 == nb) && tid == blockDim.x - 1)
+            publish(progOut, mt + 1);
+    }
+    // g = A_{n-1} / E_{n-1},  E_{n-1} = r0 * prod_k (1 - kappa_k^2): every CTA forms the product over all k in the same order
+    double prod = 1.0;
+    if (!dead) for (int k = 1 + tid; k < n; k += blockDim.x) { const double kp = kap[k]; prod *= (1.0 - kp) * (1.0 + kp); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) prod *= __shfl_xor_sync(0xffffffffu, prod, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = prod;
+    __syncthreads();
+    double E = r0;
+    for (int w = 0; w < nw; ++w) E *= red[w];
+    const double invE = dead ? __longlong_as_double(0x7ff8000000000000ll) : 1.0 / E;
+    if (dead && tid == 0 && guard) atomicOr(guard, 1 << (8 + guard_bit0 + sys));
+#pragma unroll
+    for (int i = 0; i < SCHUR_EPT; ++i) g[j0t + i] = a[i] * invE;
+}
+
 // One CTA per axis.  spec[0..3][L] (bit-reversed order, scaled like launch_toeplitz_spectrum):
 //   0: conj(G)/L   (v -> L(g)^T v)        2:  G / (L g0)   (v -> L(g) v / g0)
 //   1: conj(H)/L   (v -> L(h)^T v)        3: -H / (L g0)   (v -> -L(h) v / g0)
@@ -428,11 +617,42 @@ int toeplitz_inv_init() {
     return GPHM_OK;
 }
 
+constexpr size_t kSplitSmem = (2 * (size_t)SCHUR_MAX_N + (SCHUR_MAX_THREADS / 32) * SCHUR_RING + 34) * sizeof(double) + 4 * sizeof(int);
+
+int schur_split_factor(int n) {           // CTAs per role: GPHM_SCHUR_SPLIT (1, 2 or 4); needs n to be a multiple of 256 * split
+    static const int want = [] { const char* e = getenv("GPHM_SCHUR_SPLIT"); return e ? atoi(e) : kSchurDefaultSplit; }();
+    int ns = want >= 4 ? 4 : (want >= 2 ? 2 : 1);
+    while (ns > 1 && (n % (SCHUR_WCHUNK * ns) != 0 || n / (SCHUR_EPT * ns) < 64)) ns >>= 1;
+    return ns;
+}
+
 int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitter, double* g, long long sG,
                           double* half_logdet, long long sLd, int* status, long long sStatus, double* gkap, long long sKap,
-                          int* prog, long long sProg, int nsys, cudaStream_t st, long long* dbg, int* guard, int guard_bit0) {
+                          int* prog, long long sProg, int nsys, cudaStream_t st, long long* dbg, int* guard, int guard_bit0,
+                          double* gbnd, long long sBnd) {
     if (n < 1 || n > SCHUR_MAX_N) { set_last_error("schur: n=%d outside [1,%d]", n, SCHUR_MAX_N); return GPHM_EINVAL; }
     if (nsys < 1 || nsys > 2) { set_last_error("schur: nsys=%d", nsys); return GPHM_EINVAL; }
+    const int ns = gbnd && !dbg ? schur_split_factor(n) : 1;
+    if (ns > 1) {
+        static DeviceOnce once;
+        if (once.needed()) {
+            GPHM_ONCE_CUDA_OK(once, cudaFuncSetAttribute(schur_levinson_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSplitSmem));
+            once.done();
+        }
+        for (int s = 0; s < nsys; ++s) GPHM_CUDA_OK(cudaMemsetAsync(prog + s * sProg, 0, 8 * sizeof(int), st));
+        LaunchScope scope(CAT_CHOL_DIAG, st, 8.0 * (double)n * n * nsys);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * ns * nsys); cfg.blockDim = dim3(n / (SCHUR_EPT * ns)); cfg.dynamicSmemBytes = kSplitSmem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2 * ns; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const double gmin = toeplitz_guard_min();
+        GPHM_CUDA_OK(cudaLaunchKernelEx(&cfg, schur_levinson_split_kernel, tabK, sTab, n, jitter, g, sG, half_logdet, sLd, status, sStatus,
+                                        gkap, sKap, prog, sProg, gbnd, sBnd, ns, guard, guard_bit0, gmin));
+        GPHM_LAUNCH_OK();
+        return GPHM_OK;
+    }
     const int threads = std::min(SCHUR_MAX_THREADS, ((n + SCHUR_EPT - 1) / SCHUR_EPT + 31) / 32 * 32);
     for (int s = 0; s < nsys; ++s) GPHM_CUDA_OK(cudaMemsetAsync(prog + s * sProg, 0, sizeof(int), st));
     {
