@@ -271,11 +271,12 @@ int invert_axis(gphm_plan& p, int a, bool with_kinv, cudaStream_t st) {
 // intact: without refinement the theta-leaves are off by 5e-8 at N = 1024 and 1.4e-6 at N = 4096 against an
 // extended-precision reference (tools/extended_reference.py), with it they match the Cholesky route (1e-9 .. 5e-8).
 // The forward applications (A, Bt) do not need it (measured: no change).  The loss grows like cond(K) N: 5e-8 at N = 1024,
-// 3.2e-7 at 2048, 1.4e-6 at 4096 (same kernel and state), so axes of up to kRefineAbove points skip the step (a 20-fold
-// margin under the 1e-6 bound; every reference config has N_col <= 900).  force_general bit 5 switches it off everywhere.
-constexpr int kRefineAbove = 1024;
+// 3.2e-7 at 2048, 1.4e-6 at 4096 (same kernel and state), so axes of up to kRefineAbove = 512 points skip the step
+// (the reference's N_col = 400 configs and the ensemble; its N_col = 900 configs get it).  force_general bit 5 switches it off
+// everywhere, bit 7 on everywhere (measurements: tools/dump_gpu_grad.py).
+constexpr int kRefineAbove = 512;
 inline bool gs_refine(const gphm_plan& p) { return (p.d.force_general & 32) == 0; }
-inline bool gs_refine_axis(const gphm_plan& p, const Axis& X) { return gs_refine(p) && X.n > kRefineAbove; }
+inline bool gs_refine_axis(const gphm_plan& p, const Axis& X) { return gs_refine(p) && (X.n > kRefineAbove || (p.d.force_general & 128)); }
 
 // Uniform-grid axes a0 .. a0+count-1 without a dense factorisation: Toeplitz tables, Schur/Levinson
 // recursion for g = K^-1 e_0 and log|K|, Gohberg-Semencul spectra and the diagonal sums of K^-1.

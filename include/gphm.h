@@ -80,7 +80,8 @@ typedef struct gphm_problem_desc {
                             bit 6: the plain contractions of the general path (D A, Bt D^T, D^T G, G D, V A^T, G A^T:
                                    jnp.matmul at model_GP_solver_2d.py:112,119 and their reverse pass) on the tensor
                                    cores - Ozaki int8 slices, tcgen05.mma kind::i8, TMA operands, TMEM accumulators
-                                   (gphm_ozaki_dgemm, stated bound there); the solves stay native FP64 */
+                                   (gphm_ozaki_dgemm, stated bound there); the solves stay native FP64;
+                            bit 7: refinement step also on axes of <= 512 points (measurement only) */
     double llk_weight;   /* trick_paras['llk_weight'] */
     double logdet;       /* trick_paras['logdet'] (True -> 1.0) */
     double beta;         /* advection speed, trick_paras['beta'] (ignored otherwise) */

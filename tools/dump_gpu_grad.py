@@ -14,11 +14,14 @@ import gphm_b200 as G
 from oracle import gphm_oracle as O
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-p, _, _ = O.make_problem_2d("poisson_2d-sin_add_cos", "Matern52_Cos_1d", N, 2 * math.pi, M=8)
+KERNEL = sys.argv[2] if len(sys.argv) > 2 else "Matern52_Cos_1d"
+SCALE = float(sys.argv[3]) if len(sys.argv) > 3 else 2 * math.pi
+p, _, _ = O.make_problem_2d("poisson_2d-sin_add_cos", KERNEL, N, SCALE, M=8)
 s1 = O.state_S1(p)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-for mode, tag in ((0, ""), (16, "_chol"), (32, "_norefine")):
-    core = G.solver_core.SolverCore(2, "Matern52_Cos_1d", "poisson", p.x.numpy(), p.y.numpy(), p.src.numpy(), p.bvals.numpy(), None,
+TAG = "" if (KERNEL == "Matern52_Cos_1d" and len(sys.argv) <= 3) else "_%s_s%g" % (KERNEL, SCALE)
+for mode, tag in ((0, ""), (16, "_chol"), (32, "_norefine"), (128, "_refine")):
+    core = G.solver_core.SolverCore(2, KERNEL, "poisson", p.x.numpy(), p.y.numpy(), p.src.numpy(), p.bvals.numpy(), None,
                                     p.llk_weight, 1.0, 1.0, 1e-6, 30, force_general=mode)
     st = core.new_state(s1)
     terms, gU, gs = core.value_and_grad(st)
@@ -28,7 +31,7 @@ for mode, tag in ((0, ""), (16, "_chol"), (32, "_norefine")):
     for a in (1, 2):
         for l in ("log-w", "log-ls", "freq"):
             out["kernel_paras_%d_%s" % (a, l)] = tree["kernel_paras_%d" % a][l].cpu().numpy()
-    np.savez(os.path.join(ROOT, "gpurun_out", "gpu_grad_%d%s.npz" % (N, tag)), **out)
+    np.savez(os.path.join(ROOT, "gpurun_out", "gpu_grad_%d%s%s.npz" % (N, TAG, tag)), **out)
     print("wrote", N, tag or "default", float(terms[0]))
     del core, st
     torch.cuda.empty_cache()

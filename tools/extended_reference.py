@@ -121,10 +121,12 @@ def rel(a, b):
 
 if __name__ == "__main__":
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+    KERNEL = sys.argv[3] if len(sys.argv) > 3 else "Matern52_Cos_1d"
+    SCALE = float(sys.argv[4]) if len(sys.argv) > 4 else 2 * math.pi
     torch.set_num_threads(os.cpu_count() or 1)
-    p, _, _ = O.make_problem_2d("poisson_2d-sin_add_cos", "Matern52_Cos_1d", N, 2 * math.pi, M=8)
+    p, _, _ = O.make_problem_2d("poisson_2d-sin_add_cos", KERNEL, N, SCALE, M=8)
     s1 = O.state_S1(p)
-    cache = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "extref_%d.npz" % N)
+    cache = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "extref_%d%s.npz" % (N, "" if len(sys.argv) <= 3 else "_%s_s%g" % (KERNEL, SCALE)))
     if os.path.exists(cache):
         z = np.load(cache)
         ref = {"U": z["U"]}
@@ -142,7 +144,7 @@ if __name__ == "__main__":
                 flat["kp%d_%s" % (a, l)] = np.asarray(ref["kernel_paras_%d" % a][l], dtype=np.float64)
         np.savez(cache, **flat)
     _, ge = O.loss_and_grad_efficient(p, s1)
-    gpu = np.load(sys.argv[2]) if len(sys.argv) > 2 else None
+    gpu = np.load(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2] != "-" else None
     print("# leaf | oracle (FP64 Cholesky route) vs reference | GPU (Schur + Gohberg-Semencul route) vs reference | GPU vs oracle")
     leaves = [("U", ge["U"].numpy(), ref["U"])]
     for a in (1, 2):
