@@ -390,6 +390,48 @@ int launch_adam_inc(double* p, const double* g, double* m, double* v, size_t n, 
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }
+__global__ void __launch_bounds__(1024)
+adam_out_kernel(const double* __restrict__ p, double* __restrict__ p_out, const double* __restrict__ g, double* __restrict__ m,
+                double* __restrict__ v, int n, const long long* __restrict__ count, double lr) {
+    constexpr double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+    const double t = (double)(*count + 1);
+    const double c1 = 1.0 - pow(b1, t), c2 = 1.0 - pow(b2, t);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double gi = g[i];
+        const double mi = b1 * m[i] + (1.0 - b1) * gi;
+        const double vi = b2 * v[i] + (1.0 - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        p_out[i] = p[i] - lr * (mi / c1) / (sqrt(vi / c2) + eps);
+    }
+}
+int launch_adam_out(const double* p, double* p_out, const double* g, double* m, double* v, size_t n, const long long* count,
+                    double lr, cudaStream_t st) {
+    { LaunchScope scope(CAT_ADAM, st); adam_out_kernel<<<1, 1024, 0, st>>>(p, p_out, g, m, v, (int)n, count, lr); }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+// flags[1] (skip) = the look-ahead result is valid (flags[0]) AND was computed for exactly this theta; flags[0] is consumed
+__global__ void __launch_bounds__(256)
+lk_compare_kernel(const double* __restrict__ small, const double* __restrict__ lk_small, int n, int* __restrict__ flags) {
+    __shared__ int differ;
+    if (threadIdx.x == 0) differ = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (__double_as_longlong(small[i]) != __double_as_longlong(lk_small[i])) differ = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) { flags[1] = (flags[0] != 0 && !differ) ? 1 : 0; flags[0] = 0; }
+}
+__global__ void lk_set_kernel(int* flags, int value) { flags[0] = value; }
+int launch_lk_compare(const double* small, const double* lk_small, int n, int* flags, cudaStream_t st) {
+    { LaunchScope scope(CAT_ELEMWISE, st); lk_compare_kernel<<<1, 256, 0, st>>>(small, lk_small, n, flags); }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+int launch_lk_set(int* flags, int value, cudaStream_t st) {
+    { LaunchScope scope(CAT_ELEMWISE, st); lk_set_kernel<<<1, 1, 0, st>>>(flags, value); }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
 int launch_count_inc(long long* count, cudaStream_t st) {
     { LaunchScope scope(CAT_ADAM, st); count_inc_kernel<<<1, 1, 0, st>>>(count); }
     GPHM_LAUNCH_OK();

@@ -186,7 +186,8 @@ spectrum_to_diag_sums_kernel(const double2* __restrict__ partK, const double2* _
 // spec[p] = FFT(c)[brev(p)] / L  with  c[m] = t(m), c[L-m] = t(-m)
 __global__ void __launch_bounds__(FFT_THREADS, 1)
 toeplitz_spectrum_kernel(const double* __restrict__ tab, int n, int L, int logL, const double2* __restrict__ W,
-                         int antisym, double dirsign, double diag_add, double2* __restrict__ spec) {
+                         int antisym, double dirsign, double diag_add, double2* __restrict__ spec, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     extern __shared__ double2 xs[];
     const int tid = threadIdx.x;
     fft_load_twiddles(xs, L, logL, W, tid);
@@ -353,12 +354,12 @@ int launch_spectrum_to_diag_sums(const double* partK, const double* partD, int L
 }
 
 int launch_toeplitz_spectrum(const double* tab, int n, int L, const double* W, bool antisym, double dirsign, double* spec,
-                             cudaStream_t st, double diag_add) {
+                             cudaStream_t st, double diag_add, const int* skip) {
     GPHM_TRY(fft_init());
     {
         LaunchScope scope(CAT_FFT, st);
         toeplitz_spectrum_kernel<<<1, FFT_THREADS, fft_smem_bytes(L), st>>>(
-            tab, n, L, ilog2(L), reinterpret_cast<const double2*>(W), antisym ? 1 : 0, dirsign, diag_add, reinterpret_cast<double2*>(spec));
+            tab, n, L, ilog2(L), reinterpret_cast<const double2*>(W), antisym ? 1 : 0, dirsign, diag_add, reinterpret_cast<double2*>(spec), skip);
     }
     GPHM_LAUNCH_OK();
     return GPHM_OK;

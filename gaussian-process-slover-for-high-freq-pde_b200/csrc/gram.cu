@@ -115,7 +115,8 @@ gram_symmetric_kernel(const double* __restrict__ x, int n, const double* __restr
 template <int KID, int ORDER>
 __global__ void __launch_bounds__(128)
 toeplitz_table_kernel(const double* __restrict__ x, int n, const double* __restrict__ theta, int Q,
-                      double* __restrict__ tabK, double* __restrict__ tabD) {
+                      double* __restrict__ tabK, double* __restrict__ tabD, const int* __restrict__ skip) {
+    if (skip && *skip) return;             // the look-ahead of the previous step already factored this theta (plan.cu)
     __shared__ CompConst sc[kMaxQ];
     load_comps<KID>(sc, theta, Q);
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -223,13 +224,13 @@ int launch_gram_general(int kid, int order, const double* x1, int n1, const doub
 }
 
 int launch_toeplitz_table(int kid, int order, const double* x, int n, const double* theta, int Q, double* tabK, double* tabD,
-                          cudaStream_t st) {
+                          cudaStream_t st, const int* skip) {
     if (Q > kMaxQ || Q < 1) { set_last_error("gram: Q=%d outside [1,%d]", Q, kMaxQ); return GPHM_EINVAL; }
     if (n <= 0) return GPHM_OK;
     int rc;
     { LaunchScope scope(CAT_GRAM, st, 0.0, 24.0 * n);
     rc = GPHM_DISPATCH_KID_ORDER(kid, order,
-        toeplitz_table_kernel<KID, ORDER><<<(n + 127) / 128, 128, 0, st>>>(x, n, theta, Q, tabK, tabD)); }
+        toeplitz_table_kernel<KID, ORDER><<<(n + 127) / 128, 128, 0, st>>>(x, n, theta, Q, tabK, tabD, skip)); }
     if (rc != 0) { set_last_error("gram: bad kernel id %d / order %d", kid, order); return GPHM_EINVAL; }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
@@ -243,7 +244,7 @@ int launch_gram_toeplitz(int kid, int order, const double* x, int n, const doubl
     int rc;
     { LaunchScope scope(CAT_GRAM, st, 0.0, 24.0 * n);
     rc = GPHM_DISPATCH_KID_ORDER(kid, order,
-        toeplitz_table_kernel<KID, ORDER><<<(n + 127) / 128, 128, 0, st>>>(x, n, theta, Q, tabK, tabD)); }
+        toeplitz_table_kernel<KID, ORDER><<<(n + 127) / 128, 128, 0, st>>>(x, n, theta, Q, tabK, tabD, nullptr)); }
     if (rc != 0) { set_last_error("gram: bad kernel id %d / order %d", kid, order); return GPHM_EINVAL; }
     GPHM_LAUNCH_OK();
     dim3 block(256), grid((n + 511) / 512, (n + 3) / 4);

@@ -13,8 +13,9 @@ int launch_gram_toeplitz(int kid, int order, const double* x, int n, const doubl
                          double dirsign, double* tabK, double* tabD, double* Kout, double* Dout, int ld,
                          cudaStream_t st);
 
+// skip (optional, every launcher of the uniform-grid factor stage): device flag; non-zero turns the launch into a no-op
 int launch_toeplitz_table(int kid, int order, const double* x, int n, const double* theta, int Q, double* tabK, double* tabD,
-                          cudaStream_t st);
+                          cudaStream_t st, const int* skip = nullptr);
 int launch_kappa_pairs(int kid, int order, const double* x1, const double* x2, size_t np, const double* theta, int Q,
                        double* out, cudaStream_t st);
 
@@ -66,7 +67,7 @@ int launch_spectrum_to_diag_sums(const double* partK, const double* partD, int L
                                  cudaStream_t st);
 // spec (L complex, bit-reversed order, scaled by 1/L) of the circulant embedding of the Toeplitz matrix t(i-j) = tab[|i-j|] (* sign)
 int launch_toeplitz_spectrum(const double* tab, int n, int L, const double* W, bool antisym, double dirsign, double* spec,
-                             cudaStream_t st, double diag_add = 0.0);
+                             cudaStream_t st, double diag_add = 0.0, const int* skip = nullptr);
 // Out[r][:] = alpha * T X[r][:] + beta * Out[r][:]   for every row r (T n x n Toeplitz with spectrum `spec`)
 int launch_toeplitz_apply(const double* X, int rows, int n, int ldx, const double* spec, int L, const double* W, double alpha,
                           double beta, double* Out, int ldo, cudaStream_t st);
@@ -82,14 +83,15 @@ int toeplitz_inv_max_n();
 int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitter, double* g, long long sG,
                           double* half_logdet, long long sLd, int* status, long long sStatus, double* gkap, long long sKap,
                           int* prog, long long sProg, int nsys, cudaStream_t st, long long* dbg_cycles = nullptr,
-                          int* guard = nullptr, int guard_bit0 = 0, double* gbnd = nullptr, long long sBnd = 0);
+                          int* guard = nullptr, int guard_bit0 = 0, double* gbnd = nullptr, long long sBnd = 0,
+                          const int* skip = nullptr);
 // gbnd (optional): 6 n doubles per system - the hand-over buffers of the multi-CTA recursion (prog then needs 8 ints per system)
 int schur_split_factor(int n);
 // guard: bit (guard_bit0 + s) is OR-ed in when system s has min_k (1 - kappa_k^2) < toeplitz_guard_min()
 double toeplitz_guard_min();
 // spec[4][L] complex (strides in doubles): Gohberg-Semencul circulant spectra; sKinv[n]: diagonal sums of K^-1
 int launch_gs_prepare(const double* g, long long sG, int n, int L, const double* W, double* spec, long long sSpec,
-                      double* sKinv, long long sS, int nsys, cudaStream_t st);
+                      double* sKinv, long long sS, int nsys, cudaStream_t st, const int* skip = nullptr);
 
 // ---- toeplitz_fused.cu ---------------------------------------------------------------------
 bool toeplitz_fused_supported(int L);   // L >= 16: fused-sweep kernels; smaller sizes use the plain ones in fft.cu
@@ -145,6 +147,11 @@ int launch_adam(double* p, const double* g, double* m, double* v, size_t n, cons
                 cudaStream_t st);
 int launch_count_inc(long long* count, cudaStream_t st);
 int launch_adam_inc(double* p, const double* g, double* m, double* v, size_t n, long long* count, double lr, cudaStream_t st);
+// look-ahead bookkeeping (plan.cu): out-of-place Adam on the short vector; theta compare / flag kernels
+int launch_adam_out(const double* p, double* p_out, const double* g, double* m, double* v, size_t n, const long long* count,
+                    double lr, cudaStream_t st);
+int launch_lk_compare(const double* small, const double* lk_small, int n, int* flags, cudaStream_t st);   // flags[1] = flags[0] && equal; flags[0] = 0
+int launch_lk_set(int* flags, int value, cudaStream_t st);                                                // flags[0] = value
 int launch_rel_l2(const double* pred, const double* truth, size_t n, double* part, double* out, cudaStream_t st);
 int launch_copy(double* dst, const double* src, size_t n, cudaStream_t st);
 int launch_pair_reduce(const double* part, double* out2, cudaStream_t st);

@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(SCHUR_MAX_THREADS, 1)
 schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, double jitter, double* __restrict__ g,
                       long long sG, double* __restrict__ half_logdet, long long sLd, int* __restrict__ status,
                       long long sStatus, double* gkap, long long sKap, int* prog, long long sProg, int* guard, int guard_bit0,
-                      double guard_min, long long* dbg) {
+                      double guard_min, long long* dbg, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     const int sys = blockIdx.x >> 1, role = blockIdx.x & 1;
     const long long t_start = clock64();
     tab += sys * sTab; g += sys * sG; half_logdet += sys * sLd; status += sys * sStatus; gkap += sys * sKap; prog += sys * sProg;
@@ -376,7 +377,8 @@ __global__ void __launch_bounds__(SCHUR_MAX_THREADS, 1)
 schur_levinson_split_kernel(const double* __restrict__ tab, long long sTab, int n, double jitter, double* __restrict__ g,
                             long long sG, double* __restrict__ half_logdet, long long sLd, int* __restrict__ status,
                             long long sStatus, double* gkap, long long sKap, int* prog, long long sProg, double* gbnd,
-                            long long sBnd, int ns, int* guard, int guard_bit0, double guard_min) {
+                            long long sBnd, int ns, int* guard, int guard_bit0, double guard_min, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     extern __shared__ __align__(128) double sm_split[];
     double* kap = sm_split;                                   // [SCHUR_MAX_N]
     double* bin = kap + SCHUR_MAX_N;                          // [SCHUR_MAX_N] values entering this CTA's lowest position
@@ -551,7 +553,8 @@ schur_levinson_split_kernel(const double* __restrict__ tab, long long sTab, int 
 // sKinv[d] = sum over |i-j| = d of K^-1[i][j]  (both triangles for d > 0).
 __global__ void __launch_bounds__(FFT_THREADS, 1)
 gs_prepare_kernel(const double* __restrict__ g, long long sG, int n, int L, int logL, const double2* __restrict__ W,
-                  double2* __restrict__ spec, long long sSpec, double* __restrict__ sKinv, long long sS) {
+                  double2* __restrict__ spec, long long sSpec, double* __restrict__ sKinv, long long sS, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     g += blockIdx.x * sG; spec += blockIdx.x * sSpec; sKinv += blockIdx.x * sS;
     extern __shared__ double2 xs[];
     const int tid = threadIdx.x;
@@ -629,7 +632,7 @@ int schur_split_factor(int n) {           // CTAs per role: GPHM_SCHUR_SPLIT (1,
 int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitter, double* g, long long sG,
                           double* half_logdet, long long sLd, int* status, long long sStatus, double* gkap, long long sKap,
                           int* prog, long long sProg, int nsys, cudaStream_t st, long long* dbg, int* guard, int guard_bit0,
-                          double* gbnd, long long sBnd) {
+                          double* gbnd, long long sBnd, const int* skip) {
     if (n < 1 || n > SCHUR_MAX_N) { set_last_error("schur: n=%d outside [1,%d]", n, SCHUR_MAX_N); return GPHM_EINVAL; }
     if (nsys < 1 || nsys > 2) { set_last_error("schur: nsys=%d", nsys); return GPHM_EINVAL; }
     const int ns = gbnd && !dbg ? schur_split_factor(n) : 1;
@@ -649,7 +652,7 @@ int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitt
         cfg.attrs = attr; cfg.numAttrs = 1;
         const double gmin = toeplitz_guard_min();
         GPHM_CUDA_OK(cudaLaunchKernelEx(&cfg, schur_levinson_split_kernel, tabK, sTab, n, jitter, g, sG, half_logdet, sLd, status, sStatus,
-                                        gkap, sKap, prog, sProg, gbnd, sBnd, ns, guard, guard_bit0, gmin));
+                                        gkap, sKap, prog, sProg, gbnd, sBnd, ns, guard, guard_bit0, gmin, skip));
         GPHM_LAUNCH_OK();
         return GPHM_OK;
     }
@@ -668,20 +671,20 @@ int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitt
         cfg.attrs = attr; cfg.numAttrs = 1;
         const double gmin = toeplitz_guard_min();
         GPHM_CUDA_OK(cudaLaunchKernelEx(&cfg, schur_levinson_kernel, tabK, sTab, n, jitter, g, sG, half_logdet, sLd, status, sStatus,
-                                        gkap, sKap, prog, sProg, guard, guard_bit0, gmin, dbg));
+                                        gkap, sKap, prog, sProg, guard, guard_bit0, gmin, dbg, skip));
     }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }
 
 int launch_gs_prepare(const double* g, long long sG, int n, int L, const double* W, double* spec, long long sSpec,
-                      double* sKinv, long long sS, int nsys, cudaStream_t st) {
+                      double* sKinv, long long sS, int nsys, cudaStream_t st, const int* skip) {
     GPHM_TRY(toeplitz_inv_init());
     if (L > FFT_MAX_L || L < 2 * n) { set_last_error("gs_prepare: L=%d does not fit n=%d", L, n); return GPHM_EINVAL; }
     {
         LaunchScope scope(CAT_FFT, st);
         gs_prepare_kernel<<<nsys, FFT_THREADS, fft_smem_bytes(L), st>>>(
-            g, sG, n, L, ilog2i(L), reinterpret_cast<const double2*>(W), reinterpret_cast<double2*>(spec), sSpec / 2, sKinv, sS);
+            g, sG, n, L, ilog2i(L), reinterpret_cast<const double2*>(W), reinterpret_cast<double2*>(spec), sSpec / 2, sKinv, sS, skip);
     }
     GPHM_LAUNCH_OK();
     return GPHM_OK;

@@ -476,3 +476,32 @@ def test_evals_end_to_end_run_2d_sh_line(gphm, tmp_path, monkeypatch):
     lines = (d / "log.txt").read_text().splitlines()
     assert lines[0] == "llk_weight-200.0--nu-1-Q-30-epoch-100-lr-0.0100-freqscale=20-logdet-1-x-2pi-Ncol-400"
     assert lines[1].startswith("err_mean: 0.46") and "avg_epochs 100" in lines[1] and lines[2].startswith("err_list: [0.46")
+
+
+def test_step_lookahead_is_bitwise_the_plain_step(gphm, oracle):
+    """gphm_step on large 2-D uniform plans factors the NEXT step's theta (tables, Schur/Levinson recursion, spectra) on a
+    second stream beside dL/dU assembly + Adam(U) and skips the factor stage of the next call when - checked on the device -
+    it sees exactly that theta.  Same bits as the plain step (force_general bit 8), also when the caller changes theta
+    between two steps (the look-ahead must then be discarded) and when other entry points run in between."""
+    O = oracle
+    N = 2048
+    p, _, _ = O.make_problem_2d("poisson_2d-sin_add_cos", "Matern52_Cos_1d", N, 2 * math.pi, M=8)
+    s1 = O.state_S1(p)
+    mk = lambda mode: gphm.solver_core.SolverCore(2, "Matern52_Cos_1d", "poisson", p.x.numpy(), p.y.numpy(), p.src.numpy(), p.bvals.numpy(),
+                                                  None, p.llk_weight, 1.0, 1.0, 1e-6, 30, force_general=mode)
+    ca, cb = mk(0), mk(256)
+    sa, sb = ca.new_state(s1), cb.new_state(s1)
+    for k in range(6):
+        if k == 3:                                   # the caller edits theta in place: the stored look-ahead is stale
+            for st in (sa, sb):
+                st.small[5] += 1e-3
+        if k == 4:                                   # another entry point re-factors with a different theta in between
+            for c, st in ((ca, sa), (cb, sb)):
+                tmp = c.new_state(O.init_params_2d(N, N, 30, 20.0))
+                c.value_and_grad(tmp, forward_only=True)
+        ca.step_inplace(sa, 0.01)
+        cb.step_inplace(sb, 0.01)
+        torch.cuda.synchronize()
+        for name in ("U", "small", "mU", "vU", "msmall", "vsmall", "count", "terms"):
+            assert torch.equal(getattr(sa, name), getattr(sb, name)), (k, name)
+    ca.raise_on_bad_status(); cb.raise_on_bad_status()
