@@ -923,12 +923,18 @@ int gphm_step(gphm_plan* plan, double* d_U, double* d_small, double* d_mU, doubl
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     gphm_plan& p = *plan;
     const size_t nf = (size_t)p.d.n1 * p.d.n2, ns = 6 * (size_t)p.d.Q + 2;
-    // Look-ahead (2-D all-FFT plans with axes of >= 2048 points; force_general bit 8 or GPHM_LOOKAHEAD=0 disable it): the factor
-    // stage of the NEXT step needs only the updated theta, which exists as soon as the theta-gradient does.
-    static const bool lk_env = [] { const char* e = getenv("GPHM_LOOKAHEAD"); return !(e && e[0] == '0'); }();
-    const bool lk = lk_env && !(p.d.force_general & 256) && p.d.dim == 2 && uses_gs_path(p) && std::min(p.d.n1, p.d.n2) >= 2048;
+    // Look-ahead (2-D all-FFT plans with axes of >= 2048 points): the factor stage of the NEXT step needs only the updated theta,
+    // which exists as soon as the theta-gradient does.  OFF by default (GPHM_LOOKAHEAD=1 or force_general bit 9 switch it on, bit 8
+    // off): measured on the 4096^2 step it does not pay - 7.41 ms with it against 7.35 ms without (high-priority side stream
+    // included): the 0.5 ms chain of small dependent kernels does not finish inside the 0.25 ms of dL/dU assembly + Adam(U) it runs
+    // beside, and 13 more launches per step eat the rest.  Kept because it is bit-exact and tested.
+    static const bool lk_env = [] { const char* e = getenv("GPHM_LOOKAHEAD"); return e && e[0] == '1'; }();
+    const bool lk = (lk_env || (p.d.force_general & 512)) && !(p.d.force_general & 256) && p.d.dim == 2 && uses_gs_path(p) &&
+                    std::min(p.d.n1, p.d.n2) >= 2048;
     if (lk && !p.lk_stream) {
-        GPHM_CUDA_OK(cudaStreamCreateWithFlags(&p.lk_stream, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;          // highest priority: the 16 CTAs of the recursion must not queue behind the wide element-wise kernels
+        GPHM_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        GPHM_CUDA_OK(cudaStreamCreateWithPriority(&p.lk_stream, cudaStreamNonBlocking, prio_hi));
         GPHM_CUDA_OK(cudaEventCreateWithFlags(&p.lk_fork, cudaEventDisableTiming));
         GPHM_CUDA_OK(cudaEventCreateWithFlags(&p.lk_join, cudaEventDisableTiming));
         GPHM_CUDA_OK(cudaMalloc(&p.lk_small, sizeof(double) * ns));

@@ -81,7 +81,9 @@ typedef struct gphm_problem_desc {
                                    jnp.matmul at model_GP_solver_2d.py:112,119 and their reverse pass) on the tensor
                                    cores - Ozaki int8 slices, tcgen05.mma kind::i8, TMA operands, TMEM accumulators
                                    (gphm_ozaki_dgemm, stated bound there); the solves stay native FP64;
-                            bit 7: refinement step also on axes of <= 512 points (measurement only) */
+                            bit 7: refinement step also on axes of <= 512 points (measurement only);
+                            bit 8 / bit 9: gphm_step look-ahead of the next step's factor stage off / on (default off:
+                                   bit-exact but no faster, see plan.cu) */
     double llk_weight;   /* trick_paras['llk_weight'] */
     double logdet;       /* trick_paras['logdet'] (True -> 1.0) */
     double beta;         /* advection speed, trick_paras['beta'] (ignored otherwise) */

@@ -479,7 +479,7 @@ def test_evals_end_to_end_run_2d_sh_line(gphm, tmp_path, monkeypatch):
 
 
 def test_step_lookahead_is_bitwise_the_plain_step(gphm, oracle):
-    """gphm_step on large 2-D uniform plans factors the NEXT step's theta (tables, Schur/Levinson recursion, spectra) on a
+    """gphm_step on large 2-D uniform plans can factor (opt-in: force_general bit 9) the NEXT step's theta (tables, Schur/Levinson recursion, spectra) on a
     second stream beside dL/dU assembly + Adam(U) and skips the factor stage of the next call when - checked on the device -
     it sees exactly that theta.  Same bits as the plain step (force_general bit 8), also when the caller changes theta
     between two steps (the look-ahead must then be discarded) and when other entry points run in between."""
@@ -489,7 +489,7 @@ def test_step_lookahead_is_bitwise_the_plain_step(gphm, oracle):
     s1 = O.state_S1(p)
     mk = lambda mode: gphm.solver_core.SolverCore(2, "Matern52_Cos_1d", "poisson", p.x.numpy(), p.y.numpy(), p.src.numpy(), p.bvals.numpy(),
                                                   None, p.llk_weight, 1.0, 1.0, 1e-6, 30, force_general=mode)
-    ca, cb = mk(0), mk(256)
+    ca, cb = mk(512), mk(256)                    # look-ahead on / off
     sa, sb = ca.new_state(s1), cb.new_state(s1)
     for k in range(6):
         if k == 3:                                   # the caller edits theta in place: the stored look-ahead is stale
