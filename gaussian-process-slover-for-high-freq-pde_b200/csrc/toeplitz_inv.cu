@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "fft_core.cuh"
+#include <cooperative_groups.h>
 
 namespace gphm {
 
@@ -547,6 +548,202 @@ schur_levinson_split_kernel(const double* __restrict__ tab, long long sTab, int 
     for (int i = 0; i < SCHUR_EPT; ++i) g[j0t + i] = a[i] * invE;
 }
 
+// The split recursion with the hand-over through DISTRIBUTED SHARED MEMORY instead of global memory: producers keep what they
+// hand over (coefficients, boundary values, two counters) in their own shared memory and publish once per period with a
+// cluster-scope fence; consumers poll the producer's counter (a ~200-cycle DSMEM load instead of an L2 round trip) and pull what
+// is new.  Per-batch granularity, no gpu-scope fence, no flags in global memory.  Same arithmetic, same bits.
+__global__ void __launch_bounds__(SCHUR_MAX_THREADS, 1)
+schur_levinson_dsmem_kernel(const double* __restrict__ tab, long long sTab, int n, double jitter, double* __restrict__ g,
+                            long long sG, double* __restrict__ half_logdet, long long sLd, int* __restrict__ status,
+                            long long sStatus, double* gkap, long long sKap, int* prog, long long sProg, double* gbnd,
+                            long long sBnd, int ns, int* guard, int guard_bit0, double guard_min, const int* __restrict__ skip) {
+    if (skip && *skip) return;
+    extern __shared__ __align__(128) double sm_split[];
+    double* kap = sm_split;                                   // [SCHUR_MAX_N] coefficients (own + pulled from the leading CTA)
+    double* bin = kap + SCHUR_MAX_N;                          // [SCHUR_MAX_N] values entering this CTA's lowest position (pulled)
+    double* bout = bin + SCHUR_MAX_N;                         // [SCHUR_MAX_N] values leaving this CTA's top position (read remotely)
+    double (*ring)[SCHUR_RING] = reinterpret_cast<double (*)[SCHUR_RING]>(bout + SCHUR_MAX_N);     // [16][32]
+    double* red = reinterpret_cast<double*>(ring + SCHUR_MAX_THREADS / 32);                          // [34]
+    int* s_i = reinterpret_cast<int*>(red + 34);                                                    // [4] scratch, [4] kdone, [5] bdone
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int per_sys = 2 * ns, sys = blockIdx.x / per_sys, rr = blockIdx.x % per_sys, role = rr / ns, c = rr % ns;
+    tab += sys * sTab; g += sys * sG; half_logdet += sys * sLd; status += sys * sStatus; gkap += sys * sKap; prog += sys * sProg;
+    gbnd += sys * sBnd;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nw = blockDim.x >> 5, gw0 = c * nw, gw = gw0 + warp;
+    const int j0t = (gw * 32 + lane) * SCHUR_EPT;
+    const int nb = n / SCHUR_EPT;
+    const double r0 = tab[0] + jitter;
+    // hand-over through distributed shared memory: a producer publishes into ITS OWN shared memory (kap / bout + the counters
+    // kdone / bdone, one cluster-scope fence per period); a consumer polls the producer's counter and pulls what is new
+    volatile int* kdone = s_i + 4;
+    volatile int* bdone = s_i + 5;
+    if (tid == 0) { *kdone = 0; *bdone = 0; }
+    cluster.sync();                                            // every CTA of the system is resident and initialised
+    const double* bndIn = c > 0 ? cluster.map_shared_rank(bout, role * ns + c - 1) : nullptr;
+    const volatile int* progIn = c > 0 ? cluster.map_shared_rank(s_i + 5, role * ns + c - 1) : nullptr;
+    const bool hasOut = c < ns - 1;
+    const bool top = warp == nw - 1;
+    const int bpc = SCHUR_BPW * nw;                            // batches led per generator CTA
+    int haveK = 0, haveB = 0;
+    bool dead = false;
+    // waits (uniform) until needK coefficients and needB boundary batches have been published, then copies the new ones
+    auto fetch = [&](int needK, int needB) -> bool {
+        if (needK <= haveK && needB <= haveB) return true;
+        // the generator CTA that leads coefficient needK - 1 holds every coefficient below it as well
+        const int csrc = needK > haveK ? min(ns - 1, ((needK - 1) / SCHUR_EPT) / bpc) : 0;
+        const double* rkap = cluster.map_shared_rank(kap, csrc);
+        const volatile int* rkd = cluster.map_shared_rank(s_i + 4, csrc);
+        if (tid == 0) {
+            int vK = haveK, vB = haveB;
+            long long spins = 0;
+            while (spins < (1ll << 26)) {
+                vK = needK > haveK ? *rkd : haveK; vB = (progIn && needB > haveB) ? *progIn : max(haveB, needB);
+                if (vK >= needK && vB >= needB) break;
+                ++spins;
+            }
+            asm volatile("fence.acq_rel.cluster;" ::: "memory");
+            s_i[0] = vK; s_i[1] = vB;
+        }
+        __syncthreads();
+        const int nowK = min(s_i[0], n), nowB = min(s_i[1], nb);
+        if (nowK < needK || nowB < needB) return false;            // a producer never arrived
+        if (nowK > haveK && !(role == 0 && csrc == c))
+            for (int i = haveK + tid; i < nowK; i += blockDim.x) kap[i] = rkap[i];
+        if (bndIn) for (int i = haveB * SCHUR_EPT + tid; i < nowB * SCHUR_EPT; i += blockDim.x) bin[i] = bndIn[i];
+        __syncthreads();
+        haveK = max(haveK, nowK); haveB = max(haveB, nowB);
+        return true;
+    };
+    // one thread, after the period barrier: everything the CTA wrote so far becomes visible cluster-wide before the counters move
+    auto publish2 = [&](int kcount, int bcount) {
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+        if (kcount >= 0) *kdone = kcount;
+        if (bcount >= 0) *bdone = bcount;
+    };
+    double rin[SCHUR_EPT], kp8[SCHUR_EPT];
+
+    if (role == 0) {
+        // ---- generator ----
+        double A[SCHUR_EPT], be[SCHUR_EPT];
+#pragma unroll
+        for (int i = 0; i < SCHUR_EPT; ++i) {
+            const int p = j0t + i;
+            const double rp = p == 0 ? r0 : tab[p];
+            A[i] = rp;
+            be[i] = p == 0 ? 0.0 : rp;
+        }
+        const int lead_lo = SCHUR_BPW * gw0, lead_hi = min(nb, SCHUR_BPW * (gw0 + nw));      // batches led (and the last ones processed) here
+        int led = lead_lo;
+        __syncthreads();
+        for (int T = 0; T < lead_hi + nw - 1; ++T) {
+            if (c > 0) {       // coefficients and boundary values of the batches the CTAs below lead
+                const int nbat = min(T + 1, lead_lo);
+                if (!fetch(nbat * SCHUR_EPT, nbat)) { dead = true; break; }
+            }
+            const int m = T - warp, j0 = m * SCHUR_EPT;
+            const bool live = m >= 0 && m < nb && m < SCHUR_BPW * (gw + 1);
+            const bool lead = live && (m / SCHUR_BPW) == gw;
+            if (__all_sync(0xffffffffu, live)) {
+                const double cand = j0 == 0 ? 0.0 : neg_div(be[0], A[0]);
+                const int rs = j0 & (SCHUR_RING - 1);
+                if (warp > 0) load8(rin, &ring[warp - 1][rs]);
+                else if (c > 0 && m < lead_lo) load8(rin, bin + j0);
+                else {
+#pragma unroll
+                    for (int i = 0; i < SCHUR_EPT; ++i) rin[i] = 0.0;                        // only reaches dead positions
+                }
+                if (__all_sync(0xffffffffu, lead)) {
+                    batch_full<0, true>(cand, m % SCHUR_BPW, lane == m % SCHUR_BPW, lane == 0, lane == 31, kp8, rin, &ring[warp][rs],
+                                        kap + j0, kap + j0, A, be);
+                } else {
+                    load8(kp8, kap + j0);
+                    batch_full<0, false>(0.0, 0, false, lane == 0, lane == 31, kp8, rin, &ring[warp][rs], nullptr, nullptr, A, be);
+                }
+                if (hasOut && top && lane == 31) {
+#pragma unroll
+                    for (int i = 0; i < SCHUR_EPT; ++i) bout[j0 + i] = ring[warp][rs + i];
+                }
+            }
+            __syncthreads();
+            int kc = -1, bc = -1;
+            if (led < lead_hi && led + (led / SCHUR_BPW - gw0) == T) { ++led; kc = led * SCHUR_EPT; }
+            const int mt = T - (nw - 1);                       // batch the top warp finished in this period
+            if (hasOut && mt >= 0 && mt < lead_hi) bc = mt + 1;
+            if ((kc >= 0 || bc >= 0) && tid == blockDim.x - 1) publish2(kc, bc);
+        }
+        if (c != ns - 1) { cluster.sync(); return; }
+        // the last generator CTA holds every coefficient: log|K|, first non-positive prediction error, conditioning guard
+        if (tid == 0) s_i[2] = 0x7fffffff;
+        __syncthreads();
+        double lsum = 0.0, gmin = 1.0;
+        for (int k = 1 + tid; k < n; k += blockDim.x) {
+            const double kp = kap[k];
+            if (!(fabs(kp) < 1.0)) atomicMin(&s_i[2], k);
+            lsum += (double)(n - k) * log1p(-kp * kp);
+            gmin = fmin(gmin, (1.0 - kp) * (1.0 + kp));
+        }
+        if (!(r0 > 0.0) && tid == 0) atomicMin(&s_i[2], 0);
+        const double ltot = block_sum(lsum, red);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gmin = fmin(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
+        if (lane == 0 && gmin < guard_min && guard) atomicOr(guard, 1 << (guard_bit0 + sys));
+        if (tid == 0) {
+            half_logdet[0] = dead ? __longlong_as_double(0x7ff8000000000000ll) : 0.5 * ((double)n * log(r0) + ltot);
+            if (s_i[2] != 0x7fffffff) status[0] = s_i[2] + 1;
+            if (dead && guard) atomicOr(guard, 1 << (8 + guard_bit0 + sys));
+        }
+        cluster.sync();                                        // consumers may still be pulling from this CTA's shared memory
+        return;
+    }
+    // ---- lattice ----
+    double a[SCHUR_EPT], B[SCHUR_EPT];
+#pragma unroll
+    for (int i = 0; i < SCHUR_EPT; ++i) { a[i] = (j0t + i == 0) ? 1.0 : 0.0; B[i] = a[i]; }
+    const int mstart = max(0, SCHUR_BPW * gw0 - 1);            // warp 0 of this CTA becomes non-zero at step 256 gw0 - 1
+    haveB = mstart;                                            // older boundary batches are zeros nobody reads
+    for (int T = mstart; T < nb + nw - 1; ++T) {
+        if (!fetch(min((T + 1) * SCHUR_EPT, n), c > 0 ? min(T + 1, nb) : 0)) { dead = true; break; }
+        const int m = T - warp, j0 = m * SCHUR_EPT;
+        const bool live = m >= 0 && m < nb && (m + 1) * SCHUR_EPT >= gw * SCHUR_WCHUNK;
+        if (__all_sync(0xffffffffu, live)) {
+            const int rs = j0 & (SCHUR_RING - 1);
+            if (warp > 0) load8(rin, &ring[warp - 1][rs]);
+            else if (c > 0) load8(rin, bin + j0);
+            else {
+#pragma unroll
+                for (int i = 0; i < SCHUR_EPT; ++i) rin[i] = 0.0;                            // B[-1] = 0
+            }
+            load8(kp8, kap + j0);
+            batch_full<0, false>(0.0, 0, false, lane == 0, lane == 31, kp8, rin, &ring[warp][rs], nullptr, nullptr, B, a);
+            if (hasOut && top && lane == 31) {
+#pragma unroll
+                for (int i = 0; i < SCHUR_EPT; ++i) bout[j0 + i] = ring[warp][rs + i];
+            }
+        }
+        __syncthreads();
+        const int mt = T - (nw - 1);
+        if (hasOut && mt >= 0 && mt < nb && (mt + 1) * SCHUR_EPT >= (gw0 + nw - 1) * SCHUR_WCHUNK && tid == blockDim.x - 1)
+            publish2(-1, mt + 1);
+    }
+    // g = A_{n-1} / E_{n-1},  E_{n-1} = r0 * prod_k (1 - kappa_k^2): every CTA forms the product over all k in the same order
+    double prod = 1.0;
+    if (!dead) for (int k = 1 + tid; k < n; k += blockDim.x) { const double kp = kap[k]; prod *= (1.0 - kp) * (1.0 + kp); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) prod *= __shfl_xor_sync(0xffffffffu, prod, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = prod;
+    __syncthreads();
+    double E = r0;
+    for (int w = 0; w < nw; ++w) E *= red[w];
+    const double invE = dead ? __longlong_as_double(0x7ff8000000000000ll) : 1.0 / E;
+    if (dead && tid == 0 && guard) atomicOr(guard, 1 << (8 + guard_bit0 + sys));
+#pragma unroll
+    for (int i = 0; i < SCHUR_EPT; ++i) g[j0t + i] = a[i] * invE;
+    cluster.sync();
+}
+
 // One CTA per axis.  spec[0..3][L] (bit-reversed order, scaled like launch_toeplitz_spectrum):
 //   0: conj(G)/L   (v -> L(g)^T v)        2:  G / (L g0)   (v -> L(g) v / g0)
 //   1: conj(H)/L   (v -> L(h)^T v)        3: -H / (L g0)   (v -> -L(h) v / g0)
@@ -621,6 +818,8 @@ int toeplitz_inv_init() {
 }
 
 constexpr size_t kSplitSmem = (2 * (size_t)SCHUR_MAX_N + (SCHUR_MAX_THREADS / 32) * SCHUR_RING + 34) * sizeof(double) + 4 * sizeof(int);
+constexpr size_t kDsmemSmem = (3 * (size_t)SCHUR_MAX_N + (SCHUR_MAX_THREADS / 32) * SCHUR_RING + 34) * sizeof(double) + 8 * sizeof(int);
+constexpr int kSchurDefaultDsmem = 0;           // 1: hand-over through distributed shared memory (schur_levinson_dsmem_kernel); GPHM_SCHUR_DSMEM
 
 int schur_split_factor(int n) {           // CTAs per role: GPHM_SCHUR_SPLIT (1, 2 or 4); needs n to be a multiple of 256 * split
     static const int want = [] { const char* e = getenv("GPHM_SCHUR_SPLIT"); return e ? atoi(e) : kSchurDefaultSplit; }();
@@ -640,17 +839,23 @@ int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitt
         static DeviceOnce once;
         if (once.needed()) {
             GPHM_ONCE_CUDA_OK(once, cudaFuncSetAttribute(schur_levinson_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSplitSmem));
+            GPHM_ONCE_CUDA_OK(once, cudaFuncSetAttribute(schur_levinson_dsmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDsmemSmem));
             once.done();
         }
+        static const bool dsmem = [] { const char* e = getenv("GPHM_SCHUR_DSMEM"); return e ? atoi(e) != 0 : kSchurDefaultDsmem != 0; }();
         for (int s = 0; s < nsys; ++s) GPHM_CUDA_OK(cudaMemsetAsync(prog + s * sProg, 0, 8 * sizeof(int), st));
         LaunchScope scope(CAT_CHOL_DIAG, st, 8.0 * (double)n * n * nsys);
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * ns * nsys); cfg.blockDim = dim3(n / (SCHUR_EPT * ns)); cfg.dynamicSmemBytes = kSplitSmem; cfg.stream = st;
+        cfg.gridDim = dim3(2 * ns * nsys); cfg.blockDim = dim3(n / (SCHUR_EPT * ns)); cfg.dynamicSmemBytes = dsmem ? kDsmemSmem : kSplitSmem; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2 * ns; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         const double gmin = toeplitz_guard_min();
+        if (dsmem)
+            GPHM_CUDA_OK(cudaLaunchKernelEx(&cfg, schur_levinson_dsmem_kernel, tabK, sTab, n, jitter, g, sG, half_logdet, sLd, status, sStatus,
+                                            gkap, sKap, prog, sProg, gbnd, sBnd, ns, guard, guard_bit0, gmin, skip));
+        else
         GPHM_CUDA_OK(cudaLaunchKernelEx(&cfg, schur_levinson_split_kernel, tabK, sTab, n, jitter, g, sG, half_logdet, sLd, status, sStatus,
                                         gkap, sKap, prog, sProg, gbnd, sBnd, ns, guard, guard_bit0, gmin, skip));
         GPHM_LAUNCH_OK();
