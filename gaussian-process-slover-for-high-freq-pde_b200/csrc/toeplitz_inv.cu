@@ -374,23 +374,34 @@ schur_levinson_kernel(const double* __restrict__ tab, long long sTab, int n, dou
 // step.  Requires n to be a multiple of 256 NS (full batches, full warps); the launcher falls back to the single-CTA
 // kernel otherwise.  blockIdx.x = system * 2 NS + role * NS + c; the 2 NS CTAs of a system form one thread-block cluster
 // (co-scheduled: the consumers spin on their producers).
-__global__ void __launch_bounds__(SCHUR_MAX_THREADS, 1)
+// Threads: n / (8 NS) workers + ONE PUBLISHER WARP.  Handing a counter over costs a device-scope fence (~750 cycles measured
+// here); issued by a worker it sat between two block barriers of the leading CTA - 17 % of its time.  The workers now only
+// post the number of finished periods in shared memory after their barrier and the publisher warp, which owns no positions and joins
+// no barrier of the recursion (named barrier 1 counts the workers only), fences and stores them.  The generator runs TWO
+// batches per barrier period (the ring holds four: two being read by the warp above, two being written), which halves
+// what a period costs besides the coefficient chain (barrier, votes, ring loads: ~250 of 1100 cycles).
+__global__ void __launch_bounds__(SCHUR_MAX_THREADS / 2 + 32, 1)      // NS >= 2: at most 256 workers
 schur_levinson_split_kernel(const double* __restrict__ tab, long long sTab, int n, double jitter, double* __restrict__ g,
                             long long sG, double* __restrict__ half_logdet, long long sLd, int* __restrict__ status,
                             long long sStatus, double* gkap, long long sKap, int* prog, long long sProg, double* gbnd,
-                            long long sBnd, int ns, int* guard, int guard_bit0, double guard_min, const int* __restrict__ skip) {
+                            long long sBnd, int ns, int* guard, int guard_bit0, double guard_min, const int* __restrict__ skip,
+                            long long* dbg) {
     if (skip && *skip) return;
+    const long long t_begin = dbg ? clock64() : 0;
+    long long t_wait = 0;
     extern __shared__ __align__(128) double sm_split[];
     double* kap = sm_split;                                   // [SCHUR_MAX_N]
     double* bin = kap + SCHUR_MAX_N;                          // [SCHUR_MAX_N] values entering this CTA's lowest position
     double (*ring)[SCHUR_RING] = reinterpret_cast<double (*)[SCHUR_RING]>(bin + SCHUR_MAX_N);      // [16][32]
     double* red = reinterpret_cast<double*>(ring + SCHUR_MAX_THREADS / 32);                          // [34]
-    int* s_i = reinterpret_cast<int*>(red + 34);                                                    // [4]
+    int* s_i = reinterpret_cast<int*>(red + 34);                                                    // [8]
+    volatile int* s_pub = s_i + 4;                            // [0] periods the workers have finished, [2] abort
     const int per_sys = 2 * ns, sys = blockIdx.x / per_sys, rr = blockIdx.x % per_sys, role = rr / ns, c = rr % ns;
     tab += sys * sTab; g += sys * sG; half_logdet += sys * sLd; status += sys * sStatus; gkap += sys * sKap; prog += sys * sProg;
     gbnd += sys * sBnd;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nw = blockDim.x >> 5, gw0 = c * nw, gw = gw0 + warp;
+    const int nworkers = blockDim.x - 32;
+    const int nw = nworkers >> 5, gw0 = c * nw, gw = gw0 + warp;
     const int j0t = (gw * 32 + lane) * SCHUR_EPT;
     const int nb = n / SCHUR_EPT;
     const double r0 = tab[0] + jitter;
@@ -400,88 +411,125 @@ schur_levinson_split_kernel(const double* __restrict__ tab, long long sTab, int 
     const double* bndIn = c > 0 ? gbnd + (size_t)(role * 3 + c - 1) * n : nullptr;
     double* bndOut = c < ns - 1 ? gbnd + (size_t)(role * 3 + c) * n : nullptr;
     const bool top = warp == nw - 1;
+    const int lead_lo = SCHUR_BPW * gw0, lead_hi = min(nb, SCHUR_BPW * (gw0 + nw));          // batches the generator CTA leads
+    auto wsync = [&]() { asm volatile("bar.sync 1, %0;" :: "r"(nworkers) : "memory"); };     // the workers' barrier
+
+    if (tid >= nworkers) {
+        // ---- publisher warp: hands over the LATEST counts whenever they have moved (a fence takes longer than a lattice period) ----
+        if (role == 1 && !progOut) return;                         // the top lattice CTA hands nothing over
+        if (tid == nworkers) { s_pub[0] = 0; s_pub[2] = 0; }
+        __syncthreads();
+        if (lane == 0) {
+            // generator: batch m is led by warp m / 32 - gw0 in period m / 2 + that warp, the top warp finishes batches 2 (T - nw + 1), +1
+            // in period T;  lattice: the top warp finishes batch T - nw + 1 in period T
+            int seen = 0, led = lead_lo, pk = lead_lo, pb = 0;       // periods seen; batches led and finished; published so far
+            const int endK = role == 0 ? lead_hi : lead_lo, endB = role == 0 ? lead_hi : nb;
+            for (long long spins = 0; spins < (1ll << 28); ++spins) {
+                const int per = s_pub[0], ab = s_pub[2];
+                if (per != seen) {
+                    seen = per;
+                    const int T = per - 1;
+                    if (role == 0) while (led < lead_hi && led / 2 + (led / SCHUR_BPW - gw0) <= T) ++led;
+                    const int vk = led;
+                    const int vb = !progOut ? pb : max(pb, min(role == 0 ? 2 * (T - (nw - 1)) + 2 : T - (nw - 1) + 1, endB));
+                    if (vk != pk || vb != pb) {
+                        __threadfence();                           // cumulative over the workers' stores (ordered by their barrier)
+                        if (vk != pk) *reinterpret_cast<volatile int*>(prog) = vk * SCHUR_EPT;
+                        if (vb != pb) *reinterpret_cast<volatile int*>(progOut) = vb;
+                        pk = vk; pb = vb;
+                    }
+                }
+                if (ab || (pk == endK && (!progOut || pb == endB))) break;
+            }
+        }
+        if (role == 1) return;
+        if (c != ns - 1) return;
+    }
     int haveK = 0, haveB = 0;
     bool dead = false;
-    // waits (uniform) until needK coefficients and needB boundary batches have been published, then copies the new ones
+    // waits (uniform over the workers) until needK coefficients and needB boundary batches have been published, then copies the new ones
     auto fetch = [&](int needK, int needB) -> bool {
         if (needK <= haveK && needB <= haveB) return true;
         if (tid == 0) {
             int vK = haveK, vB = haveB;
             long long spins = 0;
+            const long long tw = dbg ? clock64() : 0;
             while (spins < (1ll << 24)) {
                 vK = *progK; vB = progIn ? *progIn : needB;
                 if (vK >= needK && vB >= needB) break;
-                __nanosleep(64); ++spins;
+                ++spins;                                           // no __nanosleep: a hand-over then took ~12 k cycles instead of ~3 k
             }
+            if (dbg) t_wait += clock64() - tw;
             s_i[0] = vK; s_i[1] = vB;
         }
-        __syncthreads();
+        wsync();
         const int nowK = min(s_i[0], n), nowB = min(s_i[1], nb);
         if (nowK < needK || nowB < needB) return false;            // a producer never arrived
-        for (int i = haveK + tid; i < nowK; i += blockDim.x) kap[i] = __ldcg(gkap + i);
-        if (bndIn) for (int i = haveB * SCHUR_EPT + tid; i < nowB * SCHUR_EPT; i += blockDim.x) bin[i] = __ldcg(bndIn + i);
-        __syncthreads();
+        for (int i = haveK + tid; i < nowK; i += nworkers) kap[i] = __ldcg(gkap + i);
+        if (bndIn) for (int i = haveB * SCHUR_EPT + tid; i < nowB * SCHUR_EPT; i += nworkers) bin[i] = __ldcg(bndIn + i);
+        wsync();
         haveK = max(haveK, nowK); haveB = max(haveB, nowB);
         return true;
     };
-    auto publish = [&](int* flag, int value) { __threadfence(); *reinterpret_cast<volatile int*>(flag) = value; };
     double rin[SCHUR_EPT], kp8[SCHUR_EPT];
 
     if (role == 0) {
         // ---- generator ----
-        double A[SCHUR_EPT], be[SCHUR_EPT];
+        if (tid < nworkers) {
+            double A[SCHUR_EPT], be[SCHUR_EPT];
 #pragma unroll
-        for (int i = 0; i < SCHUR_EPT; ++i) {
-            const int p = j0t + i;
-            const double rp = p == 0 ? r0 : tab[p];
-            A[i] = rp;
-            be[i] = p == 0 ? 0.0 : rp;
+            for (int i = 0; i < SCHUR_EPT; ++i) {
+                const int p = j0t + i;
+                const double rp = p == 0 ? r0 : tab[p];
+                A[i] = rp;
+                be[i] = p == 0 ? 0.0 : rp;
+            }
+            double cand = 0.0;                                     // kappa_0 = 0
+            __syncthreads();                                       // with the publisher: s_pub is initialised
+            const int nper = lead_hi / 2 + nw - 1;                 // lead_hi is a multiple of 32
+            for (int T = 0; T < nper; ++T) {
+                if (c > 0) {       // coefficients and boundary values of the batches the CTAs below lead
+                    const int nbat = min(2 * (T + 1), lead_lo);
+                    if (!fetch(nbat * SCHUR_EPT, nbat)) { dead = true; break; }
+                }
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    const int m = 2 * (T - warp) + h, j0 = m * SCHUR_EPT;
+                    const bool live = m >= 0 && m < nb && m < SCHUR_BPW * (gw + 1);
+                    const bool lead = live && (m / SCHUR_BPW) == gw;
+                    if (__all_sync(0xffffffffu, live)) {
+                        const int rs = j0 & (SCHUR_RING - 1);
+                        if (warp > 0) load8(rin, &ring[warp - 1][rs]);
+                        else if (c > 0 && m < lead_lo) load8(rin, bin + j0);
+                        else {
+#pragma unroll
+                            for (int i = 0; i < SCHUR_EPT; ++i) rin[i] = 0.0;                // only reaches dead positions
+                        }
+                        if (__all_sync(0xffffffffu, lead)) {
+                            batch_full<0, true>(cand, m % SCHUR_BPW, lane == m % SCHUR_BPW, lane == 0, lane == 31, kp8, rin, &ring[warp][rs],
+                                                kap + j0, gkap + j0, A, be);
+                        } else {
+                            load8(kp8, kap + j0);
+                            batch_full<0, false>(0.0, 0, false, lane == 0, lane == 31, kp8, rin, &ring[warp][rs], nullptr, nullptr, A, be);
+                        }
+                        cand = neg_div(be[0], A[0]);       // first coefficient of the next batch (meaningful in its owner lane), same
+                                                           // basic block as the batch: its chain overlaps the last step's updates
+                        if (bndOut && top && lane == 31) {
+#pragma unroll
+                            for (int i = 0; i < SCHUR_EPT; ++i) bndOut[j0 + i] = ring[warp][rs + i];
+                        }
+                    }
+                }
+                wsync();
+                if (tid == 0) { __threadfence_block(); s_pub[0] = T + 1; }                   // periods finished, for the publisher warp
+            }
+            if (dead && tid == 0) s_pub[2] = 1;
         }
-        const int lead_lo = SCHUR_BPW * gw0, lead_hi = min(nb, SCHUR_BPW * (gw0 + nw));      // batches led (and the last ones processed) here
-        int led = lead_lo;
-        __syncthreads();
-        for (int T = 0; T < lead_hi + nw - 1; ++T) {
-            if (c > 0) {       // coefficients and boundary values of the batches the CTAs below lead
-                const int nbat = min(T + 1, lead_lo);
-                if (!fetch(nbat * SCHUR_EPT, nbat)) { dead = true; break; }
-            }
-            const int m = T - warp, j0 = m * SCHUR_EPT;
-            const bool live = m >= 0 && m < nb && m < SCHUR_BPW * (gw + 1);
-            const bool lead = live && (m / SCHUR_BPW) == gw;
-            if (__all_sync(0xffffffffu, live)) {
-                const double cand = j0 == 0 ? 0.0 : neg_div(be[0], A[0]);
-                const int rs = j0 & (SCHUR_RING - 1);
-                if (warp > 0) load8(rin, &ring[warp - 1][rs]);
-                else if (c > 0 && m < lead_lo) load8(rin, bin + j0);
-                else {
-#pragma unroll
-                    for (int i = 0; i < SCHUR_EPT; ++i) rin[i] = 0.0;                        // only reaches dead positions
-                }
-                if (__all_sync(0xffffffffu, lead)) {
-                    batch_full<0, true>(cand, m % SCHUR_BPW, lane == m % SCHUR_BPW, lane == 0, lane == 31, kp8, rin, &ring[warp][rs],
-                                        kap + j0, gkap + j0, A, be);
-                } else {
-                    load8(kp8, kap + j0);
-                    batch_full<0, false>(0.0, 0, false, lane == 0, lane == 31, kp8, rin, &ring[warp][rs], nullptr, nullptr, A, be);
-                }
-                if (bndOut && top && lane == 31) {
-#pragma unroll
-                    for (int i = 0; i < SCHUR_EPT; ++i) bndOut[j0 + i] = ring[warp][rs + i];
-                }
-            }
-            __syncthreads();
-            if (led < lead_hi && led + (led / SCHUR_BPW - gw0) == T) {
-                ++led;
-                if (((led - lead_lo) % SCHUR_PUBLISH == 0 || led == lead_hi) && tid == blockDim.x - 1) publish(prog, led * SCHUR_EPT);
-            }
-            const int mt = T - (nw - 1);                       // batch the top warp finished in this period
-            if (progOut && mt >= 0 && mt < lead_hi && ((mt + 1) % SCHUR_PUBLISH == 0 || mt + 1 == lead_hi) && tid == blockDim.x - 1)
-                publish(progOut, mt + 1);
-        }
+        if (dbg && tid == 0) { dbg[2 * blockIdx.x] = clock64() - t_begin; dbg[2 * blockIdx.x + 1] = t_wait; }
         if (c != ns - 1) return;
         // the last generator CTA holds every coefficient: log|K|, first non-positive prediction error, conditioning guard
         if (tid == 0) s_i[2] = 0x7fffffff;
-        __syncthreads();
+        __syncthreads();                                           // every thread of the CTA, publisher warp included
         double lsum = 0.0, gmin = 1.0;
         for (int k = 1 + tid; k < n; k += blockDim.x) {
             const double kp = kap[k];
@@ -495,18 +543,20 @@ schur_levinson_split_kernel(const double* __restrict__ tab, long long sTab, int 
         for (int o = 16; o > 0; o >>= 1) gmin = fmin(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
         if (lane == 0 && gmin < guard_min && guard) atomicOr(guard, 1 << (guard_bit0 + sys));
         if (tid == 0) {
-            half_logdet[0] = dead ? __longlong_as_double(0x7ff8000000000000ll) : 0.5 * ((double)n * log(r0) + ltot);
+            const bool aborted = s_pub[2] != 0;
+            half_logdet[0] = aborted ? __longlong_as_double(0x7ff8000000000000ll) : 0.5 * ((double)n * log(r0) + ltot);
             if (s_i[2] != 0x7fffffff) status[0] = s_i[2] + 1;
-            if (dead && guard) atomicOr(guard, 1 << (8 + guard_bit0 + sys));
+            if (aborted && guard) atomicOr(guard, 1 << (8 + guard_bit0 + sys));
         }
         return;
     }
-    // ---- lattice ----
+    // ---- lattice (workers only: the publisher warp has left) ----
     double a[SCHUR_EPT], B[SCHUR_EPT];
 #pragma unroll
     for (int i = 0; i < SCHUR_EPT; ++i) { a[i] = (j0t + i == 0) ? 1.0 : 0.0; B[i] = a[i]; }
     const int mstart = max(0, SCHUR_BPW * gw0 - 1);            // warp 0 of this CTA becomes non-zero at step 256 gw0 - 1
-    haveB = mstart;                                            // older boundary batches are zeros nobody reads
+    haveB = mstart;                                            // older boundary batches are zeros nobody reads (nor writes)
+    if (progOut) __syncthreads();                              // with the publisher: s_pub is initialised
     for (int T = mstart; T < nb + nw - 1; ++T) {
         if (!fetch(min((T + 1) * SCHUR_EPT, n), c > 0 ? min(T + 1, nb) : 0)) { dead = true; break; }
         const int m = T - warp, j0 = m * SCHUR_EPT;
@@ -526,26 +576,25 @@ schur_levinson_split_kernel(const double* __restrict__ tab, long long sTab, int 
                 for (int i = 0; i < SCHUR_EPT; ++i) bndOut[j0 + i] = ring[warp][rs + i];
             }
         }
-        __syncthreads();
-        const int mt = T - (nw - 1);
-        if (progOut && mt >= 0 && mt < nb && (mt + 1) * SCHUR_EPT >= (gw0 + nw - 1) * SCHUR_WCHUNK &&
-            ((mt + 1) % SCHUR_PUBLISH == 0 || mt + 1 == nb) && tid == blockDim.x - 1)
-            publish(progOut, mt + 1);
+        wsync();
+        if (progOut && tid == 0) { __threadfence_block(); s_pub[0] = T + 1; }                // periods finished, for the publisher warp
     }
+    if (dead && progOut && tid == 0) s_pub[2] = 1;
     // g = A_{n-1} / E_{n-1},  E_{n-1} = r0 * prod_k (1 - kappa_k^2): every CTA forms the product over all k in the same order
     double prod = 1.0;
-    if (!dead) for (int k = 1 + tid; k < n; k += blockDim.x) { const double kp = kap[k]; prod *= (1.0 - kp) * (1.0 + kp); }
+    if (!dead) for (int k = 1 + tid; k < n; k += nworkers) { const double kp = kap[k]; prod *= (1.0 - kp) * (1.0 + kp); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) prod *= __shfl_xor_sync(0xffffffffu, prod, o);
-    __syncthreads();
+    wsync();
     if (lane == 0) red[warp] = prod;
-    __syncthreads();
+    wsync();
     double E = r0;
     for (int w = 0; w < nw; ++w) E *= red[w];
     const double invE = dead ? __longlong_as_double(0x7ff8000000000000ll) : 1.0 / E;
     if (dead && tid == 0 && guard) atomicOr(guard, 1 << (8 + guard_bit0 + sys));
 #pragma unroll
     for (int i = 0; i < SCHUR_EPT; ++i) g[j0t + i] = a[i] * invE;
+    if (dbg && tid == 0) { dbg[2 * blockIdx.x] = clock64() - t_begin; dbg[2 * blockIdx.x + 1] = t_wait; }
 }
 
 // The split recursion with the hand-over through DISTRIBUTED SHARED MEMORY instead of global memory: producers keep what they
@@ -817,7 +866,7 @@ int toeplitz_inv_init() {
     return GPHM_OK;
 }
 
-constexpr size_t kSplitSmem = (2 * (size_t)SCHUR_MAX_N + (SCHUR_MAX_THREADS / 32) * SCHUR_RING + 34) * sizeof(double) + 4 * sizeof(int);
+constexpr size_t kSplitSmem = (2 * (size_t)SCHUR_MAX_N + (SCHUR_MAX_THREADS / 32) * SCHUR_RING + 34) * sizeof(double) + 8 * sizeof(int);
 constexpr size_t kDsmemSmem = (3 * (size_t)SCHUR_MAX_N + (SCHUR_MAX_THREADS / 32) * SCHUR_RING + 34) * sizeof(double) + 8 * sizeof(int);
 constexpr int kSchurDefaultDsmem = 0;           // 1: hand-over through distributed shared memory (schur_levinson_dsmem_kernel); GPHM_SCHUR_DSMEM
 
@@ -846,7 +895,8 @@ int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitt
         for (int s = 0; s < nsys; ++s) GPHM_CUDA_OK(cudaMemsetAsync(prog + s * sProg, 0, 8 * sizeof(int), st));
         LaunchScope scope(CAT_CHOL_DIAG, st, 8.0 * (double)n * n * nsys);
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * ns * nsys); cfg.blockDim = dim3(n / (SCHUR_EPT * ns)); cfg.dynamicSmemBytes = dsmem ? kDsmemSmem : kSplitSmem; cfg.stream = st;
+        cfg.gridDim = dim3(2 * ns * nsys); cfg.blockDim = dim3(n / (SCHUR_EPT * ns) + (dsmem ? 0 : 32));      // + the publisher warp
+        cfg.dynamicSmemBytes = dsmem ? kDsmemSmem : kSplitSmem; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2 * ns; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -855,9 +905,21 @@ int launch_schur_levinson(const double* tabK, long long sTab, int n, double jitt
         if (dsmem)
             GPHM_CUDA_OK(cudaLaunchKernelEx(&cfg, schur_levinson_dsmem_kernel, tabK, sTab, n, jitter, g, sG, half_logdet, sLd, status, sStatus,
                                             gkap, sKap, prog, sProg, gbnd, sBnd, ns, guard, guard_bit0, gmin, skip));
-        else
-        GPHM_CUDA_OK(cudaLaunchKernelEx(&cfg, schur_levinson_split_kernel, tabK, sTab, n, jitter, g, sG, half_logdet, sLd, status, sStatus,
-                                        gkap, sKap, prog, sProg, gbnd, sBnd, ns, guard, guard_bit0, gmin, skip));
+        else {
+            static const bool want_dbg = getenv("GPHM_SCHUR_DBG") != nullptr;      // diagnostics: cycles per CTA, total and waiting for a producer
+            static long long* dbgbuf = nullptr;
+            if (want_dbg && !dbgbuf) GPHM_CUDA_OK(cudaMalloc(&dbgbuf, sizeof(long long) * 64));
+            GPHM_CUDA_OK(cudaLaunchKernelEx(&cfg, schur_levinson_split_kernel, tabK, sTab, n, jitter, g, sG, half_logdet, sLd, status, sStatus,
+                                            gkap, sKap, prog, sProg, gbnd, sBnd, ns, guard, guard_bit0, gmin, skip, want_dbg ? dbgbuf : nullptr));
+            if (want_dbg && nsys * 2 * ns <= 32) {
+                long long h[64];
+                GPHM_CUDA_OK(cudaStreamSynchronize(st));
+                GPHM_CUDA_OK(cudaMemcpy(h, dbgbuf, sizeof(h), cudaMemcpyDeviceToHost));
+                for (int i = 0; i < 2 * ns * nsys; ++i)
+                    fprintf(stderr, "schur split: cta %d (%s %d) %lld cycles, %lld waiting\n", i, (i % (2 * ns)) / ns ? "lattice" : "generator",
+                            i % ns, h[2 * i], h[2 * i + 1]);
+            }
+        }
         GPHM_LAUNCH_OK();
         return GPHM_OK;
     }
