@@ -75,23 +75,86 @@ def dist_env():
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region: NVML polled from a thread every 5 ms
+    (the timed region of the default run is ~0.15 s - an `nvidia-smi -lms` child does not even start in that time, and its
+    start-up disturbs the first timed step); `nvidia-smi` is the fall-back when NVML cannot be loaded.
+    Create it before the warm-up (NVML initialisation is slow), call start() right before the timed region, stop() after."""
+    SMI_FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                  "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
+        self.index = index
+        self.nvml = None
+        self.handle = None
         self.proc = None
+        self.thread = None
+        self.samples = []            # (sm_mhz, reasons bit mask)
+        self.sm_max = None
+        self.running = False
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = self._handle(pynvml, index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _handle(pynvml, index):
+        """NVML enumerates all GPUs of the box, CUDA only the visible ones: map through the PCI bus id."""
+        try:
+            pr = torch.cuda.get_device_properties(index)
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            return pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            return pynvml.nvmlDeviceGetHandleByIndex(index)
+
+    def _poll(self):
+        nv = self.nvml
+        while self.running:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((sm, mask))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nvml is not None:
+            import threading
+            self.running = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.SMI_FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
     def stop(self):
+        if self.nvml is not None:
+            nv = self.nvml
+            self.running = False
+            if self.thread is not None:
+                self.thread.join(timeout=2)
+            names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                     ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                     ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+            sm = sorted(x for x, _ in self.samples)
+            reasons = sorted(name for name, bit in names if any(m & bit for _, m in self.samples))
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "samples": len(sm),
+                    "reasons": reasons, "source": "NVML polled every 5 ms inside the timed region"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
         try:
@@ -114,7 +177,7 @@ class ClockSampler(object):
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 def measure_fp64_peak(device):
@@ -430,13 +493,15 @@ def run_ours(args, rank, world, local):
         set_state(torch.zeros(n, n, dtype=torch.float64, device=device), s0_small.to(device))
 
     # ---- timed region: profiling OFF ----
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     launches0 = lib.gphm_launch_count()
-    sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sampler:
+        sampler.start()
     e0.record()
     marks = []
     for _ in range(args.steps):
@@ -679,12 +744,14 @@ def ensemble_record(args, rank, world, local, brief=False):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if (rank == 0 and not brief) else None
     ens.step(max(args.warmup, 3))
     barrier()
     launches0 = lib.gphm_launch_count()
-    sampler = ClockSampler(local) if (rank == 0 and not brief) else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sampler:
+        sampler.start()
     e0.record()
     ens.step(steps)
     e1.record()
