@@ -234,11 +234,17 @@ int launch_diag_sums(const double* Kbar, const double* Dbar, int n, int ld, bool
 }
 
 // one CTA per mixture component q: g[t*Q+q] = sum_m sK[m]*d k/d theta_t + sD[m]*d k^(o)/d theta_t
+struct ThetaGradArgs { const double* x[2]; int n[2]; const double* theta[2]; const double* sK[2]; const double* sD[2]; double* gtheta[2]; };
 template <int KID, int ORDER>
 __global__ void __launch_bounds__(256)
-theta_grad_toeplitz_kernel(const double* __restrict__ x, int n, const double* __restrict__ theta, int Q,
-                           const double* __restrict__ sK, const double* __restrict__ sD,
-                           double* __restrict__ gtheta) {
+theta_grad_toeplitz_kernel(ThetaGradArgs A, int Q) {           // blockIdx.y = axis
+    const int ax = blockIdx.y;
+    const double* __restrict__ x = A.x[ax];
+    const double* __restrict__ theta = A.theta[ax];
+    const double* __restrict__ sK = A.sK[ax];
+    const double* __restrict__ sD = A.sD[ax];
+    double* __restrict__ gtheta = A.gtheta[ax];
+    const int n = A.n[ax];
     __shared__ double red[33];
     const int q = blockIdx.x;
     const CompConst c = make_comp(KID, theta[q], theta[Q + q], theta[2 * Q + q]);
@@ -256,14 +262,25 @@ theta_grad_toeplitz_kernel(const double* __restrict__ x, int n, const double* __
     if (threadIdx.x == 0) { gtheta[q] = a0; gtheta[Q + q] = a1; gtheta[2 * Q + q] = a2; }
 }
 
-int launch_theta_grad_toeplitz(int kid, int order, const double* x, int n, const double* theta, int Q,
-                               const double* sK, const double* sD, double* gtheta, cudaStream_t st) {
+int launch_theta_grad_toeplitz_multi(int kid, int order, const ThetaGradJob* jobs, int count, int Q, cudaStream_t st) {
+    if (count < 1 || count > 2) { set_last_error("theta_grad: %d jobs", count); return GPHM_EINVAL; }
+    ThetaGradArgs A = {};
+    for (int i = 0; i < count; ++i) {
+        A.x[i] = jobs[i].x; A.n[i] = jobs[i].n; A.theta[i] = jobs[i].theta; A.sK[i] = jobs[i].sK; A.sD[i] = jobs[i].sD;
+        A.gtheta[i] = jobs[i].gtheta;
+    }
     LaunchScope scope(CAT_ELEMWISE, st);
     int rc = GPHM_DISPATCH_KID_ORDER(kid, order,
-        theta_grad_toeplitz_kernel<KID, ORDER><<<Q, 256, 0, st>>>(x, n, theta, Q, sK, sD, gtheta));
+        theta_grad_toeplitz_kernel<KID, ORDER><<<dim3(Q, count), 256, 0, st>>>(A, Q));
     if (rc != 0) { set_last_error("theta_grad: bad kernel id %d / order %d", kid, order); return GPHM_EINVAL; }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
+}
+
+int launch_theta_grad_toeplitz(int kid, int order, const double* x, int n, const double* theta, int Q,
+                               const double* sK, const double* sD, double* gtheta, cudaStream_t st) {
+    const ThetaGradJob job = {x, n, theta, sK, sD, gtheta};
+    return launch_theta_grad_toeplitz_multi(kid, order, &job, 1, Q, st);
 }
 
 // ---------------------------------------------------------------------------------------------

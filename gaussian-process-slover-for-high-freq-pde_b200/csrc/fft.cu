@@ -122,10 +122,11 @@ xcorr_spectrum_kernel(const double* __restrict__ X, const double* __restrict__ Y
 // block (32, 8): 32 bins, the parts split over 8 lanes of the block (fixed association: part c goes to lane c % 8,
 // lanes are added 0..7) - 8 x more CTAs and 8 x shorter load chains than one thread per bin (it was 0.1 ms per call,
 // a term of the sharded step that does not shrink with the number of ranks)
+struct PartialSpectra { double2* part[4]; };           // blockIdx.y picks one (K, D of one or two axes)
 __global__ void __launch_bounds__(256)
-reduce_partial_spectra_kernel(double2* __restrict__ partK, double2* __restrict__ partD, int nparts, int L) {
+reduce_partial_spectra_kernel(PartialSpectra P, int nparts, int L) {
     __shared__ double2 red[8][33];
-    double2* part = blockIdx.y == 0 ? partK : partD;
+    double2* __restrict__ part = P.part[blockIdx.y];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int p = blockIdx.x * 32 + tx;
     double2 s = make_double2(0.0, 0.0);
@@ -142,16 +143,26 @@ reduce_partial_spectra_kernel(double2* __restrict__ partK, double2* __restrict__
     }
 }
 
-// blockIdx.x = 0: K spectrum -> sK (symmetric sums); 1: D spectrum -> sD (symmetric or antisymmetric)
+// blockIdx.x & 1 = 0: K spectrum -> sK (symmetric sums); 1: D spectrum -> sD (symmetric or antisymmetric); blockIdx.x >> 1 = axis
+struct DiagSumsArgs {
+    const double2* partK[2]; const double2* partD[2]; const double2* W[2]; int n[2]; int antisym[2]; double dirsign[2];
+    const double* addK[2]; double addK_scale[2]; double* sK[2]; double* sD[2];
+};
 __global__ void __launch_bounds__(FFT_THREADS, 1)
-spectrum_to_diag_sums_kernel(const double2* __restrict__ partK, const double2* __restrict__ partD, int nparts, int L,
-                             int logL, const double2* __restrict__ W, int n, int antisym, double dirsign,
-                             const double* __restrict__ addK, double addK_scale,
-                             double* __restrict__ sK, double* __restrict__ sD) {
+spectrum_to_diag_sums_kernel(DiagSumsArgs A, int nparts, int L, int logL) {
+    const int ax = blockIdx.x >> 1, which = blockIdx.x & 1;
+    const double2* __restrict__ partK = A.partK[ax];
+    const double2* __restrict__ partD = A.partD[ax];
+    const double2* __restrict__ W = A.W[ax];
+    const int n = A.n[ax], antisym = A.antisym[ax];
+    const double dirsign = A.dirsign[ax], addK_scale = A.addK_scale[ax];
+    const double* __restrict__ addK = A.addK[ax];
+    double* __restrict__ sK = A.sK[ax];
+    double* __restrict__ sD = A.sD[ax];
     extern __shared__ double2 xs[];
     const int tid = threadIdx.x;
     fft_load_twiddles(xs, L, logL, W, tid);
-    const double2* part = blockIdx.x == 0 ? partK : partD;
+    const double2* part = which == 0 ? partK : partD;
     for (int p = tid; p < L; p += FFT_THREADS) {
         double2 s = make_double2(0.0, 0.0);
         for (int c = 0; c < nparts; ++c) { const double2 v = part[(size_t)c * L + p]; s.x += v.x; s.y += v.y; }
@@ -160,15 +171,15 @@ spectrum_to_diag_sums_kernel(const double2* __restrict__ partK, const double2* _
     __syncthreads();
     fft_dit_inverse_inplace(xs, L, logL, W, tid);
     const double inv = 1.0 / (double)L;
-    double* out = blockIdx.x == 0 ? sK : sD;
-    const bool anti = (blockIdx.x == 1) && antisym;
+    double* out = which == 0 ? sK : sD;
+    const bool anti = (which == 1) && antisym;
     for (int m = tid; m < n; m += FFT_THREADS) {
         const double up = xs[PADI(m)].x * inv;                         // col - row = m
         const double lo = xs[PADI((L - m) & (L - 1))].x * inv;         // row - col = m
         double v;
         if (m == 0) v = anti ? 0.0 : up;
         else v = anti ? dirsign * (lo - up) : (up + lo);
-        if (blockIdx.x == 0 && addK) v += addK_scale * addK[m];      // directly summed K^-1 diagonals
+        if (which == 0 && addK) v += addK_scale * addK[m];           // directly summed K^-1 diagonals
         out[m] = v;
     }
 }
@@ -184,10 +195,17 @@ spectrum_to_diag_sums_kernel(const double2* __restrict__ partK, const double2* _
 // (jnp.matmul at model_GP_solver_2d.py:112,119 and their transposes in the reverse pass).
 // ---------------------------------------------------------------------------------------------
 // spec[p] = FFT(c)[brev(p)] / L  with  c[m] = t(m), c[L-m] = t(-m)
+// one CTA per job (the derivative-Gram and the Gram table of one or two axes share a launch)
+struct SpectrumArgs { const double* tab[4]; const double2* W[4]; double2* spec[4]; int n[4]; int antisym[4]; double dirsign[4]; double diag_add[4]; };
 __global__ void __launch_bounds__(FFT_THREADS, 1)
-toeplitz_spectrum_kernel(const double* __restrict__ tab, int n, int L, int logL, const double2* __restrict__ W,
-                         int antisym, double dirsign, double diag_add, double2* __restrict__ spec, const int* __restrict__ skip) {
+toeplitz_spectrum_kernel(SpectrumArgs A, int L, int logL, const int* __restrict__ skip) {
     if (skip && *skip) return;
+    const int b = blockIdx.x;
+    const double* __restrict__ tab = A.tab[b];
+    const double2* __restrict__ W = A.W[b];
+    double2* __restrict__ spec = A.spec[b];
+    const int n = A.n[b], antisym = A.antisym[b];
+    const double dirsign = A.dirsign[b], diag_add = A.diag_add[b];
     extern __shared__ double2 xs[];
     const int tid = threadIdx.x;
     fft_load_twiddles(xs, L, logL, W, tid);
@@ -333,21 +351,51 @@ int launch_xcorr_spectrum(const double* X, const double* Y, int rows, int cols, 
     return GPHM_OK;
 }
 
-int launch_spectrum_to_diag_sums(const double* partK, const double* partD, int L, const double* W, int n, bool antisym,
-                                 double dirsign, const double* addK, double addK_scale, double* sK, double* sD,
-                                 cudaStream_t st) {
+int launch_spectrum_to_diag_sums_multi(const DiagSumsJob* jobs, int count, int L, cudaStream_t st) {
     GPHM_TRY(fft_init());
+    if (count < 1 || count > 2) { set_last_error("spectrum_to_diag_sums: %d jobs", count); return GPHM_EINVAL; }
+    PartialSpectra P = {};
+    DiagSumsArgs A = {};
+    for (int i = 0; i < count; ++i) {
+        const DiagSumsJob& j = jobs[i];
+        P.part[2 * i] = reinterpret_cast<double2*>(const_cast<double*>(j.partK));
+        P.part[2 * i + 1] = reinterpret_cast<double2*>(const_cast<double*>(j.partD));
+        A.partK[i] = reinterpret_cast<const double2*>(j.partK); A.partD[i] = reinterpret_cast<const double2*>(j.partD);
+        A.W[i] = reinterpret_cast<const double2*>(j.W); A.n[i] = j.n; A.antisym[i] = j.antisym ? 1 : 0; A.dirsign[i] = j.dirsign;
+        A.addK[i] = j.addK; A.addK_scale[i] = j.addK_scale; A.sK[i] = j.sK; A.sD[i] = j.sD;
+    }
     {   // sum the per-CTA partial spectra with the whole GPU first (148 x L complex values each)
-        LaunchScope scope(CAT_FFT, st, 0.0, 2.0 * 16.0 * fft_grid() * (double)L);
-        reduce_partial_spectra_kernel<<<dim3((L + 31) / 32, 2), dim3(32, 8), 0, st>>>(
-            reinterpret_cast<double2*>(const_cast<double*>(partK)), reinterpret_cast<double2*>(const_cast<double*>(partD)), fft_grid(), L);
+        LaunchScope scope(CAT_FFT, st, 0.0, 2.0 * count * 16.0 * fft_grid() * (double)L);
+        reduce_partial_spectra_kernel<<<dim3((L + 31) / 32, 2 * count), dim3(32, 8), 0, st>>>(P, fft_grid(), L);
     }
     GPHM_LAUNCH_OK();
     {
         LaunchScope scope(CAT_FFT, st);
-        spectrum_to_diag_sums_kernel<<<2, FFT_THREADS, fft_smem_bytes(L), st>>>(
-            reinterpret_cast<const double2*>(partK), reinterpret_cast<const double2*>(partD), 1, L, ilog2(L),
-            reinterpret_cast<const double2*>(W), n, antisym ? 1 : 0, dirsign, addK, addK_scale, sK, sD);
+        spectrum_to_diag_sums_kernel<<<2 * count, FFT_THREADS, fft_smem_bytes(L), st>>>(A, 1, L, ilog2(L));
+    }
+    GPHM_LAUNCH_OK();
+    return GPHM_OK;
+}
+
+int launch_spectrum_to_diag_sums(const double* partK, const double* partD, int L, const double* W, int n, bool antisym,
+                                 double dirsign, const double* addK, double addK_scale, double* sK, double* sD,
+                                 cudaStream_t st) {
+    const DiagSumsJob job = {partK, partD, W, n, antisym, dirsign, addK, addK_scale, sK, sD};
+    return launch_spectrum_to_diag_sums_multi(&job, 1, L, st);
+}
+
+int launch_toeplitz_spectrum_multi(const ToeplitzSpectrumJob* jobs, int count, int L, cudaStream_t st, const int* skip) {
+    GPHM_TRY(fft_init());
+    if (count < 1 || count > 4) { set_last_error("toeplitz_spectrum: %d jobs", count); return GPHM_EINVAL; }
+    SpectrumArgs A = {};
+    for (int i = 0; i < count; ++i) {
+        const ToeplitzSpectrumJob& j = jobs[i];
+        A.tab[i] = j.tab; A.W[i] = reinterpret_cast<const double2*>(j.W); A.spec[i] = reinterpret_cast<double2*>(j.spec);
+        A.n[i] = j.n; A.antisym[i] = j.antisym ? 1 : 0; A.dirsign[i] = j.dirsign; A.diag_add[i] = j.diag_add;
+    }
+    {
+        LaunchScope scope(CAT_FFT, st);
+        toeplitz_spectrum_kernel<<<count, FFT_THREADS, fft_smem_bytes(L), st>>>(A, L, ilog2(L), skip);
     }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
@@ -355,14 +403,8 @@ int launch_spectrum_to_diag_sums(const double* partK, const double* partD, int L
 
 int launch_toeplitz_spectrum(const double* tab, int n, int L, const double* W, bool antisym, double dirsign, double* spec,
                              cudaStream_t st, double diag_add, const int* skip) {
-    GPHM_TRY(fft_init());
-    {
-        LaunchScope scope(CAT_FFT, st);
-        toeplitz_spectrum_kernel<<<1, FFT_THREADS, fft_smem_bytes(L), st>>>(
-            tab, n, L, ilog2(L), reinterpret_cast<const double2*>(W), antisym ? 1 : 0, dirsign, diag_add, reinterpret_cast<double2*>(spec), skip);
-    }
-    GPHM_LAUNCH_OK();
-    return GPHM_OK;
+    const ToeplitzSpectrumJob job = {tab, n, W, antisym, dirsign, diag_add, spec};
+    return launch_toeplitz_spectrum_multi(&job, 1, L, st, skip);
 }
 
 int launch_toeplitz_apply(const double* X, int rows, int n, int ldx, const double* spec, int L, const double* W, double alpha,

@@ -66,6 +66,13 @@ int launch_spectrum_to_diag_sums(const double* partK, const double* partD, int L
                                  double dirsign, const double* addK, double addK_scale, double* sK, double* sD,
                                  cudaStream_t st);
 // spec (L complex, bit-reversed order, scaled by 1/L) of the circulant embedding of the Toeplitz matrix t(i-j) = tab[|i-j|] (* sign)
+// one launch for up to four Toeplitz tables of the same transform length (one CTA each)
+struct ToeplitzSpectrumJob { const double* tab; int n; const double* W; bool antisym; double dirsign; double diag_add; double* spec; };
+int launch_toeplitz_spectrum_multi(const ToeplitzSpectrumJob* jobs, int count, int L, cudaStream_t st, const int* skip = nullptr);
+// the diagonal sums of one or two axes of the same transform length in one pair of launches
+struct DiagSumsJob { const double* partK; const double* partD; const double* W; int n; bool antisym; double dirsign;
+                     const double* addK; double addK_scale; double* sK; double* sD; };
+int launch_spectrum_to_diag_sums_multi(const DiagSumsJob* jobs, int count, int L, cudaStream_t st);
 int launch_toeplitz_spectrum(const double* tab, int n, int L, const double* W, bool antisym, double dirsign, double* spec,
                              cudaStream_t st, double diag_add = 0.0, const int* skip = nullptr);
 // Out[r][:] = alpha * T X[r][:] + beta * Out[r][:]   for every row r (T n x n Toeplitz with spectrum `spec`)
@@ -137,6 +144,8 @@ int launch_grad_u(const LossConsts& c, const double* base, const double* U, cons
 int launch_diag_sums(const double* Kbar, const double* Dbar, int n, int ld, bool antisym, double dirsign,
                      double* part, double* sK, double* sD, cudaStream_t st);
 size_t diag_sums_part_doubles(int n);
+struct ThetaGradJob { const double* x; int n; const double* theta; const double* sK; const double* sD; double* gtheta; };
+int launch_theta_grad_toeplitz_multi(int kid, int order, const ThetaGradJob* jobs, int count, int Q, cudaStream_t st);   // one launch for both axes
 int launch_theta_grad_toeplitz(int kid, int order, const double* x, int n, const double* theta, int Q,
                                const double* sK, const double* sD, double* gtheta, cudaStream_t st);
 int launch_theta_grad_general(int kid, int order, const double* x, int n, const double* theta, int Q,

@@ -314,17 +314,23 @@ int factor_gs(gphm_plan& p, int a0, int count, const double* small, cudaStream_t
         GPHM_TRY(launch_gs_prepare(X.gsg, Y.gsg - X.gsg, X.n, X.fftL, X.twid, X.gspec, Y.gspec - X.gspec, X.sKinv,
                                    Y.sKinv - X.sKinv, nsys, st, skip));
     }
-    if (!need_D)     // spectrum of the Toeplitz derivative Gram (FFT products)
-        for (int a = a0; a < a0 + count; ++a) {
-            Axis& X = p.ax[a];
-            GPHM_TRY(launch_toeplitz_spectrum(X.tabD, X.n, X.fftL, X.twid, order == 1, X.dirsign, X.specT, st, 0.0, skip));
-        }
-    for (int a = a0; a < a0 + count; ++a) {      // spectrum of K (with the jitter): residual b - K y of the refined applications
+    // spectra of the Toeplitz derivative Gram (FFT products) and of K with the jitter (residual b - K y of the refined
+    // applications): independent single-CTA transforms - axes of equal transform length share one launch
+    ToeplitzSpectrumJob jobs[4];
+    int nj = 0, jobL = 0;
+    auto flush = [&]() -> int {
+        const int rc = nj ? launch_toeplitz_spectrum_multi(jobs, nj, jobL, st, skip) : GPHM_OK;
+        nj = 0;
+        return rc;
+    };
+    for (int a = a0; a < a0 + count; ++a) {
         Axis& X = p.ax[a];
-        if (gs_refine_axis(p, X))
-            GPHM_TRY(launch_toeplitz_spectrum(X.tabK, X.n, X.fftL, X.twid, false, 1.0, X.specKm, st, p.d.jitter, skip));
+        if (nj && (X.fftL != jobL || nj > 2)) GPHM_TRY(flush());
+        jobL = X.fftL;
+        if (!need_D) jobs[nj++] = ToeplitzSpectrumJob{X.tabD, X.n, X.twid, order == 1, X.dirsign, 0.0, X.specT};
+        if (gs_refine_axis(p, X)) jobs[nj++] = ToeplitzSpectrumJob{X.tabK, X.n, X.twid, false, 1.0, p.d.jitter, X.specKm};
     }
-    return GPHM_OK;
+    return flush();
 }
 
 // Gram + Cholesky + L^-1 (+ K^-1) for one axis.
@@ -483,21 +489,26 @@ int logjoint_grad_gs(gphm_plan& p, const double* U, const double* small, double*
     if (p.on_gu) { GPHM_TRY(p.on_gu(p, st)); p.gu_hook_ran = true; }        // nothing below reads U or gU
     // diagonal sums of Kbar_a = ld/2 N_b K_a^-1 - V_a (.)^T and Dbar_a by row cross-correlations
     // (one transform per row PAIR against the stored transforms of A^T / Bt)
+    // (the single-CTA tails - partial-spectrum reduction, inverse transform, theta contraction - of both axes share launches)
     GPHM_TRY(launch_xcorr_pairs(V1t, n2, n1, n1, X1.specY, X1.fftL, X1.twid, -1.0, X1.specK, st));
     GPHM_TRY(launch_xcorr_pairs(Gt, n2, n1, n1, X1.specY, X1.fftL, X1.twid, c1, X1.specD, st));
-    GPHM_TRY(launch_spectrum_to_diag_sums(X1.specK, X1.specD, X1.fftL, X1.twid, n1, anti, X1.dirsign, X1.sKinv,
-                                          0.5 * d.logdet * n2, X1.sK, X1.sD, st));
+    DiagSumsJob dj[2];
+    dj[0] = DiagSumsJob{X1.specK, X1.specD, X1.twid, n1, anti, X1.dirsign, X1.sKinv, 0.5 * d.logdet * n2, X1.sK, X1.sD};
+    const bool paired = two && X1.fftL == X2.fftL;
+    if (!paired) GPHM_TRY(launch_spectrum_to_diag_sums_multi(dj, 1, X1.fftL, st));
     if (two) {
         GPHM_TRY(launch_xcorr_pairs(V2, n1, n2, n2, X2.specY, X2.fftL, X2.twid, -1.0, X2.specK, st));
         GPHM_TRY(launch_xcorr_pairs(G, n1, n2, n2, X2.specY, X2.fftL, X2.twid, 1.0, X2.specD, st));
-        GPHM_TRY(launch_spectrum_to_diag_sums(X2.specK, X2.specD, X2.fftL, X2.twid, n2, anti, X2.dirsign, X2.sKinv,
-                                              0.5 * d.logdet * n1, X2.sK, X2.sD, st));
+        dj[1] = DiagSumsJob{X2.specK, X2.specD, X2.twid, n2, anti, X2.dirsign, X2.sKinv, 0.5 * d.logdet * n1, X2.sK, X2.sD};
+        if (paired) GPHM_TRY(launch_spectrum_to_diag_sums_multi(dj, 2, X1.fftL, st));
+        else GPHM_TRY(launch_spectrum_to_diag_sums_multi(dj + 1, 1, X2.fftL, st));
     }
+    ThetaGradJob tj[2];
     for (int a = 0; a < (two ? 2 : 1); ++a) {
         Axis& X = p.ax[a];
-        GPHM_TRY(launch_theta_grad_toeplitz(d.kernel_id, order, X.x, X.n, theta_of(p, small, a), Q, X.sK, X.sD,
-                                            gsmall + (size_t)a * 3 * Q, st));
+        tj[a] = ThetaGradJob{X.x, X.n, theta_of(p, small, a), X.sK, X.sD, gsmall + (size_t)a * 3 * Q};
     }
+    GPHM_TRY(launch_theta_grad_toeplitz_multi(d.kernel_id, order, tj, two ? 2 : 1, Q, st));
     if (!two) GPHM_CUDA_OK(cudaMemsetAsync(gsmall + 3 * Q, 0, sizeof(double) * 3 * Q, st));
     return GPHM_OK;
 }
