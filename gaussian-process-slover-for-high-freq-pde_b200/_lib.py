@@ -90,6 +90,8 @@ _SIGS = {
                                       c_void_p]),
     "gphm_mg_theta_grad_pairs": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_void_p,
                                          c_void_p, c_void_p]),
+    "gphm_mg_theta_grad_pairs_both": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_double,
+                                              c_double, c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "gphm_lincomb": (c_int, [c_void_p, c_double, c_void_p, c_double, c_void_p, c_size_t, c_void_p]),
 }
 

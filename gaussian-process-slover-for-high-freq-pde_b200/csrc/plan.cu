@@ -1198,6 +1198,37 @@ int gphm_mg_theta_grad_pairs(gphm_plan* plan, int axis, const double* d_V, const
                                       d_gtheta, st);
 }
 
+int gphm_mg_theta_grad_pairs_both(gphm_plan* plan, const double* d_V1, const double* d_G1, int rows1, const double* d_V2,
+                                  const double* d_G2, int rows2, int lead, double beta1, double beta2, double cD1, double cD2,
+                                  const double* d_small, double* d_gtheta, void* stream) {
+    if (!plan || !d_V1 || !d_G1 || !d_V2 || !d_G2 || !d_small || !d_gtheta) { set_last_error("gphm_mg_theta_grad_pairs_both: null pointer"); return GPHM_EINVAL; }
+    for (int a = 0; a < 2; ++a)
+        if (plan->ax[a].n == 0 || !plan->ax[a].gs || !toeplitz_fused_supported(plan->ax[a].fftL)) {
+            set_last_error("gphm_mg_theta_grad_pairs_both: axis %d is not on the Toeplitz inverse-generator path", a);
+            return GPHM_EINVAL;
+        }
+    Axis& X1 = plan->ax[0];
+    Axis& X2 = plan->ax[1];
+    if (X1.fftL != X2.fftL) {      // different transform lengths: nothing to share
+        GPHM_TRY(gphm_mg_theta_grad_pairs(plan, 0, d_V1, d_G1, rows1, lead, beta1, cD1, d_small, d_gtheta, stream));
+        return gphm_mg_theta_grad_pairs(plan, 1, d_V2, d_G2, rows2, lead, beta2, cD2, d_small, d_gtheta + 3 * plan->d.Q, stream);
+    }
+    const int order = deriv_order(*plan), Q = plan->d.Q;
+    const bool anti = order == 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GPHM_TRY(launch_xcorr_pairs(d_V1, rows1, X1.n, X1.n, X1.specY, X1.fftL, X1.twid, -1.0, X1.specK, st));
+    GPHM_TRY(launch_xcorr_pairs(d_G1, rows1, X1.n, X1.n, X1.specY, X1.fftL, X1.twid, cD1, X1.specD, st));
+    GPHM_TRY(launch_xcorr_pairs(d_V2, rows2, X2.n, X2.n, X2.specY, X2.fftL, X2.twid, -1.0, X2.specK, st));
+    GPHM_TRY(launch_xcorr_pairs(d_G2, rows2, X2.n, X2.n, X2.specY, X2.fftL, X2.twid, cD2, X2.specD, st));
+    const DiagSumsJob dj[2] = {
+        {X1.specK, X1.specD, X1.twid, X1.n, anti, X1.dirsign, lead ? X1.sKinv : nullptr, lead ? beta1 : 0.0, X1.sK, X1.sD},
+        {X2.specK, X2.specD, X2.twid, X2.n, anti, X2.dirsign, lead ? X2.sKinv : nullptr, lead ? beta2 : 0.0, X2.sK, X2.sD}};
+    GPHM_TRY(launch_spectrum_to_diag_sums_multi(dj, 2, X1.fftL, st));
+    const ThetaGradJob tj[2] = {{X1.x, X1.n, theta_of(*plan, d_small, 0), X1.sK, X1.sD, d_gtheta},
+                                {X2.x, X2.n, theta_of(*plan, d_small, 1), X2.sK, X2.sD, d_gtheta + 3 * Q}};
+    return launch_theta_grad_toeplitz_multi(plan->d.kernel_id, order, tj, 2, Q, st);
+}
+
 int gphm_transpose(const double* d_in, int rows, int cols, double* d_out, void* stream) {
     if (rows <= 0 || cols <= 0) return GPHM_OK;
     if (!d_in || !d_out) { set_last_error("gphm_transpose: null pointer"); return GPHM_EINVAL; }

@@ -164,6 +164,13 @@ class CudaOps(object):
                                                      float(beta), float(cD), _lib.ptr(small), _lib.ptr(out), self._s()),
                    "gphm_mg_theta_grad_pairs")
 
+    def theta_grad_pairs_both(self, V1, G1, V2, G2, lead, beta1, beta2, c1, c2, small, out):
+        _lib.check(self.lib.gphm_mg_theta_grad_pairs_both(self.plan, _lib.ptr(V1), _lib.ptr(G1), V1.shape[0], _lib.ptr(V2),
+                                                          _lib.ptr(G2), V2.shape[0], int(lead), float(beta1), float(beta2),
+                                                          float(c1), float(c2), _lib.ptr(small), _lib.ptr(out), self._s()),
+                   "gphm_mg_theta_grad_pairs_both")
+        return out
+
     def grad_u_sum(self, U, G, V1, V2, bidx, eb, nseg0, small):
         gU = self._buf("gU", U.shape)
         _lib.check(self.lib.gphm_mg_grad_u(self.plan, _lib.ptr(U), _lib.ptr(G), _lib.ptr(V1), _lib.ptr(V2), None,
@@ -536,8 +543,12 @@ class ShardedSolver2D(object):
         P2 = o.toeplitz_rows_add(1, True, G_r, 1.0, 0.5, A_r, o.new("P2", G_r.shape), False)    # G D2 + A/2
         V2_r = o.kinv_rows(1, P2, "V2_r", refine=True)
         gU_r = o.grad_u_sum(U_r, G_r, V1_r, V2_r, self.bidx, eb, self.nseg0, small)
-        o.theta_grad_pairs(0, V1t, G_ct, lead, 0.5 * self.logdet * N2, c1, small, gs[0:3 * Q])
-        o.theta_grad_pairs(1, V2_r, G_r, lead, 0.5 * self.logdet * N1, 1.0, small, gs[3 * Q:6 * Q])
+        both = getattr(o, "theta_grad_pairs_both", None)       # (the CPU stand-in of the gloo tests has the per-axis call only)
+        if both is not None:
+            both(V1t, G_ct, V2_r, G_r, lead, 0.5 * self.logdet * N2, 0.5 * self.logdet * N1, c1, 1.0, small, gs[0:6 * Q])
+        else:
+            o.theta_grad_pairs(0, V1t, G_ct, lead, 0.5 * self.logdet * N2, c1, small, gs[0:3 * Q])
+            o.theta_grad_pairs(1, V2_r, G_r, lead, 0.5 * self.logdet * N1, 1.0, small, gs[3 * Q:6 * Q])
         self._allreduce(acc[0:3 + 6 * Q])            # every entry of the slice was written above (nothing to zero)
         o.finalize(acc[0:3], ld, small, self.terms, gs)                           # terms[8]; gs[6Q], gs[6Q+1]
         return self.terms, gU_r, gs

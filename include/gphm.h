@@ -333,6 +333,12 @@ GPHM_API int gphm_mg_toeplitz_rows(gphm_plan* plan, int axis, int transposed, co
                           double beta, const double* d_add, double* d_out, int keep_spectrum, void* stream);
 GPHM_API int gphm_mg_theta_grad_pairs(gphm_plan* plan, int axis, const double* d_V, const double* d_G, int rows, int lead,
                              double beta, double cD, const double* d_small, double* d_gtheta, void* stream);
+/* Both axes of the all-FFT step in one call: axis 1 gets (d_V1, d_G1: rows1 x n1 blocks, i.e. transposed column blocks),
+ * axis 2 (d_V2, d_G2: rows2 x n2); d_gtheta[0..3Q) and [3Q..6Q).  Same result as two gphm_mg_theta_grad_pairs calls; the
+ * single-CTA tails (partial-spectrum reduction, inverse transform, theta contraction) of the two axes share launches.  */
+GPHM_API int gphm_mg_theta_grad_pairs_both(gphm_plan* plan, const double* d_V1, const double* d_G1, int rows1, const double* d_V2,
+                                  const double* d_G2, int rows2, int lead, double beta1, double beta2, double cD1, double cD2,
+                                  const double* d_small, double* d_gtheta, void* stream);
 /* d_out = a*d_x + b*d_y (d_y may be NULL).                                                      */
 GPHM_API int gphm_lincomb(double* d_out, double a, const double* d_x, double b, const double* d_y, size_t n, void* stream);
 
