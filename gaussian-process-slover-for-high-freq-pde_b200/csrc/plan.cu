@@ -103,6 +103,9 @@ struct gphm_plan {
     cudaEvent_t hs_ev_u = nullptr, hs_ev_mv = nullptr, hs_ev_gu = nullptr, hs_ev_adam = nullptr;
     // hooks of gphm_step_host into the all-FFT step (null otherwise):
     cudaEvent_t u_ready = nullptr;        // waited for on the step's stream after the factor stage (U still uploading)
+    static constexpr int kUChunks = 4;    // 2-D all-FFT step: U arrives in row blocks, Bt = U K2^-1 follows block by block
+    cudaEvent_t hs_ev_chunk[kUChunks] = {};
+    int u_chunks = 0;                     // > 0: hs_ev_chunk[c] marks the arrival of rows [c n1 / u_chunks, (c+1) n1 / u_chunks)
     int (*on_gu)(gphm_plan&, cudaStream_t) = nullptr;   // called once dL/dU is complete (before the theta-gradient)
     bool gu_hook_ran = false;
     // Look-ahead of the factor stage (gphm_step on large 2-D uniform plans): the theta-only work of step t+1 (tables, recursion,
@@ -427,6 +430,16 @@ int logjoint_grad_gs(gphm_plan& p, const double* U, const double* small, double*
     } else {
         GPHM_TRY(factor_gs(p, 0, two ? 2 : 1, small, st));   // includes the spectra of D1, D2; needs only theta
     }
+    bool bt_done = false;
+    if (p.u_ready && two && p.u_chunks > 0) {               // gphm_step_host: Bt = U K2^-1 row block by row block behind the upload
+        const int rows = n1 / p.u_chunks;
+        for (int c = 0; c < p.u_chunks; ++c) {
+            GPHM_CUDA_OK(cudaStreamWaitEvent(st, p.hs_ev_chunk[c], 0));
+            GPHM_TRY(launch_gs_apply_fused(U + (size_t)c * rows * n2, rows, n2, n2, X2.gspec, X2.fftL, X2.twid, 1.0, 0.0, nullptr, 0,
+                                           p.Bt + (size_t)c * rows * n2, n2, st, X2.gsg));
+        }
+        bt_done = true;
+    }
     if (p.u_ready) GPHM_CUDA_OK(cudaStreamWaitEvent(st, p.u_ready, 0));     // gphm_step_host: U arrives meanwhile
     auto gs1 = [&](const double* Xr, double* out) {       // rows of length n1 (columns of the field)
         return launch_gs_apply_fused(Xr, n2, n1, n1, X1.gspec, X1.fftL, X1.twid, 1.0, 0.0, nullptr, 0, out, n1, st, X1.gsg);
@@ -448,7 +461,8 @@ int logjoint_grad_gs(gphm_plan& p, const double* U, const double* small, double*
     const double* Bt = U;
     const double* A = At;
     if (two) {
-        GPHM_TRY(gs2(U, p.Bt)); Bt = p.Bt;                 // Bt = U K2^-1
+        if (!bt_done) GPHM_TRY(gs2(U, p.Bt));              // Bt = U K2^-1
+        Bt = p.Bt;
         GPHM_TRY(d1(At, c1, 0.0, nullptr, p.Tf, X1.specY));   // (c1 D1 A)^T; keeps the transforms of A^T's rows
         GPHM_TRY(launch_transpose(p.Tf, n2, n1, p.R, st));
         GPHM_TRY(d2(Bt, 1.0, 1.0, nullptr, p.R, X2.specY));   // + Bt D2^T; keeps the transforms of Bt's rows
@@ -863,6 +877,7 @@ void gphm_plan_destroy(gphm_plan* plan) {
     if (plan->hs_count) cudaFree(plan->hs_count);
     if (plan->hs_stream) cudaStreamDestroy(plan->hs_stream);
     if (plan->hs_ev_u) cudaEventDestroy(plan->hs_ev_u);
+    for (cudaEvent_t e : plan->hs_ev_chunk) if (e) cudaEventDestroy(e);
     if (plan->hs_ev_mv) cudaEventDestroy(plan->hs_ev_mv);
     if (plan->hs_ev_gu) cudaEventDestroy(plan->hs_ev_gu);
     if (plan->hs_ev_adam) cudaEventDestroy(plan->hs_ev_adam);
@@ -992,6 +1007,7 @@ static int step_host_impl(gphm_plan* plan, double* h_U, double* h_small, double*
         GPHM_CUDA_OK(cudaMalloc(&plan->hs_count, sizeof(long long)));
         GPHM_CUDA_OK(cudaStreamCreateWithFlags(&plan->hs_stream, cudaStreamNonBlocking));
         GPHM_CUDA_OK(cudaEventCreateWithFlags(&plan->hs_ev_u, cudaEventDisableTiming));
+        for (cudaEvent_t& e : plan->hs_ev_chunk) GPHM_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         GPHM_CUDA_OK(cudaEventCreateWithFlags(&plan->hs_ev_mv, cudaEventDisableTiming));
         GPHM_CUDA_OK(cudaEventCreateWithFlags(&plan->hs_ev_gu, cudaEventDisableTiming));
         GPHM_CUDA_OK(cudaEventCreateWithFlags(&plan->hs_ev_adam, cudaEventDisableTiming));
@@ -1015,7 +1031,20 @@ static int step_host_impl(gphm_plan* plan, double* h_U, double* h_small, double*
         GPHM_CUDA_OK(cudaEventRecord(plan->hs_ev_mv, st));
         GPHM_CUDA_OK(cudaStreamWaitEvent(plan->hs_stream, plan->hs_ev_mv, 0));
     }
-    GPHM_CUDA_OK(cudaMemcpyAsync(U, h_U, sizeof(double) * nf, cudaMemcpyHostToDevice, plan->hs_stream));
+    // 2-D all-FFT plans: U goes up in row blocks and the step applies K2^-1 to every block as it lands (rows are independent),
+    // so only the last block's share of that kernel is exposed behind the 2.4 ms upload
+    const int n1 = plan->d.n1, n2 = plan->d.n2;
+    const int chunks = (plan->d.dim == 2 && uses_gs_path(*plan) && n1 >= 1024 && n1 % (2 * gphm_plan::kUChunks) == 0) ? gphm_plan::kUChunks : 0;
+    if (chunks) {
+        const size_t rows = (size_t)n1 / chunks;
+        for (int c = 0; c < chunks; ++c) {
+            GPHM_CUDA_OK(cudaMemcpyAsync(U + c * rows * n2, h_U + c * rows * n2, sizeof(double) * rows * n2, cudaMemcpyHostToDevice,
+                                         plan->hs_stream));
+            GPHM_CUDA_OK(cudaEventRecord(plan->hs_ev_chunk[c], plan->hs_stream));
+        }
+    } else {
+        GPHM_CUDA_OK(cudaMemcpyAsync(U, h_U, sizeof(double) * nf, cudaMemcpyHostToDevice, plan->hs_stream));
+    }
     GPHM_CUDA_OK(cudaEventRecord(plan->hs_ev_u, plan->hs_stream));
     if (!resident) {
         GPHM_CUDA_OK(cudaMemcpyAsync(mU, h_mU, sizeof(double) * nf, cudaMemcpyHostToDevice, plan->hs_stream));
@@ -1025,6 +1054,7 @@ static int step_host_impl(gphm_plan* plan, double* h_U, double* h_small, double*
     static thread_local Ctx ctx;
     ctx = Ctx{U, mU, vU, h_U, h_mU, h_vU, nf, lr, resident};
     plan->u_ready = plan->hs_ev_u;
+    plan->u_chunks = chunks;
     plan->gu_hook_ran = false;
     plan->on_gu = [](gphm_plan& p, cudaStream_t s) -> int {                  // dL/dU complete on s
         GPHM_CUDA_OK(cudaEventRecord(p.hs_ev_gu, s));
@@ -1040,6 +1070,7 @@ static int step_host_impl(gphm_plan* plan, double* h_U, double* h_small, double*
     };
     const int rc = logjoint_grad(*plan, U, sm, plan->gU, plan->gsmall, terms, 0, st);
     plan->u_ready = nullptr;
+    plan->u_chunks = 0;
     plan->on_gu = nullptr;
     if (rc != GPHM_OK) { cudaStreamSynchronize(plan->hs_stream); cudaStreamSynchronize(st); return rc; }
     if (!plan->gu_hook_ran) {            // dense path: no early hand-over, Adam(U) after the whole gradient

@@ -478,6 +478,36 @@ def test_evals_end_to_end_run_2d_sh_line(gphm, tmp_path, monkeypatch):
     assert lines[1].startswith("err_mean: 0.46") and "avg_epochs 100" in lines[1] and lines[2].startswith("err_list: [0.46")
 
 
+def test_step_host_chunked_upload_is_bitwise_the_device_step(gphm, oracle):
+    """Large 2-D all-FFT plans (n1 >= 1024): gphm_step_host / gphm_step_host_params send U up in four row blocks and apply
+    K2^-1 to every block as it lands (rows are independent), behind the upload.  Same bits as the device-resident step."""
+    O = oracle
+    N = 1024
+    p, _, _ = O.make_problem_2d("poisson_2d-sin_add_cos", "Matern52_Cos_1d", N, 2 * math.pi, M=8)
+    core = gphm.solver_core.SolverCore(2, "Matern52_Cos_1d", "poisson", p.x.numpy(), p.y.numpy(), p.src.numpy(), p.bvals.numpy(),
+                                       None, p.llk_weight, 1.0, 1.0, 1e-6, 30)
+    s1 = O.state_S1(p)
+    pin = lambda t: t.detach().cpu().clone().pin_memory()
+    st = core.new_state(s1)
+    h = [pin(st.U), pin(st.small), pin(st.mU), pin(st.vU), pin(st.msmall), pin(st.vsmall), pin(st.count)]
+    hterms = torch.zeros(8, dtype=torch.float64).pin_memory()
+    for k in range(3):
+        core.step_inplace(st, 0.01)
+        core.step_host(h[0], h[1], h[2], h[3], h[4], h[5], h[6], hterms, 0.01)
+        torch.cuda.synchronize()
+        assert torch.equal(hterms, st.terms.cpu()), k
+        for a, b in zip(h, (st.U, st.small, st.mU, st.vU, st.msmall, st.vsmall, st.count)):
+            assert torch.equal(a, b.cpu()), k
+    st2 = core.new_state(s1)
+    hU, hs = pin(st2.U), pin(st2.small)
+    for k in range(3):
+        core.step_inplace(st2, 0.01)
+        core.step_host_params(hU, hs, hterms, 0.01, reset_opt=(k == 0))
+        assert torch.equal(hterms, st2.terms.cpu()), k
+        assert torch.equal(hU, st2.U.cpu()) and torch.equal(hs, st2.small.cpu()), k
+    core.raise_on_bad_status()
+
+
 def test_step_lookahead_is_bitwise_the_plain_step(gphm, oracle):
     """gphm_step on large 2-D uniform plans can factor (opt-in: force_general bit 9) the NEXT step's theta (tables, Schur/Levinson recursion, spectra) on a
     second stream beside dL/dU assembly + Adam(U) and skips the factor stage of the next call when - checked on the device -
