@@ -1059,6 +1059,17 @@ static int step_host_impl(gphm_plan* plan, double* h_U, double* h_small, double*
     plan->on_gu = [](gphm_plan& p, cudaStream_t s) -> int {                  // dL/dU complete on s
         GPHM_CUDA_OK(cudaEventRecord(p.hs_ev_gu, s));
         GPHM_CUDA_OK(cudaStreamWaitEvent(p.hs_stream, p.hs_ev_gu, 0));
+        if (ctx.resident && p.u_chunks > 0 && ctx.nf % p.u_chunks == 0) {
+            // Adam(U) and the download block by block: only the first block's update is exposed before PCIe is busy again
+            const size_t blk = ctx.nf / p.u_chunks;
+            for (int c = 0; c < p.u_chunks; ++c) {
+                const size_t o = c * blk;
+                GPHM_TRY(launch_adam(ctx.U + o, p.gU + o, ctx.mU + o, ctx.vU + o, blk, p.hs_count, ctx.lr, p.hs_stream));
+                if (c == p.u_chunks - 1) GPHM_CUDA_OK(cudaEventRecord(p.hs_ev_adam, p.hs_stream));
+                GPHM_CUDA_OK(cudaMemcpyAsync(ctx.hU + o, ctx.U + o, sizeof(double) * blk, cudaMemcpyDeviceToHost, p.hs_stream));
+            }
+            return GPHM_OK;
+        }
         GPHM_TRY(launch_adam(ctx.U, p.gU, ctx.mU, ctx.vU, ctx.nf, p.hs_count, ctx.lr, p.hs_stream));
         GPHM_CUDA_OK(cudaEventRecord(p.hs_ev_adam, p.hs_stream));
         GPHM_CUDA_OK(cudaMemcpyAsync(ctx.hU, ctx.U, sizeof(double) * ctx.nf, cudaMemcpyDeviceToHost, p.hs_stream));
