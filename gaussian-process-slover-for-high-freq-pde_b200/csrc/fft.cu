@@ -254,20 +254,24 @@ toeplitz_apply_kernel(const double* __restrict__ X, int rows, int n, int ldx, co
     }
 }
 
-// out[c][r] = in[r][c]
+// out[c][r] = in[r][c] (+ out[c][r] when ACC); leading dimensions ldi, ldo (row blocks of a larger field)
+template <bool ACC>
 __global__ void __launch_bounds__(256)
-transpose_kernel(const double* __restrict__ in, int R, int C, double* __restrict__ out) {
+transpose_kernel(const double* __restrict__ in, int R, int C, size_t ldi, double* __restrict__ out, size_t ldo) {
     __shared__ double tile[32][33];
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int i = ty; i < 32; i += 8) {
         const int r = r0 + i, c = c0 + tx;
-        if (r < R && c < C) tile[i][tx] = in[(size_t)r * C + c];
+        if (r < R && c < C) tile[i][tx] = in[(size_t)r * ldi + c];
     }
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
         const int c = c0 + i, r = r0 + tx;
-        if (r < R && c < C) out[(size_t)c * R + r] = tile[tx][i];
+        if (r < R && c < C) {
+            double* o = out + (size_t)c * ldo + r;
+            *o = ACC ? tile[tx][i] + *o : tile[tx][i];
+        }
     }
 }
 
@@ -424,10 +428,15 @@ int launch_toeplitz_apply(const double* X, int rows, int n, int ldx, const doubl
     return GPHM_OK;
 }
 
-int launch_transpose(const double* in, int R, int C, double* out, cudaStream_t st) {
+int launch_transpose(const double* in, int R, int C, double* out, cudaStream_t st, int ldi, int ldo, bool accumulate) {
     if (R <= 0 || C <= 0) return GPHM_OK;
     dim3 grid((C + 31) / 32, (R + 31) / 32);
-    { LaunchScope scope(CAT_ELEMWISE, st); transpose_kernel<<<grid, 256, 0, st>>>(in, R, C, out); }
+    const size_t li = ldi > 0 ? ldi : C, lo = ldo > 0 ? ldo : R;
+    {
+        LaunchScope scope(CAT_ELEMWISE, st);
+        if (accumulate) transpose_kernel<true><<<grid, 256, 0, st>>>(in, R, C, li, out, lo);
+        else transpose_kernel<false><<<grid, 256, 0, st>>>(in, R, C, li, out, lo);
+    }
     GPHM_LAUNCH_OK();
     return GPHM_OK;
 }

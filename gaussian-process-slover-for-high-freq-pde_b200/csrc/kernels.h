@@ -78,7 +78,8 @@ int launch_toeplitz_spectrum(const double* tab, int n, int L, const double* W, b
 // Out[r][:] = alpha * T X[r][:] + beta * Out[r][:]   for every row r (T n x n Toeplitz with spectrum `spec`)
 int launch_toeplitz_apply(const double* X, int rows, int n, int ldx, const double* spec, int L, const double* W, double alpha,
                           double beta, double* Out, int ldo, cudaStream_t st);
-int launch_transpose(const double* in, int R, int C, double* out, cudaStream_t st);
+// out (C x R, leading dimension ldo, default R) = in^T (in: R x C, leading dimension ldi, default C), + out when accumulate
+int launch_transpose(const double* in, int R, int C, double* out, cudaStream_t st, int ldi = 0, int ldo = 0, bool accumulate = false);
 int launch_transpose_parts(const double* in, int R, int C, int wc, size_t pstride, double* out, cudaStream_t st);
 int launch_unpack_segments(const double* recv, int P, int k, int rows, int seg, double* out, cudaStream_t st);
 

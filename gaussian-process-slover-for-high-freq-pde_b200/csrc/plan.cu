@@ -431,12 +431,17 @@ int logjoint_grad_gs(gphm_plan& p, const double* U, const double* small, double*
         GPHM_TRY(factor_gs(p, 0, two ? 2 : 1, small, st));   // includes the spectra of D1, D2; needs only theta
     }
     bool bt_done = false;
-    if (p.u_ready && two && p.u_chunks > 0) {               // gphm_step_host: Bt = U K2^-1 row block by row block behind the upload
+    if (p.u_ready && two && p.u_chunks > 0) {
+        // gphm_step_host: everything that acts on ROWS of U runs row block by row block behind the upload -
+        // Bt = U K2^-1, R = Bt D2^T (with the transforms of Bt's rows kept) and the block's share of U^T
         const int rows = n1 / p.u_chunks;
         for (int c = 0; c < p.u_chunks; ++c) {
+            const size_t o = (size_t)c * rows * n2;
             GPHM_CUDA_OK(cudaStreamWaitEvent(st, p.hs_ev_chunk[c], 0));
-            GPHM_TRY(launch_gs_apply_fused(U + (size_t)c * rows * n2, rows, n2, n2, X2.gspec, X2.fftL, X2.twid, 1.0, 0.0, nullptr, 0,
-                                           p.Bt + (size_t)c * rows * n2, n2, st, X2.gsg));
+            GPHM_TRY(launch_gs_apply_fused(U + o, rows, n2, n2, X2.gspec, X2.fftL, X2.twid, 1.0, 0.0, nullptr, 0, p.Bt + o, n2, st, X2.gsg));
+            GPHM_TRY(launch_toeplitz_apply_fused(p.Bt + o, rows, n2, n2, X2.specT, X2.fftL, X2.twid, 1.0, 0.0, nullptr, n2, p.R + o, n2,
+                                                 X2.specY + (size_t)(c * rows / 2) * X2.fftL * 2, st));
+            GPHM_TRY(launch_transpose(U + o, rows, n2, p.Tf + (size_t)c * rows, st, n2, n1));
         }
         bt_done = true;
     }
@@ -455,7 +460,7 @@ int logjoint_grad_gs(gphm_plan& p, const double* U, const double* small, double*
     };
     // ---- forward ----
     const double* Ut = U;                                  // 1-D: the field is one row already
-    if (two) { GPHM_TRY(launch_transpose(U, n1, n2, p.Tf, st)); Ut = p.Tf; }
+    if (two) { if (!bt_done) GPHM_TRY(launch_transpose(U, n1, n2, p.Tf, st)); Ut = p.Tf; }
     double* At = p.P;
     GPHM_TRY(gs1(Ut, At));                                 // A^T = (K1^-1 U)^T
     const double* Bt = U;
@@ -464,8 +469,12 @@ int logjoint_grad_gs(gphm_plan& p, const double* U, const double* small, double*
         if (!bt_done) GPHM_TRY(gs2(U, p.Bt));              // Bt = U K2^-1
         Bt = p.Bt;
         GPHM_TRY(d1(At, c1, 0.0, nullptr, p.Tf, X1.specY));   // (c1 D1 A)^T; keeps the transforms of A^T's rows
-        GPHM_TRY(launch_transpose(p.Tf, n2, n1, p.R, st));
-        GPHM_TRY(d2(Bt, 1.0, 1.0, nullptr, p.R, X2.specY));   // + Bt D2^T; keeps the transforms of Bt's rows
+        if (bt_done) {
+            GPHM_TRY(launch_transpose(p.Tf, n2, n1, p.R, st, 0, 0, true));   // R = Bt D2^T is there already: same sum, same bits
+        } else {
+            GPHM_TRY(launch_transpose(p.Tf, n2, n1, p.R, st));
+            GPHM_TRY(d2(Bt, 1.0, 1.0, nullptr, p.R, X2.specY));   // + Bt D2^T; keeps the transforms of Bt's rows
+        }
         GPHM_TRY(launch_transpose(At, n2, n1, p.A, st)); A = p.A;
     } else {
         GPHM_TRY(d1(At, c1, 0.0, nullptr, p.R, X1.specY));
