@@ -59,3 +59,34 @@ def test_parity_block_helpers_on_cpu():
         assert side.compare(name, params, bad, gl["U"], bench.small_from_params(gl))["max_rel_term"] >= (9e-4 if name == "S1" else 0.0)
     run = side.steps_and_rel_l2(2)
     assert 0.0 < run["rel_l2"] < 2.0 and run["timed_iters"] == 1 and run["U"].shape == (48, 48)
+
+
+def test_clock_sampler_contract_without_nvml():
+    """The clocks record always has the contract's keys; NVML polling feeds it when the driver library loads, a fake NVML here
+    (no GPU in this container): median SM clock, max clock, the reasons seen in ANY sample."""
+    sys.path.insert(0, ROOT)
+    import time
+    import types
+    import bench
+    s = bench.ClockSampler(0)
+    if s.nvml is None:                                   # no driver: the nvidia-smi fall-back reports that it is unavailable
+        s.start()
+        rec = s.stop()
+        assert set(("sm_mhz", "sm_max_mhz", "samples", "reasons")) <= set(rec) and rec["samples"] == 0
+    calls = {"n": 0}
+
+    def clock(handle, kind):
+        calls["n"] += 1
+        return 1965 if calls["n"] != 2 else 1200         # one low sample must not move the median
+
+    fake = types.SimpleNamespace(
+        NVML_CLOCK_SM=0, nvmlDeviceGetClockInfo=clock,
+        nvmlDeviceGetCurrentClocksEventReasons=lambda h: 0x4 if calls["n"] == 3 else 0,
+        nvmlClocksThrottleReasonHwSlowdown=0x8, nvmlClocksThrottleReasonHwThermalSlowdown=0x40,
+        nvmlClocksThrottleReasonSwThermalSlowdown=0x20, nvmlClocksThrottleReasonSwPowerCap=0x4)
+    s = bench.ClockSampler.__new__(bench.ClockSampler)
+    s.index, s.nvml, s.handle, s.proc, s.thread, s.samples, s.sm_max, s.running = 0, fake, object(), None, None, [], 1965.0, False
+    s.start()
+    time.sleep(0.08)
+    rec = s.stop()
+    assert rec["samples"] >= 3 and rec["sm_mhz"] == 1965.0 and rec["sm_max_mhz"] == 1965.0 and rec["reasons"] == ["sw_power_cap"], rec
