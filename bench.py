@@ -581,14 +581,8 @@ def run_ours(args, rank, world, local):
             h.copy_(t.cpu())
         hloss = torch.zeros(1, dtype=torch.float64).pin_memory()
 
-        def host_step():
-            for h, t in zip(hostb, blocks):
-                t.copy_(h, non_blocking=True)
-            solver.step()
-            for h, t in zip(hostb, blocks):
-                h.copy_(t, non_blocking=True)
-            hloss.copy_(solver.last_loss().reshape(1), non_blocking=True)
-            torch.cuda.synchronize()
+        def host_step():       # upload beside the factor stage, Adam(U) + download beside the theta-gradient tail (dist.py)
+            solver.step_host(hostb[0], hostb[1], hloss)
         e2e_steps = min(args.steps, 10)
         host_step()
         barrier()
@@ -601,7 +595,7 @@ def run_ours(args, rank, world, local):
         per_rank = sum(t.numel() * t.element_size() for t in blocks)
         e2e = {"value": e2e_steps / float(tt), "unit": UNIT, "h2d_bytes_per_step": per_rank * world,
                "d2h_bytes_per_step": per_rank * world + 8 * world, "steps": e2e_steps,
-               "api": "ShardedSolver2D.step with every rank's row block of the params copied from / to pinned host memory "
+               "api": "ShardedSolver2D.step_host: every rank's row block of the params from / to pinned host memory every step "
                       "(Adam state resident on the device)"}
 
     # ---- ensemble sub-record (BASELINE configs[4]): this rank's share of the members, a few ensemble steps ----

@@ -380,6 +380,8 @@ class ShardedSolver2D(object):
         # all_to_all_single -> unpack (round 1; also what the gloo CPU tests drive)
         mode = os.environ.get("GPHM_MG_EXCHANGE", "peer")
         self.exchange = "peer" if (mode == "peer" and self.P > 1 and hasattr(self.ops, "peer_exchange")) else "nccl"
+        # hooks of step_host into the all-FFT step (None otherwise)
+        self._u_ready, self._on_gu, self._copy = None, None, None
 
     # ---- state ---------------------------------------------------------------------------------
     def init_state(self, freq_scale):
@@ -520,7 +522,11 @@ class ShardedSolver2D(object):
         small, U_r = self.small, self.U
         fork = getattr(o, "fork", None) or (lambda fn: (fn(), None))
         join = getattr(o, "join", None) or (lambda h: h[0])
-        hU = fork(lambda: self.r2ct([U_r]))
+        def first_exchange():
+            if self._u_ready is not None:           # step_host: this rank's rows of U are still on their way up
+                torch.cuda.current_stream(U_r.device).wait_event(self._u_ready)
+            return self.r2ct([U_r])
+        hU = fork(first_exchange)
         o.factor(small, 3)                          # O(n^2) generators + spectra, local to every rank
         ld = o.logdets()
         (U_ct,) = join(hU)
@@ -543,6 +549,8 @@ class ShardedSolver2D(object):
         P2 = o.toeplitz_rows_add(1, True, G_r, 1.0, 0.5, A_r, o.new("P2", G_r.shape), False)    # G D2 + A/2
         V2_r = o.kinv_rows(1, P2, "V2_r", refine=True)
         gU_r = o.grad_u_sum(U_r, G_r, V1_r, V2_r, self.bidx, eb, self.nseg0, small)
+        if self._on_gu is not None:                  # step_host: nothing below reads U or dL/dU
+            self._on_gu(gU_r)
         both = getattr(o, "theta_grad_pairs_both", None)       # (the CPU stand-in of the gloo tests has the per-axis call only)
         if both is not None:
             both(V1t, G_ct, V2_r, G_r, lead, 0.5 * self.logdet * N2, 0.5 * self.logdet * N1, c1, 1.0, small, gs[0:6 * Q])
@@ -639,6 +647,72 @@ class ShardedSolver2D(object):
         gs[6 * Q] = gtau
         gs[6 * Q + 1] = gv
         return self.terms, gU_r, gs
+
+    def step_host(self, hU, hsmall, hloss=None):
+        """Collective: one step on HOST params - this rank's row block of U (h x N2) and the replicated small params, both in
+        pinned memory, updated in place; hloss (1,) receives the loss.  The Adam state stays on the device (like optax's
+        state in the reference's loop).  All-FFT plans on CUDA hide the copies: the upload of U runs on a copy stream beside
+        the factor stage (which needs only theta) and gates the first exchange; once dL/dU is complete Adam(U) and the
+        download of U run on the copy stream beside the theta-gradient tail, the all-reduce and the small leaves' update.
+        Same kernels on the same data as step(): bitwise the same result."""
+        o = self.ops
+        on_cuda = self.U.is_cuda and getattr(o, "uses_gs", None) is not None and o.uses_gs(0) and o.uses_gs(1)
+        adam_inc = getattr(o, "adam_inc", None)
+        if not on_cuda:                              # general path / CPU stand-in: plain semantics
+            self.U.copy_(hU, non_blocking=True)
+            self.small.copy_(hsmall, non_blocking=True)
+            self.step()
+            hU.copy_(self.U, non_blocking=True)
+            hsmall.copy_(self.small, non_blocking=True)
+            if hloss is not None:
+                hloss.copy_(self.last_loss().reshape(1), non_blocking=True)
+            if self.U.is_cuda:
+                torch.cuda.synchronize(self.U.device)
+            return
+        dev = self.U.device
+        cur = torch.cuda.current_stream(dev)
+        if self._copy is None:
+            self._copy = torch.cuda.Stream(device=dev)
+        cs = self._copy
+        self.small.copy_(hsmall, non_blocking=True)  # tiny, and the factor stage needs it
+        cs.wait_stream(cur)                          # earlier readers of U are done
+        with torch.cuda.stream(cs):
+            self.U.copy_(hU, non_blocking=True)
+            self._u_ready = torch.cuda.Event()
+            self._u_ready.record(cs)
+        done = []
+
+        def on_gu(gU_r):
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            cs.wait_event(ev)
+            with torch.cuda.stream(cs):
+                o.adam(self.U, gU_r, self.mU, self.vU, self.count, self.lr)
+                e2 = torch.cuda.Event()
+                e2.record(cs)                            # Adam(U) has read the count
+                hU.copy_(self.U, non_blocking=True)
+            done.append(e2)
+
+        self._on_gu = on_gu
+        try:
+            _, gU_r, gs = self.value_and_grad()
+        finally:
+            self._u_ready, self._on_gu = None, None
+        if done:
+            cur.wait_event(done[0])                  # Adam(U) has read the count (the download may still be running)
+        else:
+            o.adam(self.U, gU_r, self.mU, self.vU, self.count, self.lr)
+            hU.copy_(self.U, non_blocking=True)
+        if adam_inc is not None:
+            adam_inc(self.small, gs, self.msmall, self.vsmall, self.count, self.lr)
+        else:
+            o.adam(self.small, gs, self.msmall, self.vsmall, self.count, self.lr)
+            self.count += 1
+        hsmall.copy_(self.small, non_blocking=True)
+        if hloss is not None:
+            hloss.copy_(self.last_loss().reshape(1), non_blocking=True)
+        cur.synchronize()
+        cs.synchronize()
 
     def step(self):
         """Collective: value_and_grad + Adam on the local U rows and on the (replicated) small params."""

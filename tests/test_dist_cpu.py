@@ -56,6 +56,17 @@ def _run_case(equation, eq_name, kernel, beta, N1, N2, Q, steps, gs=True):
     assert float((U - params["U"]).abs().max()) <= 1e-8
     assert float((solver.small - _small_from(params, Q)).abs().max()) <= 1e-8
     assert int(solver.count) == steps
+    # step_host on host copies of this rank's params (plain semantics on the CPU stand-in): the same update as step()
+    names = ("U", "small", "mU", "vU", "msmall", "vsmall", "count")
+    saved = {k: getattr(solver, k).clone() for k in names}
+    solver.step()
+    want = {k: getattr(solver, k).clone() for k in names}
+    for k in names:
+        getattr(solver, k).copy_(saved[k])
+    hU, hs, hloss = saved["U"].clone(), saved["small"].clone(), torch.zeros(1, dtype=DT)
+    solver.step_host(hU, hs, hloss)
+    assert all(torch.equal(getattr(solver, k), want[k]) for k in names)
+    assert torch.equal(hU, want["U"]) and torch.equal(hs, want["small"]) and float(hloss) == float(solver.last_loss())
     return True
 
 

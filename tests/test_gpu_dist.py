@@ -68,6 +68,22 @@ def _compare(equation, eq_name, kernel, beta, N, Q, steps=2, mode=0):
     assert float((solver.gather_U() - st.U.reshape(N, N)).abs().max()) <= 1e-6
     assert abs(float(solver.last_loss()) - float(st.terms[0])) <= 1e-6 * abs(float(st.terms[0]))
     torch.cuda.synchronize()
+    # step_host (pinned host params in / out, copies overlapped with the factor stage and the theta-gradient tail): bitwise step()
+    names = ("U", "small", "mU", "vU", "msmall", "vsmall", "count")
+    saved = {k: getattr(solver, k).clone() for k in names}
+    solver.step()
+    want = {k: getattr(solver, k).clone() for k in names}
+    want_loss = float(solver.last_loss())
+    for k in names:
+        getattr(solver, k).copy_(saved[k])
+    hU, hs = saved["U"].cpu().pin_memory(), saved["small"].cpu().pin_memory()
+    hloss = torch.zeros(1, dtype=DT).pin_memory()
+    solver.step_host(hU, hs, hloss)
+    for k in names:
+        assert torch.equal(getattr(solver, k), want[k]), k
+    assert torch.equal(hU, want["U"].cpu()) and torch.equal(hs, want["small"].cpu()) and float(hloss) == want_loss
+    solver.step_host(hU, hs, hloss)                      # a second call reuses the streams; state keeps advancing
+    assert int(solver.count) == int(want["count"]) + 1 and torch.equal(hU, solver.U.cpu())
 
 
 @pytest.mark.parametrize("equation,eq_name,kernel,beta", [("poisson_2d-sin_add_cos", "poisson", "Matern52_Cos_1d", 1.0),
